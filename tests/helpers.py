@@ -1,0 +1,43 @@
+"""Shared helpers of the test-suite: golden fixture loading and oracle model construction."""
+import glob
+import json
+import os
+
+import numpy as np
+
+from pastml_b200.tree import FlatForest
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+MODEL_KIND = {'F81': 0, 'JC': 0, 'EFT': 0, 'HKY': 1, 'JTT': 2, 'CUSTOM_RATES': 2}
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz')))
+
+
+class Golden(object):
+    def __init__(self, name):
+        self.name = name
+        self.z = np.load(os.path.join(GOLDEN_DIR, name + '.npz'), allow_pickle=False)
+        self.meta = json.loads(str(self.z['meta']))
+        self.flat = FlatForest(self.z['parent'], self.z['dist'], names=[str(_) for _ in self.z['names']])
+        self.states = [str(_) for _ in self.z['states']]
+        self.K = len(self.states)
+        self.model_name = self.meta['model']
+        self.kind = MODEL_KIND[self.model_name]
+
+    def __getitem__(self, key):
+        return self.z[key]
+
+    def __contains__(self, key):
+        return key in self.z.files
+
+    def oracle_model(self):
+        from oracle.cpu_oracle import OracleModel
+        z = self.z
+        kw = {}
+        if self.kind == 2:
+            kw = dict(d=z['eig_d'], A=z['eig_A'], Ainv=z['eig_Ainv'])
+        return OracleModel(self.kind, z['pi'], float(z['sf']), float(z['tau']), float(z['tau_factor']),
+                           float(z['kappa']), **kw)
