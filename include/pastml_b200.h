@@ -1,0 +1,146 @@
+/*
+ * pastml_b200 -- C ABI of the B200-native ancestral-character-reconstruction engine.
+ *
+ * This is the drop-in boundary for the numerical hot path of evolbioinfo/pastml (pure Python + numpy):
+ *   pastml/ml.py          get_bottom_up_loglikelihood, calculate_top_down_likelihood,
+ *                         calculate_marginal_likelihoods, choose_ancestral_states_{joint,map,mppa}
+ *   pastml/parsimony.py   uppass, acctran, downpass, deltran, get_num_parsimonious_steps
+ *   pastml/models/*.py    Model.get_Pij_t
+ * The reference has no FFI of its own; these entry points are what a ctypes binding inside pastml would bind
+ * (INTEGRATION.md shows that binding).  Plain pointers and sizes only, no torch / CUDA types.
+ *
+ * Conventions
+ *   - Return value 0 = success; non-zero = error, text in pml_last_error() (per calling thread).
+ *   - Host pointers are borrowed for the duration of the call.  Device memory belongs to the handle.
+ *   - One handle = one forest x C characters ("columns") that share the number of states K and the model
+ *     family.  A handle owns one CUDA stream; calls on one handle must not overlap, different handles may be
+ *     used from different threads.
+ *   - Nodes are numbered in level order over the forest: all roots, then all depth-1 nodes, ...; siblings are
+ *     contiguous and ordered by parent, so `parent[]` is non-decreasing.  For one tree this is ete3's default
+ *     traverse() order, i.e. the row order of the reference's marginal-probability table (ml.py:498-502).
+ *   - State sets are bit masks in a uint64 (bit k = state k); K <= 62.
+ *   - "Parameter set": the reference evaluates its objective for one parameter vector at a time
+ *     (ml.py:202-208); here B parameter sets x C columns are evaluated by one launch sequence.  params is
+ *     [B][C][pml_param_stride()] doubles:
+ *        [0] sf  [1] tau  [2] tau_factor               (Model.transform_t, models/__init__.py:269-270, 39-42)
+ *        F81 family (F81/JC/EFT): [3] mu = 1/(1 - pi.pi)  [4..4+K) pi                    (F81Model.py:18-46)
+ *        HKY:                     [3] kappa               [4..8)  pi (A,C,G,T)             (HKYModel.py:44-82)
+ *        EIG (CUSTOM_RATES/JTT):  [3] unused  [4..4+K) pi  then d[K], A[K*K], Ainv[K*K] row-major
+ *                                                                                       (generator.py:16-65)
+ */
+#ifndef PASTML_B200_H
+#define PASTML_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pml_problem pml_problem;
+
+/* model families (what get_Pij_t computes) */
+#define PML_MODEL_F81 0
+#define PML_MODEL_HKY 1
+#define PML_MODEL_EIG 2
+
+/* which allowed-state masks a likelihood pass uses (the reference keeps them in <col>_ALLOWED_STATES) */
+#define PML_MASK_ANNOTATION 0   /* initialize_allowed_states, ml.py:293-318 */
+#define PML_MASK_JOINT 1        /* after choose_ancestral_states_joint  */
+#define PML_MASK_MAP 2          /* after choose_ancestral_states_map    */
+#define PML_MASK_MPPA 3         /* after choose_ancestral_states_mppa   */
+#define PML_MASK_CUSTOM 4       /* uploaded with pml_set_custom_masks (e.g. parsimony states, ml.py:724) */
+
+/* parsimony methods (bit flags) */
+#define PML_PARS_ACCTRAN 1
+#define PML_PARS_DOWNPASS 2
+#define PML_PARS_DELTRAN 4
+
+/* error codes */
+#define PML_OK 0
+#define PML_ERR_INVALID 1
+#define PML_ERR_CUDA 2
+#define PML_ERR_ZERO_LIKELIHOOD 3   /* PastMLLikelihoodError of ml.py:139-145: see pml_zero_likelihood_info */
+#define PML_ERR_NO_DEVICE 4
+
+const char *pml_last_error(void);
+int pml_version(void);
+int pml_device_count(void);
+int pml_param_stride(int32_t model_kind, int32_t n_states);
+
+/* Creates a problem: topology (level-ordered), C columns with K states, annotation masks.
+ *   annot_mask[C][N]  annotated state set of each node, 0 = none (=> all states allowed, ml.py:311-313)
+ *   has_state[C][N]   node carries the annotation feature at all (ml.py:329-331), drives zero-branch clusters
+ *   max_param_sets    capacity B of parameter sets per launch (>= 1)
+ *   device            CUDA device ordinal */
+int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dist,
+                       int32_t n_columns, int32_t n_states, int32_t model_kind,
+                       const uint64_t *annot_mask, const uint8_t *has_state,
+                       int32_t max_param_sets, int32_t device, pml_problem **out);
+void pml_problem_destroy(pml_problem *p);
+
+/* get_bottom_up_loglikelihood(tree, character, model, is_marginal, alter) summed over the forest's trees
+ * (ml.py:82-121, 206-207) for n_sets x C (parameter set, column) pairs in one launch sequence.
+ *   mask_kind  PML_MASK_*;   is_marginal 1 = sum-product, 0 = max-product (no pointers kept);
+ *   alter      1 = apply the zero-branch cluster alteration where tau == 0 (ml.py:100-102, 352-387)
+ *   out_loglh  [n_sets][C]
+ * On PML_ERR_ZERO_LIKELIHOOD the other lanes' values are still written (the failing lane gets -inf). */
+int pml_loglik(pml_problem *p, const double *params, int32_t n_sets, int32_t mask_kind, int32_t is_marginal,
+               int32_t alter, double *out_loglh);
+
+/* JOINT reconstruction (ml.py:687-695): max-product bottom-up pass on the annotation masks with argmax
+ * pointers, unalter_zero_node_joint_states, top-down traceback.  params = one set [C][stride].
+ *   out_loglh[C]        log_likelihood_restricted_JOINT            (may be NULL)
+ *   out_state[N][C]     JOINT_STATE index of every node (int32)    (may be NULL)
+ * Leaves the JOINT masks and states on the device for later passes. */
+int pml_joint(pml_problem *p, const double *params, double *out_loglh, int32_t *out_state);
+
+/* Marginal reconstruction (ml.py:697-714, 735-742): bottom-up, top-down, marginal likelihoods,
+ * probabilities, MAP and MPPA state selection, fused in one level-synchronous sweep.
+ *   force_joint        MPPA keeps room for the JOINT state (needs a previous pml_joint call)
+ *   out_loglh[C]       marginal log-likelihood                                     (may be NULL)
+ *   out_probs[N][C][K] marginal probabilities, ml.py:486-502                        (may be NULL)
+ *   out_node_log10lh[N][C]  log10 of the node's total marginal likelihood = log10(sum LIKELIHOOD) -
+ *                      LIKELIHOOD_SF of the reference before MAP masking            (may be NULL)
+ *   out_map_mask[N][C], out_mppa_mask[N][C]   selected state sets                   (may be NULL)
+ *   out_k_hist[C][K+1] histogram of the number of states MPPA kept per node         (may be NULL)
+ * The MPPA outputs are final only after pml_mppa_finalize. */
+int pml_marginal(pml_problem *p, const double *params, int32_t force_joint,
+                 double *out_loglh, double *out_probs, double *out_node_log10lh,
+                 uint64_t *out_map_mask, uint64_t *out_mppa_mask, int64_t *out_k_hist);
+
+/* The reference selects MPPA states after the MAP-restricted likelihood pass, whose zero-branch alteration
+ * may have replaced the '.initial' masks MPPA multiplies by (ml.py:541-542, 384-385).  Call this after
+ * pml_loglik(PML_MASK_MAP, alter=1) to replay that for the few affected nodes.  Outputs as in pml_marginal. */
+int pml_mppa_finalize(pml_problem *p, int32_t force_joint, uint64_t *out_mppa_mask, int64_t *out_k_hist);
+
+/* Parsimony (parsimony.py:245-331): uppass, then the requested methods.  out_mask[m][N][C] for m in
+ * ACCTRAN, DOWNPASS, DELTRAN order restricted to the requested ones; out_steps[m][C]. */
+int pml_parsimony(pml_problem *p, int32_t methods, uint64_t *out_mask, int64_t *out_steps);
+
+/* Uploads [C][N] masks into the PML_MASK_CUSTOM slot. */
+int pml_set_custom_masks(pml_problem *p, const uint64_t *mask);
+/* Downloads a mask slot as [N][C]. */
+int pml_get_masks(pml_problem *p, int32_t mask_kind, uint64_t *out_mask);
+/* Nodes that currently carry the reference's '<col>_ALLOWED_STATES.initial' feature: out_has[N][C] (0/1),
+ * out_initial[N][C]. */
+int pml_get_initial(pml_problem *p, uint8_t *out_has, uint64_t *out_initial);
+
+/* After PML_ERR_ZERO_LIKELIHOOD: first failing (column, parameter set, parent node, child node). */
+int pml_zero_likelihood_info(pml_problem *p, int32_t *column, int32_t *param_set, int32_t *parent, int32_t *child);
+
+/* Timing of the last call on this handle: device time between the first and last kernel of the call, measured
+ * with CUDA events on the handle's stream (ms), and the number of kernels launched. */
+int pml_last_call_stats(pml_problem *p, double *device_ms, int64_t *kernel_launches);
+
+/* Device-resident variants used by bench.py: run the pass n_iter times back to back on resident inputs,
+ * returning the average device time per pass (CUDA events).  which: 0 = pml_loglik(annotation masks,
+ * marginal, alter), 1 = pml_marginal sweep (BU + TD/marginal/MAP/MPPA), 2 = pml_joint.  flush_l2 != 0 writes
+ * a buffer larger than L2 between iterations (outside the timed intervals). */
+int pml_bench_pass(pml_problem *p, const double *params, int32_t n_sets, int32_t which, int32_t n_iter,
+                   int32_t flush_l2, double *avg_ms, double *min_ms, int64_t *kernel_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -260,7 +260,7 @@ def case_albania_tau():
 def case_denv2(column):
     make, states = table_forest(os.path.join(REF, 'examples/DENV2/data/real/raxml_tree.dated.nwk'),
                                 os.path.join(REF, 'examples/DENV2/data/real/metadata.tab'), column, sep='\t',
-                                index_col=1, do_name=True)
+                                index_col=0, do_name=True)
     run_case('denv2_{}_f81'.format(column.lower()), make, column, states, 'F81')
 
 

@@ -1,0 +1,961 @@
+// Device code of the pastml_b200 engine (sm_100a).  All arithmetic is fp64 on the CUDA cores: the hot path is
+// HBM-bound (O(K) flops per node-state for the F81 family), so nothing here is shaped into a GEMM.
+//
+// Work decomposition: one thread per (internal node of a depth level, lane) where a lane is one
+// (parameter set, column) pair; the K-vector of the node lives in registers.  Partial likelihoods are stored
+// k-major / lane-minor, [slot][k][lane], so that the lanes of a warp read and write contiguous runs.
+//
+// Scaling: the reference keeps log10 likelihoods and shifts them by real-valued factors (rescale_log,
+// /root/reference/pastml/ml.py:151-171).  Here a node vector is a mantissa vector whose maximum is kept in [1, 2)
+// plus an exact power-of-two exponent (int32): true value = mant * 2^ex.  The likelihood is invariant to the
+// choice of shifts, so results agree with the reference to rounding while the per-child log10/pow calls vanish.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace pml {
+
+constexpr uint64_t kMemberFlag = 1ULL << 63;  // (node, column) belongs to a zero-branch cluster (see alter_kernel)
+constexpr int kBlock = 128;
+
+struct TreeDev {
+    int n_nodes;
+    int n_internal;
+    const int *parent;       // [N]
+    const int *first_child;  // [N]
+    const int *n_children;   // [N]
+    const int *slot;         // [N]  rank among internal nodes or -1
+    const int *int_nodes;    // [NI] slot -> node
+    const double *dist;      // [N]
+    const int *zc_index;     // [N]  row in the zero-cluster table or -1
+};
+
+struct ZcDev {              // zero-branch cluster table, rows x C
+    const uint64_t *alt;     // effective mask of the member for the current pass
+    const uint8_t *altflag;  // member was altered by the current pass' alteration
+    const uint64_t *initial; // '<col>_ALLOWED_STATES.initial'
+    const uint8_t *hasinit;
+};
+
+struct LaneDev {
+    int C;                   // columns
+    int J;                   // lanes = sets * C
+    int K;                   // states
+    int stride;              // doubles per lane in params
+    const double *params;    // [J][stride]
+    uint64_t kmask;          // (1 << K) - 1
+};
+
+// ------------------------------------------------------------------------------------------ helpers
+
+__device__ __forceinline__ int exponent_of(double x) {  // floor(log2 x) for positive normal x
+    return ((__double2hiint(x) >> 20) & 0x7ff) - 1023;
+}
+
+__device__ __forceinline__ double pow2(int e) {  // exact 2^e for -1022 <= e <= 1023
+    return __hiloint2double((e + 1023) << 20, 0);
+}
+
+__device__ __forceinline__ uint64_t eff_mask(const uint64_t *base, const TreeDev &t, const ZcDev &zc, int C,
+                                             int node, int c, bool use_alt, uint64_t kmask) {
+    uint64_t m = base[(size_t) node * C + c];
+    if (use_alt && (m & kMemberFlag)) m = zc.alt[(size_t) t.zc_index[node] * C + c];
+    return m & kmask;
+}
+
+// Brings the maximum of v[0..K) into [1, 2) by an exact power of two; returns the exponent removed (0 if the
+// vector is all zero).  Entries are non-negative.
+template <int KP>
+__device__ __forceinline__ int normalise(double (&v)[KP], int K, double &vmax) {
+    double m = 0.;
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+        if (k < K) m = fmax(m, v[k]);
+    vmax = m;
+    if (!(m > 0.) || isinf(m)) return 0;
+    int e = exponent_of(m);
+    if (e == -1023) {  // subnormal maximum: lift it first
+#pragma unroll
+        for (int k = 0; k < KP; ++k) v[k] *= 0x1p+200;
+        m *= 0x1p+200;
+        e = exponent_of(m);
+        const double s = pow2(-e);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) v[k] *= s;
+        return e - 200;
+    }
+    if (e == 0) return 0;
+    // 2^-e may be out of range for |e| > 1022: split
+    int e1 = e / 2, e2 = e - e1;
+    const double s1 = pow2(-e1), s2 = pow2(-e2);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) v[k] = (v[k] * s1) * s2;
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------ models
+// A "lane model" exposes: load(params), branch(dist) -> Branch, matvec(out = P(t) in),
+// maxvec(out_i = max_j P_ij in_j, arg_i = first argmax).
+
+template <int KP>
+struct F81Lane {  // F81 / JC / EFT: P_ij = (1 - e) pi_j + delta_ij e, e = exp(-mu t')  (F81Model.py:28-46)
+    double sf, tau, tauf, mu;
+    double pi[KP];
+    struct Branch { double e, ome; };
+
+    __device__ __forceinline__ void load(const double *p, int K) {
+        sf = p[0]; tau = p[1]; tauf = p[2]; mu = p[3];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) pi[k] = (k < K) ? p[4 + k] : 0.;
+    }
+    __device__ __forceinline__ Branch branch(double dist, int) const {
+        const double t = (dist + tau) * tauf * sf;                 // Model.transform_t
+        const double e = isinf(mu) ? 0. : exp(-mu * t);            // F81Model.py:44-45
+        return Branch{e, 1. - e};
+    }
+    __device__ __forceinline__ void matvec(const Branch &b, const double (&in)[KP], double (&out)[KP], int K) const {
+        double s = 0.;
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < K) s = fma(pi[k], in[k], s);
+        const double base = b.ome * s;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) out[k] = (k < K) ? fmax(fma(b.e, in[k], base), 0.) : 0.;
+    }
+    // max_j P_ij in_j in O(K): off-diagonal candidates are w_j = ((1-e) pi_j) in_j for every row, the diagonal one
+    // is ((1-e) pi_i + e) in_i; products are formed exactly like numpy forms P * L (no contraction).
+    __device__ __forceinline__ void maxvec(const Branch &b, const double (&in)[KP], double (&out)[KP],
+                                           uint8_t (&arg)[KP], int K) const {
+        double t1 = -CUDART_INF, t2 = -CUDART_INF;
+        int i1 = 0, i2 = 0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < K) {
+                const double w = __dmul_rn(__dmul_rn(b.ome, pi[k]), in[k]);
+                if (w > t1) { t2 = t1; i2 = i1; t1 = w; i1 = k; }
+                else if (w > t2) { t2 = w; i2 = k; }
+            }
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < K) {
+                const double dv = __dmul_rn(__dadd_rn(__dmul_rn(b.ome, pi[k]), b.e), in[k]);
+                const double ov = (i1 == k) ? t2 : t1;
+                const int oi = (i1 == k) ? i2 : i1;
+                double best; int bi;
+                if (K == 1 || dv > ov) { best = dv; bi = k; }
+                else if (dv < ov) { best = ov; bi = oi; }
+                else { best = dv; bi = k < oi ? k : oi; }
+                out[k] = fmax(best, 0.);
+                arg[k] = (uint8_t) bi;
+            } else { out[k] = 0.; arg[k] = 0; }
+    }
+};
+
+template <int KP>
+struct HKYLane {  // HKY85 closed form, states A, C, G, T  (HKYModel.py:44-82); KP == 4
+    double sf, tau, tauf, kappa;
+    double pi[KP];
+    struct Branch { double P[4][4]; };
+
+    __device__ __forceinline__ void load(const double *p, int) {
+        sf = p[0]; tau = p[1]; tauf = p[2]; kappa = p[3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pi[k] = p[4 + k];
+    }
+    __device__ __forceinline__ Branch branch(double dist, int) const {
+        const double t = (dist + tau) * tauf * sf;
+        const double pa = pi[0], pc = pi[1], pg = pi[2], pt = pi[3];
+        const double pag = pa + pg, pct = pc + pt;
+        const double beta = .5 / (pag * pct + kappa * (pa * pg + pc * pt));
+        const double e1 = exp(-beta * t);
+        const double ect = exp(-beta * t * (1. + pct * (kappa - 1.))) / pct;
+        const double eag = exp(-beta * t * (1. + pag * (kappa - 1.))) / pag;
+        const double ct_sum = (pct + pag * e1) / pct;
+        const double ag_sum = (pag + pct * e1) / pag;
+        Branch b;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b.P[i][j] = (1. - e1) * pi[j];
+        b.P[3][3] = pt * ct_sum + pc * ect;
+        b.P[3][1] = pc * ct_sum - pc * ect;
+        b.P[1][3] = pt * ct_sum - pt * ect;
+        b.P[1][1] = pc * ct_sum + pt * ect;
+        b.P[0][0] = pa * ag_sum + pg * eag;
+        b.P[0][2] = pg * ag_sum - pg * eag;
+        b.P[2][0] = pa * ag_sum - pa * eag;
+        b.P[2][2] = pg * ag_sum + pa * eag;
+        return b;
+    }
+    __device__ __forceinline__ void matvec(const Branch &b, const double (&in)[KP], double (&out)[KP], int) const {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double s = b.P[i][0] * in[0];
+#pragma unroll
+            for (int j = 1; j < 4; ++j) s = fma(b.P[i][j], in[j], s);
+            out[i] = fmax(s, 0.);
+        }
+    }
+    __device__ __forceinline__ void maxvec(const Branch &b, const double (&in)[KP], double (&out)[KP],
+                                           uint8_t (&arg)[KP], int) const {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double best = __dmul_rn(b.P[i][0], in[0]);
+            int bi = 0;
+#pragma unroll
+            for (int j = 1; j < 4; ++j) {
+                const double x = __dmul_rn(b.P[i][j], in[j]);
+                if (x > best) { best = x; bi = j; }
+            }
+            out[i] = fmax(best, 0.);
+            arg[i] = (uint8_t) bi;
+        }
+    }
+};
+
+template <int KP>
+struct EigLane {  // CUSTOM_RATES / JTT: P = A diag(exp(d t')) A^-1  (generator.py:54-65)
+    double sf, tau, tauf;
+    double pi[KP];
+    const double *d, *A, *Ainv;  // this lane's eigen-decomposition in global memory (read-only path)
+    struct Branch { double ed[KP]; };
+
+    __device__ __forceinline__ void load(const double *p, int K) {
+        sf = p[0]; tau = p[1]; tauf = p[2];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) pi[k] = (k < K) ? p[4 + k] : 0.;
+        d = p + 4 + K;
+        A = d + K;
+        Ainv = A + K * K;
+    }
+    __device__ __forceinline__ Branch branch(double dist, int K) const {
+        const double t = (dist + tau) * tauf * sf;
+        Branch b;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) b.ed[k] = (k < K) ? exp(__ldg(d + k) * t) : 0.;
+        return b;
+    }
+    // out = A (ed o (A^-1 in)): 2 K^2 fused multiply-adds instead of forming P (2 K^3)
+    __device__ __forceinline__ void matvec(const Branch &b, const double (&in)[KP], double (&out)[KP], int K) const {
+        double w[KP];
+#pragma unroll
+        for (int m = 0; m < KP; ++m) {
+            double s = 0.;
+            if (m < K) {
+#pragma unroll
+                for (int j = 0; j < KP; ++j)
+                    if (j < K) s = fma(__ldg(Ainv + m * K + j), in[j], s);
+            }
+            w[m] = s * b.ed[m];
+        }
+#pragma unroll
+        for (int i = 0; i < KP; ++i) {
+            double s = 0.;
+            if (i < K) {
+#pragma unroll
+                for (int m = 0; m < KP; ++m)
+                    if (m < K) s = fma(__ldg(A + i * K + m), w[m], s);
+            }
+            out[i] = fmax(s, 0.);
+        }
+    }
+    __device__ __forceinline__ void maxvec(const Branch &b, const double (&in)[KP], double (&out)[KP],
+                                           uint8_t (&arg)[KP], int K) const {
+#pragma unroll 1
+        for (int i = 0; i < K; ++i) {
+            double row[KP];
+#pragma unroll
+            for (int m = 0; m < KP; ++m) row[m] = (m < K) ? __ldg(A + i * K + m) * b.ed[m] : 0.;
+            double best = -CUDART_INF;
+            int bi = 0;
+#pragma unroll 1
+            for (int j = 0; j < K; ++j) {
+                double s = 0.;
+#pragma unroll
+                for (int m = 0; m < KP; ++m)
+                    if (m < K) s = fma(row[m], __ldg(Ainv + m * K + j), s);
+                double inj = 0.;
+#pragma unroll
+                for (int q = 0; q < KP; ++q) inj = (q == j) ? in[q] : inj;
+                const double x = __dmul_rn(s, inj);
+                if (x > best) { best = x; bi = j; }
+            }
+#pragma unroll
+            for (int q = 0; q < KP; ++q)
+                if (q == i) { out[q] = fmax(best, 0.); arg[q] = (uint8_t) bi; }
+        }
+#pragma unroll
+        for (int q = 0; q < KP; ++q)
+            if (q >= K) { out[q] = 0.; arg[q] = 0; }
+    }
+};
+
+// ------------------------------------------------------------------------------------------ zero clusters
+
+// get_zero_clusters_with_states + alter_zero_node_allowed_states (ml.py:321-387) for one (cluster, column) per
+// thread.  Writes the effective masks of all members into the cluster table; when the members share no state the
+// union is assigned to all of them and (if record_col[c]) the old masks become their '.initial'.
+__global__ void alter_kernel(int n_clusters, const int *cl_col, const int *cl_ptr, const int *cl_mem,
+                             const int *zc_index, const uint64_t *src, int C, uint64_t kmask,
+                             const uint8_t *record_col, uint64_t *alt, uint8_t *altflag, uint64_t *initial,
+                             uint8_t *hasinit) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_clusters) return;
+    const int c = cl_col[q];
+    uint64_t common = ~0ULL, uni = 0ULL;
+    for (int i = cl_ptr[q]; i < cl_ptr[q + 1]; ++i) {
+        const uint64_t v = src[(size_t) cl_mem[i] * C + c] & kmask;
+        common &= v;
+        uni |= v;
+    }
+    const bool altered = (common == 0ULL);
+    for (int i = cl_ptr[q]; i < cl_ptr[q + 1]; ++i) {
+        const int node = cl_mem[i];
+        const size_t r = (size_t) zc_index[node] * C + c;
+        const uint64_t v = src[(size_t) node * C + c] & kmask;
+        alt[r] = altered ? uni : v;
+        altflag[r] = altered ? 1 : 0;
+        if (altered && record_col[c]) {
+            initial[r] = v;
+            hasinit[r] = 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ bottom-up
+
+struct BuArgs {
+    TreeDev t;
+    ZcDev zc;
+    LaneDev ln;
+    const uint64_t *mask;   // [N][C]
+    int alter;              // apply the cluster table where the lane's tau == 0
+    double *bu;             // [NI][K][J]
+    int *bu_ex;             // [NI][J]
+    uint8_t *ptr;           // joint mode: [N][C][K] argmax pointers stored on the child (may be null)
+    int *err;               // [J][2] first failing (parent, child), initialised to -1
+};
+
+// calc_node_bu_likelihood (ml.py:124-148) for the internal nodes [slot_begin, slot_begin + n_slots) of one level.
+template <int KP, template <int> class Lane, bool MAXP>
+__global__ void __launch_bounds__(kBlock) bu_level_kernel(BuArgs a, int slot_begin, int n_slots) {
+    const int J = a.ln.J, K = a.ln.K, C = a.ln.C;
+    const long long n_items = (long long) n_slots * J;
+    for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
+         g += (long long) gridDim.x * blockDim.x) {
+        const int slot = slot_begin + (int) (g / J);
+        const int j = (int) (g % J);
+        const int c = j % C;
+        Lane<KP> lane;
+        lane.load(a.ln.params + (size_t) j * a.ln.stride, K);
+        const bool use_alt = a.alter && lane.tau == 0.;
+        const int node = a.t.int_nodes[slot];
+        const int fc = a.t.first_child[node], nc = a.t.n_children[node];
+
+        double acc[KP];
+        {
+            const uint64_t m = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
+#pragma unroll
+            for (int k = 0; k < KP; ++k) acc[k] = (double) ((m >> k) & 1ULL);   // 10 ** log10(allowed), ml.py:127
+        }
+        int ex = 0;
+        for (int ch = fc; ch < fc + nc; ++ch) {
+            const typename Lane<KP>::Branch br = lane.branch(a.t.dist[ch], K);
+            double in[KP], v[KP];
+            const int cs = a.t.slot[ch];
+            if (cs >= 0) {
+                const double *src = a.bu + ((size_t) cs * K) * J + j;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) in[k] = (k < K) ? src[(size_t) k * J] : 0.;
+                ex += a.bu_ex[(size_t) cs * J + j];
+            } else {
+                const uint64_t m = eff_mask(a.mask, a.t, a.zc, C, ch, c, use_alt, a.ln.kmask);
+#pragma unroll
+                for (int k = 0; k < KP; ++k) in[k] = (double) ((m >> k) & 1ULL);   // tip: BU = allowed, SF = 0
+            }
+            if (MAXP) {
+                uint8_t arg[KP];
+                lane.maxvec(br, in, v, arg, K);
+                if (a.ptr) {
+                    uint8_t *dst = a.ptr + ((size_t) ch * C + c) * K;
+#pragma unroll
+                    for (int k = 0; k < KP; ++k)
+                        if (k < K) dst[k] = arg[k];
+                }
+            } else {
+                lane.matvec(br, in, v, K);
+            }
+#pragma unroll
+            for (int k = 0; k < KP; ++k) acc[k] *= v[k];
+            double vmax;
+            ex += normalise<KP>(acc, K, vmax);
+            if (vmax == 0.) {   // all entries zero: PastMLLikelihoodError of ml.py:139-145
+                if (atomicCAS(a.err + 2 * j, -1, node) == -1) a.err[2 * j + 1] = ch;
+            }
+        }
+        double *dst = a.bu + ((size_t) slot * K) * J + j;
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < K) dst[(size_t) k * J] = acc[k];
+        a.bu_ex[(size_t) slot * J + j] = ex;
+    }
+}
+
+// ln(sum_i L_root,i pi_i) - SF ln 10 summed over the roots (ml.py:112-121); a root may be a tip.
+template <int KP>
+__global__ void root_loglik_kernel(TreeDev t, ZcDev zc, LaneDev ln, const uint64_t *mask, int alter,
+                                   const double *bu, const int *bu_ex, const int *roots, int n_roots,
+                                   int is_marginal, double *out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ln.J) return;
+    const int K = ln.K, J = ln.J, c = j % ln.C;
+    const double *p = ln.params + (size_t) j * ln.stride;
+    const bool use_alt = alter && p[1] == 0.;
+    double total = 0.;
+    for (int r = 0; r < n_roots; ++r) {
+        const int node = roots[r];
+        const int s = t.slot[node];
+        double acc = is_marginal ? 0. : -CUDART_INF;
+        int ex = 0;
+        if (s >= 0) ex = bu_ex[(size_t) s * J + j];
+        const uint64_t m = (s >= 0) ? 0ULL : eff_mask(mask, t, zc, ln.C, node, c, use_alt, ln.kmask);
+        for (int k = 0; k < K; ++k) {
+            const double l = (s >= 0) ? bu[((size_t) s * K + k) * J + j] : (double) ((m >> k) & 1ULL);
+            const double x = l * p[4 + k];
+            acc = is_marginal ? acc + x : fmax(acc, x);
+        }
+        total += log(acc) + (double) ex * 0.69314718055994530942;
+    }
+    out[j] = total;
+}
+
+// ------------------------------------------------------------------------------------------ joint traceback
+
+struct JointArgs {
+    TreeDev t;
+    ZcDev zc;
+    LaneDev ln;
+    const uint64_t *base_mask;  // annotation masks (carry the member flags)
+    const double *bu;           // joint bottom-up mantissas
+    const uint8_t *ptr;         // [N][C][K]
+    int *state;                 // [N][C]
+    uint64_t *out_mask;         // [N][C]
+};
+
+// choose_ancestral_states_joint (ml.py:598-622) + unalter_zero_node_joint_states (ml.py:408-428) for the nodes
+// [node_begin, node_begin + n_nodes) of one level.
+__global__ void joint_trace_kernel(JointArgs a, int node_begin, int n_nodes) {
+    const int C = a.ln.C, K = a.ln.K;
+    const long long n_items = (long long) n_nodes * C;
+    for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
+         g += (long long) gridDim.x * blockDim.x) {
+        const int node = node_begin + (int) (g / C);
+        const int c = (int) (g % C);
+        const int par = a.t.parent[node];
+        const uint64_t base = a.base_mask[(size_t) node * C + c];
+        int s;
+        if (par < 0) {
+            const double *p = a.ln.params + (size_t) c * a.ln.stride;
+            const int sl = a.t.slot[node];
+            const bool use_alt = p[1] == 0.;
+            const uint64_t m = eff_mask(a.base_mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
+            double best = -CUDART_INF;
+            s = 0;
+            for (int k = 0; k < K; ++k) {
+                const double l = (sl >= 0) ? a.bu[((size_t) sl * K + k) * C + c] : (double) ((m >> k) & 1ULL);
+                const double x = __dmul_rn(l, p[4 + k]);
+                if (x > best) { best = x; s = k; }
+            }
+        } else {
+            s = a.ptr[((size_t) node * C + c) * K + a.state[(size_t) par * C + c]];
+            if (base & kMemberFlag) {
+                const size_t r = (size_t) a.t.zc_index[node] * C + c;
+                if (a.zc.altflag[r]) {
+                    const uint64_t init = a.zc.initial[r];
+                    if (!((init >> s) & 1ULL) && init) s = __ffsll((long long) init) - 1;
+                }
+            }
+        }
+        a.state[(size_t) node * C + c] = s;
+        a.out_mask[(size_t) node * C + c] = (1ULL << s) | (base & kMemberFlag);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ top-down sweep
+
+struct TdArgs {
+    TreeDev t;
+    ZcDev zc;
+    LaneDev ln;                 // J == C (one parameter set)
+    const uint64_t *mask;       // annotation masks
+    const double *bu;
+    const int *bu_ex;
+    double *td;                 // [NI][K][C]
+    int *td_ex;                 // [NI][C]
+    const int *joint_state;     // [N][C] or null
+    int force_joint;
+    double *probs;              // [N][C][K] or null
+    double *node_log10lh;       // [N][C] or null
+    uint64_t *map_mask;         // [N][C]
+    uint64_t *mppa_mask;        // [N][C]
+    unsigned long long *k_hist; // [C][K+1]
+    double *zc_lh;              // [rows][C][K]  marginal mantissas of cluster members (for pml_mppa_finalize)
+    uint8_t *zc_k;              // [rows][C]     best_k chosen here
+};
+
+// MPPA state selection (choose_ancestral_states_mppa, ml.py:539-572) on a likelihood vector already multiplied by
+// the '.initial' mask where the node has one.  Returns the selected mask and k.
+template <int KP>
+__device__ __forceinline__ uint64_t mppa_select(const double (&lh)[KP], int K, int joint_index, bool force_joint,
+                                                int &best_k) {
+    double sum = 0.;
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+        if (k < K) sum += lh[k];
+    double p[KP], d[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        p[k] = (k < K) ? lh[k] / sum : -1.;
+        d[k] = (force_joint && k == joint_index) ? -1. : p[k];
+    }
+    double pj = 0.;
+    if (force_joint) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) pj = (k == joint_index) ? p[k] : pj;
+    }
+    // descending odd-even transposition sort on registers (padding and the joint state sink to the end)
+#pragma unroll
+    for (int round = 0; round < KP; ++round) {
+#pragma unroll
+        for (int i = (round & 1); i + 1 < KP; i += 2) {
+            const double hi = fmax(d[i], d[i + 1]), lo = fmin(d[i], d[i + 1]);
+            d[i] = hi;
+            d[i + 1] = lo;
+        }
+    }
+    // the reference's ascending array is [d[n-1], ..., d[0]] (+ [pj] when the joint state is forced last)
+    const int n_sorted = force_joint ? K - 1 : K;
+    best_k = K;
+    double best_corr = CUDART_INF;
+    for (int k = 1; k <= K; ++k) {
+        const double target = 1. / (double) k;
+        const int top = force_joint ? k - 1 : k;   // how many of d[] receive 1/k
+        double corr = 0.;
+#pragma unroll
+        for (int r = KP - 1; r >= 0; --r)
+            if (r < n_sorted) {
+                const double dl = (r < top ? target : 0.) - d[r];
+                corr = fma(dl, dl, corr);
+            }
+        if (force_joint) {
+            const double dl = target - pj;
+            corr = fma(dl, dl, corr);
+        }
+        if (corr < best_corr) { best_corr = corr; best_k = k; }
+    }
+    // top best_k by likelihood, ties to the lower index (stable sort, ml.py:562-565)
+    uint64_t sel = 0ULL;
+#pragma unroll
+    for (int i = 0; i < KP; ++i)
+        if (i < K) {
+            int rank = 0;
+#pragma unroll
+            for (int q = 0; q < KP; ++q)
+                if (q < K) rank += (lh[q] > lh[i]) || (lh[q] == lh[i] && q < i);
+            if (rank < best_k) sel |= 1ULL << i;
+        }
+    return sel;
+}
+
+// calc_node_marginal_likelihood + probabilities + MAP + MPPA for one node (ml.py:454-465, 498-500, 577-595, 539-572)
+template <int KP>
+__device__ __forceinline__ void emit_node(const TdArgs &a, int node, int c, const double (&L)[KP],
+                                          const double (&TD)[KP], const double (&pi)[KP], uint64_t allowed,
+                                          int ex, unsigned int *sh_hist) {
+    const int K = a.ln.K, C = a.ln.C;
+    double m[KP];
+    double sum = 0.;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        m[k] = (k < K && ((allowed >> k) & 1ULL)) ? L[k] * TD[k] * pi[k] : 0.;
+        sum += m[k];
+    }
+    const size_t nc = (size_t) node * C + c;
+    if (a.probs) {
+        double *dst = a.probs + nc * K;
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < K) dst[k] = m[k] / sum;
+    }
+    if (a.node_log10lh) a.node_log10lh[nc] = log10(sum) + (double) ex * 0.30102999566398119521;
+    const uint64_t base = a.mask[nc];
+    const uint64_t flag = base & kMemberFlag;
+    if (flag) {
+        const size_t r = (size_t) a.t.zc_index[node] * C + c;
+        double *z = a.zc_lh + r * K;
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < K) z[k] = m[k];
+        if (a.zc.hasinit[r]) {
+            const uint64_t init = a.zc.initial[r];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) m[k] = ((init >> k) & 1ULL) ? m[k] : 0.;   // lh *= initial, ml.py:593-594
+        }
+    }
+    int best = 0;   // first arg max (ml.py:595)
+    {
+        double bv = m[0];
+#pragma unroll
+        for (int k = 1; k < KP; ++k)
+            if (k < K && m[k] > bv) { bv = m[k]; best = k; }
+    }
+    a.map_mask[nc] = (1ULL << best) | flag;
+    int best_k;
+    const int ji = a.force_joint ? a.joint_state[nc] : 0;
+    double msum = 0.;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) msum += m[k];
+    uint64_t sel;
+    if (msum > 0.) sel = mppa_select<KP>(m, K, ji, a.force_joint != 0, best_k);
+    else { sel = a.ln.kmask; best_k = K; }   // NaN probabilities: no k beats +inf, all states kept
+    a.mppa_mask[nc] = sel | flag;
+    if (flag) a.zc_k[(size_t) a.t.zc_index[node] * C + c] = (uint8_t) best_k;
+    atomicAdd(sh_hist + c * (K + 1) + best_k, 1u);
+}
+
+// calc_node_td_likelihood (ml.py:273-290) for the children of the internal nodes of one level, fused with the
+// marginal step of the nodes themselves and of their tip children.
+template <int KP, template <int> class Lane>
+__global__ void __launch_bounds__(kBlock) td_level_kernel(TdArgs a, int slot_begin, int n_slots) {
+    extern __shared__ unsigned int sh_hist[];   // [C][K+1]
+    const int C = a.ln.C, K = a.ln.K;
+    for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x) sh_hist[i] = 0u;
+    __syncthreads();
+    const long long n_items = (long long) n_slots * C;
+    for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
+         g += (long long) gridDim.x * blockDim.x) {
+        const int slot = slot_begin + (int) (g / C);
+        const int c = (int) (g % C);
+        Lane<KP> lane;
+        lane.load(a.ln.params + (size_t) c * a.ln.stride, K);
+        const bool use_alt = lane.tau == 0.;   // ml.py:702-703
+        const int node = a.t.int_nodes[slot];
+        const int fc = a.t.first_child[node], nc = a.t.n_children[node];
+
+        double Lp[KP], TDp[KP];
+        {
+            const double *src = a.bu + ((size_t) slot * K) * C + c;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) Lp[k] = (k < K) ? src[(size_t) k * C] : 0.;
+        }
+        const int exp_ = a.bu_ex[(size_t) slot * C + c];
+        int extd = 0;
+        if (a.t.parent[node] < 0) {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) TDp[k] = (k < K) ? 1. : 0.;   // ml.py:274-277
+        } else {
+            const double *src = a.td + ((size_t) slot * K) * C + c;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) TDp[k] = (k < K) ? src[(size_t) k * C] : 0.;
+            extd = a.td_ex[(size_t) slot * C + c];
+        }
+        const uint64_t mp = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
+        emit_node<KP>(a, node, c, Lp, TDp, lane.pi, mp, exp_ + extd, sh_hist);
+
+        // parent part of every child's top-down vector: TD_p * L_p (divided by the child's own contribution below)
+#pragma unroll
+        for (int k = 0; k < KP; ++k) TDp[k] *= Lp[k];
+
+        for (int ch = fc; ch < fc + nc; ++ch) {
+            const typename Lane<KP>::Branch br = lane.branch(a.t.dist[ch], K);
+            double Lc[KP], cv[KP], q[KP];
+            const int cs = a.t.slot[ch];
+            int exc = 0;
+            uint64_t mc = 0ULL;
+            if (cs >= 0) {
+                const double *src = a.bu + ((size_t) cs * K) * C + c;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) Lc[k] = (k < K) ? src[(size_t) k * C] : 0.;
+                exc = a.bu_ex[(size_t) cs * C + c];
+            } else {
+                mc = eff_mask(a.mask, a.t, a.zc, C, ch, c, use_alt, a.ln.kmask);
+#pragma unroll
+                for (int k = 0; k < KP; ++k) Lc[k] = (double) ((mc >> k) & 1ULL);
+            }
+            lane.matvec(br, Lc, cv, K);                                  // node_contribution, ml.py:280
+#pragma unroll
+            for (int k = 0; k < KP; ++k) q[k] = (cv[k] > 0.) ? TDp[k] / cv[k] : TDp[k];   // ml.py:281-283
+            double qmax;
+            int qex = extd + exp_ - exc + normalise<KP>(q, K, qmax);     // ml.py:284-286
+            double tdc[KP];
+            lane.matvec(br, q, tdc, K);                                  // ml.py:288-289
+            if (cs >= 0) {
+                double tmax;
+                qex += normalise<KP>(tdc, K, tmax);
+                double *dst = a.td + ((size_t) cs * K) * C + c;
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+                    if (k < K) dst[(size_t) k * C] = tdc[k];
+                a.td_ex[(size_t) cs * C + c] = qex;
+            } else {
+                emit_node<KP>(a, ch, c, Lc, tdc, lane.pi, mc, qex, sh_hist);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x)
+        if (sh_hist[i]) atomicAdd(a.k_hist + i, (unsigned long long) sh_hist[i]);
+}
+
+// Single-node forests (a root that is a tip) never enter td_level_kernel: emit them here.
+template <int KP, template <int> class Lane>
+__global__ void td_tip_roots_kernel(TdArgs a, const int *roots, int n_roots) {
+    extern __shared__ unsigned int sh_hist[];
+    const int C = a.ln.C, K = a.ln.K;
+    for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x) sh_hist[i] = 0u;
+    __syncthreads();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n_roots * C) {
+        const int node = roots[g / C], c = g % C;
+        if (a.t.slot[node] < 0) {
+            Lane<KP> lane;
+            lane.load(a.ln.params + (size_t) c * a.ln.stride, K);
+            const uint64_t m = eff_mask(a.mask, a.t, a.zc, C, node, c, lane.tau == 0., a.ln.kmask);
+            double L[KP], TD[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) { L[k] = (double) ((m >> k) & 1ULL); TD[k] = (k < K) ? 1. : 0.; }
+            emit_node<KP>(a, node, c, L, TD, lane.pi, m, 0, sh_hist);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x)
+        if (sh_hist[i]) atomicAdd(a.k_hist + i, (unsigned long long) sh_hist[i]);
+}
+
+// pml_mppa_finalize: redo the MPPA choice of cluster members whose '.initial' was replaced by the MAP-restricted
+// pass' alteration (ml.py:384-385, 541-542).  One thread per (table row, column).
+template <int KP>
+__global__ void mppa_fix_kernel(int n_rows, const int *row_node, int C, int K, uint64_t kmask, ZcDev zc,
+                                const uint64_t *base_mask, const uint64_t *prev_initial, const uint8_t *prev_hasinit,
+                                const double *zc_lh, uint8_t *zc_k, const int *joint_state, int force_joint,
+                                uint64_t *mppa_mask, unsigned long long *k_hist) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_rows * C) return;
+    const int row = g / C, c = g % C;
+    const size_t r = (size_t) row * C + c;
+    const int node = row_node[row];
+    const size_t nc = (size_t) node * C + c;
+    if (!(base_mask[nc] & kMemberFlag) || !zc.altflag[r]) return;   // '.initial' untouched by the last alteration
+    double m[KP];
+    const uint64_t i0 = prev_hasinit[r] ? prev_initial[r] : kmask;    // applied in place by MAP (ml.py:593-594)
+    const uint64_t i1 = zc.initial[r];                                // applied again by MPPA (ml.py:541-542)
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+        m[k] = (k < K && ((i0 >> k) & (i1 >> k) & 1ULL)) ? zc_lh[r * K + k] : 0.;
+    double msum = 0.;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) msum += m[k];
+    int best_k;
+    uint64_t sel;
+    if (msum > 0.) sel = mppa_select<KP>(m, K, force_joint ? joint_state[nc] : 0, force_joint != 0, best_k);
+    else { sel = kmask; best_k = K; }
+    const int old_k = zc_k[r];
+    mppa_mask[nc] = sel | kMemberFlag;
+    zc_k[r] = (uint8_t) best_k;
+    if (old_k != best_k) {
+        atomicAdd(k_hist + c * (K + 1) + old_k, (unsigned long long) -1LL);
+        atomicAdd(k_hist + c * (K + 1) + best_k, 1ULL);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ parsimony
+
+// get_most_common_states (parsimony.py:76-89) over `first` plus the masks m[0..n): states with the maximal count.
+__device__ __forceinline__ uint64_t most_common(uint64_t first, bool has_first, const uint64_t *m, size_t stride,
+                                                int n, int skip, uint64_t kmask) {
+    const int total = n + (has_first ? 1 : 0) - (skip >= 0 ? 1 : 0);
+    if (total <= 6) {
+        // bit-sliced 3-bit counters: c2 c1 c0 hold, per state, how many sets contain it
+        uint64_t c0 = 0, c1 = 0, c2 = 0;
+        auto add = [&](uint64_t x) {
+            uint64_t carry = c0 & x;
+            c0 ^= x;
+            const uint64_t carry2 = c1 & carry;
+            c1 ^= carry;
+            c2 ^= carry2;
+        };
+        if (has_first) add(first & kmask);
+        for (int i = 0; i < n; ++i)
+            if (i != skip) add(m[(size_t) i * stride] & kmask);
+        uint64_t cand = kmask;
+        if (cand & c2) cand &= c2;
+        if (cand & c1) cand &= c1;
+        if (cand & c0) cand &= c0;
+        return (c0 | c1 | c2) ? cand : 0ULL;
+    }
+    int best = 0;
+    uint64_t out = 0ULL;
+    for (int s = 0; s < 64 && ((kmask >> s) & 1ULL); ++s) {
+        int cnt = has_first ? (int) ((first >> s) & 1ULL) : 0;
+        for (int i = 0; i < n; ++i)
+            if (i != skip) cnt += (int) ((m[(size_t) i * stride] >> s) & 1ULL);
+        if (cnt > best) { best = cnt; out = 1ULL << s; }
+        else if (cnt == best && cnt > 0) out |= 1ULL << s;
+    }
+    return out;
+}
+
+// uppass (parsimony.py:92-122) for the internal nodes of one level; down[] was initialised to the annotation sets.
+__global__ void pars_uppass_kernel(TreeDev t, int C, uint64_t kmask, uint64_t *down, int slot_begin, int n_slots) {
+    const long long n_items = (long long) n_slots * C;
+    for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
+         g += (long long) gridDim.x * blockDim.x) {
+        const int node = t.int_nodes[slot_begin + (int) (g / C)], c = (int) (g % C);
+        const uint64_t mc = most_common(0, false, down + (size_t) t.first_child[node] * C + c, C, t.n_children[node],
+                                        -1, kmask);
+        const uint64_t own = down[(size_t) node * C + c];
+        const uint64_t inter = own & mc;
+        if (inter) down[(size_t) node * C + c] = inter;
+    }
+}
+
+// acctran (parsimony.py:125-158): the children of the internal nodes of one level.
+__global__ void pars_acctran_kernel(TreeDev t, int C, const uint64_t *down, uint64_t *out, int slot_begin,
+                                    int n_slots) {
+    const long long n_items = (long long) n_slots * C;
+    for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
+         g += (long long) gridDim.x * blockDim.x) {
+        const int node = t.int_nodes[slot_begin + (int) (g / C)], c = (int) (g % C);
+        const uint64_t own = out[(size_t) node * C + c];
+        const int fc = t.first_child[node];
+        for (int ch = fc; ch < fc + t.n_children[node]; ++ch) {
+            const uint64_t d = down[(size_t) ch * C + c];
+            const uint64_t inter = own & d;
+            out[(size_t) ch * C + c] = inter ? inter : d;
+        }
+    }
+}
+
+// downpass (parsimony.py:161-210): an internal node's own state from up(node) and its children's down sets, then
+// up() of its children; tip children are finished on the spot.  res[] starts as the pre-uppass sets.
+__global__ void pars_downpass_kernel(TreeDev t, int C, uint64_t kmask, const uint64_t *down, uint64_t *up,
+                                     uint64_t *res, int slot_begin, int n_slots) {
+    const long long n_items = (long long) n_slots * C;
+    for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
+         g += (long long) gridDim.x * blockDim.x) {
+        const int node = t.int_nodes[slot_begin + (int) (g / C)], c = (int) (g % C);
+        const size_t nc = (size_t) node * C + c;
+        const uint64_t upn = (t.parent[node] < 0) ? kmask : up[nc];
+        const int fc = t.first_child[node], n = t.n_children[node];
+        const uint64_t *kids = down + (size_t) fc * C + c;
+        const uint64_t du = most_common(upn, true, kids, C, n, -1, kmask);
+        const uint64_t pre = res[nc];
+        res[nc] = (du & pre) ? (du & pre) : pre;
+        for (int i = 0; i < n; ++i) {
+            const int ch = fc + i;
+            const uint64_t upc = most_common(upn, true, kids, C, n, i, kmask);
+            const size_t cc = (size_t) ch * C + c;
+            if (t.slot[ch] >= 0) up[cc] = upc;
+            else {
+                const uint64_t prec = res[cc];
+                res[cc] = (upc & prec) ? (upc & prec) : prec;
+            }
+        }
+    }
+}
+
+// deltran (parsimony.py:213-242): children of the internal nodes of one level, on top of the DOWNPASS result.
+__global__ void pars_deltran_kernel(TreeDev t, int C, uint64_t *res, int slot_begin, int n_slots) {
+    const long long n_items = (long long) n_slots * C;
+    for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
+         g += (long long) gridDim.x * blockDim.x) {
+        const int node = t.int_nodes[slot_begin + (int) (g / C)], c = (int) (g % C);
+        const uint64_t own = res[(size_t) node * C + c];
+        const int fc = t.first_child[node];
+        for (int ch = fc; ch < fc + t.n_children[node]; ++ch) {
+            const uint64_t inter = res[(size_t) ch * C + c] & own;
+            if (inter) res[(size_t) ch * C + c] = inter;
+        }
+    }
+}
+
+// get_num_parsimonious_steps (parsimony.py:360-380): min-plus DP, one thread per (internal node, column);
+// num[slot][k][C] int32 (INF for states outside the node's set).
+__global__ void pars_steps_kernel(TreeDev t, int C, int K, const uint64_t *states, int *num, int slot_begin,
+                                  int n_slots) {
+    const int INF = 1 << 29;
+    const long long n_items = (long long) n_slots * C;
+    for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
+         g += (long long) gridDim.x * blockDim.x) {
+        const int slot = slot_begin + (int) (g / C);
+        const int node = t.int_nodes[slot], c = (int) (g % C);
+        const uint64_t own = states[(size_t) node * C + c];
+        const int fc = t.first_child[node], n = t.n_children[node];
+        int *dst = num + ((size_t) slot * K) * C + c;
+        for (int s = 0; s < K; ++s) dst[(size_t) s * C] = ((own >> s) & 1ULL) ? 0 : INF;
+        for (int ch = fc; ch < fc + n; ++ch) {
+            const int cs = t.slot[ch];
+            const uint64_t cm = states[(size_t) ch * C + c];
+            const int *src = (cs >= 0) ? num + ((size_t) cs * K) * C + c : nullptr;
+            int mn = INF;
+            for (int s = 0; s < K; ++s) {
+                const int v = src ? src[(size_t) s * C] : (((cm >> s) & 1ULL) ? 0 : INF);
+                mn = min(mn, v);
+            }
+            for (int s = 0; s < K; ++s)
+                if ((own >> s) & 1ULL) {
+                    const int v = src ? src[(size_t) s * C] : (((cm >> s) & 1ULL) ? 0 : INF);
+                    dst[(size_t) s * C] += min(v, mn + 1);
+                }
+        }
+    }
+}
+
+__global__ void pars_steps_root_kernel(TreeDev t, int C, int K, const uint64_t *states, const int *num,
+                                       const int *roots, int n_roots, long long *out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    long long total = 0;
+    for (int r = 0; r < n_roots; ++r) {
+        const int node = roots[r], s0 = t.slot[node];
+        if (s0 < 0) continue;   // a single-node tree needs no change
+        int mn = 1 << 29;
+        for (int s = 0; s < K; ++s) mn = min(mn, num[((size_t) s0 * K + s) * C + c]);
+        total += mn;
+    }
+    out[c] = total;
+}
+
+// ------------------------------------------------------------------------------------------ utilities
+
+// [C][N] host layout -> [N][C] device layout, adding the allowed-states rule "no annotation => all states"
+// (initialize_allowed_states, ml.py:311-313) and the cluster-member flag.
+__global__ void init_masks_kernel(int N, int C, uint64_t kmask, const uint64_t *annot_cn, const uint8_t *member_cn,
+                                  uint64_t *base_nc, int apply_default) {
+    const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long) N * C) return;
+    const int node = (int) (g / C), c = (int) (g % C);
+    uint64_t m = annot_cn[(size_t) c * N + node] & kmask;
+    if (apply_default && !m) m = kmask;
+    if (member_cn && member_cn[(size_t) c * N + node]) m |= kMemberFlag;
+    base_nc[g] = m;
+}
+
+__global__ void strip_flag_kernel(long long n, uint64_t kmask, const uint64_t *in, uint64_t *out) {
+    const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) out[g] = in[g] & kmask;
+}
+
+__global__ void fill_int_kernel(long long n, int value, int *out) {
+    const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) out[g] = value;
+}
+
+__global__ void flush_kernel(long long n, float *buf, float v) {
+    for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n;
+         g += (long long) gridDim.x * blockDim.x)
+        buf[g] = v;
+}
+
+}  // namespace pml
