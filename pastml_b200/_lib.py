@@ -1,0 +1,77 @@
+"""ctypes binding of ``libpastml_b200.so`` (the C ABI of ``include/pastml_b200.h``).
+
+The product path has no CPU fallback: importing this module never builds or computes anything, but
+:func:`load` raises if the CUDA engine has not been built, and the engine itself refuses to create a problem
+without a CUDA device.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libpastml_b200.so')
+
+EXPORTS = ['pml_last_error', 'pml_version', 'pml_device_count', 'pml_param_stride', 'pml_problem_create',
+           'pml_problem_destroy', 'pml_loglik', 'pml_joint', 'pml_marginal', 'pml_mppa_finalize', 'pml_parsimony',
+           'pml_set_custom_masks', 'pml_get_masks', 'pml_get_initial', 'pml_zero_likelihood_info',
+           'pml_last_call_stats', 'pml_bench_pass']
+
+PML_OK, PML_ERR_INVALID, PML_ERR_CUDA, PML_ERR_ZERO_LIKELIHOOD, PML_ERR_NO_DEVICE = 0, 1, 2, 3, 4
+MODEL_F81, MODEL_HKY, MODEL_EIG = 0, 1, 2
+MASK_ANNOTATION, MASK_JOINT, MASK_MAP, MASK_MPPA, MASK_CUSTOM = 0, 1, 2, 3, 4
+PARS_ACCTRAN, PARS_DOWNPASS, PARS_DELTRAN = 1, 2, 4
+
+_lib = None
+
+
+class EngineNotBuilt(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the engine library (built by ``python -m pastml_b200.build`` / ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineNotBuilt('{} is missing: build the CUDA engine first (python pastml_b200/build.py). '
+                             'pastml_b200 has no CPU fallback.'.format(LIB_PATH))
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, dbl = C.c_void_p, C.c_int32, C.c_double
+    lib.pml_last_error.restype = C.c_char_p
+    lib.pml_last_error.argtypes = []
+    lib.pml_version.restype = C.c_int
+    lib.pml_device_count.restype = C.c_int
+    lib.pml_param_stride.restype = C.c_int
+    lib.pml_param_stride.argtypes = [i32, i32]
+    lib.pml_problem_create.restype = C.c_int
+    lib.pml_problem_create.argtypes = [i32, vp, vp, i32, i32, i32, vp, vp, i32, i32, C.POINTER(vp)]
+    lib.pml_problem_destroy.restype = None
+    lib.pml_problem_destroy.argtypes = [vp]
+    lib.pml_loglik.restype = C.c_int
+    lib.pml_loglik.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.pml_joint.restype = C.c_int
+    lib.pml_joint.argtypes = [vp, vp, vp, vp]
+    lib.pml_marginal.restype = C.c_int
+    lib.pml_marginal.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.pml_mppa_finalize.restype = C.c_int
+    lib.pml_mppa_finalize.argtypes = [vp, i32, vp, vp]
+    lib.pml_parsimony.restype = C.c_int
+    lib.pml_parsimony.argtypes = [vp, i32, vp, vp]
+    lib.pml_set_custom_masks.restype = C.c_int
+    lib.pml_set_custom_masks.argtypes = [vp, vp]
+    lib.pml_get_masks.restype = C.c_int
+    lib.pml_get_masks.argtypes = [vp, i32, vp]
+    lib.pml_get_initial.restype = C.c_int
+    lib.pml_get_initial.argtypes = [vp, vp, vp]
+    lib.pml_zero_likelihood_info.restype = C.c_int
+    lib.pml_zero_likelihood_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    lib.pml_last_call_stats.restype = C.c_int
+    lib.pml_last_call_stats.argtypes = [vp, C.POINTER(dbl), C.POINTER(C.c_int64)]
+    lib.pml_bench_pass.restype = C.c_int
+    lib.pml_bench_pass.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(C.c_int64)]
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().pml_last_error().decode('utf-8', 'replace')

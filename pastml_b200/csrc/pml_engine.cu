@@ -1,0 +1,791 @@
+// Host side of the pastml_b200 engine: problem handles, level-synchronous launch sequences, the C ABI declared
+// in include/pastml_b200.h.  Built by nvcc for sm_100a only (see pastml_b200/build.py).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pastml_b200.h"
+#include "pml_launch.h"
+
+using namespace pml;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(PML_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *ptr = nullptr;
+    size_t count = 0;
+    cudaError_t alloc(size_t n) {
+        release();
+        count = n;
+        if (n == 0) return cudaSuccess;
+        return cudaMalloc((void **) &ptr, n * sizeof(T));
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        count = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+int kp_for(int K) {
+    const int sizes[] = {2, 4, 8, 12, 16, 20, 24, 32, 48, 62};
+    for (int s : sizes)
+        if (K <= s) return s;
+    return -1;
+}
+
+}  // namespace
+
+struct pml_problem {
+    int device = 0;
+    int N = 0, NI = 0, C = 0, K = 0, KP = 0, kind = 0, B = 1, stride = 0, n_levels = 0, n_roots = 0;
+    uint64_t kmask = 0;
+    std::vector<int> level_ptr, int_level_ptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // topology
+    DevBuf<int> parent, first_child, n_children, slot, int_nodes, zc_index, roots;
+    DevBuf<double> dist;
+    // zero clusters
+    int n_clusters = 0, n_rows = 0;
+    DevBuf<int> cl_col, cl_ptr, cl_mem, row_node;
+    DevBuf<uint64_t> zc_alt, zc_initial, zc_prev_initial;
+    DevBuf<uint8_t> zc_altflag, zc_hasinit, zc_prev_hasinit, zc_k, record_col;
+    DevBuf<double> zc_lh;
+    // masks [N][C]
+    DevBuf<uint64_t> mask[5];
+    bool mask_valid[5] = {false, false, false, false, false};
+    // state
+    DevBuf<double> params, bu, td, probs, node_lh, out_lh;
+    DevBuf<int> bu_ex, td_ex, err, joint_state, steps_num;
+    DevBuf<uint8_t> ptr;
+    DevBuf<unsigned long long> k_hist;
+    DevBuf<uint64_t> scratch_a, scratch_b, scratch_c;
+    DevBuf<long long> steps_out;
+    DevBuf<float> flush;
+    bool joint_done = false, marginal_done = false;
+    // host staging
+    std::vector<double> h_out;
+    std::vector<int> h_err;
+    int zero_info[4] = {-1, -1, -1, -1};
+    double last_ms = 0.;
+    long long last_launches = 0, launches = 0;
+    const KernelSet *ks = nullptr;
+
+    TreeDev tree() const {
+        return TreeDev{N, NI, parent.ptr, first_child.ptr, n_children.ptr, slot.ptr, int_nodes.ptr, dist.ptr,
+                       zc_index.ptr};
+    }
+    ZcDev zc() const { return ZcDev{zc_alt.ptr, zc_altflag.ptr, zc_initial.ptr, zc_hasinit.ptr}; }
+    LaneDev lanes(int n_sets) const { return LaneDev{C, n_sets * C, K, stride, params.ptr, kmask}; }
+};
+
+namespace {
+
+void run_root_loglik(pml_problem *p, const LaneDev &ln, const uint64_t *mask, int alter, int is_marginal) {
+    p->ks->root_loglik(p->stream, p->tree(), p->zc(), ln, mask, alter, p->bu.ptr, p->bu_ex.ptr, p->roots.ptr,
+                       p->n_roots, is_marginal, p->out_lh.ptr);
+    p->launches++;
+}
+
+// zero-branch cluster alteration of `src` masks; record[c] tells whether '.initial' is written for column c
+void run_alter(pml_problem *p, const uint64_t *src) {
+    if (!p->n_clusters) return;
+    alter_kernel<<<grid_for(p->n_clusters), kBlock, 0, p->stream>>>(
+        p->n_clusters, p->cl_col.ptr, p->cl_ptr.ptr, p->cl_mem.ptr, p->zc_index.ptr, src, p->C, p->kmask,
+        p->record_col.ptr, p->zc_alt.ptr, p->zc_altflag.ptr, p->zc_initial.ptr, p->zc_hasinit.ptr);
+    p->launches++;
+}
+
+// uploads params [n_sets][C][stride] and the per-column "tau == 0 somewhere" flags
+int upload_params(pml_problem *p, const double *params, int n_sets) {
+    const size_t n = (size_t) n_sets * p->C * p->stride;
+    CUDA_TRY(cudaMemcpyAsync(p->params.ptr, params, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    std::vector<uint8_t> rec(p->C, 0);
+    for (int b = 0; b < n_sets; ++b)
+        for (int c = 0; c < p->C; ++c)
+            if (params[((size_t) b * p->C + c) * p->stride + 1] == 0.) rec[c] = 1;
+    CUDA_TRY(cudaMemcpyAsync(p->record_col.ptr, rec.data(), p->C, cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));   // rec is a stack-local host buffer
+    return PML_OK;
+}
+
+// the bottom-up sweep on resident params/masks; leaves out_lh on the device
+void run_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marginal, int alter, bool keep_ptr) {
+    const LaneDev ln = p->lanes(n_sets);
+    if (alter) run_alter(p, mask);
+    fill_int_kernel<<<grid_for(2LL * ln.J), kBlock, 0, p->stream>>>(2LL * ln.J, -1, p->err.ptr);
+    p->launches++;
+    BuArgs a{p->tree(), p->zc(), ln, mask, alter, p->bu.ptr, p->bu_ex.ptr, keep_ptr ? p->ptr.ptr : nullptr,
+             p->err.ptr};
+    const bool maxp = !is_marginal;
+    for (int lvl = p->n_levels - 1; lvl >= 0; --lvl) {
+        const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
+        if (ns <= 0) continue;
+        p->ks->bu(p->stream, a, maxp, s0, ns);
+        p->launches++;
+    }
+    run_root_loglik(p, ln, mask, alter, is_marginal);
+}
+
+int fetch_loglik(pml_problem *p, int n_sets, double *out) {
+    const int J = n_sets * p->C;
+    p->h_out.resize(J);
+    p->h_err.resize(2 * (size_t) J);
+    CUDA_TRY(cudaMemcpyAsync(p->h_out.data(), p->out_lh.ptr, J * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->h_err.data(), p->err.ptr, 2 * (size_t) J * sizeof(int), cudaMemcpyDeviceToHost,
+                             p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    int rc = PML_OK;
+    for (int j = 0; j < J; ++j) {
+        if (p->h_err[2 * j] >= 0) {
+            if (rc == PML_OK) {
+                p->zero_info[0] = j % p->C;
+                p->zero_info[1] = j / p->C;
+                p->zero_info[2] = p->h_err[2 * j];
+                p->zero_info[3] = p->h_err[2 * j + 1];
+            }
+            rc = PML_ERR_ZERO_LIKELIHOOD;
+            p->h_out[j] = -INFINITY;
+        }
+        if (out) out[j] = p->h_out[j];
+    }
+    if (rc != PML_OK) g_last_error = "zero likelihood: a parent and a child connected by a zero-length branch have "
+                                     "non-intersecting states";
+    return rc;
+}
+
+struct CallTimer {
+    pml_problem *p;
+    long long l0;
+    explicit CallTimer(pml_problem *pp) : p(pp), l0(pp->launches) { cudaEventRecord(p->ev0, p->stream); }
+    void stop() {
+        cudaEventRecord(p->ev1, p->stream);
+        cudaEventSynchronize(p->ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p->ev0, p->ev1);
+        p->last_ms = ms;
+        p->last_launches = p->launches - l0;
+    }
+};
+
+int ensure_marginal_buffers(pml_problem *p, bool want_probs, bool want_node_lh) {
+    const size_t nik = (size_t) p->NI * p->K * p->C;
+    if (!p->td.ptr && nik) CUDA_TRY(p->td.alloc(nik));
+    if (!p->td_ex.ptr && p->NI) CUDA_TRY(p->td_ex.alloc((size_t) p->NI * p->C));
+    if (want_probs && !p->probs.ptr) CUDA_TRY(p->probs.alloc((size_t) p->N * p->C * p->K));
+    if (want_node_lh && !p->node_lh.ptr) CUDA_TRY(p->node_lh.alloc((size_t) p->N * p->C));
+    if (!p->k_hist.ptr) CUDA_TRY(p->k_hist.alloc((size_t) p->C * (p->K + 1)));
+    return PML_OK;
+}
+
+// the fused top-down sweep on resident bottom-up state
+void run_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh) {
+    const LaneDev ln = p->lanes(1);
+    cudaMemsetAsync(p->k_hist.ptr, 0, sizeof(unsigned long long) * p->C * (p->K + 1), p->stream);
+    TdArgs a{p->tree(), p->zc(), ln, p->mask[PML_MASK_ANNOTATION].ptr, p->bu.ptr, p->bu_ex.ptr, p->td.ptr,
+             p->td_ex.ptr, p->joint_state.ptr, force_joint, want_probs ? p->probs.ptr : nullptr,
+             want_node_lh ? p->node_lh.ptr : nullptr, p->mask[PML_MASK_MAP].ptr, p->mask[PML_MASK_MPPA].ptr,
+             p->k_hist.ptr, p->zc_lh.ptr, p->zc_k.ptr};
+    p->ks->td_tip_roots(p->stream, a, p->roots.ptr, p->n_roots);
+    p->launches++;
+    for (int lvl = 0; lvl < p->n_levels; ++lvl) {
+        const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
+        if (ns <= 0) continue;
+        p->ks->td(p->stream, a, s0, ns);
+        p->launches++;
+    }
+}
+
+int copy_masks_out(pml_problem *p, const uint64_t *dev, uint64_t *host) {
+    const long long n = (long long) p->N * p->C;
+    if (!p->scratch_a.ptr) CUDA_TRY(p->scratch_a.alloc(n));
+    strip_flag_kernel<<<grid_for(n), kBlock, 0, p->stream>>>(n, p->kmask, dev, p->scratch_a.ptr);
+    p->launches++;
+    CUDA_TRY(cudaMemcpyAsync(host, p->scratch_a.ptr, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return PML_OK;
+}
+
+int copy_khist_out(pml_problem *p, int64_t *out) {
+    CUDA_TRY(cudaMemcpyAsync(out, p->k_hist.ptr, sizeof(int64_t) * p->C * (p->K + 1), cudaMemcpyDeviceToHost,
+                             p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return PML_OK;
+}
+
+}  // namespace
+
+namespace pml {
+#define PML_DECL(f, k) const KernelSet *pml_ks_##f##_##k();
+#define PML_CASE(f, k) if (family == f && kp == k) return pml_ks_##f##_##k();
+#define PML_ALL(X) X(0, 2) X(0, 4) X(0, 8) X(0, 12) X(0, 16) X(0, 20) X(0, 24) X(0, 32) X(0, 48) X(0, 62) \
+                   X(1, 4) X(2, 2) X(2, 4) X(2, 8) X(2, 12) X(2, 16) X(2, 20) X(2, 24) X(2, 32)
+PML_ALL(PML_DECL)
+const KernelSet *kernel_set(int family, int kp) {
+    PML_ALL(PML_CASE)
+    return nullptr;
+}
+}  // namespace pml
+
+// ====================================================================================== C ABI
+
+extern "C" {
+
+const char *pml_last_error(void) { return g_last_error.c_str(); }
+
+int pml_version(void) { return 100; }
+
+int pml_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int pml_param_stride(int32_t model_kind, int32_t K) {
+    if (K < 1) return -1;
+    switch (model_kind) {
+        case PML_MODEL_F81: return 4 + K;
+        case PML_MODEL_HKY: return 8;
+        case PML_MODEL_EIG: return 4 + 2 * K + 2 * K * K;
+        default: return -1;
+    }
+}
+
+int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dist, int32_t n_columns,
+                       int32_t n_states, int32_t model_kind, const uint64_t *annot_mask, const uint8_t *has_state,
+                       int32_t max_param_sets, int32_t device, pml_problem **out) {
+    if (!out) return fail(PML_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (n_nodes < 1 || !parent || !dist || !annot_mask || !has_state)
+        return fail(PML_ERR_INVALID, "empty forest or null input arrays");
+    if (n_columns < 1 || max_param_sets < 1) return fail(PML_ERR_INVALID, "need at least one column and one set");
+    if (n_states < 1 || n_states > 62) return fail(PML_ERR_INVALID, "the number of states must be in [1, 62]");
+    if (model_kind == PML_MODEL_HKY && n_states != 4) return fail(PML_ERR_INVALID, "HKY needs exactly 4 states");
+    if (model_kind < 0 || model_kind > PML_MODEL_EIG) return fail(PML_ERR_INVALID, "unknown model family");
+    if (model_kind == PML_MODEL_EIG && n_states > 32)
+        return fail(PML_ERR_INVALID, "eigen-decomposition models support at most 32 states");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(PML_ERR_NO_DEVICE, "no CUDA device available: pastml_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(PML_ERR_INVALID, "bad device ordinal");
+    CUDA_TRY(cudaSetDevice(device));
+
+    const int N = n_nodes, C = n_columns, K = n_states;
+    // ---- topology checks and derived arrays (level order: parents non-decreasing and before children)
+    std::vector<int> nch(N, 0), fch(N, 0), slot(N, -1), roots;
+    for (int v = 0; v < N; ++v) {
+        const int q = parent[v];
+        if (q >= v) return fail(PML_ERR_INVALID, "nodes are not in level order (a parent must precede its children)");
+        if (v > 0 && q < parent[v - 1]) return fail(PML_ERR_INVALID, "nodes are not in level order (parents must be non-decreasing)");
+        if (q < 0) roots.push_back(v);
+        else nch[q]++;
+    }
+    if (roots.empty() || roots.back() != (int) roots.size() - 1)
+        return fail(PML_ERR_INVALID, "roots must come first in level order");
+    {
+        long long next = (long long) roots.size();
+        for (int v = 0; v < N; ++v) { fch[v] = (int) next; next += nch[v]; }
+        if (next != N) return fail(PML_ERR_INVALID, "inconsistent parent array");
+    }
+    std::vector<int> level_ptr{0, (int) roots.size()};
+    while (level_ptr.back() < N) {
+        const int lo = level_ptr[level_ptr.size() - 2], hi = level_ptr.back();
+        long long nxt = hi;
+        for (int v = lo; v < hi; ++v) nxt += nch[v];
+        if (nxt == hi) return fail(PML_ERR_INVALID, "disconnected nodes");
+        level_ptr.push_back((int) nxt);
+    }
+    std::vector<int> int_nodes;
+    int_nodes.reserve(N / 2 + 1);
+    for (int v = 0; v < N; ++v)
+        if (nch[v]) { slot[v] = (int) int_nodes.size(); int_nodes.push_back(v); }
+    const int NI = (int) int_nodes.size();
+    const int n_levels = (int) level_ptr.size() - 1;
+    std::vector<int> int_level_ptr(n_levels + 1, 0);
+    for (int l = 0; l <= n_levels; ++l)
+        int_level_ptr[l] = (int) (std::lower_bound(int_nodes.begin(), int_nodes.end(), level_ptr[l]) - int_nodes.begin());
+
+    // ---- zero-branch clusters per column (get_zero_clusters_with_states, ml.py:321-349)
+    std::vector<int> top(N);
+    bool any_zero = false;
+    for (int v = 0; v < N; ++v) {
+        const int q = parent[v];
+        if (q >= 0 && dist[v] == 0.) { top[v] = top[q]; any_zero = true; }
+        else top[v] = v;
+    }
+    std::vector<int> cl_col, cl_ptr{0}, cl_mem, zc_index(N, -1), row_node;
+    std::vector<uint8_t> member((size_t) C * N, 0);
+    if (any_zero) {
+        std::vector<int> cnt(N), start(N + 1), fill(N), order;
+        for (int c = 0; c < C; ++c) {
+            const uint8_t *hs = has_state + (size_t) c * N;
+            std::fill(cnt.begin(), cnt.end(), 0);
+            for (int v = 0; v < N; ++v)
+                if (hs[v]) cnt[top[v]]++;
+            start[0] = 0;
+            for (int v = 0; v < N; ++v) start[v + 1] = start[v] + cnt[v];
+            order.assign(start[N], 0);
+            std::fill(fill.begin(), fill.end(), 0);
+            for (int v = 0; v < N; ++v)
+                if (hs[v]) order[start[top[v]] + fill[top[v]]++] = v;
+            for (int t = 0; t < N; ++t) {
+                if (cnt[t] < 2) continue;
+                cl_col.push_back(c);
+                for (int i = start[t]; i < start[t + 1]; ++i) {
+                    const int v = order[i];
+                    cl_mem.push_back(v);
+                    member[(size_t) c * N + v] = 1;
+                    if (zc_index[v] < 0) { zc_index[v] = (int) row_node.size(); row_node.push_back(v); }
+                }
+                cl_ptr.push_back((int) cl_mem.size());
+            }
+        }
+    }
+
+    pml_problem *p = new pml_problem();
+    p->device = device;
+    p->N = N; p->NI = NI; p->C = C; p->K = K; p->kind = model_kind; p->B = max_param_sets;
+    p->KP = (model_kind == PML_MODEL_HKY) ? 4 : kp_for(K);
+    p->ks = kernel_set(model_kind, p->KP);
+    if (!p->ks) {
+        delete p;
+        return fail(PML_ERR_INVALID, "no kernels built for this model family / number of states");
+    }
+    p->stride = pml_param_stride(model_kind, K);
+    p->kmask = (K >= 64) ? ~0ULL : ((1ULL << K) - 1ULL);
+    p->n_levels = n_levels;
+    p->n_roots = (int) roots.size();
+    p->level_ptr = level_ptr;
+    p->int_level_ptr = int_level_ptr;
+    p->n_clusters = (int) cl_col.size();
+    p->n_rows = (int) row_node.size();
+
+#define PML_TRY_FREE(expr)                                                                               \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e);                          \
+            pml_problem_destroy(p);                                                                      \
+            return fail(PML_ERR_CUDA, m);                                                                \
+        }                                                                                                \
+    } while (0)
+#define PML_UPLOAD(buf, vec)                                                                             \
+    do {                                                                                                 \
+        PML_TRY_FREE((buf).alloc((vec).size()));                                                         \
+        if (!(vec).empty())                                                                              \
+            PML_TRY_FREE(cudaMemcpy((buf).ptr, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice)); \
+    } while (0)
+
+    PML_TRY_FREE(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    PML_TRY_FREE(cudaEventCreate(&p->ev0));
+    PML_TRY_FREE(cudaEventCreate(&p->ev1));
+    {
+        std::vector<int> par(parent, parent + N);
+        std::vector<double> dst(dist, dist + N);
+        PML_UPLOAD(p->parent, par);
+        PML_UPLOAD(p->dist, dst);
+    }
+    PML_UPLOAD(p->first_child, fch);
+    PML_UPLOAD(p->n_children, nch);
+    PML_UPLOAD(p->slot, slot);
+    PML_UPLOAD(p->int_nodes, int_nodes);
+    PML_UPLOAD(p->zc_index, zc_index);
+    PML_UPLOAD(p->roots, roots);
+    PML_UPLOAD(p->cl_col, cl_col);
+    PML_UPLOAD(p->cl_ptr, cl_ptr);
+    PML_UPLOAD(p->cl_mem, cl_mem);
+    PML_UPLOAD(p->row_node, row_node);
+    const size_t rc = (size_t) std::max(p->n_rows, 1) * C;
+    PML_TRY_FREE(p->zc_alt.alloc(rc));
+    PML_TRY_FREE(p->zc_initial.alloc(rc));
+    PML_TRY_FREE(p->zc_prev_initial.alloc(rc));
+    PML_TRY_FREE(p->zc_altflag.alloc(rc));
+    PML_TRY_FREE(p->zc_hasinit.alloc(rc));
+    PML_TRY_FREE(p->zc_prev_hasinit.alloc(rc));
+    PML_TRY_FREE(p->zc_k.alloc(rc));
+    PML_TRY_FREE(p->zc_lh.alloc(rc * K));
+    PML_TRY_FREE(p->record_col.alloc(C));
+    PML_TRY_FREE(cudaMemset(p->zc_alt.ptr, 0, rc * sizeof(uint64_t)));
+    PML_TRY_FREE(cudaMemset(p->zc_initial.ptr, 0, rc * sizeof(uint64_t)));
+    PML_TRY_FREE(cudaMemset(p->zc_altflag.ptr, 0, rc));
+    PML_TRY_FREE(cudaMemset(p->zc_hasinit.ptr, 0, rc));
+    PML_TRY_FREE(cudaMemset(p->zc_k.ptr, 0, rc));
+    PML_TRY_FREE(cudaMemset(p->zc_lh.ptr, 0, rc * K * sizeof(double)));
+
+    const size_t nc = (size_t) N * C;
+    for (int m = 0; m < 5; ++m) PML_TRY_FREE(p->mask[m].alloc(nc));
+    {
+        // [C][N] -> [N][C] on the device
+        DevBuf<uint64_t> tmp_mask;
+        DevBuf<uint8_t> tmp_mem;
+        PML_TRY_FREE(tmp_mask.alloc(nc));
+        PML_TRY_FREE(tmp_mem.alloc(nc));
+        PML_TRY_FREE(cudaMemcpy(tmp_mask.ptr, annot_mask, nc * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        PML_TRY_FREE(cudaMemcpy(tmp_mem.ptr, member.data(), nc, cudaMemcpyHostToDevice));
+        init_masks_kernel<<<grid_for((long long) nc), kBlock, 0, p->stream>>>(N, C, p->kmask, tmp_mask.ptr, tmp_mem.ptr,
+                                                                              p->mask[PML_MASK_ANNOTATION].ptr, 1);
+        PML_TRY_FREE(cudaStreamSynchronize(p->stream));
+        p->mask_valid[PML_MASK_ANNOTATION] = true;
+    }
+    const size_t J = (size_t) p->B * C;
+    PML_TRY_FREE(p->params.alloc(J * p->stride));
+    PML_TRY_FREE(p->bu.alloc(std::max<size_t>((size_t) NI * K * J, 1)));
+    PML_TRY_FREE(p->bu_ex.alloc(std::max<size_t>((size_t) NI * J, 1)));
+    PML_TRY_FREE(p->err.alloc(2 * J));
+    PML_TRY_FREE(p->out_lh.alloc(J));
+    PML_TRY_FREE(p->joint_state.alloc(nc));
+    PML_TRY_FREE(cudaMemset(p->joint_state.ptr, 0, nc * sizeof(int)));
+#undef PML_UPLOAD
+#undef PML_TRY_FREE
+    *out = p;
+    return PML_OK;
+}
+
+void pml_problem_destroy(pml_problem *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+int pml_loglik(pml_problem *p, const double *params, int32_t n_sets, int32_t mask_kind, int32_t is_marginal,
+               int32_t alter, double *out_loglh) {
+    if (!p || !params) return fail(PML_ERR_INVALID, "null argument");
+    if (n_sets < 1 || n_sets > p->B) return fail(PML_ERR_INVALID, "n_sets exceeds the capacity given at creation");
+    if (mask_kind < 0 || mask_kind > PML_MASK_CUSTOM || !p->mask_valid[mask_kind])
+        return fail(PML_ERR_INVALID, "the requested mask set has not been produced yet");
+    CUDA_TRY(cudaSetDevice(p->device));
+    int rc = upload_params(p, params, n_sets);
+    if (rc) return rc;
+    CallTimer timer(p);
+    run_bottom_up(p, n_sets, p->mask[mask_kind].ptr, is_marginal, alter, false);
+    timer.stop();
+    CUDA_TRY(cudaGetLastError());
+    return fetch_loglik(p, n_sets, out_loglh);
+}
+
+int pml_joint(pml_problem *p, const double *params, double *out_loglh, int32_t *out_state) {
+    if (!p || !params) return fail(PML_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const size_t nck = (size_t) p->N * p->C * p->K;
+    if (!p->ptr.ptr) CUDA_TRY(p->ptr.alloc(nck));
+    int rc = upload_params(p, params, 1);
+    if (rc) return rc;
+    CallTimer timer(p);
+    const uint64_t *base = p->mask[PML_MASK_ANNOTATION].ptr;
+    run_bottom_up(p, 1, base, 0, 1, true);
+    JointArgs a{p->tree(), p->zc(), p->lanes(1), base, p->bu.ptr, p->ptr.ptr, p->joint_state.ptr,
+                p->mask[PML_MASK_JOINT].ptr};
+    for (int lvl = 0; lvl < p->n_levels; ++lvl) {
+        const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
+        joint_trace_kernel<<<grid_for((long long) nn * p->C), kBlock, 0, p->stream>>>(a, n0, nn);
+        p->launches++;
+    }
+    timer.stop();
+    CUDA_TRY(cudaGetLastError());
+    p->mask_valid[PML_MASK_JOINT] = true;
+    p->joint_done = true;
+    rc = fetch_loglik(p, 1, out_loglh);
+    if (out_state) {
+        CUDA_TRY(cudaMemcpyAsync(out_state, p->joint_state.ptr, sizeof(int) * (size_t) p->N * p->C,
+                                 cudaMemcpyDeviceToHost, p->stream));
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+    }
+    return rc;
+}
+
+int pml_marginal(pml_problem *p, const double *params, int32_t force_joint, double *out_loglh, double *out_probs,
+                 double *out_node_log10lh, uint64_t *out_map_mask, uint64_t *out_mppa_mask, int64_t *out_k_hist) {
+    if (!p || !params) return fail(PML_ERR_INVALID, "null argument");
+    if (force_joint && !p->joint_done)
+        return fail(PML_ERR_INVALID, "force_joint needs the JOINT states: call pml_joint first");
+    CUDA_TRY(cudaSetDevice(p->device));
+    int rc = ensure_marginal_buffers(p, out_probs != nullptr, out_node_log10lh != nullptr);
+    if (rc) return rc;
+    rc = upload_params(p, params, 1);
+    if (rc) return rc;
+    CallTimer timer(p);
+    // ml.py:700-706: allowed states are re-initialised and altered, then BU(alter=False), TD, marginals
+    run_bottom_up(p, 1, p->mask[PML_MASK_ANNOTATION].ptr, 1, 1, false);
+    run_top_down(p, force_joint, out_probs != nullptr, out_node_log10lh != nullptr);
+    // remember the '.initial' state MAP saw: pml_mppa_finalize needs it
+    if (p->n_rows) {
+        cudaMemcpyAsync(p->zc_prev_initial.ptr, p->zc_initial.ptr, sizeof(uint64_t) * (size_t) p->n_rows * p->C,
+                        cudaMemcpyDeviceToDevice, p->stream);
+        cudaMemcpyAsync(p->zc_prev_hasinit.ptr, p->zc_hasinit.ptr, (size_t) p->n_rows * p->C,
+                        cudaMemcpyDeviceToDevice, p->stream);
+    }
+    timer.stop();
+    CUDA_TRY(cudaGetLastError());
+    p->mask_valid[PML_MASK_MAP] = p->mask_valid[PML_MASK_MPPA] = true;
+    p->marginal_done = true;
+    rc = fetch_loglik(p, 1, out_loglh);
+    const size_t nc = (size_t) p->N * p->C;
+    if (out_probs)
+        CUDA_TRY(cudaMemcpyAsync(out_probs, p->probs.ptr, nc * p->K * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (out_node_log10lh)
+        CUDA_TRY(cudaMemcpyAsync(out_node_log10lh, p->node_lh.ptr, nc * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (out_map_mask) { int r2 = copy_masks_out(p, p->mask[PML_MASK_MAP].ptr, out_map_mask); if (r2) return r2; }
+    if (out_mppa_mask) { int r2 = copy_masks_out(p, p->mask[PML_MASK_MPPA].ptr, out_mppa_mask); if (r2) return r2; }
+    if (out_k_hist) { int r2 = copy_khist_out(p, out_k_hist); if (r2) return r2; }
+    return rc;
+}
+
+int pml_mppa_finalize(pml_problem *p, int32_t force_joint, uint64_t *out_mppa_mask, int64_t *out_k_hist) {
+    if (!p) return fail(PML_ERR_INVALID, "null argument");
+    if (!p->marginal_done) return fail(PML_ERR_INVALID, "call pml_marginal first");
+    CUDA_TRY(cudaSetDevice(p->device));
+    CallTimer timer(p);
+    if (p->n_rows) {
+        p->ks->mppa_fix(p->stream, p->n_rows, p->row_node.ptr, p->C, p->K, p->kmask, p->zc(),
+                        p->mask[PML_MASK_ANNOTATION].ptr, p->zc_prev_initial.ptr, p->zc_prev_hasinit.ptr,
+                        p->zc_lh.ptr, p->zc_k.ptr, p->joint_state.ptr, force_joint, p->mask[PML_MASK_MPPA].ptr,
+                        p->k_hist.ptr);
+        p->launches++;
+    }
+    timer.stop();
+    CUDA_TRY(cudaGetLastError());
+    if (out_mppa_mask) { int r2 = copy_masks_out(p, p->mask[PML_MASK_MPPA].ptr, out_mppa_mask); if (r2) return r2; }
+    if (out_k_hist) { int r2 = copy_khist_out(p, out_k_hist); if (r2) return r2; }
+    return PML_OK;
+}
+
+int pml_parsimony(pml_problem *p, int32_t methods, uint64_t *out_mask, int64_t *out_steps) {
+    if (!p) return fail(PML_ERR_INVALID, "null argument");
+    if (!(methods & (PML_PARS_ACCTRAN | PML_PARS_DOWNPASS | PML_PARS_DELTRAN)))
+        return fail(PML_ERR_INVALID, "no parsimony method requested");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const int C = p->C, K = p->K;
+    const long long nc = (long long) p->N * C;
+    if (!p->scratch_a.ptr) CUDA_TRY(p->scratch_a.alloc(nc));
+    if (!p->scratch_b.ptr) CUDA_TRY(p->scratch_b.alloc(nc));
+    if (!p->scratch_c.ptr) CUDA_TRY(p->scratch_c.alloc(nc));
+    if (!p->steps_num.ptr) CUDA_TRY(p->steps_num.alloc(std::max<size_t>((size_t) p->NI * K * C, 1)));
+    if (!p->steps_out.ptr) CUDA_TRY(p->steps_out.alloc(C));
+    uint64_t *down = p->scratch_a.ptr, *res = p->scratch_b.ptr, *up = p->scratch_c.ptr;
+    const TreeDev t = p->tree();
+    CallTimer timer(p);
+    // initialise_parsimonious_states (parsimony.py:51-73): annotation sets, all states where there is none
+    strip_flag_kernel<<<grid_for(nc), kBlock, 0, p->stream>>>(nc, p->kmask, p->mask[PML_MASK_ANNOTATION].ptr, down);
+    p->launches++;
+    for (int lvl = p->n_levels - 1; lvl >= 0; --lvl) {
+        const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
+        if (ns <= 0) continue;
+        pars_uppass_kernel<<<grid_for((long long) ns * C), kBlock, 0, p->stream>>>(t, C, p->kmask, down, s0, ns);
+        p->launches++;
+    }
+    int slot_out = 0;
+    auto steps_of = [&](const uint64_t *states, int64_t *dst) -> int {
+        for (int lvl = p->n_levels - 1; lvl >= 0; --lvl) {
+            const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
+            if (ns <= 0) continue;
+            pars_steps_kernel<<<grid_for((long long) ns * C), kBlock, 0, p->stream>>>(t, C, K, states,
+                                                                                     p->steps_num.ptr, s0, ns);
+            p->launches++;
+        }
+        pars_steps_root_kernel<<<grid_for(C), kBlock, 0, p->stream>>>(t, C, K, states, p->steps_num.ptr, p->roots.ptr,
+                                                                    p->n_roots, p->steps_out.ptr);
+        p->launches++;
+        if (dst) {
+            CUDA_TRY(cudaMemcpyAsync(dst, p->steps_out.ptr, sizeof(long long) * C, cudaMemcpyDeviceToHost, p->stream));
+            CUDA_TRY(cudaStreamSynchronize(p->stream));
+        }
+        return PML_OK;
+    };
+    auto emit = [&](const uint64_t *states) -> int {
+        int rc = steps_of(states, out_steps ? out_steps + (size_t) slot_out * C : nullptr);
+        if (rc) return rc;
+        if (out_mask) {
+            CUDA_TRY(cudaMemcpyAsync(out_mask + (size_t) slot_out * nc, states, nc * sizeof(uint64_t),
+                                     cudaMemcpyDeviceToHost, p->stream));
+            CUDA_TRY(cudaStreamSynchronize(p->stream));
+        }
+        ++slot_out;
+        return PML_OK;
+    };
+    if (methods & PML_PARS_ACCTRAN) {
+        // roots take their uppass sets (parsimony.py:152-153)
+        CUDA_TRY(cudaMemcpyAsync(res, down, sizeof(uint64_t) * (size_t) p->n_roots * C, cudaMemcpyDeviceToDevice,
+                                 p->stream));
+        for (int lvl = 0; lvl < p->n_levels; ++lvl) {
+            const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
+            if (ns <= 0) continue;
+            pars_acctran_kernel<<<grid_for((long long) ns * C), kBlock, 0, p->stream>>>(t, C, down, res, s0, ns);
+            p->launches++;
+        }
+        int rc = emit(res);
+        if (rc) return rc;
+    }
+    if (methods & (PML_PARS_DOWNPASS | PML_PARS_DELTRAN)) {
+        // the PARSIMONY feature starts as the pre-uppass sets (parsimony.py:72-73)
+        strip_flag_kernel<<<grid_for(nc), kBlock, 0, p->stream>>>(nc, p->kmask, p->mask[PML_MASK_ANNOTATION].ptr, res);
+        p->launches++;
+        for (int lvl = 0; lvl < p->n_levels; ++lvl) {
+            const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
+            if (ns <= 0) continue;
+            pars_downpass_kernel<<<grid_for((long long) ns * C), kBlock, 0, p->stream>>>(t, C, p->kmask, down, up, res,
+                                                                                        s0, ns);
+            p->launches++;
+        }
+        if (methods & PML_PARS_DOWNPASS) {
+            int rc = emit(res);
+            if (rc) return rc;
+        }
+        if (methods & PML_PARS_DELTRAN) {
+            for (int lvl = 0; lvl < p->n_levels; ++lvl) {
+                const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
+                if (ns <= 0) continue;
+                pars_deltran_kernel<<<grid_for((long long) ns * C), kBlock, 0, p->stream>>>(t, C, res, s0, ns);
+                p->launches++;
+            }
+            int rc = emit(res);
+            if (rc) return rc;
+        }
+    }
+    timer.stop();
+    CUDA_TRY(cudaGetLastError());
+    return PML_OK;
+}
+
+int pml_set_custom_masks(pml_problem *p, const uint64_t *mask) {
+    if (!p || !mask) return fail(PML_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const size_t nc = (size_t) p->N * p->C;
+    if (!p->scratch_a.ptr) CUDA_TRY(p->scratch_a.alloc(nc));
+    if (!p->scratch_b.ptr) CUDA_TRY(p->scratch_b.alloc(nc));
+    CUDA_TRY(cudaMemcpyAsync(p->scratch_a.ptr, mask, nc * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
+    // member flags are taken from the annotation masks: [C][N] -> [N][C], then OR the flags in
+    init_masks_kernel<<<grid_for((long long) nc), kBlock, 0, p->stream>>>(p->N, p->C, p->kmask, p->scratch_a.ptr, nullptr,
+                                                                          p->scratch_b.ptr, 0);
+    merge_flag_kernel<<<grid_for((long long) nc), kBlock, 0, p->stream>>>((long long) nc, p->mask[PML_MASK_ANNOTATION].ptr,
+                                                                          p->scratch_b.ptr, p->mask[PML_MASK_CUSTOM].ptr);
+    p->launches += 2;
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    CUDA_TRY(cudaGetLastError());
+    p->mask_valid[PML_MASK_CUSTOM] = true;
+    return PML_OK;
+}
+
+int pml_get_masks(pml_problem *p, int32_t mask_kind, uint64_t *out_mask) {
+    if (!p || !out_mask) return fail(PML_ERR_INVALID, "null argument");
+    if (mask_kind < 0 || mask_kind > PML_MASK_CUSTOM || !p->mask_valid[mask_kind])
+        return fail(PML_ERR_INVALID, "the requested mask set has not been produced yet");
+    CUDA_TRY(cudaSetDevice(p->device));
+    return copy_masks_out(p, p->mask[mask_kind].ptr, out_mask);
+}
+
+int pml_get_initial(pml_problem *p, uint8_t *out_has, uint64_t *out_initial) {
+    if (!p || !out_has || !out_initial) return fail(PML_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const size_t nc = (size_t) p->N * p->C;
+    std::memset(out_has, 0, nc);
+    std::memset(out_initial, 0, nc * sizeof(uint64_t));
+    if (!p->n_rows) return PML_OK;
+    const size_t rc = (size_t) p->n_rows * p->C;
+    std::vector<uint64_t> init(rc);
+    std::vector<uint8_t> has(rc);
+    std::vector<int> rows(p->n_rows);
+    CUDA_TRY(cudaMemcpy(init.data(), p->zc_initial.ptr, rc * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(has.data(), p->zc_hasinit.ptr, rc, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(rows.data(), p->row_node.ptr, sizeof(int) * p->n_rows, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < p->n_rows; ++r)
+        for (int c = 0; c < p->C; ++c)
+            if (has[(size_t) r * p->C + c]) {
+                out_has[(size_t) rows[r] * p->C + c] = 1;
+                out_initial[(size_t) rows[r] * p->C + c] = init[(size_t) r * p->C + c];
+            }
+    return PML_OK;
+}
+
+int pml_zero_likelihood_info(pml_problem *p, int32_t *column, int32_t *param_set, int32_t *parent, int32_t *child) {
+    if (!p) return fail(PML_ERR_INVALID, "null argument");
+    if (column) *column = p->zero_info[0];
+    if (param_set) *param_set = p->zero_info[1];
+    if (parent) *parent = p->zero_info[2];
+    if (child) *child = p->zero_info[3];
+    return PML_OK;
+}
+
+int pml_last_call_stats(pml_problem *p, double *device_ms, int64_t *kernel_launches) {
+    if (!p) return fail(PML_ERR_INVALID, "null argument");
+    if (device_ms) *device_ms = p->last_ms;
+    if (kernel_launches) *kernel_launches = p->last_launches;
+    return PML_OK;
+}
+
+int pml_bench_pass(pml_problem *p, const double *params, int32_t n_sets, int32_t which, int32_t n_iter,
+                   int32_t flush_l2, double *avg_ms, double *min_ms, int64_t *kernel_launches) {
+    if (!p || !params || n_iter < 1) return fail(PML_ERR_INVALID, "bad argument");
+    if (n_sets < 1 || n_sets > p->B) return fail(PML_ERR_INVALID, "n_sets exceeds the capacity given at creation");
+    if (which != 0 && n_sets != 1) return fail(PML_ERR_INVALID, "this pass takes one parameter set");
+    CUDA_TRY(cudaSetDevice(p->device));
+    if (which == 1) {
+        int rc = ensure_marginal_buffers(p, true, true);
+        if (rc) return rc;
+        if (!p->joint_done) return fail(PML_ERR_INVALID, "call pml_joint first");
+    }
+    if (which == 2 && !p->ptr.ptr) CUDA_TRY(p->ptr.alloc((size_t) p->N * p->C * p->K));
+    int rc = upload_params(p, params, n_sets);
+    if (rc) return rc;
+    const long long flush_n = 64LL << 20;   // 256 MiB of floats > 126 MB L2
+    if (flush_l2 && !p->flush.ptr) CUDA_TRY(p->flush.alloc(flush_n));
+    double total = 0., best = 1e300;
+    const long long l0 = p->launches;
+    for (int it = 0; it < n_iter; ++it) {
+        if (flush_l2) flush_kernel<<<148 * 8, 256, 0, p->stream>>>(flush_n, p->flush.ptr, (float) it);
+        cudaEventRecord(p->ev0, p->stream);
+        const uint64_t *base = p->mask[PML_MASK_ANNOTATION].ptr;
+        if (which == 0) run_bottom_up(p, n_sets, base, 1, 1, false);
+        else if (which == 1) {
+            run_bottom_up(p, 1, base, 1, 1, false);
+            run_top_down(p, 1, true, true);
+        } else {
+            run_bottom_up(p, 1, base, 0, 1, true);
+            JointArgs a{p->tree(), p->zc(), p->lanes(1), base, p->bu.ptr, p->ptr.ptr, p->joint_state.ptr,
+                        p->mask[PML_MASK_JOINT].ptr};
+            for (int lvl = 0; lvl < p->n_levels; ++lvl) {
+                const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
+                joint_trace_kernel<<<grid_for((long long) nn * p->C), kBlock, 0, p->stream>>>(a, n0, nn);
+                p->launches++;
+            }
+        }
+        cudaEventRecord(p->ev1, p->stream);
+        CUDA_TRY(cudaEventSynchronize(p->ev1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p->ev0, p->ev1);
+        total += ms;
+        best = std::min(best, (double) ms);
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (which == 1) p->mask_valid[PML_MASK_MAP] = p->mask_valid[PML_MASK_MPPA] = p->marginal_done = true;
+    if (avg_ms) *avg_ms = total / n_iter;
+    if (min_ms) *min_ms = best;
+    if (kernel_launches) *kernel_launches = (p->launches - l0) / n_iter;
+    return PML_OK;
+}
+
+}  // extern "C"

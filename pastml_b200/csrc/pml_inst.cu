@@ -1,0 +1,69 @@
+// One (model family, KP) instantiation of the level kernels.  Compile with -DPML_FAMILY={0,1,2} -DPML_KP=<n>.
+#include "pml_launch.h"
+
+#ifndef PML_FAMILY
+#error "PML_FAMILY must be defined"
+#endif
+#ifndef PML_KP
+#error "PML_KP must be defined"
+#endif
+
+#define PML_CAT2(a, b, c) pml_ks_##a##_##b##c
+#define PML_CAT(a, b) PML_CAT2(a, b, )
+
+namespace pml {
+
+#if PML_FAMILY == 0
+template <int KP> using TheLane = F81Lane<KP>;
+#elif PML_FAMILY == 1
+template <int KP> using TheLane = HKYLane<KP>;
+#else
+template <int KP> using TheLane = EigLane<KP>;
+#endif
+
+namespace {
+constexpr int KP = PML_KP;
+
+void bu_launch(cudaStream_t st, const BuArgs &a, bool maxp, int s0, int ns) {
+    const long long items = (long long) ns * a.ln.J;
+    if (maxp) bu_level_kernel<KP, TheLane, true><<<grid_for(items), kBlock, 0, st>>>(a, s0, ns);
+    else bu_level_kernel<KP, TheLane, false><<<grid_for(items), kBlock, 0, st>>>(a, s0, ns);
+}
+
+void root_launch(cudaStream_t st, const TreeDev &t, const ZcDev &zc, const LaneDev &ln, const uint64_t *mask,
+                 int alter, const double *bu, const int *bu_ex, const int *roots, int n_roots, int is_marginal,
+                 double *out) {
+    root_loglik_kernel<<<grid_for(ln.J), kBlock, 0, st>>>(t, zc, ln, mask, alter, bu, bu_ex, roots, n_roots,
+                                                          is_marginal, out);
+}
+
+void td_launch(cudaStream_t st, const TdArgs &a, int s0, int ns) {
+    const size_t sh = sizeof(unsigned) * a.ln.C * (a.ln.K + 1);
+    td_level_kernel<KP, TheLane><<<grid_for((long long) ns * a.ln.C), kBlock, sh, st>>>(a, s0, ns);
+}
+
+void td_tip_roots_launch(cudaStream_t st, const TdArgs &a, const int *roots, int n_roots) {
+    const size_t sh = sizeof(unsigned) * a.ln.C * (a.ln.K + 1);
+    td_tip_roots_kernel<KP, TheLane><<<grid_for((long long) n_roots * a.ln.C), kBlock, sh, st>>>(a, roots, n_roots);
+}
+
+void mppa_fix_launch(cudaStream_t st, int n_rows, const int *row_node, int C, int K, uint64_t kmask, const ZcDev &zc,
+                     const uint64_t *base_mask, const uint64_t *prev_initial, const uint8_t *prev_hasinit,
+                     const double *zc_lh, uint8_t *zc_k, const int *joint_state, int force_joint, uint64_t *mppa_mask,
+                     unsigned long long *k_hist) {
+    mppa_fix_kernel<KP><<<grid_for((long long) n_rows * C), kBlock, 0, st>>>(
+        n_rows, row_node, C, K, kmask, zc, base_mask, prev_initial, prev_hasinit, zc_lh, zc_k, joint_state,
+        force_joint, mppa_mask, k_hist);
+}
+}  // namespace
+
+#define PML_KS_NAME3(f, k) pml_ks_##f##_##k
+#define PML_KS_NAME2(f, k) PML_KS_NAME3(f, k)
+#define PML_KS_NAME PML_KS_NAME2(PML_FAMILY, PML_KP)
+
+const KernelSet *PML_KS_NAME() {
+    static const KernelSet ks = {bu_launch, root_launch, td_launch, td_tip_roots_launch, mppa_fix_launch};
+    return &ks;
+}
+
+}  // namespace pml

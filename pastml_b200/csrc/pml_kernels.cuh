@@ -296,7 +296,7 @@ struct EigLane {  // CUSTOM_RATES / JTT: P = A diag(exp(d t')) A^-1  (generator.
 // get_zero_clusters_with_states + alter_zero_node_allowed_states (ml.py:321-387) for one (cluster, column) per
 // thread.  Writes the effective masks of all members into the cluster table; when the members share no state the
 // union is assigned to all of them and (if record_col[c]) the old masks become their '.initial'.
-__global__ void alter_kernel(int n_clusters, const int *cl_col, const int *cl_ptr, const int *cl_mem,
+static __global__ void alter_kernel(int n_clusters, const int *cl_col, const int *cl_ptr, const int *cl_mem,
                              const int *zc_index, const uint64_t *src, int C, uint64_t kmask,
                              const uint8_t *record_col, uint64_t *alt, uint8_t *altflag, uint64_t *initial,
                              uint8_t *hasinit) {
@@ -403,8 +403,7 @@ __global__ void __launch_bounds__(kBlock) bu_level_kernel(BuArgs a, int slot_beg
 }
 
 // ln(sum_i L_root,i pi_i) - SF ln 10 summed over the roots (ml.py:112-121); a root may be a tip.
-template <int KP>
-__global__ void root_loglik_kernel(TreeDev t, ZcDev zc, LaneDev ln, const uint64_t *mask, int alter,
+static __global__ void root_loglik_kernel(TreeDev t, ZcDev zc, LaneDev ln, const uint64_t *mask, int alter,
                                    const double *bu, const int *bu_ex, const int *roots, int n_roots,
                                    int is_marginal, double *out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -445,7 +444,7 @@ struct JointArgs {
 
 // choose_ancestral_states_joint (ml.py:598-622) + unalter_zero_node_joint_states (ml.py:408-428) for the nodes
 // [node_begin, node_begin + n_nodes) of one level.
-__global__ void joint_trace_kernel(JointArgs a, int node_begin, int n_nodes) {
+static __global__ void joint_trace_kernel(JointArgs a, int node_begin, int n_nodes) {
     const int C = a.ln.C, K = a.ln.K;
     const long long n_items = (long long) n_nodes * C;
     for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
@@ -807,7 +806,7 @@ __device__ __forceinline__ uint64_t most_common(uint64_t first, bool has_first, 
 }
 
 // uppass (parsimony.py:92-122) for the internal nodes of one level; down[] was initialised to the annotation sets.
-__global__ void pars_uppass_kernel(TreeDev t, int C, uint64_t kmask, uint64_t *down, int slot_begin, int n_slots) {
+static __global__ void pars_uppass_kernel(TreeDev t, int C, uint64_t kmask, uint64_t *down, int slot_begin, int n_slots) {
     const long long n_items = (long long) n_slots * C;
     for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
          g += (long long) gridDim.x * blockDim.x) {
@@ -821,7 +820,7 @@ __global__ void pars_uppass_kernel(TreeDev t, int C, uint64_t kmask, uint64_t *d
 }
 
 // acctran (parsimony.py:125-158): the children of the internal nodes of one level.
-__global__ void pars_acctran_kernel(TreeDev t, int C, const uint64_t *down, uint64_t *out, int slot_begin,
+static __global__ void pars_acctran_kernel(TreeDev t, int C, const uint64_t *down, uint64_t *out, int slot_begin,
                                     int n_slots) {
     const long long n_items = (long long) n_slots * C;
     for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
@@ -839,7 +838,7 @@ __global__ void pars_acctran_kernel(TreeDev t, int C, const uint64_t *down, uint
 
 // downpass (parsimony.py:161-210): an internal node's own state from up(node) and its children's down sets, then
 // up() of its children; tip children are finished on the spot.  res[] starts as the pre-uppass sets.
-__global__ void pars_downpass_kernel(TreeDev t, int C, uint64_t kmask, const uint64_t *down, uint64_t *up,
+static __global__ void pars_downpass_kernel(TreeDev t, int C, uint64_t kmask, const uint64_t *down, uint64_t *up,
                                      uint64_t *res, int slot_begin, int n_slots) {
     const long long n_items = (long long) n_slots * C;
     for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
@@ -866,7 +865,7 @@ __global__ void pars_downpass_kernel(TreeDev t, int C, uint64_t kmask, const uin
 }
 
 // deltran (parsimony.py:213-242): children of the internal nodes of one level, on top of the DOWNPASS result.
-__global__ void pars_deltran_kernel(TreeDev t, int C, uint64_t *res, int slot_begin, int n_slots) {
+static __global__ void pars_deltran_kernel(TreeDev t, int C, uint64_t *res, int slot_begin, int n_slots) {
     const long long n_items = (long long) n_slots * C;
     for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
          g += (long long) gridDim.x * blockDim.x) {
@@ -882,7 +881,7 @@ __global__ void pars_deltran_kernel(TreeDev t, int C, uint64_t *res, int slot_be
 
 // get_num_parsimonious_steps (parsimony.py:360-380): min-plus DP, one thread per (internal node, column);
 // num[slot][k][C] int32 (INF for states outside the node's set).
-__global__ void pars_steps_kernel(TreeDev t, int C, int K, const uint64_t *states, int *num, int slot_begin,
+static __global__ void pars_steps_kernel(TreeDev t, int C, int K, const uint64_t *states, int *num, int slot_begin,
                                   int n_slots) {
     const int INF = 1 << 29;
     const long long n_items = (long long) n_slots * C;
@@ -912,7 +911,7 @@ __global__ void pars_steps_kernel(TreeDev t, int C, int K, const uint64_t *state
     }
 }
 
-__global__ void pars_steps_root_kernel(TreeDev t, int C, int K, const uint64_t *states, const int *num,
+static __global__ void pars_steps_root_kernel(TreeDev t, int C, int K, const uint64_t *states, const int *num,
                                        const int *roots, int n_roots, long long *out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -931,7 +930,7 @@ __global__ void pars_steps_root_kernel(TreeDev t, int C, int K, const uint64_t *
 
 // [C][N] host layout -> [N][C] device layout, adding the allowed-states rule "no annotation => all states"
 // (initialize_allowed_states, ml.py:311-313) and the cluster-member flag.
-__global__ void init_masks_kernel(int N, int C, uint64_t kmask, const uint64_t *annot_cn, const uint8_t *member_cn,
+static __global__ void init_masks_kernel(int N, int C, uint64_t kmask, const uint64_t *annot_cn, const uint8_t *member_cn,
                                   uint64_t *base_nc, int apply_default) {
     const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long) N * C) return;
@@ -942,17 +941,22 @@ __global__ void init_masks_kernel(int N, int C, uint64_t kmask, const uint64_t *
     base_nc[g] = m;
 }
 
-__global__ void strip_flag_kernel(long long n, uint64_t kmask, const uint64_t *in, uint64_t *out) {
+static __global__ void strip_flag_kernel(long long n, uint64_t kmask, const uint64_t *in, uint64_t *out) {
     const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (g < n) out[g] = in[g] & kmask;
 }
 
-__global__ void fill_int_kernel(long long n, int value, int *out) {
+static __global__ void merge_flag_kernel(long long n, const uint64_t *base, const uint64_t *src, uint64_t *dst) {
+    const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) dst[g] = src[g] | (base[g] & kMemberFlag);
+}
+
+static __global__ void fill_int_kernel(long long n, int value, int *out) {
     const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (g < n) out[g] = value;
 }
 
-__global__ void flush_kernel(long long n, float *buf, float v) {
+static __global__ void flush_kernel(long long n, float *buf, float v) {
     for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n;
          g += (long long) gridDim.x * blockDim.x)
         buf[g] = v;

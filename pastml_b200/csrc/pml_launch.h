@@ -1,0 +1,32 @@
+// Table of host-side launchers for one (model family, padded state count) instantiation of the templated kernels.
+// Every instantiation lives in its own translation unit (pml_inst.cu compiled with -DPML_FAMILY=.. -DPML_KP=..)
+// so that the build parallelises; the engine picks the table once per problem.
+#pragma once
+#include "pml_kernels.cuh"
+
+namespace pml {
+
+struct KernelSet {
+    void (*bu)(cudaStream_t, const BuArgs &, bool maxp, int slot_begin, int n_slots);
+    void (*root_loglik)(cudaStream_t, const TreeDev &, const ZcDev &, const LaneDev &, const uint64_t *mask,
+                        int alter, const double *bu, const int *bu_ex, const int *roots, int n_roots,
+                        int is_marginal, double *out);
+    void (*td)(cudaStream_t, const TdArgs &, int slot_begin, int n_slots);
+    void (*td_tip_roots)(cudaStream_t, const TdArgs &, const int *roots, int n_roots);
+    void (*mppa_fix)(cudaStream_t, int n_rows, const int *row_node, int C, int K, uint64_t kmask, const ZcDev &,
+                     const uint64_t *base_mask, const uint64_t *prev_initial, const uint8_t *prev_hasinit,
+                     const double *zc_lh, uint8_t *zc_k, const int *joint_state, int force_joint,
+                     uint64_t *mppa_mask, unsigned long long *k_hist);
+};
+
+inline unsigned grid_for(long long items) {
+    long long g = (items + kBlock - 1) / kBlock;
+    if (g < 1) g = 1;
+    if (g > 0x7fffffffLL) g = 0x7fffffffLL;
+    return (unsigned) g;
+}
+
+// family: 0 = F81, 1 = HKY, 2 = EIG (PML_MODEL_*); returns nullptr when the combination is not built
+const KernelSet *kernel_set(int family, int kp);
+
+}  // namespace pml

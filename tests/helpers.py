@@ -41,3 +41,15 @@ class Golden(object):
             kw = dict(d=z['eig_d'], A=z['eig_A'], Ainv=z['eig_Ainv'])
         return OracleModel(self.kind, z['pi'], float(z['sf']), float(z['tau']), float(z['tau_factor']),
                            float(z['kappa']), **kw)
+
+
+def engine_params(g):
+    """One lane's parameter block for the engine from a golden fixture."""
+    from pastml_b200.engine import pack_params
+    z = g.z
+    kw = {}
+    if g.kind == 2:
+        kw = dict(d=z['eig_d'], A=z['eig_A'], Ainv=z['eig_Ainv'])
+    if g.kind == 1:
+        kw = dict(kappa=float(z['kappa']))
+    return pack_params(g.kind, g.K, float(z['sf']), float(z['tau']), float(z['tau_factor']), z['pi'], **kw)

@@ -1,0 +1,164 @@
+"""GPU parity tests: the CUDA engine, called through its C ABI, against (i) the golden fixtures produced by the
+unmodified reference and (ii) the CPU oracle on seeded synthetic inputs.
+
+Tolerances (BASELINE.json north_star): log-likelihood 1e-10 relative, marginal probabilities 1e-9 absolute,
+state assignments exact.
+"""
+import numpy as np
+import pytest
+
+from helpers import Golden, golden_names, engine_params
+
+pytestmark = pytest.mark.gpu
+
+LH_RTOL = 1e-10
+PROB_ATOL = 1e-9
+
+
+def _problem(g, **kw):
+    from pastml_b200.engine import Problem
+    return Problem(g.flat, g.K, g.kind, g['annot_mask'][None, :], g['has_state'][None, :], **kw)
+
+
+def _run_ml(pb, params, force_joint):
+    """The call sequence of ml_acr (ml.py:640-750) at fixed parameters on the engine."""
+    from pastml_b200.engine import MASK_ANNOTATION, MASK_MAP, MASK_MPPA
+    out = {}
+    out['lh'] = pb.loglik(params, mask_kind=MASK_ANNOTATION)[0]
+    out['lh_joint'], out['joint_state'] = pb.joint(params)
+    out.update(pb.marginal(params, force_joint=force_joint, want_node_lh=True))
+    out['lh_map'] = pb.loglik(params, mask_kind=MASK_MAP)[0]
+    out['mppa_mask'], out['k_hist'] = pb.mppa_finalize(force_joint=force_joint)
+    out['lh_mppa'] = pb.loglik(params, mask_kind=MASK_MPPA)[0]
+    return out
+
+
+@pytest.fixture(scope='module', params=golden_names())
+def golden_run(request):
+    g = Golden(request.param)
+    pb = _problem(g)
+    res = _run_ml(pb, engine_params(g), g.meta['force_joint'])
+    res['pars'] = pb.parsimony()
+    pb.close()
+    return g, res
+
+
+def test_golden_loglikelihoods(golden_run):
+    g, r = golden_run
+    assert r['lh'][0] == pytest.approx(float(g['log_likelihood']), rel=LH_RTOL)
+    assert r['loglh'][0] == pytest.approx(float(g['log_likelihood']), rel=LH_RTOL)
+    assert r['lh_joint'][0] == pytest.approx(float(g['lh_restricted_JOINT']), rel=LH_RTOL)
+    assert r['lh_map'][0] == pytest.approx(float(g['lh_restricted_MAP']), rel=LH_RTOL)
+    assert r['lh_mppa'][0] == pytest.approx(float(g['lh_restricted_MPPA']), rel=LH_RTOL)
+
+
+def test_golden_marginal_probabilities(golden_run):
+    g, r = golden_run
+    np.testing.assert_allclose(r['probs'][:, 0, :], g['marginal_probabilities'], rtol=0, atol=PROB_ATOL)
+
+
+def test_golden_node_likelihoods(golden_run):
+    g, r = golden_run
+    # log10(sum LIKELIHOOD) - LIKELIHOOD_SF of the reference, for nodes whose vector MAP/MPPA did not mask in place
+    ref = np.log10(g['lh'].sum(axis=1)) - g['lh_sf']
+    keep = g['has_initial'] == 0
+    np.testing.assert_allclose(r['node_log10lh'][keep, 0], ref[keep], rtol=0, atol=1e-8)
+
+
+def test_golden_states(golden_run):
+    g, r = golden_run
+    assert np.array_equal(np.uint64(1) << r['joint_state'][:, 0].astype(np.uint64), g['joint_mask'])
+    assert np.array_equal(r['map_mask'][:, 0], g['map_mask'])
+    assert np.array_equal(r['mppa_mask'][:, 0], g['mppa_mask'])
+    num_scenarios = 1
+    for k, cnt in enumerate(r['k_hist'][0]):
+        num_scenarios *= k ** int(cnt)
+    assert str(num_scenarios) == g.meta['num_scenarios']
+    assert int(r['k_hist'][0][2:].sum()) == int(g['num_unresolved_nodes'])
+
+
+def test_golden_parsimony(golden_run):
+    g, r = golden_run
+    if 'DOWNPASS_mask' not in g:
+        pytest.skip('no parsimony outputs in this fixture')
+    for m in ('ACCTRAN', 'DOWNPASS', 'DELTRAN'):
+        mask, steps = r['pars'][m]
+        assert np.array_equal(mask[:, 0], g[m + '_mask']), m
+        assert int(steps[0]) == int(g[m + '_steps']), m
+
+
+def test_columns_and_parameter_sets_batched():
+    """Three Albania columns (F81, JC, EFT parameters) x 3 parameter sets in one problem."""
+    from pastml_b200.engine import Problem
+    gs = [Golden(n) for n in ('albania_f81', 'albania_jc', 'albania_eft')]
+    g0 = gs[0]
+    masks = np.stack([g['annot_mask'] for g in gs])
+    has = np.stack([g['has_state'] for g in gs])
+    pb = Problem(g0.flat, g0.K, 0, masks, has, max_param_sets=3)
+    base = np.stack([engine_params(g) for g in gs])            # [C][stride]
+    sets = np.stack([base, base, base])                          # [B][C][stride]
+    sets[1, :, 0] *= 1.5
+    sets[2, :, 0] *= 0.25
+    lh = pb.loglik(sets, n_sets=3)
+    from oracle import cpu_oracle
+    for c, g in enumerate(gs):
+        assert lh[0, c] == pytest.approx(float(g['log_likelihood']), rel=LH_RTOL)
+        for b in (1, 2):
+            m = g.oracle_model()
+            m.sf = float(sets[b, c, 0])
+            tree = cpu_oracle.OracleTree(g.flat)
+            want = cpu_oracle.loglikelihood(tree, m, np.where(g['annot_mask'] == 0, np.uint64((1 << g.K) - 1),
+                                                              g['annot_mask']), g['has_state'])
+            assert lh[b, c] == pytest.approx(want, rel=LH_RTOL)
+    res = pb.marginal(base, force_joint=False)
+    for c, g in enumerate(gs):
+        np.testing.assert_allclose(res['probs'][:, c, :], g['marginal_probabilities'], rtol=0, atol=PROB_ATOL)
+    pb.close()
+
+
+@pytest.mark.parametrize('n_tips,K,C,kind', [(3000, 10, 4, 'yule'), (2000, 20, 3, 'coalescent'), (1500, 3, 8, 'yule'),
+                                            (1000, 30, 2, 'yule')])
+def test_synthetic_against_oracle(n_tips, K, C, kind):
+    from pastml_b200.engine import Problem, MASK_MAP, MASK_MPPA, pack_params
+    from pastml_b200 import synth
+    from oracle import cpu_oracle
+    rng = np.random.default_rng(1000 + n_tips + K)
+    flat = synth.yule_tree(n_tips, rng) if kind == 'yule' else synth.coalescent_tree(n_tips, rng)
+    masks, has, pis, sfs = synth.simulate_tip_masks(flat, K, C, rng, missing=0.05)
+    params = np.stack([pack_params(0, K, sfs[c], 0., 1., pis[c]) for c in range(C)])
+    pb = Problem(flat, K, 0, masks, has)
+    r = _run_ml(pb, params, True)
+    pars = pb.parsimony()
+    pb.close()
+    for c in range(C):
+        model = cpu_oracle.OracleModel(0, pis[c], sfs[c])
+        want = cpu_oracle.ml_acr_fixed(flat, model, masks[c], has[c], method='MPPA', force_joint=True)
+        assert r['lh'][c] == pytest.approx(want['log_likelihood'], rel=LH_RTOL)
+        assert r['lh_joint'][c] == pytest.approx(want['log_likelihood_restricted_JOINT'], rel=LH_RTOL)
+        assert r['lh_map'][c] == pytest.approx(want['log_likelihood_restricted_MAP'], rel=LH_RTOL)
+        assert r['lh_mppa'][c] == pytest.approx(want['log_likelihood_restricted_MPPA'], rel=LH_RTOL)
+        np.testing.assert_allclose(r['probs'][:, c, :], want['marginal_probabilities'], rtol=0, atol=PROB_ATOL)
+        assert np.array_equal(r['joint_state'][:, c], want['joint_state'])
+        assert np.array_equal(r['map_mask'][:, c], want['map_mask'])
+        assert np.array_equal(r['mppa_mask'][:, c], want['mppa_mask'])
+        wp = cpu_oracle.parsimony_fixed(flat, K, masks[c])
+        for m in ('ACCTRAN', 'DOWNPASS', 'DELTRAN'):
+            assert np.array_equal(pars[m][0][:, c], wp[m + '_mask']), m
+            assert int(pars[m][1][c]) == wp[m + '_steps'], m
+
+
+def test_zero_likelihood_is_reported():
+    """Two zero-distance tips with different states under tau = 0 are merged by the alteration; with alter off the
+    engine must report the reference's PastMLLikelihoodError condition (ml.py:139-145)."""
+    from pastml_b200.engine import Problem, ZeroLikelihoodError, pack_params
+    from pastml_b200.tree import FlatForest
+    flat = FlatForest(np.array([-1, 0, 0], dtype=np.int32), np.array([0., 0., 0.]))
+    masks = np.array([[0, 1, 2]], dtype=np.uint64)
+    has = np.array([[0, 1, 1]], dtype=np.uint8)
+    pb = Problem(flat, 2, 0, masks, has)
+    params = pack_params(0, 2, 1., 0., 1., [0.5, 0.5])
+    assert np.isfinite(pb.loglik(params, alter=True)[0, 0])
+    with pytest.raises(ZeroLikelihoodError) as e:
+        pb.loglik(params, alter=False)
+    assert (e.value.parent, e.value.child) == (0, 2)
+    pb.close()
