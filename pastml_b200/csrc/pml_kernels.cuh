@@ -309,14 +309,14 @@ static __global__ void alter_kernel(int n_clusters, const int *cl_col, const int
         common &= v;
         uni |= v;
     }
-    const bool altered = (common == 0ULL);
+    const bool altered = (common == 0ULL) && record_col[c];   // the reference alters only while tau == 0 (ml.py:101)
     for (int i = cl_ptr[q]; i < cl_ptr[q + 1]; ++i) {
         const int node = cl_mem[i];
         const size_t r = (size_t) zc_index[node] * C + c;
         const uint64_t v = src[(size_t) node * C + c] & kmask;
         alt[r] = altered ? uni : v;
         altflag[r] = altered ? 1 : 0;
-        if (altered && record_col[c]) {
+        if (altered) {
             initial[r] = v;
             hasinit[r] = 1;
         }
