@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the ACR hot path: MPPA node-states/s on a synthetic 1M-tip tree, K=20, 8 columns, F81.
+
+A "step" is one pass of the fixed-parameter MPPA pipeline (metric i) over one forest:
+zero-branch alteration, bottom-up (pruning) sweep, fused top-down / marginal / probabilities / MAP / MPPA sweep;
+node-states = nodes x states x columns.  ``value`` is timed on the device with CUDA events on resident inputs
+(L2 flushed between steps; the working set, 2.7 GB of partials, is far larger than L2 anyway); ``e2e`` goes through
+the C ABI with pinned host buffers: problem creation (H2D of topology and annotation masks), the pipeline, and D2H
+of the marginal probabilities, MAP/MPPA masks and the k histogram, every step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--tips T] [--states K] [--columns C]
+
+With --gpus N > 1 the driver launches one rank per GPU through torchrun; every rank owns an independent
+(tree x columns) batch of the same shape (weak scaling, no data-path collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = 'mppa_node_states_per_s'
+UNIT = 'node-states/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--tips', type=int, default=1_000_000)
+    ap.add_argument('--states', type=int, default=20)
+    ap.add_argument('--columns', type=int, default=8)
+    ap.add_argument('--tree', default='yule', choices=['yule', 'coalescent'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    return ap.parse_args()
+
+
+def make_workload(args, rank):
+    from pastml_b200 import synth
+    from pastml_b200.engine import pack_params
+    rng = np.random.default_rng(4000 + rank)
+    flat = synth.yule_tree(args.tips, rng) if args.tree == 'yule' else synth.coalescent_tree(args.tips, rng)
+    masks, has, pis, sfs = synth.simulate_tip_masks(flat, args.states, args.columns, rng)
+    params = np.stack([pack_params(0, args.states, sfs[c], 0., 1., pis[c]) for c in range(args.columns)])
+    return flat, masks, has, pis, sfs, params
+
+
+def workload_config(args, flat):
+    return {'workload': 'synthetic {} tree, {} tips ({} nodes, {} levels), K={} states, {} columns, F81, MPPA pipeline '
+                        '(bottom-up + top-down + marginal + MAP + MPPA) at fixed parameters'
+                        .format(args.tree, args.tips, flat.n_nodes, flat.n_levels, args.states, args.columns),
+            'tips': args.tips, 'nodes': int(flat.n_nodes), 'states': args.states, 'columns': args.columns,
+            'model': 'F81', 'method': 'MPPA', 'l2': 'flushed between steps (256 MiB write); inputs >> L2',
+            'sharding': 'independent (tree x columns) batch per GPU'}
+
+
+# ------------------------------------------------------------------ algorithmic bytes
+
+def algorithmic_bytes(flat, K, C):
+    """Bytes one sweep must move for C columns batched in one launch sequence, by the formulas of SURVEY.md 8(d):
+    B_bu = (2 NI - T)(8K + 8) + 4 Ntip per column + 20 N topology bytes per launch sequence;
+    B_td = (2 NI - T)(8K + 8) + 4 Ntip + 2 (NI - T)(8K + 8) + 8K N + 8 N per column + 20 N."""
+    n, ni, nt, t = flat.n_nodes, flat.n_internal, flat.n_tips, flat.n_trees
+    vec = 8 * K + 8
+    bu = C * ((2 * ni - t) * vec + 4 * nt) + 20 * n
+    td = C * ((2 * ni - t) * vec + 4 * nt + 2 * (ni - t) * vec + 8 * K * n + 8 * n) + 20 * n
+    return bu, td
+
+
+# ------------------------------------------------------------------ clocks
+
+class ClockSampler(object):
+    QUERY = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(',')]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[2:]):
+                    if val.lower().startswith('active'):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thread.join(timeout=10)
+
+    def summary(self):
+        return {'sm_mhz': float(np.median(self.samples)) if self.samples else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+# ------------------------------------------------------------------ CPU arm (oracle port)
+
+def cpu_pipeline_rate(flat, masks, has, pis, sfs, K, columns, threads, repeats=1):
+    """node-states/s of the oracle's MPPA pipeline on `columns` columns of the workload with `threads` host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import cpu_oracle
+    cpu_oracle.build()
+    cpu_oracle.lib()
+
+    def one(c):
+        cpu_oracle.marginal_pipeline(flat, cpu_oracle.OracleModel(0, pis[c], sfs[c]), masks[c], has[c])
+
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            list(pool.map(one, columns))
+    dt = (time.perf_counter() - t0) / repeats
+    return flat.n_nodes * K * len(columns) / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference's algorithm (oracle/pastml_oracle.c; the reference itself is
+    pure Python and does not travel to the GPU box) on all the host threads it can use -- one per column."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    flat, masks, has, pis, sfs, _ = make_workload(args, 0)
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, args.columns))
+    # bounded sample: a 100k-tip subsample would change the level structure, so keep the tree and bound the work
+    # by the number of steps instead; each step = all columns of the workload
+    columns = list(range(args.columns))
+    steps = max(1, min(args.steps, 2))
+    warm = 1 if args.warmup else 0
+    for _ in range(warm):
+        cpu_pipeline_rate(flat, masks, has, pis, sfs, args.states, columns[:threads], threads)
+    rate, dt = cpu_pipeline_rate(flat, masks, has, pis, sfs, args.states, columns, threads, repeats=steps)
+    sample = '{} step(s) of all {} columns of the workload, {} threads (one per column)'.format(steps, args.columns, threads)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+            'warmup': warm, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, flat),
+            'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0, 'host_cores': cores}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ B200 arm
+
+def run_b200(args):
+    import torch
+    from pastml_b200.engine import Problem
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the engine has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flat, masks, has, pis, sfs, params = make_workload(args, rank)
+    K, C = args.states, args.columns
+    node_states = flat.n_nodes * K * C
+    pb = Problem(flat, K, 0, masks, has, max_param_sets=1, device=local_rank)
+
+    # ---- device-resident timing: W warm-up steps, then exactly K steps
+    pb.bench_pass(params, which=1, n_iter=max(args.warmup, 3), flush_l2=True)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        t_wall0 = time.perf_counter()
+        avg_ms, min_ms, launches = pb.bench_pass(params, which=1, n_iter=args.steps, flush_l2=True)
+        barrier()
+        wall = time.perf_counter() - t_wall0
+        # per-sweep split for the roofline, same settings
+        bu_ms, _, bu_launches = pb.bench_pass(params, which=0, n_iter=args.steps, flush_l2=True)
+        td_ms, _, td_launches = pb.bench_pass(params, which=3, n_iter=args.steps, flush_l2=True)
+    step_ms = avg_ms
+    if dist is not None:
+        t = torch.tensor([step_ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t.item())
+    value = node_states * world / (step_ms * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers
+    def pinned(shape, dtype):
+        t = torch.empty(shape, dtype=dtype, pin_memory=True)
+        return t, t.numpy()
+
+    _, h_parent = pinned(flat.n_nodes, torch.int32)
+    _, h_dist = pinned(flat.n_nodes, torch.float64)
+    _, h_masks = pinned((C, flat.n_nodes), torch.int64)
+    _, h_has = pinned((C, flat.n_nodes), torch.uint8)
+    h_parent[:] = flat.parent
+    h_dist[:] = flat.dist
+    h_masks_u = h_masks.view(np.uint64)
+    h_masks_u[:] = masks
+    h_has[:] = has
+    _, h_probs = pinned((flat.n_nodes, C, K), torch.float64)
+    _, h_map = pinned((flat.n_nodes, C), torch.int64)
+    _, h_mppa = pinned((flat.n_nodes, C), torch.int64)
+    pb.close()
+    import ctypes as CT
+    from pastml_b200 import _lib
+    lib = _lib.load()
+
+    def vp(a):
+        return a.ctypes.data_as(CT.c_void_p)
+
+    h_lh = np.empty(C)
+    h_hist = np.empty((C, K + 1), dtype=np.int64)
+
+    def e2e_step():
+        handle = CT.c_void_p()
+        rc = lib.pml_problem_create(flat.n_nodes, vp(h_parent), vp(h_dist), C, K, 0, vp(h_masks), vp(h_has), 1,
+                                    local_rank, CT.byref(handle))
+        assert rc == 0, _lib.last_error()
+        rc = lib.pml_marginal(handle, vp(params), 0, vp(h_lh), vp(h_probs), None, vp(h_map), vp(h_mppa), vp(h_hist))
+        assert rc == 0, _lib.last_error()
+        lib.pml_problem_destroy(handle)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_dt = (time.perf_counter() - t0) / args.e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_dt], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    e2e_value = node_states * world / e2e_dt
+    h2d = h_parent.nbytes + h_dist.nbytes + h_masks.nbytes + h_has.nbytes + params.nbytes
+    d2h = h_probs.nbytes + h_map.nbytes + h_mppa.nbytes + h_lh.nbytes + h_hist.nbytes
+
+    # ---- roofline of the dominant kernel family (per-level launches of one templated kernel)
+    peaks_path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650., 'fallback (B200_PROFILING.md)'
+    bu_bytes, td_bytes = algorithmic_bytes(flat, K, C)
+    sweeps = {'td_level_kernel': (td_bytes, td_ms, td_launches), 'bu_level_kernel': (bu_bytes, bu_ms, bu_launches)}
+    dom = max(sweeps, key=lambda k: sweeps[k][1])
+
+    def roof(name):
+        b, ms, n = sweeps[name]
+        ach = b / (ms * 1e-3) / 1e9
+        return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                'traffic': None, 'algorithmic_bytes_per_sweep': int(b), 'launches_per_sweep': int(n),
+                'avg_launch_us': ms * 1e3 / max(n, 1), 'sweep_ms': ms, 'peak_source': peak_src}
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, flat),
+            'clocks': clocks.summary(),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                    'ms_per_step': e2e_dt * 1e3, 'steps': args.e2e_steps,
+                    'what': 'pml_problem_create + pml_marginal (all outputs to pinned host memory) + destroy'},
+            'gpu_launches': int(launches * args.steps),
+            'roofline': roof(dom), 'roofline_other': roof([k for k in sweeps if k != dom][0]),
+            'min_ms_per_step': min_ms, 'wall_s_timed_region': wall,
+            'bu_objective_ms': bu_ms, 'bu_node_states_per_s': node_states / (bu_ms * 1e-3)}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        threads = max(1, min(cores, C))
+        cols = list(range(threads))
+        rate, dt = cpu_pipeline_rate(flat, masks, has, pis, sfs, K, cols, threads)
+        line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                'sample': 'one step of {} of the {} columns of the same tree, one thread per column '
+                                          '({:.1f} s)'.format(len(cols), C, dt), 'host_cores': cores}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

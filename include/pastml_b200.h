@@ -133,10 +133,12 @@ int pml_zero_likelihood_info(pml_problem *p, int32_t *column, int32_t *param_set
  * with CUDA events on the handle's stream (ms), and the number of kernels launched. */
 int pml_last_call_stats(pml_problem *p, double *device_ms, int64_t *kernel_launches);
 
-/* Device-resident variants used by bench.py: run the pass n_iter times back to back on resident inputs,
- * returning the average device time per pass (CUDA events).  which: 0 = pml_loglik(annotation masks,
- * marginal, alter), 1 = pml_marginal sweep (BU + TD/marginal/MAP/MPPA), 2 = pml_joint.  flush_l2 != 0 writes
- * a buffer larger than L2 between iterations (outside the timed intervals). */
+/* Device-resident variant used by bench.py: runs a pass n_iter times back to back on resident inputs and returns
+ * the average / minimum device time per pass (CUDA events on the handle's stream).  which: 0 = bottom-up
+ * objective (annotation masks, marginal, alter) for n_sets parameter sets; 1 = the marginal sweep (bottom-up +
+ * fused top-down/marginal/MAP/MPPA, force_joint off); 2 = JOINT (max-product bottom-up + traceback); 3 = the
+ * fused top-down sweep alone; 4 = like 1 with force_joint on (needs pml_joint).  flush_l2 != 0 writes a 256 MiB
+ * buffer between iterations, outside the timed intervals. */
 int pml_bench_pass(pml_problem *p, const double *params, int32_t n_sets, int32_t which, int32_t n_iter,
                    int32_t flush_l2, double *avg_ms, double *min_ms, int64_t *kernel_launches);
 

@@ -247,6 +247,40 @@ def ml_acr_fixed(flat, model, annot_mask, has_state, method='MPPA', force_joint=
     return out
 
 
+def marginal_pipeline(flat, model, annot_mask, has_state, force_joint=False, joint_state=None):
+    """The fixed-parameter MPPA pipeline the benchmark times (metric i): zero-branch
+    alteration, bottom-up pass, top-down pass, marginal likelihoods + probabilities, MAP and MPPA selection
+    (``/root/reference/pastml/ml.py:697-712, 735-742``).  Returns (loglh, probs, map_mask, mppa_mask)."""
+    tree = OracleTree(flat)
+    n, K = flat.n_nodes, model.K
+    full = np.uint64((1 << K) - 1) if K < 64 else np.uint64(0xFFFFFFFFFFFFFFFF)
+    annot_mask = _u64(annot_mask)
+    has_state = np.ascontiguousarray(has_state, dtype=np.uint8)
+    L = lib()
+    m = model.c_struct()
+    allowed = np.where(annot_mask == 0, full, annot_mask).astype(np.uint64)
+    initial = np.zeros(n, dtype=np.uint64)
+    has_initial = np.zeros(n, dtype=np.uint8)
+    altered = alter_zero_clusters(tree, has_state, K, allowed, initial, has_initial) if model.tau == 0 else None
+    loglh, bu, bu_sf, _ = bottom_up(tree, model, allowed, True)
+    td = np.zeros((n, K), dtype=np.float64)
+    td_sf = np.zeros(n, dtype=np.float64)
+    L.orc_top_down(tree.ref(), C.byref(m), _ptr(bu), _ptr(bu_sf), _ptr(td), _ptr(td_sf))
+    lh = np.zeros((n, K), dtype=np.float64)
+    lh_sf = np.zeros(n, dtype=np.float64)
+    probs = np.zeros((n, K), dtype=np.float64)
+    L.orc_marginal(tree.ref(), C.byref(m), _ptr(allowed), _ptr(bu), _ptr(bu_sf), _ptr(td), _ptr(td_sf),
+                   _ptr(lh), _ptr(lh_sf), _ptr(probs))
+    if altered is not None:
+        L.orc_unalter_allowed(C.c_int(n), _ptr(altered), _ptr(allowed), _ptr(initial))
+    L.orc_choose_map(C.c_int(n), C.c_int(K), _ptr(lh), _ptr(initial), _ptr(has_initial), _ptr(allowed))
+    map_mask = allowed.copy()
+    k_hist = np.zeros(K + 1, dtype=np.int64)
+    L.orc_choose_mppa(C.c_int(n), C.c_int(K), _ptr(lh), _ptr(initial), _ptr(has_initial), _ptr(joint_state),
+                      C.c_int(1 if force_joint else 0), _ptr(allowed), _ptr(k_hist), None)
+    return loglh, probs, map_mask, allowed
+
+
 def parsimony_fixed(flat, K, annot_mask):
     """parsimonious_acr(..., prediction_method=MP) (``/root/reference/pastml/parsimony.py:245-331``): returns the
     ACCTRAN, DOWNPASS and DELTRAN state masks and step counts."""

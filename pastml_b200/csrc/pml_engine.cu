@@ -742,11 +742,13 @@ int pml_bench_pass(pml_problem *p, const double *params, int32_t n_sets, int32_t
     if (!p || !params || n_iter < 1) return fail(PML_ERR_INVALID, "bad argument");
     if (n_sets < 1 || n_sets > p->B) return fail(PML_ERR_INVALID, "n_sets exceeds the capacity given at creation");
     if (which != 0 && n_sets != 1) return fail(PML_ERR_INVALID, "this pass takes one parameter set");
+    if (which < 0 || which > 4) return fail(PML_ERR_INVALID, "unknown pass");
     CUDA_TRY(cudaSetDevice(p->device));
-    if (which == 1) {
+    const int force_joint = (which == 4) ? 1 : 0;
+    if (which == 1 || which == 3 || which == 4) {
         int rc = ensure_marginal_buffers(p, true, true);
         if (rc) return rc;
-        if (!p->joint_done) return fail(PML_ERR_INVALID, "call pml_joint first");
+        if (force_joint && !p->joint_done) return fail(PML_ERR_INVALID, "call pml_joint first");
     }
     if (which == 2 && !p->ptr.ptr) CUDA_TRY(p->ptr.alloc((size_t) p->N * p->C * p->K));
     int rc = upload_params(p, params, n_sets);
@@ -754,15 +756,20 @@ int pml_bench_pass(pml_problem *p, const double *params, int32_t n_sets, int32_t
     const long long flush_n = 64LL << 20;   // 256 MiB of floats > 126 MB L2
     if (flush_l2 && !p->flush.ptr) CUDA_TRY(p->flush.alloc(flush_n));
     double total = 0., best = 1e300;
+    const uint64_t *base = p->mask[PML_MASK_ANNOTATION].ptr;
+    if (which == 3) {   // the top-down sweep alone needs a resident bottom-up state
+        run_bottom_up(p, 1, base, 1, 1, false);
+    }
     const long long l0 = p->launches;
     for (int it = 0; it < n_iter; ++it) {
         if (flush_l2) flush_kernel<<<148 * 8, 256, 0, p->stream>>>(flush_n, p->flush.ptr, (float) it);
         cudaEventRecord(p->ev0, p->stream);
-        const uint64_t *base = p->mask[PML_MASK_ANNOTATION].ptr;
         if (which == 0) run_bottom_up(p, n_sets, base, 1, 1, false);
-        else if (which == 1) {
+        else if (which == 1 || which == 4) {
             run_bottom_up(p, 1, base, 1, 1, false);
-            run_top_down(p, 1, true, true);
+            run_top_down(p, force_joint, true, true);
+        } else if (which == 3) {
+            run_top_down(p, 0, true, true);
         } else {
             run_bottom_up(p, 1, base, 0, 1, true);
             JointArgs a{p->tree(), p->zc(), p->lanes(1), base, p->bu.ptr, p->ptr.ptr, p->joint_state.ptr,
@@ -781,7 +788,8 @@ int pml_bench_pass(pml_problem *p, const double *params, int32_t n_sets, int32_t
         best = std::min(best, (double) ms);
     }
     CUDA_TRY(cudaGetLastError());
-    if (which == 1) p->mask_valid[PML_MASK_MAP] = p->mask_valid[PML_MASK_MPPA] = p->marginal_done = true;
+    if (which == 1 || which == 3 || which == 4) p->mask_valid[PML_MASK_MAP] = p->mask_valid[PML_MASK_MPPA] = p->marginal_done = true;
+    if (which == 2) { p->mask_valid[PML_MASK_JOINT] = true; p->joint_done = true; }
     if (avg_ms) *avg_ms = total / n_iter;
     if (min_ms) *min_ms = best;
     if (kernel_launches) *kernel_launches = (p->launches - l0) / n_iter;
