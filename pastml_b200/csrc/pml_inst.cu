@@ -24,10 +24,25 @@ template <int KP> using TheLane = EigLane<KP>;
 namespace {
 constexpr int KP = PML_KP;
 
+constexpr int kFamily = TheLane<KP>::family;
+constexpr size_t kMaxDynSmem = 200 * 1024;
+
+template <class Kern>
+void allow_big_smem(Kern kern, size_t bytes) {
+    // kernels need an opt-in above 48 KB of dynamic shared memory (many parameter sets x columns)
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+}
+
 void bu_launch(cudaStream_t st, const BuArgs &a, bool maxp, int s0, int ns) {
     const long long items = (long long) ns * a.ln.J;
-    if (maxp) bu_level_kernel<KP, TheLane, true><<<grid_for(items), kBlock, 0, st>>>(a, s0, ns);
-    else bu_level_kernel<KP, TheLane, false><<<grid_for(items), kBlock, 0, st>>>(a, s0, ns);
+    const size_t sh = sizeof(double) * staged_fields(kFamily, a.ln.K) * a.ln.J;
+    if (maxp) {
+        allow_big_smem(bu_level_kernel<KP, TheLane, true>, sh);
+        bu_level_kernel<KP, TheLane, true><<<grid_for(items), kBlock, sh, st>>>(a, s0, ns);
+    } else {
+        allow_big_smem(bu_level_kernel<KP, TheLane, false>, sh);
+        bu_level_kernel<KP, TheLane, false><<<grid_for(items), kBlock, sh, st>>>(a, s0, ns);
+    }
 }
 
 void root_launch(cudaStream_t st, const TreeDev &t, const ZcDev &zc, const LaneDev &ln, const uint64_t *mask,
@@ -37,13 +52,19 @@ void root_launch(cudaStream_t st, const TreeDev &t, const ZcDev &zc, const LaneD
                                                           is_marginal, out);
 }
 
+size_t td_smem(const TdArgs &a) {
+    return sizeof(double) * staged_fields(kFamily, a.ln.K) * a.ln.C + sizeof(unsigned) * a.ln.C * (a.ln.K + 1);
+}
+
 void td_launch(cudaStream_t st, const TdArgs &a, int s0, int ns) {
-    const size_t sh = sizeof(unsigned) * a.ln.C * (a.ln.K + 1);
+    const size_t sh = td_smem(a);
+    allow_big_smem(td_level_kernel<KP, TheLane>, sh);
     td_level_kernel<KP, TheLane><<<grid_for((long long) ns * a.ln.C), kBlock, sh, st>>>(a, s0, ns);
 }
 
 void td_tip_roots_launch(cudaStream_t st, const TdArgs &a, const int *roots, int n_roots) {
-    const size_t sh = sizeof(unsigned) * a.ln.C * (a.ln.K + 1);
+    const size_t sh = td_smem(a);
+    allow_big_smem(td_tip_roots_kernel<KP, TheLane>, sh);
     td_tip_roots_kernel<KP, TheLane><<<grid_for((long long) n_roots * a.ln.C), kBlock, sh, st>>>(a, roots, n_roots);
 }
 

@@ -64,64 +64,109 @@ __device__ __forceinline__ uint64_t eff_mask(const uint64_t *base, const TreeDev
     return m & kmask;
 }
 
-// Brings the maximum of v[0..K) into [1, 2) by an exact power of two; returns the exponent removed (0 if the
-// vector is all zero).  Entries are non-negative.
+// 1.0 where bit k of m is set, else 0.0, without an int -> double conversion
+__device__ __forceinline__ double bit_as_double(uint64_t m, int k) {
+    const unsigned w = (k < 32) ? (unsigned) m : (unsigned) (m >> 32);
+    return __hiloint2double(((w >> (k & 31)) & 1u) ? 0x3ff00000 : 0, 0);
+}
+
+// Keeps a non-negative vector in range: when the exponent of its maximum leaves [-kKeep, kKeep] (or `always`)
+// the vector is multiplied by an exact power of two that brings the maximum into [1, 2).  Returns the exponent
+// removed.  vmax = 0 (or NaN) is left alone: the caller reports the all-zero vector.
+constexpr int kKeep = 96;
 template <int KP>
-__device__ __forceinline__ int normalise(double (&v)[KP], int K, double &vmax) {
-    double m = 0.;
-#pragma unroll
-    for (int k = 0; k < KP; ++k)
-        if (k < K) m = fmax(m, v[k]);
-    vmax = m;
-    if (!(m > 0.) || isinf(m)) return 0;
-    int e = exponent_of(m);
+__device__ __forceinline__ int rescale(double (&v)[KP], double vmax, bool always) {
+    if (!(vmax > 0.) || isinf(vmax)) return 0;
+    int e = exponent_of(vmax);
+    if (!always && e >= -kKeep && e <= kKeep) return 0;
+    int extra = 0;
     if (e == -1023) {  // subnormal maximum: lift it first
 #pragma unroll
         for (int k = 0; k < KP; ++k) v[k] *= 0x1p+200;
-        m *= 0x1p+200;
-        e = exponent_of(m);
-        const double s = pow2(-e);
-#pragma unroll
-        for (int k = 0; k < KP; ++k) v[k] *= s;
-        return e - 200;
+        e = exponent_of(vmax * 0x1p+200);
+        extra = -200;
     }
-    if (e == 0) return 0;
-    // 2^-e may be out of range for |e| > 1022: split
-    int e1 = e / 2, e2 = e - e1;
-    const double s1 = pow2(-e1), s2 = pow2(-e2);
+    if (e != 0) {
+        // 2^-e alone may be out of range: apply it in two exact halves
+        const int e1 = e / 2, e2 = e - e1;
+        const double s1 = pow2(-e1), s2 = pow2(-e2);
 #pragma unroll
-    for (int k = 0; k < KP; ++k) v[k] = (v[k] * s1) * s2;
-    return e;
+        for (int k = 0; k < KP; ++k) v[k] = (v[k] * s1) * s2;
+    }
+    return e + extra;
+}
+
+template <int KP>
+__device__ __forceinline__ double vec_max(const double (&v)[KP]) {
+    // two chains to shorten the dependency path
+    double m0 = 0., m1 = 0.;
+#pragma unroll
+    for (int k = 0; k + 1 < KP; k += 2) { m0 = fmax(m0, v[k]); m1 = fmax(m1, v[k + 1]); }
+    if (KP & 1) m0 = fmax(m0, v[KP - 1]);
+    return fmax(m0, m1);
 }
 
 // ------------------------------------------------------------------------------------------ models
-// A "lane model" exposes: load(params), branch(dist) -> Branch, matvec(out = P(t) in),
-// maxvec(out_i = max_j P_ij in_j, arg_i = first argmax).
+// Per-lane parameters are staged once per block in shared memory, transposed to [field][lane] so that the lanes of
+// a warp read consecutive words.  A lane model exposes: branch(dist) -> Branch, matvec(out = max(P(t) in, 0)),
+// maxvec(out_i = max_j P_ij in_j with the first argmax), pi(k).  Entries k >= K of every register vector are zero
+// and stay zero, so arithmetic runs unguarded over the padded length KP and only memory accesses are guarded.
+
+struct LaneSmem {
+    const double *s;   // staged fields of this lane: field f at s[f * J]
+    int J;
+    __device__ __forceinline__ double f(int i) const { return s[i * J]; }
+};
+
+// number of leading parameter fields staged in shared memory
+__host__ __device__ inline int staged_fields(int family, int K) { return family == 1 ? 8 : 4 + K; }
+
+__device__ __forceinline__ void stage_params(double *smem, const LaneDev &ln, int nf) {
+    const int total = nf * ln.J;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int f = i / ln.J, j = i - f * ln.J;
+        smem[i] = ln.params[(size_t) j * ln.stride + f];
+    }
+    __syncthreads();
+}
 
 template <int KP>
 struct F81Lane {  // F81 / JC / EFT: P_ij = (1 - e) pi_j + delta_ij e, e = exp(-mu t')  (F81Model.py:28-46)
+    static constexpr int family = 0;
+    LaneSmem sm;
     double sf, tau, tauf, mu;
-    double pi[KP];
     struct Branch { double e, ome; };
 
-    __device__ __forceinline__ void load(const double *p, int K) {
-        sf = p[0]; tau = p[1]; tauf = p[2]; mu = p[3];
-#pragma unroll
-        for (int k = 0; k < KP; ++k) pi[k] = (k < K) ? p[4 + k] : 0.;
+    __device__ __forceinline__ void init(const LaneSmem &l, const double *, int) {
+        sm = l;
+        sf = l.f(0); tau = l.f(1); tauf = l.f(2); mu = l.f(3);
     }
+    __device__ __forceinline__ double pi(int k) const { return sm.f(4 + k); }
     __device__ __forceinline__ Branch branch(double dist, int) const {
         const double t = (dist + tau) * tauf * sf;                 // Model.transform_t
         const double e = isinf(mu) ? 0. : exp(-mu * t);            // F81Model.py:44-45
         return Branch{e, 1. - e};
     }
-    __device__ __forceinline__ void matvec(const Branch &b, const double (&in)[KP], double (&out)[KP], int K) const {
-        double s = 0.;
+    __device__ __forceinline__ double weighted_sum(const double (&in)[KP], int K) const {
+        double s0 = 0., s1 = 0.;
 #pragma unroll
-        for (int k = 0; k < KP; ++k)
-            if (k < K) s = fma(pi[k], in[k], s);
-        const double base = b.ome * s;
+        for (int k = 0; k + 1 < KP; k += 2) {
+            if (k < K) s0 = fma(pi(k), in[k], s0);
+            if (k + 1 < K) s1 = fma(pi(k + 1), in[k + 1], s1);
+        }
+        if ((KP & 1) && KP - 1 < K) s0 = fma(pi(KP - 1), in[KP - 1], s0);
+        return s0 + s1;
+    }
+    __device__ __forceinline__ void matvec(const Branch &b, const double (&in)[KP], double (&out)[KP], int K) const {
+        const double base = b.ome * weighted_sum(in, K);
 #pragma unroll
         for (int k = 0; k < KP; ++k) out[k] = (k < K) ? fmax(fma(b.e, in[k], base), 0.) : 0.;
+    }
+    // acc *= max(P in, 0) without a temporary vector
+    __device__ __forceinline__ void mul_matvec(const Branch &b, const double (&in)[KP], double (&acc)[KP], int K) const {
+        const double base = b.ome * weighted_sum(in, K);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[k] *= fmax(fma(b.e, in[k], base), 0.);
     }
     // max_j P_ij in_j in O(K): off-diagonal candidates are w_j = ((1-e) pi_j) in_j for every row, the diagonal one
     // is ((1-e) pi_i + e) in_i; products are formed exactly like numpy forms P * L (no contraction).
@@ -132,14 +177,14 @@ struct F81Lane {  // F81 / JC / EFT: P_ij = (1 - e) pi_j + delta_ij e, e = exp(-
 #pragma unroll
         for (int k = 0; k < KP; ++k)
             if (k < K) {
-                const double w = __dmul_rn(__dmul_rn(b.ome, pi[k]), in[k]);
+                const double w = __dmul_rn(__dmul_rn(b.ome, pi(k)), in[k]);
                 if (w > t1) { t2 = t1; i2 = i1; t1 = w; i1 = k; }
                 else if (w > t2) { t2 = w; i2 = k; }
             }
 #pragma unroll
         for (int k = 0; k < KP; ++k)
             if (k < K) {
-                const double dv = __dmul_rn(__dadd_rn(__dmul_rn(b.ome, pi[k]), b.e), in[k]);
+                const double dv = __dmul_rn(__dadd_rn(__dmul_rn(b.ome, pi(k)), b.e), in[k]);
                 const double ov = (i1 == k) ? t2 : t1;
                 const int oi = (i1 == k) ? i2 : i1;
                 double best; int bi;
@@ -154,18 +199,22 @@ struct F81Lane {  // F81 / JC / EFT: P_ij = (1 - e) pi_j + delta_ij e, e = exp(-
 
 template <int KP>
 struct HKYLane {  // HKY85 closed form, states A, C, G, T  (HKYModel.py:44-82); KP == 4
+    static constexpr int family = 1;
+    LaneSmem sm;
     double sf, tau, tauf, kappa;
-    double pi[KP];
+    double p4[4];
     struct Branch { double P[4][4]; };
 
-    __device__ __forceinline__ void load(const double *p, int) {
-        sf = p[0]; tau = p[1]; tauf = p[2]; kappa = p[3];
+    __device__ __forceinline__ void init(const LaneSmem &l, const double *, int) {
+        sm = l;
+        sf = l.f(0); tau = l.f(1); tauf = l.f(2); kappa = l.f(3);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) pi[k] = p[4 + k];
+        for (int k = 0; k < 4; ++k) p4[k] = l.f(4 + k);
     }
+    __device__ __forceinline__ double pi(int k) const { return sm.f(4 + k); }
     __device__ __forceinline__ Branch branch(double dist, int) const {
         const double t = (dist + tau) * tauf * sf;
-        const double pa = pi[0], pc = pi[1], pg = pi[2], pt = pi[3];
+        const double pa = p4[0], pc = p4[1], pg = p4[2], pt = p4[3];
         const double pag = pa + pg, pct = pc + pt;
         const double beta = .5 / (pag * pct + kappa * (pa * pg + pc * pt));
         const double e1 = exp(-beta * t);
@@ -177,7 +226,7 @@ struct HKYLane {  // HKY85 closed form, states A, C, G, T  (HKYModel.py:44-82); 
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b.P[i][j] = (1. - e1) * pi[j];
+            for (int j = 0; j < 4; ++j) b.P[i][j] = (1. - e1) * p4[j];
         b.P[3][3] = pt * ct_sum + pc * ect;
         b.P[3][1] = pc * ct_sum - pc * ect;
         b.P[1][3] = pt * ct_sum - pt * ect;
@@ -196,6 +245,12 @@ struct HKYLane {  // HKY85 closed form, states A, C, G, T  (HKYModel.py:44-82); 
             for (int j = 1; j < 4; ++j) s = fma(b.P[i][j], in[j], s);
             out[i] = fmax(s, 0.);
         }
+    }
+    __device__ __forceinline__ void mul_matvec(const Branch &b, const double (&in)[KP], double (&acc)[KP], int K) const {
+        double v[KP];
+        matvec(b, in, v, K);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[k] *= v[k];
     }
     __device__ __forceinline__ void maxvec(const Branch &b, const double (&in)[KP], double (&out)[KP],
                                            uint8_t (&arg)[KP], int) const {
@@ -216,19 +271,20 @@ struct HKYLane {  // HKY85 closed form, states A, C, G, T  (HKYModel.py:44-82); 
 
 template <int KP>
 struct EigLane {  // CUSTOM_RATES / JTT: P = A diag(exp(d t')) A^-1  (generator.py:54-65)
+    static constexpr int family = 2;
+    LaneSmem sm;
     double sf, tau, tauf;
-    double pi[KP];
     const double *d, *A, *Ainv;  // this lane's eigen-decomposition in global memory (read-only path)
     struct Branch { double ed[KP]; };
 
-    __device__ __forceinline__ void load(const double *p, int K) {
-        sf = p[0]; tau = p[1]; tauf = p[2];
-#pragma unroll
-        for (int k = 0; k < KP; ++k) pi[k] = (k < K) ? p[4 + k] : 0.;
-        d = p + 4 + K;
+    __device__ __forceinline__ void init(const LaneSmem &l, const double *gp, int K) {
+        sm = l;
+        sf = l.f(0); tau = l.f(1); tauf = l.f(2);
+        d = gp + 4 + K;
         A = d + K;
         Ainv = A + K * K;
     }
+    __device__ __forceinline__ double pi(int k) const { return sm.f(4 + k); }
     __device__ __forceinline__ Branch branch(double dist, int K) const {
         const double t = (dist + tau) * tauf * sf;
         Branch b;
@@ -259,6 +315,12 @@ struct EigLane {  // CUSTOM_RATES / JTT: P = A diag(exp(d t')) A^-1  (generator.
             }
             out[i] = fmax(s, 0.);
         }
+    }
+    __device__ __forceinline__ void mul_matvec(const Branch &b, const double (&in)[KP], double (&acc)[KP], int K) const {
+        double v[KP];
+        matvec(b, in, v, K);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[k] *= v[k];
     }
     __device__ __forceinline__ void maxvec(const Branch &b, const double (&in)[KP], double (&out)[KP],
                                            uint8_t (&arg)[KP], int K) const {
@@ -337,10 +399,32 @@ struct BuArgs {
     int *err;               // [J][2] first failing (parent, child), initialised to -1
 };
 
+// loads the K-vector of a child: a stored mantissa vector for internal nodes, the allowed-state mask for tips
+// (tips: BOTTOM_UP_LIKELIHOOD = allowed states, SF = 0)
+template <int KP>
+__device__ __forceinline__ int load_child(const TreeDev &t, const ZcDev &zc, const LaneDev &ln, const uint64_t *mask,
+                                          const double *bu, const int *bu_ex, int ch, int j, int c, bool use_alt,
+                                          double (&in)[KP], uint64_t &tip_mask) {
+    const int cs = t.slot[ch];
+    if (cs >= 0) {
+        const double *src = bu + ((size_t) cs * ln.K) * ln.J + j;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) in[k] = (k < ln.K) ? src[(size_t) k * ln.J] : 0.;
+        tip_mask = 0ULL;
+        return bu_ex[(size_t) cs * ln.J + j];
+    }
+    tip_mask = eff_mask(mask, t, zc, ln.C, ch, c, use_alt, ln.kmask);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) in[k] = bit_as_double(tip_mask, k);
+    return 0;
+}
+
 // calc_node_bu_likelihood (ml.py:124-148) for the internal nodes [slot_begin, slot_begin + n_slots) of one level.
 template <int KP, template <int> class Lane, bool MAXP>
 __global__ void __launch_bounds__(kBlock) bu_level_kernel(BuArgs a, int slot_begin, int n_slots) {
+    extern __shared__ double s_par[];
     const int J = a.ln.J, K = a.ln.K, C = a.ln.C;
+    stage_params(s_par, a.ln, staged_fields(Lane<KP>::family, K));
     const long long n_items = (long long) n_slots * J;
     for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
          g += (long long) gridDim.x * blockDim.x) {
@@ -348,7 +432,7 @@ __global__ void __launch_bounds__(kBlock) bu_level_kernel(BuArgs a, int slot_beg
         const int j = (int) (g % J);
         const int c = j % C;
         Lane<KP> lane;
-        lane.load(a.ln.params + (size_t) j * a.ln.stride, K);
+        lane.init(LaneSmem{s_par + j, J}, a.ln.params + (size_t) j * a.ln.stride, K);
         const bool use_alt = a.alter && lane.tau == 0.;
         const int node = a.t.int_nodes[slot];
         const int fc = a.t.first_child[node], nc = a.t.n_children[node];
@@ -357,24 +441,16 @@ __global__ void __launch_bounds__(kBlock) bu_level_kernel(BuArgs a, int slot_beg
         {
             const uint64_t m = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
 #pragma unroll
-            for (int k = 0; k < KP; ++k) acc[k] = (double) ((m >> k) & 1ULL);   // 10 ** log10(allowed), ml.py:127
+            for (int k = 0; k < KP; ++k) acc[k] = bit_as_double(m, k);   // 10 ** log10(allowed), ml.py:127
         }
         int ex = 0;
         for (int ch = fc; ch < fc + nc; ++ch) {
             const typename Lane<KP>::Branch br = lane.branch(a.t.dist[ch], K);
-            double in[KP], v[KP];
-            const int cs = a.t.slot[ch];
-            if (cs >= 0) {
-                const double *src = a.bu + ((size_t) cs * K) * J + j;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) in[k] = (k < K) ? src[(size_t) k * J] : 0.;
-                ex += a.bu_ex[(size_t) cs * J + j];
-            } else {
-                const uint64_t m = eff_mask(a.mask, a.t, a.zc, C, ch, c, use_alt, a.ln.kmask);
-#pragma unroll
-                for (int k = 0; k < KP; ++k) in[k] = (double) ((m >> k) & 1ULL);   // tip: BU = allowed, SF = 0
-            }
+            double in[KP];
+            uint64_t tm;
+            ex += load_child<KP>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, ch, j, c, use_alt, in, tm);
             if (MAXP) {
+                double v[KP];
                 uint8_t arg[KP];
                 lane.maxvec(br, in, v, arg, K);
                 if (a.ptr) {
@@ -383,16 +459,16 @@ __global__ void __launch_bounds__(kBlock) bu_level_kernel(BuArgs a, int slot_beg
                     for (int k = 0; k < KP; ++k)
                         if (k < K) dst[k] = arg[k];
                 }
-            } else {
-                lane.matvec(br, in, v, K);
-            }
 #pragma unroll
-            for (int k = 0; k < KP; ++k) acc[k] *= v[k];
-            double vmax;
-            ex += normalise<KP>(acc, K, vmax);
+                for (int k = 0; k < KP; ++k) acc[k] *= v[k];
+            } else {
+                lane.mul_matvec(br, in, acc, K);
+            }
+            const double vmax = vec_max<KP>(acc);
             if (vmax == 0.) {   // all entries zero: PastMLLikelihoodError of ml.py:139-145
                 if (atomicCAS(a.err + 2 * j, -1, node) == -1) a.err[2 * j + 1] = ch;
             }
+            ex += rescale<KP>(acc, vmax, ch == fc + nc - 1);   // always normalised when the node is complete
         }
         double *dst = a.bu + ((size_t) slot * K) * J + j;
 #pragma unroll
@@ -404,8 +480,8 @@ __global__ void __launch_bounds__(kBlock) bu_level_kernel(BuArgs a, int slot_beg
 
 // ln(sum_i L_root,i pi_i) - SF ln 10 summed over the roots (ml.py:112-121); a root may be a tip.
 static __global__ void root_loglik_kernel(TreeDev t, ZcDev zc, LaneDev ln, const uint64_t *mask, int alter,
-                                   const double *bu, const int *bu_ex, const int *roots, int n_roots,
-                                   int is_marginal, double *out) {
+                                          const double *bu, const int *bu_ex, const int *roots, int n_roots,
+                                          int is_marginal, double *out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ln.J) return;
     const int K = ln.K, J = ln.J, c = j % ln.C;
@@ -420,7 +496,7 @@ static __global__ void root_loglik_kernel(TreeDev t, ZcDev zc, LaneDev ln, const
         if (s >= 0) ex = bu_ex[(size_t) s * J + j];
         const uint64_t m = (s >= 0) ? 0ULL : eff_mask(mask, t, zc, ln.C, node, c, use_alt, ln.kmask);
         for (int k = 0; k < K; ++k) {
-            const double l = (s >= 0) ? bu[((size_t) s * K + k) * J + j] : (double) ((m >> k) & 1ULL);
+            const double l = (s >= 0) ? bu[((size_t) s * K + k) * J + j] : bit_as_double(m, k);
             const double x = l * p[4 + k];
             acc = is_marginal ? acc + x : fmax(acc, x);
         }
@@ -462,7 +538,7 @@ static __global__ void joint_trace_kernel(JointArgs a, int node_begin, int n_nod
             double best = -CUDART_INF;
             s = 0;
             for (int k = 0; k < K; ++k) {
-                const double l = (sl >= 0) ? a.bu[((size_t) sl * K + k) * C + c] : (double) ((m >> k) & 1ULL);
+                const double l = (sl >= 0) ? a.bu[((size_t) sl * K + k) * C + c] : bit_as_double(m, k);
                 const double x = __dmul_rn(l, p[4 + k]);
                 if (x > best) { best = x; s = k; }
             }
@@ -504,88 +580,67 @@ struct TdArgs {
 };
 
 // MPPA state selection (choose_ancestral_states_mppa, ml.py:539-572) on a likelihood vector already multiplied by
-// the '.initial' mask where the node has one.  Returns the selected mask and k.
+// the '.initial' mask where the node has one.
+//
+// The reference sorts the probabilities, and for k = 1..n scores the array against (0, .., 0, 1/k, .., 1/k) with a
+// squared distance, keeping the first minimum; the distance equals sum(p^2) + (1 - 2 T_k) / k with T_k the sum of
+// the k entries that receive 1/k (the joint state first when it is forced, then the others by decreasing
+// probability).  (1 - 2 T_k) / k is unimodal in k, so states are extracted one at a time by decreasing likelihood
+// (ties to the lower index, which is the reference's stable order, ml.py:562-565) until the score has clearly
+// passed its minimum.  The selected set is the first best_k extracted states.
 template <int KP>
-__device__ __forceinline__ uint64_t mppa_select(const double (&lh)[KP], int K, int joint_index, bool force_joint,
-                                                int &best_k) {
-    double sum = 0.;
-#pragma unroll
-    for (int k = 0; k < KP; ++k)
-        if (k < K) sum += lh[k];
-    double p[KP], d[KP];
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-        p[k] = (k < K) ? lh[k] / sum : -1.;
-        d[k] = (force_joint && k == joint_index) ? -1. : p[k];
-    }
+__device__ __forceinline__ uint64_t mppa_select(const double (&lh)[KP], double inv_sum, int K, int joint_index,
+                                                bool force_joint, int &best_k) {
     double pj = 0.;
     if (force_joint) {
 #pragma unroll
-        for (int k = 0; k < KP; ++k) pj = (k == joint_index) ? p[k] : pj;
+        for (int k = 0; k < KP; ++k) pj = (k == joint_index) ? lh[k] * inv_sum : pj;
     }
-    // descending odd-even transposition sort on registers (padding and the joint state sink to the end)
-#pragma unroll
-    for (int round = 0; round < KP; ++round) {
-#pragma unroll
-        for (int i = (round & 1); i + 1 < KP; i += 2) {
-            const double hi = fmax(d[i], d[i + 1]), lo = fmin(d[i], d[i + 1]);
-            d[i] = hi;
-            d[i + 1] = lo;
-        }
-    }
-    // the reference's ascending array is [d[n-1], ..., d[0]] (+ [pj] when the joint state is forced last)
-    const int n_sorted = force_joint ? K - 1 : K;
+    uint64_t used = 0ULL, best_sel = 0ULL;
+    double run = 0.;             // sum of the extracted probabilities
+    double best_score = CUDART_INF;
+    bool joint_seen = false;
     best_k = K;
-    double best_corr = CUDART_INF;
     for (int k = 1; k <= K; ++k) {
-        const double target = 1. / (double) k;
-        const int top = force_joint ? k - 1 : k;   // how many of d[] receive 1/k
-        double corr = 0.;
+        // next state by decreasing likelihood, first index on ties
+        double bv = -1.;
+        int bi = 0;
 #pragma unroll
-        for (int r = KP - 1; r >= 0; --r)
-            if (r < n_sorted) {
-                const double dl = (r < top ? target : 0.) - d[r];
-                corr = fma(dl, dl, corr);
-            }
-        if (force_joint) {
-            const double dl = target - pj;
-            corr = fma(dl, dl, corr);
+        for (int i = 0; i < KP; ++i) {
+            const bool free_i = i < K && !((used >> i) & 1ULL);
+            if (free_i && lh[i] > bv) { bv = lh[i]; bi = i; }
         }
-        if (corr < best_corr) { best_corr = corr; best_k = k; }
+        const double prev = run;
+        run += bv * inv_sum;
+        used |= 1ULL << bi;
+        joint_seen = joint_seen || (bi == joint_index);
+        const double tk = (!force_joint || joint_seen) ? run : pj + prev;
+        const double score = (1. - 2. * tk) / (double) k;
+        if (score < best_score) { best_score = score; best_k = k; best_sel = used; }
+        else if (score > best_score + 1e-9) break;   // past the minimum of a unimodal sequence
     }
-    // top best_k by likelihood, ties to the lower index (stable sort, ml.py:562-565)
-    uint64_t sel = 0ULL;
-#pragma unroll
-    for (int i = 0; i < KP; ++i)
-        if (i < K) {
-            int rank = 0;
-#pragma unroll
-            for (int q = 0; q < KP; ++q)
-                if (q < K) rank += (lh[q] > lh[i]) || (lh[q] == lh[i] && q < i);
-            if (rank < best_k) sel |= 1ULL << i;
-        }
-    return sel;
+    return best_sel;
 }
 
-// calc_node_marginal_likelihood + probabilities + MAP + MPPA for one node (ml.py:454-465, 498-500, 577-595, 539-572)
-template <int KP>
-__device__ __forceinline__ void emit_node(const TdArgs &a, int node, int c, const double (&L)[KP],
-                                          const double (&TD)[KP], const double (&pi)[KP], uint64_t allowed,
-                                          int ex, unsigned int *sh_hist) {
+// calc_node_marginal_likelihood + probabilities + MAP + MPPA for one node (ml.py:454-465, 498-500, 577-595, 539-572).
+// m[] comes in as L * TD (unscaled marginal without frequencies) and is consumed.
+template <int KP, class LaneT>
+__device__ __forceinline__ void emit_node(const TdArgs &a, const LaneT &lane, int node, int c, double (&m)[KP],
+                                          uint64_t allowed, int ex, unsigned int *sh_hist) {
     const int K = a.ln.K, C = a.ln.C;
-    double m[KP];
     double sum = 0.;
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
-        m[k] = (k < K && ((allowed >> k) & 1ULL)) ? L[k] * TD[k] * pi[k] : 0.;
+        m[k] = (k < K && ((allowed >> k) & 1ULL)) ? m[k] * lane.pi(k) : 0.;
         sum += m[k];
     }
     const size_t nc = (size_t) node * C + c;
+    double inv = 1. / sum;
     if (a.probs) {
         double *dst = a.probs + nc * K;
 #pragma unroll
         for (int k = 0; k < KP; ++k)
-            if (k < K) dst[k] = m[k] / sum;
+            if (k < K) dst[k] = m[k] * inv;
     }
     if (a.node_log10lh) a.node_log10lh[nc] = log10(sum) + (double) ex * 0.30102999566398119521;
     const uint64_t base = a.mask[nc];
@@ -598,107 +653,99 @@ __device__ __forceinline__ void emit_node(const TdArgs &a, int node, int c, cons
             if (k < K) z[k] = m[k];
         if (a.zc.hasinit[r]) {
             const uint64_t init = a.zc.initial[r];
+            sum = 0.;
 #pragma unroll
-            for (int k = 0; k < KP; ++k) m[k] = ((init >> k) & 1ULL) ? m[k] : 0.;   // lh *= initial, ml.py:593-594
+            for (int k = 0; k < KP; ++k) {
+                m[k] = ((init >> k) & 1ULL) ? m[k] : 0.;   // lh *= initial, ml.py:593-594
+                sum += m[k];
+            }
+            inv = 1. / sum;
         }
     }
     int best = 0;   // first arg max (ml.py:595)
-    {
-        double bv = m[0];
+    double bv = m[0];
 #pragma unroll
-        for (int k = 1; k < KP; ++k)
-            if (k < K && m[k] > bv) { bv = m[k]; best = k; }
-    }
+    for (int k = 1; k < KP; ++k)
+        if (m[k] > bv) { bv = m[k]; best = k; }
     a.map_mask[nc] = (1ULL << best) | flag;
     int best_k;
-    const int ji = a.force_joint ? a.joint_state[nc] : 0;
-    double msum = 0.;
-#pragma unroll
-    for (int k = 0; k < KP; ++k) msum += m[k];
     uint64_t sel;
-    if (msum > 0.) sel = mppa_select<KP>(m, K, ji, a.force_joint != 0, best_k);
-    else { sel = a.ln.kmask; best_k = K; }   // NaN probabilities: no k beats +inf, all states kept
+    const int ji = a.force_joint ? a.joint_state[nc] : best;
+    if (!(sum > 0.)) { sel = a.ln.kmask; best_k = K; }   // NaN probabilities: no k beats +inf, all states kept
+    else if (bv * inv >= 0.76 && ji == best) { sel = 1ULL << best; best_k = 1; }   // k = 1 is optimal when p1 > 3/4
+    else sel = mppa_select<KP>(m, inv, K, ji, a.force_joint != 0, best_k);
     a.mppa_mask[nc] = sel | flag;
     if (flag) a.zc_k[(size_t) a.t.zc_index[node] * C + c] = (uint8_t) best_k;
     atomicAdd(sh_hist + c * (K + 1) + best_k, 1u);
 }
 
 // calc_node_td_likelihood (ml.py:273-290) for the children of the internal nodes of one level, fused with the
-// marginal step of the nodes themselves and of their tip children.
+// marginal step of the nodes themselves and of their tip children.  Shared memory: staged parameters, then the
+// block's k histogram.
 template <int KP, template <int> class Lane>
 __global__ void __launch_bounds__(kBlock) td_level_kernel(TdArgs a, int slot_begin, int n_slots) {
-    extern __shared__ unsigned int sh_hist[];   // [C][K+1]
+    extern __shared__ double s_par[];
     const int C = a.ln.C, K = a.ln.K;
+    const int nf = staged_fields(Lane<KP>::family, K);
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(s_par + (size_t) nf * C);   // [C][K+1]
     for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x) sh_hist[i] = 0u;
-    __syncthreads();
+    stage_params(s_par, a.ln, nf);
     const long long n_items = (long long) n_slots * C;
     for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
          g += (long long) gridDim.x * blockDim.x) {
         const int slot = slot_begin + (int) (g / C);
         const int c = (int) (g % C);
         Lane<KP> lane;
-        lane.load(a.ln.params + (size_t) c * a.ln.stride, K);
+        lane.init(LaneSmem{s_par + c, C}, a.ln.params + (size_t) c * a.ln.stride, K);
         const bool use_alt = lane.tau == 0.;   // ml.py:702-703
         const int node = a.t.int_nodes[slot];
         const int fc = a.t.first_child[node], nc = a.t.n_children[node];
 
-        double Lp[KP], TDp[KP];
+        double X[KP];   // L_p, then TD_p * L_p: the parent part of every child's top-down vector
         {
             const double *src = a.bu + ((size_t) slot * K) * C + c;
 #pragma unroll
-            for (int k = 0; k < KP; ++k) Lp[k] = (k < K) ? src[(size_t) k * C] : 0.;
+            for (int k = 0; k < KP; ++k) X[k] = (k < K) ? src[(size_t) k * C] : 0.;
         }
         const int exp_ = a.bu_ex[(size_t) slot * C + c];
         int extd = 0;
-        if (a.t.parent[node] < 0) {
-#pragma unroll
-            for (int k = 0; k < KP; ++k) TDp[k] = (k < K) ? 1. : 0.;   // ml.py:274-277
-        } else {
+        if (a.t.parent[node] >= 0) {   // the root's top-down vector is all ones (ml.py:274-277)
             const double *src = a.td + ((size_t) slot * K) * C + c;
 #pragma unroll
-            for (int k = 0; k < KP; ++k) TDp[k] = (k < K) ? src[(size_t) k * C] : 0.;
+            for (int k = 0; k < KP; ++k) X[k] *= (k < K) ? src[(size_t) k * C] : 0.;
             extd = a.td_ex[(size_t) slot * C + c];
         }
-        const uint64_t mp = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
-        emit_node<KP>(a, node, c, Lp, TDp, lane.pi, mp, exp_ + extd, sh_hist);
-
-        // parent part of every child's top-down vector: TD_p * L_p (divided by the child's own contribution below)
+        {
+            double m[KP];
 #pragma unroll
-        for (int k = 0; k < KP; ++k) TDp[k] *= Lp[k];
-
+            for (int k = 0; k < KP; ++k) m[k] = X[k];
+            const uint64_t mp = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
+            emit_node<KP>(a, lane, node, c, m, mp, exp_ + extd, sh_hist);
+        }
         for (int ch = fc; ch < fc + nc; ++ch) {
             const typename Lane<KP>::Branch br = lane.branch(a.t.dist[ch], K);
-            double Lc[KP], cv[KP], q[KP];
+            double Lc[KP], q[KP];
+            uint64_t mc;
+            const int exc = load_child<KP>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, ch, c, c, use_alt, Lc, mc);
+            lane.matvec(br, Lc, q, K);                                   // node_contribution, ml.py:280
+#pragma unroll
+            for (int k = 0; k < KP; ++k) q[k] = (q[k] > 0.) ? X[k] * __drcp_rn(q[k]) : X[k];   // ml.py:281-283
+            int qex = extd + exp_ - exc + rescale<KP>(q, vec_max<KP>(q), false);            // ml.py:284-286
             const int cs = a.t.slot[ch];
-            int exc = 0;
-            uint64_t mc = 0ULL;
             if (cs >= 0) {
-                const double *src = a.bu + ((size_t) cs * K) * C + c;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) Lc[k] = (k < K) ? src[(size_t) k * C] : 0.;
-                exc = a.bu_ex[(size_t) cs * C + c];
-            } else {
-                mc = eff_mask(a.mask, a.t, a.zc, C, ch, c, use_alt, a.ln.kmask);
-#pragma unroll
-                for (int k = 0; k < KP; ++k) Lc[k] = (double) ((mc >> k) & 1ULL);
-            }
-            lane.matvec(br, Lc, cv, K);                                  // node_contribution, ml.py:280
-#pragma unroll
-            for (int k = 0; k < KP; ++k) q[k] = (cv[k] > 0.) ? TDp[k] / cv[k] : TDp[k];   // ml.py:281-283
-            double qmax;
-            int qex = extd + exp_ - exc + normalise<KP>(q, K, qmax);     // ml.py:284-286
-            double tdc[KP];
-            lane.matvec(br, q, tdc, K);                                  // ml.py:288-289
-            if (cs >= 0) {
-                double tmax;
-                qex += normalise<KP>(tdc, K, tmax);
+                lane.matvec(br, q, Lc, K);                               // ml.py:288-289
+                qex += rescale<KP>(Lc, vec_max<KP>(Lc), true);
                 double *dst = a.td + ((size_t) cs * K) * C + c;
 #pragma unroll
                 for (int k = 0; k < KP; ++k)
-                    if (k < K) dst[(size_t) k * C] = tdc[k];
+                    if (k < K) dst[(size_t) k * C] = Lc[k];
                 a.td_ex[(size_t) cs * C + c] = qex;
             } else {
-                emit_node<KP>(a, ch, c, Lc, tdc, lane.pi, mc, qex, sh_hist);
+                double tdc[KP];
+                lane.matvec(br, q, tdc, K);
+#pragma unroll
+                for (int k = 0; k < KP; ++k) tdc[k] *= Lc[k];
+                emit_node<KP>(a, lane, ch, c, tdc, mc, qex, sh_hist);
             }
         }
     }
@@ -707,24 +754,26 @@ __global__ void __launch_bounds__(kBlock) td_level_kernel(TdArgs a, int slot_beg
         if (sh_hist[i]) atomicAdd(a.k_hist + i, (unsigned long long) sh_hist[i]);
 }
 
-// Single-node forests (a root that is a tip) never enter td_level_kernel: emit them here.
+// Single-node trees (a root that is a tip) never enter td_level_kernel: emit them here.
 template <int KP, template <int> class Lane>
 __global__ void td_tip_roots_kernel(TdArgs a, const int *roots, int n_roots) {
-    extern __shared__ unsigned int sh_hist[];
+    extern __shared__ double s_par[];
     const int C = a.ln.C, K = a.ln.K;
+    const int nf = staged_fields(Lane<KP>::family, K);
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(s_par + (size_t) nf * C);
     for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x) sh_hist[i] = 0u;
-    __syncthreads();
+    stage_params(s_par, a.ln, nf);
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < n_roots * C) {
         const int node = roots[g / C], c = g % C;
         if (a.t.slot[node] < 0) {
             Lane<KP> lane;
-            lane.load(a.ln.params + (size_t) c * a.ln.stride, K);
+            lane.init(LaneSmem{s_par + c, C}, a.ln.params + (size_t) c * a.ln.stride, K);
             const uint64_t m = eff_mask(a.mask, a.t, a.zc, C, node, c, lane.tau == 0., a.ln.kmask);
-            double L[KP], TD[KP];
+            double L[KP];
 #pragma unroll
-            for (int k = 0; k < KP; ++k) { L[k] = (double) ((m >> k) & 1ULL); TD[k] = (k < K) ? 1. : 0.; }
-            emit_node<KP>(a, node, c, L, TD, lane.pi, m, 0, sh_hist);
+            for (int k = 0; k < KP; ++k) L[k] = bit_as_double(m, k);
+            emit_node<KP>(a, lane, node, c, L, m, 0, sh_hist);
         }
     }
     __syncthreads();
@@ -749,15 +798,15 @@ __global__ void mppa_fix_kernel(int n_rows, const int *row_node, int C, int K, u
     double m[KP];
     const uint64_t i0 = prev_hasinit[r] ? prev_initial[r] : kmask;    // applied in place by MAP (ml.py:593-594)
     const uint64_t i1 = zc.initial[r];                                // applied again by MPPA (ml.py:541-542)
-#pragma unroll
-    for (int k = 0; k < KP; ++k)
-        m[k] = (k < K && ((i0 >> k) & (i1 >> k) & 1ULL)) ? zc_lh[r * K + k] : 0.;
     double msum = 0.;
 #pragma unroll
-    for (int k = 0; k < KP; ++k) msum += m[k];
+    for (int k = 0; k < KP; ++k) {
+        m[k] = (k < K && ((i0 >> k) & (i1 >> k) & 1ULL)) ? zc_lh[r * K + k] : 0.;
+        msum += m[k];
+    }
     int best_k;
     uint64_t sel;
-    if (msum > 0.) sel = mppa_select<KP>(m, K, force_joint ? joint_state[nc] : 0, force_joint != 0, best_k);
+    if (msum > 0.) sel = mppa_select<KP>(m, 1. / msum, K, force_joint ? joint_state[nc] : 0, force_joint != 0, best_k);
     else { sel = kmask; best_k = K; }
     const int old_k = zc_k[r];
     mppa_mask[nc] = sel | kMemberFlag;
