@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument('--tree', default='yule', choices=['yule', 'coalescent'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--sweeps-only', action='store_true', help='development: print the sweep timings and exit')
     return ap.parse_args()
 
 
@@ -207,6 +208,10 @@ def run_b200(args):
         # per-sweep split for the roofline, same settings
         bu_ms, _, bu_launches = pb.bench_pass(params, which=0, n_iter=args.steps, flush_l2=True)
         td_ms, _, td_launches = pb.bench_pass(params, which=3, n_iter=args.steps, flush_l2=True)
+    if args.sweeps_only:
+        print('sweeps step_ms={:.3f} min={:.3f} bu_ms={:.3f} td_ms={:.3f} launches={} lib={}'.format(
+            avg_ms, min_ms, bu_ms, td_ms, launches, os.environ.get('PASTML_B200_LIB', 'default')))
+        return
     step_ms = avg_ms
     if dist is not None:
         t = torch.tensor([step_ms], dtype=torch.float64, device='cuda')

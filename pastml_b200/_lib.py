@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libpastml_b200.so')
+LIB_PATH = os.environ.get('PASTML_B200_LIB') or os.path.join(HERE, 'libpastml_b200.so')
 
 EXPORTS = ['pml_last_error', 'pml_version', 'pml_device_count', 'pml_param_stride', 'pml_problem_create',
            'pml_problem_destroy', 'pml_loglik', 'pml_joint', 'pml_marginal', 'pml_mppa_finalize', 'pml_parsimony',

@@ -63,7 +63,8 @@ struct pml_problem {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // topology
-    DevBuf<int> parent, first_child, n_children, slot, int_nodes, zc_index, roots;
+    DevBuf<int> parent, first_child, n_children, slot, int_nodes, zc_index, roots, fc_slot, nc_slot, pslot;
+    int n_root_slots = 0;
     DevBuf<double> dist;
     // zero clusters
     int n_clusters = 0, n_rows = 0;
@@ -93,10 +94,13 @@ struct pml_problem {
 
     TreeDev tree() const {
         return TreeDev{N, NI, parent.ptr, first_child.ptr, n_children.ptr, slot.ptr, int_nodes.ptr, dist.ptr,
-                       zc_index.ptr};
+                       zc_index.ptr, fc_slot.ptr, nc_slot.ptr, pslot.ptr, n_root_slots};
     }
     ZcDev zc() const { return ZcDev{zc_alt.ptr, zc_altflag.ptr, zc_initial.ptr, zc_hasinit.ptr}; }
-    LaneDev lanes(int n_sets) const { return LaneDev{C, n_sets * C, K, stride, params.ptr, kmask}; }
+    LaneDev lanes(int n_sets) const {
+        return LaneDev{C, n_sets * C, K, stride, params.ptr, kmask, FastDiv::make((unsigned) (n_sets * C)),
+                       FastDiv::make((unsigned) C)};
+    }
 };
 
 namespace {
@@ -141,8 +145,11 @@ void run_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marg
     for (int lvl = p->n_levels - 1; lvl >= 0; --lvl) {
         const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
         if (ns <= 0) continue;
-        p->ks->bu(p->stream, a, maxp, s0, ns);
-        p->launches++;
+        const int chunk = (int) std::max<long long>(1, kMaxItemsPerLaunch / ln.J);
+        for (int off = 0; off < ns; off += chunk) {
+            p->ks->bu(p->stream, a, maxp, s0 + off, std::min(chunk, ns - off));
+            p->launches++;
+        }
     }
     run_root_loglik(p, ln, mask, alter, is_marginal);
 }
@@ -206,13 +213,13 @@ void run_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_no
              p->td_ex.ptr, p->joint_state.ptr, force_joint, want_probs ? p->probs.ptr : nullptr,
              want_node_lh ? p->node_lh.ptr : nullptr, p->mask[PML_MASK_MAP].ptr, p->mask[PML_MASK_MPPA].ptr,
              p->k_hist.ptr, p->zc_lh.ptr, p->zc_k.ptr};
-    p->ks->td_tip_roots(p->stream, a, p->roots.ptr, p->n_roots);
-    p->launches++;
     for (int lvl = 0; lvl < p->n_levels; ++lvl) {
-        const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
-        if (ns <= 0) continue;
-        p->ks->td(p->stream, a, s0, ns);
-        p->launches++;
+        const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
+        const int chunk = (int) std::max<long long>(1, kMaxItemsPerLaunch / ln.C);
+        for (int off = 0; off < nn; off += chunk) {
+            p->ks->td(p->stream, a, n0 + off, std::min(chunk, nn - off));
+            p->launches++;
+        }
     }
 }
 
@@ -238,8 +245,12 @@ int copy_khist_out(pml_problem *p, int64_t *out) {
 namespace pml {
 #define PML_DECL(f, k) const KernelSet *pml_ks_##f##_##k();
 #define PML_CASE(f, k) if (family == f && kp == k) return pml_ks_##f##_##k();
+#ifdef PML_ONLY_F81_20   /* development builds (tools/exp_variants.py) */
+#define PML_ALL(X) X(0, 20)
+#else
 #define PML_ALL(X) X(0, 2) X(0, 4) X(0, 8) X(0, 12) X(0, 16) X(0, 20) X(0, 24) X(0, 32) X(0, 48) X(0, 62) \
                    X(1, 4) X(2, 2) X(2, 4) X(2, 8) X(2, 12) X(2, 16) X(2, 20) X(2, 24) X(2, 32)
+#endif
 PML_ALL(PML_DECL)
 const KernelSet *kernel_set(int family, int kp) {
     PML_ALL(PML_CASE)
@@ -409,6 +420,15 @@ int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dis
     PML_UPLOAD(p->n_children, nch);
     PML_UPLOAD(p->slot, slot);
     PML_UPLOAD(p->int_nodes, int_nodes);
+    {
+        std::vector<int> fcs(NI), ncs(NI), ps(N);
+        for (int s = 0; s < NI; ++s) { fcs[s] = fch[int_nodes[s]]; ncs[s] = nch[int_nodes[s]]; }
+        for (int v = 0; v < N; ++v) ps[v] = parent[v] < 0 ? -1 : slot[parent[v]];
+        PML_UPLOAD(p->fc_slot, fcs);
+        PML_UPLOAD(p->nc_slot, ncs);
+        PML_UPLOAD(p->pslot, ps);
+        p->n_root_slots = int_level_ptr[1];
+    }
     PML_UPLOAD(p->zc_index, zc_index);
     PML_UPLOAD(p->roots, roots);
     PML_UPLOAD(p->cl_col, cl_col);

@@ -62,12 +62,6 @@ void td_launch(cudaStream_t st, const TdArgs &a, int s0, int ns) {
     td_level_kernel<KP, TheLane><<<grid_for((long long) ns * a.ln.C), kBlock, sh, st>>>(a, s0, ns);
 }
 
-void td_tip_roots_launch(cudaStream_t st, const TdArgs &a, const int *roots, int n_roots) {
-    const size_t sh = td_smem(a);
-    allow_big_smem(td_tip_roots_kernel<KP, TheLane>, sh);
-    td_tip_roots_kernel<KP, TheLane><<<grid_for((long long) n_roots * a.ln.C), kBlock, sh, st>>>(a, roots, n_roots);
-}
-
 void mppa_fix_launch(cudaStream_t st, int n_rows, const int *row_node, int C, int K, uint64_t kmask, const ZcDev &zc,
                      const uint64_t *base_mask, const uint64_t *prev_initial, const uint8_t *prev_hasinit,
                      const double *zc_lh, uint8_t *zc_k, const int *joint_state, int force_joint, uint64_t *mppa_mask,
@@ -83,7 +77,7 @@ void mppa_fix_launch(cudaStream_t st, int n_rows, const int *row_node, int C, in
 #define PML_KS_NAME PML_KS_NAME2(PML_FAMILY, PML_KP)
 
 const KernelSet *PML_KS_NAME() {
-    static const KernelSet ks = {bu_launch, root_launch, td_launch, td_tip_roots_launch, mppa_fix_launch};
+    static const KernelSet ks = {bu_launch, root_launch, td_launch, mppa_fix_launch};
     return &ks;
 }
 

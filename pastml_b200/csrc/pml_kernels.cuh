@@ -17,7 +17,16 @@
 namespace pml {
 
 constexpr uint64_t kMemberFlag = 1ULL << 63;  // (node, column) belongs to a zero-branch cluster (see alter_kernel)
-constexpr int kBlock = 128;
+#ifndef PML_BLOCK
+#define PML_BLOCK 128
+#endif
+#ifndef PML_BU_MINB
+#define PML_BU_MINB 3
+#endif
+#ifndef PML_TD_MINB
+#define PML_TD_MINB 3
+#endif
+constexpr int kBlock = PML_BLOCK;
 
 struct TreeDev {
     int n_nodes;
@@ -29,6 +38,10 @@ struct TreeDev {
     const int *int_nodes;    // [NI] slot -> node
     const double *dist;      // [N]
     const int *zc_index;     // [N]  row in the zero-cluster table or -1
+    const int *fc_slot;      // [NI] first child of the slot's node (saves a dependent load in the sweeps)
+    const int *nc_slot;      // [NI] number of children of the slot's node
+    const int *pslot;        // [N]  slot of the parent, -1 for roots
+    int n_root_slots;        // internal roots occupy slots [0, n_root_slots)
 };
 
 struct ZcDev {              // zero-branch cluster table, rows x C
@@ -38,6 +51,19 @@ struct ZcDev {              // zero-branch cluster table, rows x C
     const uint8_t *hasinit;
 };
 
+// exact n / d for 0 <= n < 2^31 with one 32x32->64 multiply (m = floor(2^(31+s) / d) + 1, s = ceil(log2 d))
+struct FastDiv {
+    unsigned m, s, d;
+    __host__ static FastDiv make(unsigned d) {
+        unsigned s = 0;
+        while ((1ull << s) < d) ++s;
+        return FastDiv{(unsigned) (((1ull << (31 + s)) / d) + 1ull), s, d};
+    }
+    __device__ __forceinline__ unsigned div(unsigned n) const {
+        return (unsigned) (((unsigned long long) n * m) >> (31 + s));
+    }
+};
+
 struct LaneDev {
     int C;                   // columns
     int J;                   // lanes = sets * C
@@ -45,7 +71,11 @@ struct LaneDev {
     int stride;              // doubles per lane in params
     const double *params;    // [J][stride]
     uint64_t kmask;          // (1 << K) - 1
+    FastDiv divJ, divC;
 };
+
+// Launches cover at most this many (node, lane) items, so that item indices fit 31 bits
+constexpr long long kMaxItemsPerLaunch = 1LL << 30;
 
 // ------------------------------------------------------------------------------------------ helpers
 
@@ -421,21 +451,21 @@ __device__ __forceinline__ int load_child(const TreeDev &t, const ZcDev &zc, con
 
 // calc_node_bu_likelihood (ml.py:124-148) for the internal nodes [slot_begin, slot_begin + n_slots) of one level.
 template <int KP, template <int> class Lane, bool MAXP>
-__global__ void __launch_bounds__(kBlock) bu_level_kernel(BuArgs a, int slot_begin, int n_slots) {
+__global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_BU_MINB : 1)) bu_level_kernel(BuArgs a, int slot_begin, int n_slots) {
     extern __shared__ double s_par[];
     const int J = a.ln.J, K = a.ln.K, C = a.ln.C;
     stage_params(s_par, a.ln, staged_fields(Lane<KP>::family, K));
-    const long long n_items = (long long) n_slots * J;
-    for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
-         g += (long long) gridDim.x * blockDim.x) {
-        const int slot = slot_begin + (int) (g / J);
-        const int j = (int) (g % J);
-        const int c = j % C;
+    const unsigned n_items = (unsigned) n_slots * (unsigned) J;
+    for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n_items; g += gridDim.x * blockDim.x) {
+        const unsigned sl = a.ln.divJ.div(g);
+        const int slot = slot_begin + (int) sl;
+        const int j = (int) (g - sl * (unsigned) J);
+        const int c = j - (int) a.ln.divC.div((unsigned) j) * C;
         Lane<KP> lane;
         lane.init(LaneSmem{s_par + j, J}, a.ln.params + (size_t) j * a.ln.stride, K);
         const bool use_alt = a.alter && lane.tau == 0.;
+        const int fc = a.t.fc_slot[slot], nc = a.t.nc_slot[slot];
         const int node = a.t.int_nodes[slot];
-        const int fc = a.t.first_child[node], nc = a.t.n_children[node];
 
         double acc[KP];
         {
@@ -444,31 +474,49 @@ __global__ void __launch_bounds__(kBlock) bu_level_kernel(BuArgs a, int slot_beg
             for (int k = 0; k < KP; ++k) acc[k] = bit_as_double(m, k);   // 10 ** log10(allowed), ml.py:127
         }
         int ex = 0;
-        for (int ch = fc; ch < fc + nc; ++ch) {
-            const typename Lane<KP>::Branch br = lane.branch(a.t.dist[ch], K);
-            double in[KP];
+        if (!MAXP && nc == 2) {
+            // binary node: both children's vectors are requested before any arithmetic (twice the bytes in flight)
+            double in0[KP], in1[KP];
             uint64_t tm;
-            ex += load_child<KP>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, ch, j, c, use_alt, in, tm);
-            if (MAXP) {
-                double v[KP];
-                uint8_t arg[KP];
-                lane.maxvec(br, in, v, arg, K);
-                if (a.ptr) {
-                    uint8_t *dst = a.ptr + ((size_t) ch * C + c) * K;
-#pragma unroll
-                    for (int k = 0; k < KP; ++k)
-                        if (k < K) dst[k] = arg[k];
-                }
-#pragma unroll
-                for (int k = 0; k < KP; ++k) acc[k] *= v[k];
-            } else {
-                lane.mul_matvec(br, in, acc, K);
-            }
+            const double d0 = a.t.dist[fc], d1 = a.t.dist[fc + 1];
+            ex += load_child<KP>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, fc, j, c, use_alt, in0, tm);
+            ex += load_child<KP>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, j, c, use_alt, in1, tm);
+            const typename Lane<KP>::Branch b0 = lane.branch(d0, K), b1 = lane.branch(d1, K);
+            lane.mul_matvec(b0, in0, acc, K);
+            const double vmax0 = vec_max<KP>(acc);
+            lane.mul_matvec(b1, in1, acc, K);
             const double vmax = vec_max<KP>(acc);
             if (vmax == 0.) {   // all entries zero: PastMLLikelihoodError of ml.py:139-145
-                if (atomicCAS(a.err + 2 * j, -1, node) == -1) a.err[2 * j + 1] = ch;
+                if (atomicCAS(a.err + 2 * j, -1, node) == -1) a.err[2 * j + 1] = (vmax0 == 0.) ? fc : fc + 1;
             }
-            ex += rescale<KP>(acc, vmax, ch == fc + nc - 1);   // always normalised when the node is complete
+            ex += rescale<KP>(acc, vmax, true);
+        } else {
+            for (int ch = fc; ch < fc + nc; ++ch) {
+                const typename Lane<KP>::Branch br = lane.branch(a.t.dist[ch], K);
+                double in[KP];
+                uint64_t tm;
+                ex += load_child<KP>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, ch, j, c, use_alt, in, tm);
+                if (MAXP) {
+                    double v[KP];
+                    uint8_t arg[KP];
+                    lane.maxvec(br, in, v, arg, K);
+                    if (a.ptr) {
+                        uint8_t *dst = a.ptr + ((size_t) ch * C + c) * K;
+#pragma unroll
+                        for (int k = 0; k < KP; ++k)
+                            if (k < K) dst[k] = arg[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) acc[k] *= v[k];
+                } else {
+                    lane.mul_matvec(br, in, acc, K);
+                }
+                const double vmax = vec_max<KP>(acc);
+                if (vmax == 0.) {   // all entries zero: PastMLLikelihoodError of ml.py:139-145
+                    if (atomicCAS(a.err + 2 * j, -1, node) == -1) a.err[2 * j + 1] = ch;
+                }
+                ex += rescale<KP>(acc, vmax, ch == fc + nc - 1);   // always normalised when the node is complete
+            }
         }
         double *dst = a.bu + ((size_t) slot * K) * J + j;
 #pragma unroll
@@ -679,102 +727,73 @@ __device__ __forceinline__ void emit_node(const TdArgs &a, const LaneT &lane, in
     atomicAdd(sh_hist + c * (K + 1) + best_k, 1u);
 }
 
-// calc_node_td_likelihood (ml.py:273-290) for the children of the internal nodes of one level, fused with the
-// marginal step of the nodes themselves and of their tip children.  Shared memory: staged parameters, then the
-// block's k histogram.
+// calc_node_td_likelihood (ml.py:273-290) fused with the node's marginal step, node-centric: one thread per
+// (node of a depth level, column) reads the parent's bottom-up and top-down vectors and the node's own bottom-up
+// vector (or tip mask), forms the node's top-down vector, stores it if the node is internal, and emits the node's
+// marginal probabilities, MAP and MPPA states.  Roots take the all-ones top-down vector (ml.py:274-277).
+// Shared memory: staged parameters, then the block's k histogram.
 template <int KP, template <int> class Lane>
-__global__ void __launch_bounds__(kBlock) td_level_kernel(TdArgs a, int slot_begin, int n_slots) {
+__global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_TD_MINB : 1)) td_level_kernel(TdArgs a, int node_begin, int n_nodes) {
     extern __shared__ double s_par[];
     const int C = a.ln.C, K = a.ln.K;
     const int nf = staged_fields(Lane<KP>::family, K);
     unsigned int *sh_hist = reinterpret_cast<unsigned int *>(s_par + (size_t) nf * C);   // [C][K+1]
     for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x) sh_hist[i] = 0u;
     stage_params(s_par, a.ln, nf);
-    const long long n_items = (long long) n_slots * C;
-    for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
-         g += (long long) gridDim.x * blockDim.x) {
-        const int slot = slot_begin + (int) (g / C);
-        const int c = (int) (g % C);
+    const unsigned n_items = (unsigned) n_nodes * (unsigned) C;
+    for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n_items; g += gridDim.x * blockDim.x) {
+        const unsigned nd = a.ln.divC.div(g);
+        const int node = node_begin + (int) nd;
+        const int c = (int) (g - nd * (unsigned) C);
         Lane<KP> lane;
         lane.init(LaneSmem{s_par + c, C}, a.ln.params + (size_t) c * a.ln.stride, K);
         const bool use_alt = lane.tau == 0.;   // ml.py:702-703
-        const int node = a.t.int_nodes[slot];
-        const int fc = a.t.first_child[node], nc = a.t.n_children[node];
+        const int ps = a.t.pslot[node];
+        const int cs = a.t.slot[node];
 
-        double X[KP];   // L_p, then TD_p * L_p: the parent part of every child's top-down vector
-        {
-            const double *src = a.bu + ((size_t) slot * K) * C + c;
+        double Lc[KP], X[KP];
+        uint64_t mc;
+        const int exc = load_child<KP>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, node, c, c, use_alt, Lc, mc);
+        if (cs >= 0) mc = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
+        int ex_total;
+        if (ps < 0) {
 #pragma unroll
-            for (int k = 0; k < KP; ++k) X[k] = (k < K) ? src[(size_t) k * C] : 0.;
-        }
-        const int exp_ = a.bu_ex[(size_t) slot * C + c];
-        int extd = 0;
-        if (a.t.parent[node] >= 0) {   // the root's top-down vector is all ones (ml.py:274-277)
-            const double *src = a.td + ((size_t) slot * K) * C + c;
+            for (int k = 0; k < KP; ++k) X[k] = Lc[k];   // TD(root) = 1
+            ex_total = exc;
+        } else {
+            // parent part of the node's top-down vector: TD_p * L_p, divided below by the node's own contribution
+            {
+                const double *src = a.bu + ((size_t) ps * K) * C + c;
 #pragma unroll
-            for (int k = 0; k < KP; ++k) X[k] *= (k < K) ? src[(size_t) k * C] : 0.;
-            extd = a.td_ex[(size_t) slot * C + c];
-        }
-        {
-            double m[KP];
+                for (int k = 0; k < KP; ++k) X[k] = (k < K) ? src[(size_t) k * C] : 0.;
+            }
+            int pex = a.bu_ex[(size_t) ps * C + c];
+            if (ps >= a.t.n_root_slots) {
+                const double *src = a.td + ((size_t) ps * K) * C + c;
 #pragma unroll
-            for (int k = 0; k < KP; ++k) m[k] = X[k];
-            const uint64_t mp = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
-            emit_node<KP>(a, lane, node, c, m, mp, exp_ + extd, sh_hist);
-        }
-        for (int ch = fc; ch < fc + nc; ++ch) {
-            const typename Lane<KP>::Branch br = lane.branch(a.t.dist[ch], K);
-            double Lc[KP], q[KP];
-            uint64_t mc;
-            const int exc = load_child<KP>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, ch, c, c, use_alt, Lc, mc);
+                for (int k = 0; k < KP; ++k) X[k] *= (k < K) ? src[(size_t) k * C] : 0.;
+                pex += a.td_ex[(size_t) ps * C + c];
+            }
+            const typename Lane<KP>::Branch br = lane.branch(a.t.dist[node], K);
+            double q[KP];
             lane.matvec(br, Lc, q, K);                                   // node_contribution, ml.py:280
 #pragma unroll
             for (int k = 0; k < KP; ++k) q[k] = (q[k] > 0.) ? X[k] * __drcp_rn(q[k]) : X[k];   // ml.py:281-283
-            int qex = extd + exp_ - exc + rescale<KP>(q, vec_max<KP>(q), false);            // ml.py:284-286
-            const int cs = a.t.slot[ch];
+            int qex = pex - exc + rescale<KP>(q, vec_max<KP>(q), false);                    // ml.py:284-286
+            lane.matvec(br, q, X, K);                                    // ml.py:288-289
             if (cs >= 0) {
-                lane.matvec(br, q, Lc, K);                               // ml.py:288-289
-                qex += rescale<KP>(Lc, vec_max<KP>(Lc), true);
+                qex += rescale<KP>(X, vec_max<KP>(X), true);
                 double *dst = a.td + ((size_t) cs * K) * C + c;
 #pragma unroll
                 for (int k = 0; k < KP; ++k)
-                    if (k < K) dst[(size_t) k * C] = Lc[k];
+                    if (k < K) dst[(size_t) k * C] = X[k];
                 a.td_ex[(size_t) cs * C + c] = qex;
-            } else {
-                double tdc[KP];
-                lane.matvec(br, q, tdc, K);
-#pragma unroll
-                for (int k = 0; k < KP; ++k) tdc[k] *= Lc[k];
-                emit_node<KP>(a, lane, ch, c, tdc, mc, qex, sh_hist);
             }
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x)
-        if (sh_hist[i]) atomicAdd(a.k_hist + i, (unsigned long long) sh_hist[i]);
-}
-
-// Single-node trees (a root that is a tip) never enter td_level_kernel: emit them here.
-template <int KP, template <int> class Lane>
-__global__ void td_tip_roots_kernel(TdArgs a, const int *roots, int n_roots) {
-    extern __shared__ double s_par[];
-    const int C = a.ln.C, K = a.ln.K;
-    const int nf = staged_fields(Lane<KP>::family, K);
-    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(s_par + (size_t) nf * C);
-    for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x) sh_hist[i] = 0u;
-    stage_params(s_par, a.ln, nf);
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < n_roots * C) {
-        const int node = roots[g / C], c = g % C;
-        if (a.t.slot[node] < 0) {
-            Lane<KP> lane;
-            lane.init(LaneSmem{s_par + c, C}, a.ln.params + (size_t) c * a.ln.stride, K);
-            const uint64_t m = eff_mask(a.mask, a.t, a.zc, C, node, c, lane.tau == 0., a.ln.kmask);
-            double L[KP];
 #pragma unroll
-            for (int k = 0; k < KP; ++k) L[k] = bit_as_double(m, k);
-            emit_node<KP>(a, lane, node, c, L, m, 0, sh_hist);
+            for (int k = 0; k < KP; ++k) X[k] *= Lc[k];
+            ex_total = qex + exc;
         }
+        emit_node<KP>(a, lane, node, c, X, mc, ex_total, sh_hist);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x)

@@ -11,8 +11,7 @@ struct KernelSet {
     void (*root_loglik)(cudaStream_t, const TreeDev &, const ZcDev &, const LaneDev &, const uint64_t *mask,
                         int alter, const double *bu, const int *bu_ex, const int *roots, int n_roots,
                         int is_marginal, double *out);
-    void (*td)(cudaStream_t, const TdArgs &, int slot_begin, int n_slots);
-    void (*td_tip_roots)(cudaStream_t, const TdArgs &, const int *roots, int n_roots);
+    void (*td)(cudaStream_t, const TdArgs &, int node_begin, int n_nodes);
     void (*mppa_fix)(cudaStream_t, int n_rows, const int *row_node, int C, int K, uint64_t kmask, const ZcDev &,
                      const uint64_t *base_mask, const uint64_t *prev_initial, const uint8_t *prev_hasinit,
                      const double *zc_lh, uint8_t *zc_k, const int *joint_state, int force_joint,
