@@ -129,6 +129,10 @@ int pml_get_initial(pml_problem *p, uint8_t *out_has, uint64_t *out_initial);
 /* After PML_ERR_ZERO_LIKELIHOOD: first failing (column, parameter set, parent node, child node). */
 int pml_zero_likelihood_info(pml_problem *p, int32_t *column, int32_t *param_set, int32_t *parent, int32_t *child);
 
+/* After PML_ERR_ZERO_LIKELIHOOD from pml_loglik: (parent, child) of every lane of that call, -1 where the lane
+ * was fine.  out_pairs[n_lanes][2], lane = param_set * C + column. */
+int pml_zero_likelihood_all(pml_problem *p, int32_t *out_pairs, int32_t n_lanes);
+
 /* Timing of the last call on this handle: device time between the first and last kernel of the call, measured
  * with CUDA events on the handle's stream (ms), and the number of kernels launched. */
 int pml_last_call_stats(pml_problem *p, double *device_ms, int64_t *kernel_launches);

@@ -70,7 +70,7 @@ struct pml_problem {
     int n_clusters = 0, n_rows = 0;
     DevBuf<int> cl_col, cl_ptr, cl_mem, row_node;
     DevBuf<uint64_t> zc_alt, zc_initial, zc_prev_initial;
-    DevBuf<uint8_t> zc_altflag, zc_hasinit, zc_prev_hasinit, zc_k, record_col;
+    DevBuf<uint8_t> zc_altflag, zc_hasinit, zc_prev_hasinit, zc_k, zc_touched, record_col;
     DevBuf<double> zc_lh;
     // masks [N][C]
     DevBuf<uint64_t> mask[5];
@@ -96,7 +96,7 @@ struct pml_problem {
         return TreeDev{N, NI, parent.ptr, first_child.ptr, n_children.ptr, slot.ptr, int_nodes.ptr, dist.ptr,
                        zc_index.ptr, fc_slot.ptr, nc_slot.ptr, pslot.ptr, n_root_slots};
     }
-    ZcDev zc() const { return ZcDev{zc_alt.ptr, zc_altflag.ptr, zc_initial.ptr, zc_hasinit.ptr}; }
+    ZcDev zc() const { return ZcDev{zc_alt.ptr, zc_altflag.ptr, zc_initial.ptr, zc_hasinit.ptr, zc_touched.ptr}; }
     LaneDev lanes(int n_sets) const {
         return LaneDev{C, n_sets * C, K, stride, params.ptr, kmask, FastDiv::make((unsigned) (n_sets * C)),
                        FastDiv::make((unsigned) C)};
@@ -116,7 +116,7 @@ void run_alter(pml_problem *p, const uint64_t *src) {
     if (!p->n_clusters) return;
     alter_kernel<<<grid_for(p->n_clusters), kBlock, 0, p->stream>>>(
         p->n_clusters, p->cl_col.ptr, p->cl_ptr.ptr, p->cl_mem.ptr, p->zc_index.ptr, src, p->C, p->kmask,
-        p->record_col.ptr, p->zc_alt.ptr, p->zc_altflag.ptr, p->zc_initial.ptr, p->zc_hasinit.ptr);
+        p->record_col.ptr, p->zc_alt.ptr, p->zc_altflag.ptr, p->zc_initial.ptr, p->zc_hasinit.ptr, p->zc_touched.ptr);
     p->launches++;
 }
 
@@ -443,6 +443,8 @@ int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dis
     PML_TRY_FREE(p->zc_hasinit.alloc(rc));
     PML_TRY_FREE(p->zc_prev_hasinit.alloc(rc));
     PML_TRY_FREE(p->zc_k.alloc(rc));
+    PML_TRY_FREE(p->zc_touched.alloc(rc));
+    PML_TRY_FREE(cudaMemset(p->zc_touched.ptr, 0, rc));
     PML_TRY_FREE(p->zc_lh.alloc(rc * K));
     PML_TRY_FREE(p->record_col.alloc(C));
     PML_TRY_FREE(cudaMemset(p->zc_alt.ptr, 0, rc * sizeof(uint64_t)));
@@ -557,6 +559,8 @@ int pml_marginal(pml_problem *p, const double *params, int32_t force_joint, doub
                         cudaMemcpyDeviceToDevice, p->stream);
         cudaMemcpyAsync(p->zc_prev_hasinit.ptr, p->zc_hasinit.ptr, (size_t) p->n_rows * p->C,
                         cudaMemcpyDeviceToDevice, p->stream);
+        // from here on, alterations that rewrite '.initial' are what pml_mppa_finalize has to replay
+        cudaMemsetAsync(p->zc_touched.ptr, 0, (size_t) p->n_rows * p->C, p->stream);
     }
     timer.stop();
     CUDA_TRY(cudaGetLastError());
@@ -747,6 +751,16 @@ int pml_zero_likelihood_info(pml_problem *p, int32_t *column, int32_t *param_set
     if (param_set) *param_set = p->zero_info[1];
     if (parent) *parent = p->zero_info[2];
     if (child) *child = p->zero_info[3];
+    return PML_OK;
+}
+
+int pml_zero_likelihood_all(pml_problem *p, int32_t *out_pairs, int32_t n_lanes) {
+    if (!p || !out_pairs) return fail(PML_ERR_INVALID, "null argument");
+    for (int j = 0; j < n_lanes; ++j) {
+        const bool have = (size_t) (2 * j + 1) < p->h_err.size();
+        out_pairs[2 * j] = have ? p->h_err[2 * j] : -1;
+        out_pairs[2 * j + 1] = have ? p->h_err[2 * j + 1] : -1;
+    }
     return PML_OK;
 }
 

@@ -49,6 +49,7 @@ struct ZcDev {              // zero-branch cluster table, rows x C
     const uint8_t *altflag;  // member was altered by the current pass' alteration
     const uint64_t *initial; // '<col>_ALLOWED_STATES.initial'
     const uint8_t *hasinit;
+    const uint8_t *touched;  // '.initial' was rewritten since the last marginal sweep
 };
 
 // exact n / d for 0 <= n < 2^31 with one 32x32->64 multiply (m = floor(2^(31+s) / d) + 1, s = ceil(log2 d))
@@ -391,7 +392,7 @@ struct EigLane {  // CUSTOM_RATES / JTT: P = A diag(exp(d t')) A^-1  (generator.
 static __global__ void alter_kernel(int n_clusters, const int *cl_col, const int *cl_ptr, const int *cl_mem,
                              const int *zc_index, const uint64_t *src, int C, uint64_t kmask,
                              const uint8_t *record_col, uint64_t *alt, uint8_t *altflag, uint64_t *initial,
-                             uint8_t *hasinit) {
+                             uint8_t *hasinit, uint8_t *touched) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_clusters) return;
     const int c = cl_col[q];
@@ -411,6 +412,7 @@ static __global__ void alter_kernel(int n_clusters, const int *cl_col, const int
         if (altered) {
             initial[r] = v;
             hasinit[r] = 1;
+            touched[r] = 1;
         }
     }
 }
@@ -813,7 +815,7 @@ __global__ void mppa_fix_kernel(int n_rows, const int *row_node, int C, int K, u
     const size_t r = (size_t) row * C + c;
     const int node = row_node[row];
     const size_t nc = (size_t) node * C + c;
-    if (!(base_mask[nc] & kMemberFlag) || !zc.altflag[r]) return;   // '.initial' untouched by the last alteration
+    if (!(base_mask[nc] & kMemberFlag) || !zc.touched[r]) return;   // '.initial' not rewritten since MAP used it
     double m[KP];
     const uint64_t i0 = prev_hasinit[r] ? prev_initial[r] : kmask;    // applied in place by MAP (ml.py:593-594)
     const uint64_t i1 = zc.initial[r];                                // applied again by MPPA (ml.py:541-542)

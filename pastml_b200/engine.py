@@ -105,13 +105,26 @@ class Problem(object):
         return params
 
     # ------------------------------------------------------------------ passes
-    def loglik(self, params, n_sets=1, mask_kind=MASK_ANNOTATION, is_marginal=True, alter=True):
-        """[n_sets][C] log-likelihoods (get_bottom_up_loglikelihood summed over the trees)."""
+    def loglik(self, params, n_sets=1, mask_kind=MASK_ANNOTATION, is_marginal=True, alter=True, tolerate_zero=False):
+        """[n_sets][C] log-likelihoods (get_bottom_up_loglikelihood summed over the trees).
+
+        With ``tolerate_zero`` a zero-likelihood lane does not raise: the call returns (values, {lane: (parent,
+        child)}) with -inf in the failing lanes."""
         params = self._params(params, n_sets)
         out = np.empty((n_sets, self.C), dtype=np.float64)
-        self._check(self.lib.pml_loglik(self._h, _p(params), n_sets, mask_kind, 1 if is_marginal else 0,
-                                        1 if alter else 0, _p(out)))
-        return out
+        rc = self.lib.pml_loglik(self._h, _p(params), n_sets, mask_kind, 1 if is_marginal else 0,
+                                 1 if alter else 0, _p(out))
+        if not tolerate_zero:
+            self._check(rc)
+            return out
+        bad = {}
+        if rc == _lib.PML_ERR_ZERO_LIKELIHOOD:
+            pairs = np.empty((n_sets * self.C, 2), dtype=np.int32)
+            self._check(self.lib.pml_zero_likelihood_all(self._h, _p(pairs), n_sets * self.C))
+            bad = {int(j): (int(pairs[j, 0]), int(pairs[j, 1])) for j in np.flatnonzero(pairs[:, 0] >= 0)}
+        else:
+            self._check(rc)
+        return out, bad
 
     def joint(self, params, want_states=True):
         params = self._params(params, 1)

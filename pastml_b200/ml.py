@@ -1,0 +1,468 @@
+"""Maximum-likelihood ancestral character reconstruction on the CUDA engine.
+
+Host-side mirror of ``pastml.ml`` (``/root/reference/pastml/ml.py``): the same entry points (``ml_acr``,
+``optimise_likelihood``, ``get_bottom_up_loglikelihood``), result-dictionary keys and node features, but every
+likelihood pass is one device-resident launch sequence over *all* the columns that share a model family and a
+number of states (a :class:`ColumnBatch`), instead of per-node numpy code per column.
+
+What stays on the host, exactly as in the reference: the two-stage parameter fit with
+``scipy.optimize.minimize(method='L-BFGS-B', bounds=...)``, its starting points, restarts and acceptance rule
+(``ml.py:174-237, 865-920``).  Columns of a batch are fitted concurrently -- one optimiser thread per column whose
+objective evaluations meet in a :class:`LockstepEvaluator`, so that one launch sequence serves one evaluation of
+every column still being fitted.
+"""
+import logging
+import threading
+
+import numpy as np
+import pandas as pd
+from scipy.optimize import minimize
+
+from pastml_b200 import get_personalized_feature_name, CHARACTER, METHOD, NUM_SCENARIOS, NUM_UNRESOLVED_NODES, \
+    NUM_STATES_PER_NODE, PERC_UNRESOLVED, STATES
+from pastml_b200.engine import Problem, ZeroLikelihoodError, MASK_ANNOTATION, MASK_JOINT, MASK_MAP, MASK_MPPA, \
+    MASK_CUSTOM
+from pastml_b200.models import ModelWithFrequencies
+from pastml_b200.tree import flatten_forest
+
+LOG_LIKELIHOOD = 'log_likelihood'
+RESTRICTED_LOG_LIKELIHOOD_FORMAT_STR = '{}_restricted_{{}}'.format(LOG_LIKELIHOOD)
+
+JOINT = 'JOINT'
+MPPA = 'MPPA'
+MAP = 'MAP'
+ALL = 'ALL'
+ML = 'ML'
+
+MARGINAL_PROBABILITIES = 'marginal_probabilities'
+MODEL = 'model'
+
+MARGINAL_ML_METHODS = {MPPA, MAP}
+ML_METHODS = MARGINAL_ML_METHODS | {JOINT}
+META_ML_METHODS = {ML, ALL}
+
+BU_LH = 'BOTTOM_UP_LIKELIHOOD'
+TD_LH = 'TOP_DOWN_LIKELIHOOD'
+LH = 'LIKELIHOOD'
+LH_SF = 'LIKELIHOOD_SF'
+BU_LH_SF = 'BOTTOM_UP_LIKELIHOOD_SF'
+BU_LH_JOINT_STATES = 'BOTTOM_UP_LIKELIHOOD_JOINT_STATES'
+TD_LH_SF = 'TOP_DOWM_LIKELIHOOD_SF'
+ALLOWED_STATES = 'ALLOWED_STATES'
+JOINT_STATE = 'JOINT_STATE'
+
+
+def is_marginal(method):
+    return method in MARGINAL_ML_METHODS or method in META_ML_METHODS
+
+
+def is_ml(method):
+    return method in ML_METHODS or method in META_ML_METHODS
+
+
+def is_meta_ml(method):
+    return method in META_ML_METHODS
+
+
+def get_default_ml_method():
+    return MPPA
+
+
+class PastMLLikelihoodError(Exception):
+
+    def __init__(self, *args):
+        self.message = args[0] if args else None
+
+    def __str__(self):
+        if self.message:
+            return 'PastMLLikelihoodError, {}'.format(self.message)
+        return 'PastMLLikelihoodError has been raised.'
+
+
+# ---------------------------------------------------------------------------------------- annotation masks
+
+def state_masks(flat, character, states):
+    """(annot_mask uint64 [N], has_state uint8 [N]) of one character from the node features, the inputs of
+    ``initialize_allowed_states`` / ``get_zero_clusters_with_states`` (``ml.py:293-349``)."""
+    s2i = {s: i for i, s in enumerate(states)}
+    mask = np.zeros(flat.n_nodes, dtype=np.uint64)
+    has = np.zeros(flat.n_nodes, dtype=np.uint8)
+    for i, node in enumerate(flat.nodes):
+        value = getattr(node, character, None)
+        if value is None or (isinstance(value, str) and value == ''):
+            continue
+        has[i] = 1
+        m = 0
+        for s in value:
+            m |= 1 << s2i[s]
+        mask[i] = m
+    return mask, has
+
+
+def mask_to_sets(mask_column, states):
+    """uint64 masks -> list of fresh python sets of state names (what pastml stores in ``node.<character>``)."""
+    cache = {}
+    out = []
+    for m in mask_column.tolist():
+        proto = cache.get(m)
+        if proto is None:
+            proto = cache[m] = frozenset(states[k] for k in range(len(states)) if (m >> k) & 1)
+        out.append(set(proto))
+    return out
+
+
+# ---------------------------------------------------------------------------------------- lock-step objective
+
+class LockstepEvaluator(object):
+    """Rendezvous of the per-column optimiser threads: when every column that is still being fitted has asked
+    for one objective value, a single batched pass evaluates all of them."""
+
+    def __init__(self, batch):
+        self.batch = batch
+        self.cond = threading.Condition()
+        self.active = set(range(batch.C))
+        self.pending = {}
+        self.results = {}
+        self.errors = {}
+        self.n_passes = 0
+
+    def _flush(self):
+        cols = sorted(self.pending)
+        values, errs = self.batch.loglik_columns(cols)
+        self.n_passes += 1
+        for c in cols:
+            self.results[c] = values[c]
+            if c in errs:
+                self.errors[c] = errs[c]
+        self.pending.clear()
+        self.cond.notify_all()
+
+    def evaluate(self, c):
+        """Log-likelihood of column c at its model's current parameters."""
+        with self.cond:
+            self.pending[c] = True
+            self.results.pop(c, None)
+            if set(self.pending) >= self.active:
+                self._flush()
+            else:
+                while c not in self.results:
+                    self.cond.wait()
+            if c in self.errors:
+                raise self.errors.pop(c)
+            return self.results[c]
+
+    def retire(self, c):
+        with self.cond:
+            self.active.discard(c)
+            if self.pending and set(self.pending) >= self.active:
+                self._flush()
+
+
+class ColumnBatch(object):
+    """Columns of one forest that share the model family and the number of states: one engine problem."""
+
+    def __init__(self, flat, characters, models, device=0):
+        self.flat = flat
+        self.characters = list(characters)
+        self.models = list(models)
+        self.C = len(self.characters)
+        m0 = self.models[0]
+        self.K = len(m0.states)
+        self.kind = m0.engine_kind
+        masks, has = zip(*(state_masks(flat, ch, list(m.states)) for ch, m in zip(self.characters, self.models)))
+        self.annot_mask = np.stack(masks)
+        self.has_state = np.stack(has)
+        self.problem = Problem(flat, self.K, self.kind, self.annot_mask, self.has_state, max_param_sets=1,
+                               device=device)
+
+    def close(self):
+        self.problem.close()
+
+    def params(self):
+        return np.stack([m.engine_block() for m in self.models])
+
+    def _error_for(self, c, parent, child):
+        names = self.flat.names
+        return PastMLLikelihoodError(
+            'The parent node {} and its child node {} have non-intersecting states, and are connected by a '
+            'zero-length ({:g}) branch. This creates a zero likelihood value. To avoid this issue check the '
+            'restrictions on these node states and/or use a smoothing factor (tau).'
+            .format(names[parent], names[child], self.flat.dist[child]))
+
+    def loglik_columns(self, cols=None, mask_kind=MASK_ANNOTATION, is_marginal=True, alter=True):
+        """({column: log-likelihood}, {column: PastMLLikelihoodError}) for one batched pass."""
+        values, bad = self.problem.loglik(self.params(), 1, mask_kind, is_marginal, alter, tolerate_zero=True)
+        cols = range(self.C) if cols is None else cols
+        errs = {c: self._error_for(c, *bad[c]) for c in cols if c in bad}
+        return {c: float(values[0, c]) for c in cols}, errs
+
+
+# ---------------------------------------------------------------------------------------- parameter fit
+
+def optimize_likelihood_params(evaluate, observed_frequencies, model):
+    """One stage of the fit for one column (``ml.py:174-237``): L-BFGS-B from the current parameters, then from the
+    observed frequencies, then from uniform random points, returning at the first successful run that is not worse
+    than the better starting point.  ``evaluate()`` returns the log-likelihood at the model's current parameters."""
+    bounds = model.get_bounds()
+
+    def get_v(ps):
+        if np.any(pd.isnull(ps)):
+            return np.nan
+        model.set_params_from_optimised(ps)
+        res = evaluate()
+        return np.inf if pd.isnull(res) else -res
+
+    if np.any(observed_frequencies <= 0):
+        observed_frequencies = np.maximum(observed_frequencies, 1e-10)
+
+    x0_JC = model.get_optimised_parameters()
+    optimise_frequencies = isinstance(model, ModelWithFrequencies) and model._optimise_frequencies
+    x0_EFT = x0_JC
+    if optimise_frequencies:
+        model.frequencies = observed_frequencies
+        x0_EFT = model.get_optimised_parameters()
+    log_lh_JC = -get_v(x0_JC)
+    log_lh_EFT = log_lh_JC if not optimise_frequencies else -get_v(x0_EFT)
+    best_log_lh = max(log_lh_JC, log_lh_EFT)
+
+    for i in range(100):
+        if i == 0:
+            vs = x0_JC
+        elif optimise_frequencies and i == 1:
+            vs = x0_EFT
+        else:
+            vs = np.random.uniform(bounds[:, 0], bounds[:, 1])
+        fres = minimize(get_v, x0=vs, method='L-BFGS-B', bounds=bounds)
+        if fres.success and not np.any(np.isnan(fres.x)):
+            if -fres.fun >= best_log_lh:
+                model.set_params_from_optimised(fres.x)
+                return -fres.fun
+    model.set_params_from_optimised(x0_JC if log_lh_JC >= log_lh_EFT else x0_EFT)
+    return best_log_lh
+
+
+def _fit_one(evaluate, character, model, observed_frequencies):
+    """optimise_likelihood for one column (``ml.py:865-920``) given its objective."""
+    logger = logging.getLogger('pastml')
+    likelihood = evaluate()
+    if np.isnan(likelihood):
+        raise PastMLLikelihoodError('Failed to calculate the likelihood for your tree, please check that you do not '
+                                    'have contradicting {} states specified for internal tree nodes, and if not - '
+                                    'submit a bug at https://github.com/evolbioinfo/pastml/issues'.format(character))
+    if not model.get_num_params():
+        logger.debug('All the parameters are fixed for {}:\n{}\tlog likelihood:\t{:.6f}.'
+                     .format(character, model._print_parameters(), likelihood))
+        return likelihood
+    logger.debug('Initial values for {} parameter optimisation:\n{}\tlog likelihood:\t{:.6f}.'
+                 .format(character, model._print_parameters(), likelihood))
+    failure = 'Failed to optimise the likelihood for your tree, please check that you do not have contradicting {} ' \
+              'states specified for internal tree nodes, and if not - submit a bug at ' \
+              'https://github.com/evolbioinfo/pastml/issues'.format(character)
+    if not model.basic_params_fixed():
+        model.fix_extra_params()
+        likelihood = optimize_likelihood_params(evaluate, observed_frequencies, model)
+        if np.isnan(likelihood) or likelihood == -np.inf:
+            raise PastMLLikelihoodError(failure)
+        model.unfix_extra_params()
+        if not model.extra_params_fixed():
+            logger.debug('Pre-optimised basic parameters for {}:\n{}\tlog likelihood:\t{:.6f}.'
+                         .format(character, model._print_basic_parameters(), likelihood))
+    if not model.extra_params_fixed():
+        likelihood = optimize_likelihood_params(evaluate, observed_frequencies, model)
+        if np.isnan(likelihood) or likelihood == -np.inf:
+            raise PastMLLikelihoodError(failure)
+    logger.debug('Optimised parameters for {}:\n{}\tlog likelihood:\t{:.6f}'
+                 .format(character, model._print_parameters(), likelihood))
+    return likelihood
+
+
+def fit_batch(batch, observed_frequencies):
+    """Fits all the columns of a batch concurrently; returns ([log-likelihood per column], n device passes)."""
+    ev = LockstepEvaluator(batch)
+    out = [None] * batch.C
+    failures = [None] * batch.C
+
+    def work(c):
+        try:
+            out[c] = _fit_one(lambda: ev.evaluate(c), batch.characters[c], batch.models[c], observed_frequencies[c])
+        except BaseException as e:  # re-raised in the caller's thread
+            failures[c] = e
+        finally:
+            ev.retire(c)
+
+    if batch.C == 1:
+        work(0)
+    else:
+        threads = [threading.Thread(target=work, args=(c,), daemon=True) for c in range(batch.C)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    for e in failures:
+        if e is not None:
+            raise e
+    return out, ev.n_passes
+
+
+def optimise_likelihood(forest, character, model, observed_frequencies):
+    """Drop-in for ``pastml.ml.optimise_likelihood``: fits one character's model on the forest."""
+    flat = forest if hasattr(forest, 'level_ptr') else flatten_forest(forest)
+    batch = ColumnBatch(flat, [character], [model])
+    try:
+        return fit_batch(batch, [observed_frequencies])[0][0]
+    finally:
+        batch.close()
+
+
+def get_bottom_up_loglikelihood(tree, character, model, is_marginal=True, alter=True):
+    """Drop-in for ``pastml.ml.get_bottom_up_loglikelihood`` (``ml.py:82-121``): log-likelihood of one tree for one
+    character.  The allowed states are the ``<character>_ALLOWED_STATES`` node features when present
+    (0/1 arrays, as ``initialize_allowed_states`` writes them), otherwise the annotation sets."""
+    flat = flatten_forest(tree)
+    batch = ColumnBatch(flat, [character], [model])
+    try:
+        feature = get_personalized_feature_name(character, ALLOWED_STATES)
+        mask_kind = MASK_ANNOTATION
+        if all(hasattr(n, feature) for n in flat.nodes):
+            custom = np.zeros((1, flat.n_nodes), dtype=np.uint64)
+            for i, n in enumerate(flat.nodes):
+                bits = 0
+                for k, v in enumerate(getattr(n, feature)):
+                    if v:
+                        bits |= 1 << k
+                custom[0, i] = bits
+            batch.problem.set_custom_masks(custom)
+            mask_kind = MASK_CUSTOM
+        values, errs = batch.loglik_columns([0], mask_kind, is_marginal, alter)
+        if errs:
+            raise errs[0]
+        return values[0]
+    finally:
+        batch.close()
+
+
+# ---------------------------------------------------------------------------------------- reconstruction
+
+def _write_states(flat, mask_column, states, feature):
+    for node, value in zip(flat.nodes, mask_to_sets(mask_column, states)):
+        node.add_feature(feature, value)
+
+
+def reconstruct_batch(batch, prediction_method, likelihoods, force_joint=True, write_likelihood_features=True,
+                      parsimony_hook=None):
+    """Everything ``ml_acr`` does after the fit (``ml.py:659-750``) for all the columns of a batch; returns one list
+    of result dictionaries per column."""
+    logger = logging.getLogger('pastml')
+    flat, pb = batch.flat, batch.problem
+    params = batch.params()
+    C, N = batch.C, flat.n_nodes
+    order = flat.ref_order
+    names = flat.names
+    index = [names[i] for i in order]
+    results = [[] for _ in range(C)]
+    current = [{LOG_LIKELIHOOD: likelihoods[c], CHARACTER: batch.characters[c], METHOD: prediction_method,
+                MODEL: batch.models[c], STATES: batch.models[c].states} for c in range(C)]
+
+    def emit(method, mask_nc):
+        if method != prediction_method and not is_meta_ml(prediction_method):
+            return
+        for c in range(C):
+            character = batch.characters[c]
+            feature = get_personalized_feature_name(character, method) if prediction_method != method else character
+            _write_states(flat, mask_nc[:, c], batch.models[c].states, feature)
+            res = current[c].copy()
+            res[CHARACTER] = feature
+            res[METHOD] = method
+            results[c].append(res)
+
+    def note_restricted(method, mask_kind):
+        values, errs = batch.loglik_columns(None, mask_kind, True, True)
+        for c in range(C):
+            if c in errs:
+                raise errs[c]
+            logger.debug('Log likelihood for {} after {} state selection:\t{:.6f}'
+                         .format(batch.characters[c], method, values[c]))
+            current[c][RESTRICTED_LOG_LIKELIHOOD_FORMAT_STR.format(method)] = values[c]
+
+    have_joint = False
+    if prediction_method != MAP:
+        lh_joint, joint_state = pb.joint(params, want_states=True)
+        have_joint = True
+        for c in range(C):
+            current[c][RESTRICTED_LOG_LIKELIHOOD_FORMAT_STR.format(JOINT)] = float(lh_joint[c])
+        if prediction_method == JOINT or is_meta_ml(prediction_method):
+            emit(JOINT, np.uint64(1) << joint_state.astype(np.uint64))
+
+    if is_marginal(prediction_method):
+        use_fj = bool(force_joint) and have_joint
+        res = pb.marginal(params, force_joint=use_fj, want_probs=True, want_node_lh=write_likelihood_features,
+                          want_masks=True)
+        probs = res['probs']
+        for c in range(C):
+            states = batch.models[c].states
+            current[c][MARGINAL_PROBABILITIES] = pd.DataFrame(probs[order, c, :], index=index, columns=states)
+        if write_likelihood_features:
+            has_init, init = pb.get_initial()
+            for c in range(C):
+                lh_f = get_personalized_feature_name(batch.characters[c], LH)
+                sf_f = get_personalized_feature_name(batch.characters[c], LH_SF)
+                K = batch.K
+                bits = ((init[:, c][:, None] >> np.arange(K, dtype=np.uint64)) & np.uint64(1)).astype(np.float64)
+                for i, node in enumerate(flat.nodes):
+                    vec = probs[i, c, :].copy()
+                    if has_init[i, c]:
+                        vec *= bits[i]
+                    node.add_feature(lh_f, vec)
+                    node.add_feature(sf_f, -float(res['node_log10lh'][i, c]))
+        note_restricted(MAP, MASK_MAP)
+        emit(MAP, res['map_mask'])
+
+        if prediction_method == MPPA or is_meta_ml(prediction_method):
+            if prediction_method == ALL and parsimony_hook is not None:
+                parsimony_hook(batch, current, results, note_restricted)
+            mppa_mask, k_hist = pb.mppa_finalize(force_joint=use_fj, want_masks=True)
+            for c in range(C):
+                num_nodes = batch.models[c].forest_stats.num_nodes
+                scenarios, unresolved, n_states = 1, 0, 0
+                for k in range(1, batch.K + 1):
+                    cnt = int(k_hist[c, k])
+                    scenarios *= k ** cnt
+                    n_states += k * cnt
+                    if k > 1:
+                        unresolved += cnt
+                current[c][NUM_SCENARIOS] = scenarios
+                current[c][NUM_UNRESOLVED_NODES] = unresolved
+                current[c][NUM_STATES_PER_NODE] = n_states / num_nodes
+                current[c][PERC_UNRESOLVED] = unresolved * 100 / num_nodes
+                logger.debug('{} node{} unresolved ({:.2f}%) for {} by {}, i.e. {:.4f} state{} per node in average.'
+                             .format(unresolved, 's are' if unresolved != 1 else ' is', current[c][PERC_UNRESOLVED],
+                                     batch.characters[c], MPPA, current[c][NUM_STATES_PER_NODE],
+                                     's' if current[c][NUM_STATES_PER_NODE] > 1 else ''))
+            note_restricted(MPPA, MASK_MPPA)
+            emit(MPPA, mppa_mask)
+    return results
+
+
+def ml_acr(forest, character, prediction_method, model, observed_frequencies, force_joint=True):
+    """Drop-in for ``pastml.ml.ml_acr`` (``ml.py:640-750``): fits the model of one character and reconstructs its
+    ancestral states; returns the list of result dictionaries (one per produced method)."""
+    return ml_acr_batch(forest, [character], prediction_method, [model], [observed_frequencies], force_joint)[0]
+
+
+def ml_acr_batch(forest, characters, prediction_method, models, observed_frequencies, force_joint=True,
+                 flat=None, device=0, write_likelihood_features=True):
+    """``ml_acr`` for several characters that share the model family and the number of states, in one engine
+    problem.  Returns one list of result dictionaries per character."""
+    if flat is None:
+        flat = flatten_forest(forest)
+    batch = ColumnBatch(flat, characters, models, device=device)
+    try:
+        likelihoods, _ = fit_batch(batch, observed_frequencies)
+        hook = None
+        if prediction_method == ALL:
+            from pastml_b200.parsimony import all_methods_hook
+            hook = all_methods_hook
+        return reconstruct_batch(batch, prediction_method, likelihoods, force_joint,
+                                 write_likelihood_features=write_likelihood_features, parsimony_hook=hook)
+    finally:
+        batch.close()

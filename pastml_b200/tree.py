@@ -735,3 +735,21 @@ def flatten_forest(forest):
         frontier = nxt
     dist = np.fromiter((node.dist for node in nodes), dtype=np.float64, count=len(nodes))
     return FlatForest(np.asarray(parent, dtype=np.int32), dist, nodes=nodes)
+
+
+def forest_from_arrays(parent, dist, names=None):
+    """Builds :class:`Tree` objects from level-ordered arrays (the inverse of :func:`flatten_forest`);
+    returns the list of roots."""
+    nodes = []
+    roots = []
+    for i, p in enumerate(parent):
+        node = Tree()
+        node.dist = float(dist[i])
+        node.name = '' if names is None else str(names[i])
+        nodes.append(node)
+        if p < 0:
+            roots.append(node)
+        else:
+            node.up = nodes[p]
+            nodes[p].children.append(node)
+    return roots

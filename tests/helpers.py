@@ -53,3 +53,32 @@ def engine_params(g):
     if g.kind == 1:
         kw = dict(kappa=float(z['kappa']))
     return pack_params(g.kind, g.K, float(z['sf']), float(z['tau']), float(z['tau_factor']), z['pi'], **kw)
+
+
+def annotated_forest(g, column=None):
+    """Tree objects of a golden fixture with the annotation sets on the nodes, as acr() expects pre-annotated
+    forests (columns + column2states call path)."""
+    from pastml_b200.tree import forest_from_arrays
+    column = column or g.meta['column']
+    roots = forest_from_arrays(g['parent'], g['dist'], g.flat.names)
+    nodes = []
+    frontier = list(roots)
+    while frontier:
+        nodes.extend(frontier)
+        frontier = [ch for n in frontier for ch in n.children]
+    for node, m, h in zip(nodes, g['annot_mask'].tolist(), g['has_state'].tolist()):
+        if h:
+            node.add_feature(column, {g.states[k] for k in range(g.K) if (m >> k) & 1})
+    return roots
+
+
+def masks_from_feature(flat_nodes, states, feature):
+    s2i = {s: i for i, s in enumerate(states)}
+    out = []
+    for node in flat_nodes:
+        m = 0
+        for s in getattr(node, feature):
+            m |= 1 << s2i[s]
+        out.append(m)
+    import numpy as np
+    return np.array(out, dtype=np.uint64)

@@ -1,0 +1,91 @@
+"""CPU-only checks (no CUDA device needed): the C ABI library loads and exports every symbol the header declares,
+host-side logic (tree flattening, forest statistics, models, fast division) behaves, and the engine refuses to
+run without a GPU instead of falling back."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import Golden, golden_names, annotated_forest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pastml_b200 import _lib
+    header = open(os.path.join(REPO, 'include', 'pastml_b200.h')).read()
+    declared = set(re.findall(r'\b(pml_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_lib.EXPORTS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pml_version() >= 100
+    assert lib.pml_param_stride(0, 5) == 9 and lib.pml_param_stride(1, 4) == 8 and lib.pml_param_stride(2, 20) == 844
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from pastml_b200.engine import Problem, EngineError
+    g = Golden('synth_s1_n40_k4_f81')
+    with pytest.raises(EngineError):
+        Problem(g.flat, g.K, 0, g['annot_mask'][None, :], g['has_state'][None, :])
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_flatten_round_trip_and_stats(name):
+    from pastml_b200.tree import flatten_forest
+    from pastml_b200.annotation import ForestStats
+    g = Golden(name)
+    forest = annotated_forest(g)
+    flat = flatten_forest(forest)
+    assert np.array_equal(flat.parent, g['parent']) and np.array_equal(flat.dist, g['dist'])
+    assert flat.names == g.flat.names
+    fs = ForestStats(flat=flat)
+    ref = g['forest_stats']
+    assert (fs.avg_nonzero_brlen, fs.num_nodes, fs.num_tips, fs.forest_length) == tuple(ref)
+    # level order invariants the kernels rely on
+    assert np.all(np.diff(flat.parent) >= 0)
+    kids = flat.first_child[flat.int_nodes] + flat.n_children[flat.int_nodes]
+    assert np.all(kids[:-1] == flat.first_child[flat.int_nodes][1:])
+    assert flat.level_ptr[-1] == flat.n_nodes and flat.int_level_ptr[-1] == flat.n_internal
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_models_reproduce_reference_pij(name):
+    """get_Pij_t of the host model classes against the oracle's restatement at the fixture's parameters."""
+    from pastml_b200.models import model2class
+    from pastml_b200.annotation import ForestStats
+    g = Golden(name)
+    fs = ForestStats(flat=g.flat)
+    params = {'scaling_factor': float(g['sf']), 'smoothing_factor': float(g['tau'])}
+    if g.model_name in ('F81', 'HKY', 'CUSTOM_RATES'):
+        params.update({s: float(f) for s, f in zip(g.states, g['pi'])})
+    if g.model_name == 'HKY':
+        params['kappa'] = float(g['kappa'])
+    kw = {}
+    if g.model_name == 'CUSTOM_RATES':
+        kw = dict(rate_matrix=g['rate_matrix'])
+    model = model2class[g.model_name](states=np.array(g.states), forest_stats=fs, parameter_file=params,
+                                      observed_frequencies=g['pi'], tau=float(g['tau']), **kw)
+    assert model.get_num_params() == 0
+    om = g.oracle_model()
+    for t in (0., 1e-3, 0.05, 1.7):
+        np.testing.assert_allclose(model.get_Pij_t(t), om.pij(t), rtol=1e-12, atol=1e-15)
+    block = model.engine_block()
+    assert block[0] == float(g['sf']) and block[2] == pytest.approx(float(g['tau_factor']), rel=1e-15)
+
+
+def test_newick_round_trip_and_naming():
+    from pastml_b200.tree import Tree, name_tree, collapse_zero_branches
+    t = Tree('((A:1,B:0.5):0.25,(C:1,(D:1,E:2):0):0.5,F:3);', format=1)
+    name_tree(t)
+    assert t.name == 'root' and len({n.name for n in t.traverse()}) == 10
+    # the reference's naming rule (tree.py:76-105): a preorder counter that only advances on name clashes
+    assert [n.name for n in t.traverse('postorder')] == ['A', 'B', 'n0', 'C', 'D', 'E', 'n1', 'n00', 'F', 'root']
+    again = Tree(t.write(format=1, format_root_node=True), format=1)
+    assert [n.name for n in again.traverse()] == [n.name for n in t.traverse()]
+    collapse_zero_branches([t])
+    assert sum(1 for _ in t.traverse()) == 9
