@@ -20,13 +20,19 @@ LIB_NAME = 'libpastml_b200.so'
 LIB_PATH = os.path.join(HERE, LIB_NAME)
 ENGINE_SRC = os.path.join(CSRC, 'pml_engine.cu')
 INST_SRC = os.path.join(CSRC, 'pml_inst.cu')
-HEADERS = [os.path.join(CSRC, 'pml_kernels.cuh'), os.path.join(CSRC, 'pml_launch.h'),
+COOP_SRC = os.path.join(CSRC, 'pml_coop_inst.cu')
+HEADERS = [os.path.join(CSRC, 'pml_kernels.cuh'), os.path.join(CSRC, 'pml_coop.cuh'), os.path.join(CSRC, 'pml_launch.h'),
            os.path.join(os.path.dirname(HERE), 'include', 'pastml_b200.h')]
 
 # (family, KP): 0 = F81/JC/EFT, 1 = HKY, 2 = eigen-decomposition models (CUSTOM_RATES, JTT); keep in sync with
 # PML_ALL in pml_engine.cu
 INSTANCES = [(0, k) for k in (2, 4, 8, 12, 16, 20, 24, 32, 48, 62)] + [(1, 4)] + \
             [(2, k) for k in (2, 4, 8, 12, 16, 20, 24, 32)]
+
+# (G, KT) of the warp-cooperative F81 sweeps; keep in sync with PML_COOP_ALL in pml_engine.cu
+COOP_INSTANCES = [(2, k, 0) for k in (2, 3, 4, 5, 6, 8, 10, 12, 16)] + [(4, k, 0) for k in (2, 3, 4, 5, 6, 8, 10, 12, 16)] + \
+                 [(8, k, 0) for k in (2, 3, 4, 5, 6, 8)] + [(16, k, 0) for k in (2, 3, 4)] + [(32, 2, 0)] + \
+                 [(4, 5, 8), (2, 5, 16), (2, 5, 8), (4, 5, 4), (2, 2, 16), (2, 2, 8), (2, 10, 8)]   # compile-time lanes / K
 
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2']
@@ -75,9 +81,13 @@ def build(force=False, verbose=False, jobs=None):
     for fam, kp in INSTANCES:
         tasks.append((INST_SRC, os.path.join(OBJ_DIR, 'pml_inst_{}_{}.o'.format(fam, kp)),
                       ['-DPML_FAMILY={}'.format(fam), '-DPML_KP={}'.format(kp)], inst_digest))
+    coop_digest = _digest([COOP_SRC] + HEADERS, flags)
+    for g, kt, jt in COOP_INSTANCES:
+        tasks.append((COOP_SRC, os.path.join(OBJ_DIR, 'pml_coop_{}_{}_{}.o'.format(g, kt, jt)),
+                      ['-DPML_G={}'.format(g), '-DPML_KT={}'.format(kt), '-DPML_JT={}'.format(jt)], coop_digest))
     jobs = jobs or max(1, min(len(tasks), os.cpu_count() or 1))
     # biggest instantiations first so that they do not end up alone at the tail
-    tasks.sort(key=lambda t: -int(t[2][1].split('=')[1]) if t[2] else 0)
+    tasks.sort(key=lambda t: -int(t[2][1].split('=')[1]) * (1 if 'PML_KP' in t[2][1] else 0) if t[2] else 0)
     with ThreadPoolExecutor(max_workers=jobs) as pool:
         rebuilt = list(pool.map(lambda t: _compile(nvcc, t[0], t[1], t[2], t[3], verbose), tasks))
     if any(rebuilt) or not os.path.exists(LIB_PATH):

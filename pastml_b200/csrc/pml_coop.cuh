@@ -1,0 +1,483 @@
+// Warp-cooperative sweeps for the F81 family (F81 / JC / EFT), the headline path.
+//
+// A (node, lane) item is shared by G threads of one warp, each holding KT states (k = r + G i, r = rank in the
+// group): the register footprint drops from ~3 K doubles to ~3 KT, so 5-6 blocks of 128 threads stay resident per SM
+// instead of 2-3, and on the [slot][k][lane] layout the G x J threads of a node read and write one contiguous run
+// (256 B per request for K = 20 states x 8 lanes).  The only cross-thread quantities of the F81 recursion are
+// sum_k pi_k L_k and max_k L_k, two butterfly reductions over the group.  Used when G * J <= 32 (otherwise the
+// thread-per-item kernels of pml_kernels.cuh already coalesce over the lanes).
+#pragma once
+#include "pml_kernels.cuh"
+
+namespace pml {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kCoopBlock = 128;
+
+template <int G>
+struct GroupOps {
+    static constexpr int kSteps = (G >= 32) ? 5 : (G >= 16) ? 4 : (G >= 8) ? 3 : (G >= 4) ? 2 : (G >= 2) ? 1 : 0;
+    int lane, r, J;
+    int pl[kSteps > 0 ? kSteps : 1];   // partner lane of every butterfly step
+    __device__ __forceinline__ GroupOps(int lane_, int r_, int J_) : lane(lane_), r(r_), J(J_) {
+#pragma unroll
+        for (int q = 0; q < kSteps; ++q) pl[q] = lane + ((r ^ (1 << q)) - r) * J;
+    }
+    __device__ __forceinline__ double sum(double v) const {
+#pragma unroll
+        for (int q = 0; q < kSteps; ++q) v += __shfl_sync(kFullMask, v, pl[q]);
+        return v;
+    }
+    __device__ __forceinline__ double max(double v) const {
+#pragma unroll
+        for (int q = 0; q < kSteps; ++q) v = fmax(v, __shfl_sync(kFullMask, v, pl[q]));
+        return v;
+    }
+    __device__ __forceinline__ unsigned long long bit_or(unsigned long long v) const {
+#pragma unroll
+        for (int q = 0; q < kSteps; ++q) v |= __shfl_sync(kFullMask, v, pl[q]);
+        return v;
+    }
+    // arg max with the reference's tie rule (first index): larger value wins, equal values -> smaller index
+    __device__ __forceinline__ void argmax(double &v, int &k) const {
+#pragma unroll
+        for (int q = 0; q < kSteps; ++q) {
+            const double ov = __shfl_sync(kFullMask, v, pl[q]);
+            const int ok = __shfl_sync(kFullMask, k, pl[q]);
+            if (ov > v || (ov == v && ok < k)) { v = ov; k = ok; }
+        }
+    }
+    // value held by the group member of rank `src`
+    __device__ __forceinline__ double from_rank(double v, int src) const {
+        return __shfl_sync(kFullMask, v, lane + (src - r) * J);
+    }
+};
+
+struct CoopLane {   // where a thread sits: which node of the warp's batch, which lane (column), which rank
+    int sub, r, j, c, npw;
+    bool lane_on;
+};
+
+#ifndef PML_COOP_MINB
+#define PML_COOP_MINB 8
+#endif
+
+// resident blocks per SM the kernels are compiled for: 64 registers per thread up to 5 states per thread (measured
+// best for K = 20: more warps in flight beat the few spills), fewer blocks when a thread holds more states
+constexpr int coop_min_blocks(int kt) { return kt <= 5 ? PML_COOP_MINB : kt <= 8 ? 5 : 3; }
+
+template <int G>
+__device__ __forceinline__ CoopLane coop_lane(int J, int C) {
+    const int lane = threadIdx.x & 31;
+    const int gj = G * J;
+    CoopLane cl;
+    cl.npw = 32 / gj;
+    cl.sub = lane / gj;
+    const int rem = lane - cl.sub * gj;
+    cl.r = rem / J;
+    cl.j = rem - cl.r * J;
+    cl.c = cl.j % C;
+    cl.lane_on = cl.sub < cl.npw;
+    return cl;
+}
+
+template <int KT, int G>
+__device__ __forceinline__ int exponent_rescale(double (&v)[KT], double vmax, bool always) {
+    // same policy as rescale<> of the thread-per-item kernels; vmax is the group-wide maximum
+    if (!(vmax > 0.) || isinf(vmax)) return 0;
+    int e = exponent_of(vmax);
+    if (!always && e >= -kKeep && e <= kKeep) return 0;
+    int extra = 0;
+    if (e == -1023) {
+#pragma unroll
+        for (int i = 0; i < KT; ++i) v[i] *= 0x1p+200;
+        e = exponent_of(vmax * 0x1p+200);
+        extra = -200;
+    }
+    if (e != 0) {
+        const int e1 = e / 2, e2 = e - e1;
+        const double s1 = pow2(-e1), s2 = pow2(-e2);
+#pragma unroll
+        for (int i = 0; i < KT; ++i) v[i] = (v[i] * s1) * s2;
+    }
+    return e + extra;
+}
+
+// loads this thread's KT states of a node's bottom-up vector (or of its tip mask); returns the exponent
+// state index r + G i is a real state (always true when K == G * KT, which the KX instantiations know)
+#define PML_VALID(i) (KX || (r + G * (i) < K))
+
+// K and J are passed explicitly so that the instantiations with compile-time K / J fold the address arithmetic
+template <int KT, int G, bool KX>
+__device__ __forceinline__ int coop_load(const TreeDev &t, const ZcDev &zc, const LaneDev &ln, const uint64_t *mask,
+                                         const double *bu, const int *bu_ex, int node, int cs, int r, int j, int c,
+                                         bool use_alt, double (&in)[KT], int K, int J) {
+    if (cs >= 0) {
+        const double *src = bu + ((size_t) (cs * K + r) * J + j);
+#pragma unroll
+        for (int i = 0; i < KT; ++i) in[i] = PML_VALID(i) ? src[(G * i) * J] : 0.;
+        return bu_ex[(size_t) cs * J + j];
+    }
+    const uint64_t m = eff_mask(mask, t, zc, ln.C, node, c, use_alt, ln.kmask) >> r;
+#pragma unroll
+    for (int i = 0; i < KT; ++i) in[i] = bit_as_double(m, G * i);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ bottom-up
+
+// JT > 0: the number of lanes J is the compile-time constant JT; KX: K == G * KT exactly
+template <int KT, int G, int JT, bool KX>
+__global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kernel(BuArgs a, int slot_begin, int n_slots) {
+    extern __shared__ double s_par[];
+    const int J = JT ? JT : a.ln.J, K = KX ? G * KT : a.ln.K, C = a.ln.C;
+    stage_params(s_par, a.ln, 4 + K);
+    const CoopLane cl = coop_lane<G>(J, C);
+    const int r = cl.r, j = cl.j, c = cl.c;
+    const GroupOps<G> grp((int) (threadIdx.x & 31), r, J);
+    const double sf = s_par[j], tau = s_par[J + j], tauf = s_par[2 * J + j], mu = s_par[3 * J + j];
+    double pi[KT];
+#pragma unroll
+    for (int i = 0; i < KT; ++i) pi[i] = PML_VALID(i) ? s_par[(4 + r + G * i) * J + j] : 0.;
+    const bool use_alt = a.alter && tau == 0.;
+    const bool mu_inf = isinf(mu);
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+
+    // the loop is software-pipelined by one step: the packed descriptor (and node id) of the next batch is requested
+    // before the current batch is processed, so that only the vector loads remain on the dependent path
+    const int stride = n_warps * cl.npw;
+    int base = warp_global * cl.npw;
+    int4 nx_top = make_int4(0, 0, 0, 0), nx_len = make_int4(0, 0, 0, 0);
+    int nx_node = 0;
+    if (base < n_slots) {
+        const int sl = base + cl.sub;
+        const size_t slot = (size_t) slot_begin + ((cl.lane_on && sl < n_slots) ? sl : base);
+        nx_top = a.t.bu_desc[2 * slot];
+        nx_len = a.t.bu_desc[2 * slot + 1];
+        nx_node = a.t.int_nodes[slot];
+    }
+    for (; base < n_slots; base += stride) {
+        const int sl = base + cl.sub;
+        const bool on = cl.lane_on && sl < n_slots;
+        const int slot = slot_begin + (on ? sl : base);
+        const int4 d_top = nx_top, d_len = nx_len;
+        const int node = nx_node;
+        if (base + stride < n_slots) {
+            const int nsl = base + stride + cl.sub;
+            const size_t nslot = (size_t) slot_begin + ((cl.lane_on && nsl < n_slots) ? nsl : base + stride);
+            nx_top = a.t.bu_desc[2 * nslot];
+            nx_len = a.t.bu_desc[2 * nslot + 1];
+            nx_node = a.t.int_nodes[nslot];
+        }
+        const int fc = d_top.x, nc = d_top.y;
+        double acc[KT];
+        {
+            const uint64_t m = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask) >> r;
+#pragma unroll
+            for (int i = 0; i < KT; ++i) acc[i] = bit_as_double(m, G * i);   // 10 ** log10(allowed), ml.py:127
+        }
+        int ex = 0;
+        int bad_child = -1;
+        if (__all_sync(kFullMask, nc == 2)) {
+            // binary nodes: both children's vectors are requested before any arithmetic; rank 0 and rank 1 of the
+            // group evaluate one exp each and hand it to the others
+            double in0[KT], in1[KT];
+            const int cs0 = d_top.z, cs1 = d_top.w;
+            const double dmine = (r & 1) ? __hiloint2double(d_len.w, d_len.z) : __hiloint2double(d_len.y, d_len.x);
+            ex += coop_load<KT, G, KX>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, fc, cs0, r, j, c, use_alt, in0, K, J);
+            ex += coop_load<KT, G, KX>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, cs1, r, j, c, use_alt, in1, K, J);
+            const double emine = mu_inf ? 0. : exp(-mu * ((dmine + tau) * tauf * sf));
+            const double e0 = grp.from_rank(emine, 0), e1 = grp.from_rank(emine, 1);
+            double s0 = 0., s1 = 0.;
+#pragma unroll
+            for (int i = 0; i < KT; ++i) { s0 = fma(pi[i], in0[i], s0); s1 = fma(pi[i], in1[i], s1); }
+            s0 = grp.sum(s0);
+            s1 = grp.sum(s1);
+            const double b0 = (1. - e0) * s0, b1 = (1. - e1) * s1;
+            double m0 = 0., m1 = 0.;
+#pragma unroll
+            for (int i = 0; i < KT; ++i) {
+                acc[i] *= fmax(fma(e0, in0[i], b0), 0.);
+                m0 = fmax(m0, acc[i]);
+                acc[i] *= fmax(fma(e1, in1[i], b1), 0.);
+                m1 = fmax(m1, acc[i]);
+            }
+            m1 = grp.max(m1);
+            if (__any_sync(kFullMask, m1 == 0.)) {   // error path only: which child emptied the vector
+                m0 = grp.max(m0);
+                if (m1 == 0.) bad_child = (m0 == 0.) ? fc : fc + 1;
+            }
+            ex += exponent_rescale<KT, G>(acc, m1, false);
+        } else {
+            const int ncmax = __reduce_max_sync(kFullMask, nc);
+            for (int q = 0; q < ncmax; ++q) {
+                const bool valid = q < nc;
+                const int ch = fc + (valid ? q : 0);
+                double in[KT];
+                const int exc = coop_load<KT, G, KX>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, ch, a.t.slot[ch], r, j, c,
+                                                 use_alt, in, K, J);
+                const double e = mu_inf ? 0. : exp(-mu * ((a.t.dist[ch] + tau) * tauf * sf));
+                double s = 0.;
+#pragma unroll
+                for (int i = 0; i < KT; ++i) s = fma(pi[i], in[i], s);
+                s = grp.sum(s);
+                const double b = (1. - e) * s;
+                double mx = 0.;
+#pragma unroll
+                for (int i = 0; i < KT; ++i) {
+                    if (valid) acc[i] *= fmax(fma(e, in[i], b), 0.);
+                    mx = fmax(mx, acc[i]);
+                }
+                mx = grp.max(mx);
+                if (valid) {
+                    ex += exc;
+                    if (mx == 0. && bad_child < 0) bad_child = ch;
+                    ex += exponent_rescale<KT, G>(acc, mx, false);
+                }
+            }
+        }
+        if (on) {
+            if (bad_child >= 0 && r == 0) {   // all entries zero: PastMLLikelihoodError of ml.py:139-145
+                if (atomicCAS(a.err + 2 * j, -1, node) == -1) a.err[2 * j + 1] = bad_child;
+            }
+            double *dst = a.bu + ((size_t) (slot * K + r) * J + j);
+#pragma unroll
+            for (int i = 0; i < KT; ++i)
+                if (PML_VALID(i)) dst[(G * i) * J] = acc[i];
+            if (r == 0) a.bu_ex[(size_t) slot * J + j] = ex;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ top-down sweep
+
+// node-centric fused top-down / marginal / MAP / MPPA step (see td_level_kernel) with the K-vector split over G threads
+template <int KT, int G, int JT, bool KX>
+__global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) td_coop_kernel(TdArgs a, int node_begin, int n_nodes) {
+    extern __shared__ double s_par[];
+    const int C = JT ? JT : a.ln.C, K = KX ? G * KT : a.ln.K;
+    const int nf = 4 + K;
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(s_par + (size_t) nf * C);   // [C][K+1]
+    for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x) sh_hist[i] = 0u;
+    stage_params(s_par, a.ln, nf);
+    const CoopLane cl = coop_lane<G>(C, C);
+    const int r = cl.r, c = cl.j;
+    const GroupOps<G> grp((int) (threadIdx.x & 31), r, C);
+    const double sf = s_par[c], tau = s_par[C + c], tauf = s_par[2 * C + c], mu = s_par[3 * C + c];
+    double pi[KT];
+#pragma unroll
+    for (int i = 0; i < KT; ++i) pi[i] = PML_VALID(i) ? s_par[(4 + r + G * i) * C + c] : 0.;
+    const bool use_alt = tau == 0.;   // ml.py:702-703
+    const bool mu_inf = isinf(mu);
+    const bool fj = a.force_joint != 0;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+
+    const int stride = n_warps * cl.npw;
+    int base = warp_global * cl.npw;
+    int4 nx_desc = make_int4(-1, -1, 0, 0);
+    if (base < n_nodes) {
+        const int nd = base + cl.sub;
+        nx_desc = a.t.td_desc[node_begin + ((cl.lane_on && nd < n_nodes) ? nd : base)];
+    }
+    for (; base < n_nodes; base += stride) {
+        const int nd = base + cl.sub;
+        const bool on = cl.lane_on && nd < n_nodes;
+        const int node = node_begin + (on ? nd : base);
+        const int4 desc = nx_desc;   // {parent slot, own slot, dist}
+        if (base + stride < n_nodes) {
+            const int nnd = base + stride + cl.sub;
+            nx_desc = a.t.td_desc[node_begin + ((cl.lane_on && nnd < n_nodes) ? nnd : base + stride)];
+        }
+        const int ps = desc.x;
+        const int cs = desc.y;
+        const size_t nc = (size_t) node * C + c;
+
+        double Lc[KT], X[KT];
+        const int exc = coop_load<KT, G, KX>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, node, cs, r, c, c, use_alt, Lc, K, C);
+        const uint64_t base_mask = a.mask[nc];
+        const uint64_t flag = base_mask & kMemberFlag;
+        const uint64_t allowed = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
+        int ex_total = exc;
+        const bool has_parent = ps >= 0;
+        // parent part of the node's top-down vector: TD_p * L_p (all ones above a root, ml.py:274-277)
+        int pex = 0;
+        if (has_parent) {
+            const size_t off = (size_t) (ps * K + r) * C + c;
+            const double *src = a.bu + off;
+#pragma unroll
+            for (int i = 0; i < KT; ++i) X[i] = PML_VALID(i) ? src[(G * i) * C] : 0.;
+            pex = a.bu_ex[(size_t) ps * C + c];
+            if (ps >= a.t.n_root_slots) {
+                const double *src2 = a.td + off;
+#pragma unroll
+                for (int i = 0; i < KT; ++i) X[i] *= PML_VALID(i) ? src2[(G * i) * C] : 0.;
+                pex += a.td_ex[(size_t) ps * C + c];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < KT; ++i) X[i] = 1.;
+        }
+        // the branch above the node: rank 0 evaluates the exponential for its group
+        double e = 0.;
+        if (r == 0 && !mu_inf) e = exp(-mu * ((__hiloint2double(desc.w, desc.z) + tau) * tauf * sf));
+        e = grp.from_rank(e, 0);
+        const double ome = 1. - e;
+        // node_contribution = P L_node (ml.py:280); q = TD_p L_p / contribution, contribution <= 0 -> 1 (ml.py:281-283)
+        double s = 0.;
+#pragma unroll
+        for (int i = 0; i < KT; ++i) s = fma(pi[i], Lc[i], s);
+        s = grp.sum(s);
+        double q[KT];
+#pragma unroll
+        for (int i = 0; i < KT; ++i) {
+            const double cv = fmax(fma(e, Lc[i], ome * s), 0.);
+            q[i] = (cv > 0.) ? X[i] * __drcp_rn(cv) : X[i];
+        }
+        double s2 = 0.;
+#pragma unroll
+        for (int i = 0; i < KT; ++i) s2 = fma(pi[i], q[i], s2);
+        s2 = grp.sum(s2);
+        // keeping the vector in range (ml.py:284-286): the frequency-weighted sum is already reduced over the group
+        // and is within a factor 1/min(pi) of the maximum, so its exponent decides the power-of-two rescale
+        int qex = pex - exc;
+        double scale = 1.;
+        if (s2 > 0. && !isinf(s2)) {
+            const int e2 = exponent_of(s2);
+            if (e2 < -kKeep || e2 > kKeep) {
+                const int ee = (e2 == -1023) ? -1022 : e2;
+                scale = pow2(-ee / 2) * pow2(-(ee - ee / 2));
+                if (!(scale > 0.) || isinf(scale)) { scale = (ee > 0) ? 0x1p-1000 : 0x1p+1000; qex += (ee > 0) ? 1000 : -1000; }
+                else qex += ee;
+            }
+        }
+        double tdv[KT];
+#pragma unroll
+        for (int i = 0; i < KT; ++i)
+            tdv[i] = PML_VALID(i) ? fmax(fma(e, q[i], ome * s2), 0.) * scale : 0.;   // ml.py:288-289
+        if (has_parent) {
+            if (cs >= 0) {
+                if (on) {
+                    double *dst = a.td + ((size_t) (cs * K + r) * C + c);
+#pragma unroll
+                    for (int i = 0; i < KT; ++i)
+                        if (PML_VALID(i)) dst[(G * i) * C] = tdv[i];
+                    if (r == 0) a.td_ex[(size_t) cs * C + c] = qex;
+                }
+            }
+            ex_total = qex + exc;
+        }
+        // marginal likelihood vector (ml.py:454-465): L * TD * pi * allowed
+        double m[KT];
+        double sum = 0.;
+        const uint64_t allowed_r = allowed >> r;
+#pragma unroll
+        for (int i = 0; i < KT; ++i) {
+            const double tdi = has_parent ? tdv[i] : 1.;
+            m[i] = ((allowed_r >> (G * i)) & 1ULL) ? Lc[i] * tdi * pi[i] : 0.;
+            sum += m[i];
+        }
+        sum = grp.sum(sum);
+        double inv = __drcp_rn(sum);
+        if (on) {
+            if (a.probs) {
+                double *dst = a.probs + nc * K + r;
+#pragma unroll
+                for (int i = 0; i < KT; ++i)
+                    if (PML_VALID(i)) dst[G * i] = m[i] * inv;
+            }
+            // the logarithm is taken by log10_finish_kernel over the whole array afterwards: here it would be
+            // evaluated by one rank per group with the rest of the warp idle
+            if (a.node_log10lh && r == 0) {
+                a.node_log10lh[nc] = sum;
+                a.node_ex[nc] = ex_total;
+            }
+        }
+        // members of zero-branch clusters: remember the vector, apply '.initial' (ml.py:593-594)
+        uint64_t init = a.ln.kmask;
+        size_t zr = 0;
+        if (flag) {
+            zr = (size_t) a.t.zc_index[node] * C + c;
+            if (on) {
+                double *z = a.zc_lh + zr * K + r;
+#pragma unroll
+                for (int i = 0; i < KT; ++i)
+                    if (PML_VALID(i)) z[G * i] = m[i];
+            }
+            if (a.zc.hasinit[zr]) init = a.zc.initial[zr];
+        }
+        if (__any_sync(kFullMask, flag != 0ULL)) {   // rare: some node of the warp's batch sits in a zero-branch cluster
+            double sum2 = 0.;
+            const uint64_t init_r = init >> r;
+#pragma unroll
+            for (int i = 0; i < KT; ++i) {
+                m[i] = ((init_r >> (G * i)) & 1ULL) ? m[i] : 0.;
+                sum2 += m[i];
+            }
+            sum2 = grp.sum(sum2);
+            if (flag) { sum = sum2; inv = 1. / sum2; }
+        }
+        // MAP: first arg max (ml.py:595)
+        double bv = -1.;
+        int best = 0;
+#pragma unroll
+        for (int i = 0; i < KT; ++i)
+            if (PML_VALID(i) && m[i] > bv) { bv = m[i]; best = r + G * i; }
+        grp.argmax(bv, best);
+        const int ji = fj ? a.joint_state[nc] : best;
+        // MPPA (ml.py:539-572), see mppa_select in pml_kernels.cuh for the derivation
+        int best_k = 1;
+        uint64_t sel = 1ULL << best;
+        bool done = true;
+        if (!(sum > 0.)) { sel = a.ln.kmask; best_k = K; }
+        else if (!(bv * inv >= 0.76 && ji == best)) done = false;
+        if (!__all_sync(kFullMask, done)) {
+            double pj = 0.;
+#pragma unroll
+            for (int i = 0; i < KT; ++i) pj += (r + G * i == ji) ? m[i] * inv : 0.;
+            pj = grp.sum(pj);
+            unsigned used = 0u, best_used = 0u;
+            double run = 0., best_score = CUDART_INF;
+            bool joint_seen = false;
+            int bk = K;
+            for (int k = 1; k <= K; ++k) {
+                if (__all_sync(kFullMask, done)) break;
+                double lv = -1.;
+                int lk = 1 << 20;
+#pragma unroll
+                for (int i = 0; i < KT; ++i)
+                    if (PML_VALID(i) && !((used >> i) & 1u) && m[i] > lv) { lv = m[i]; lk = r + G * i; }
+                grp.argmax(lv, lk);
+                if (!done) {
+                    if (lk < K && lk >= r && (lk - r) % G == 0) used |= 1u << ((lk - r) / G);
+                    const double prev = run;
+                    run += lv * inv;
+                    joint_seen = joint_seen || (lk == ji);
+                    const double tk = (!fj || joint_seen) ? run : pj + prev;
+                    const double score = (1. - 2. * tk) / (double) k;
+                    if (score < best_score) { best_score = score; bk = k; best_used = used; }
+                    else if (score > best_score + 1e-9) done = true;
+                    if (k == K) done = true;
+                }
+            }
+            unsigned long long mine = 0ULL;
+#pragma unroll
+            for (int i = 0; i < KT; ++i)
+                if ((best_used >> i) & 1u) mine |= 1ULL << (r + G * i);
+            mine = grp.bit_or(mine);
+            if (sum > 0. && !(bv * inv >= 0.76 && ji == best)) { sel = mine; best_k = bk; }
+        }
+        if (on && r == 0) {
+            a.map_mask[nc] = (1ULL << best) | flag;
+            a.mppa_mask[nc] = sel | flag;
+            if (flag) a.zc_k[zr] = (uint8_t) best_k;
+            atomicAdd(sh_hist + c * (K + 1) + best_k, 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x)
+        if (sh_hist[i]) atomicAdd(a.k_hist + i, (unsigned long long) sh_hist[i]);
+}
+
+}  // namespace pml

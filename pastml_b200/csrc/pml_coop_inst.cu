@@ -1,0 +1,55 @@
+// One (G, KT) instantiation of the warp-cooperative F81 sweeps.  Compile with -DPML_G=<threads per item>
+// -DPML_KT=<states per thread>; optionally -DPML_JT=<lanes> for a variant with compile-time lane count and
+// K == G * KT (address arithmetic folded into immediates).
+#include "pml_coop.cuh"
+#include "pml_launch.h"
+
+#if !defined(PML_G) || !defined(PML_KT)
+#error "PML_G and PML_KT must be defined"
+#endif
+
+namespace pml {
+namespace {
+#ifndef PML_JT
+#define PML_JT 0
+#endif
+constexpr int G = PML_G, KT = PML_KT, JT = PML_JT;
+constexpr bool KX = JT != 0;
+constexpr size_t kMaxDynSmem = 200 * 1024;
+#ifndef PML_COOP_GRID
+#define PML_COOP_GRID 8
+#endif
+
+unsigned coop_grid(int n, int lanes) {
+    const int per_block = (kCoopBlock / 32) * (32 / (G * lanes));
+    long long g = ((long long) n + per_block - 1) / per_block;
+    const long long cap = 148LL * PML_COOP_GRID;   // one resident wave; the kernels loop (and prefetch) beyond it
+    if (g > cap) g = cap;
+    return (unsigned) (g < 1 ? 1 : g);
+}
+
+void bu_launch(cudaStream_t st, const BuArgs &a, int s0, int ns) {
+    const size_t sh = sizeof(double) * (4 + a.ln.K) * a.ln.J;
+    if (sh > 48 * 1024)
+        cudaFuncSetAttribute(bu_coop_kernel<KT, G, JT, KX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+    bu_coop_kernel<KT, G, JT, KX><<<coop_grid(ns, a.ln.J), kCoopBlock, sh, st>>>(a, s0, ns);
+}
+
+void td_launch(cudaStream_t st, const TdArgs &a, int n0, int nn) {
+    const size_t sh = sizeof(double) * (4 + a.ln.K) * a.ln.C + sizeof(unsigned) * a.ln.C * (a.ln.K + 1);
+    if (sh > 48 * 1024)
+        cudaFuncSetAttribute(td_coop_kernel<KT, G, JT, KX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+    td_coop_kernel<KT, G, JT, KX><<<coop_grid(nn, a.ln.C), kCoopBlock, sh, st>>>(a, n0, nn);
+}
+}  // namespace
+
+#define PML_CS_NAME3(g, k, j) pml_coop_##g##_##k##_##j
+#define PML_CS_NAME2(g, k, j) PML_CS_NAME3(g, k, j)
+#define PML_CS_NAME PML_CS_NAME2(PML_G, PML_KT, PML_JT)
+
+const CoopSet *PML_CS_NAME() {
+    static const CoopSet cs = {bu_launch, td_launch, G, KT, JT};
+    return &cs;
+}
+
+}  // namespace pml

@@ -64,6 +64,7 @@ struct pml_problem {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // topology
     DevBuf<int> parent, first_child, n_children, slot, int_nodes, zc_index, roots, fc_slot, nc_slot, pslot;
+    DevBuf<int4> bu_desc, td_desc;
     int n_root_slots = 0;
     DevBuf<double> dist;
     // zero clusters
@@ -77,7 +78,7 @@ struct pml_problem {
     bool mask_valid[5] = {false, false, false, false, false};
     // state
     DevBuf<double> params, bu, td, probs, node_lh, out_lh;
-    DevBuf<int> bu_ex, td_ex, err, joint_state, steps_num;
+    DevBuf<int> bu_ex, td_ex, err, joint_state, steps_num, node_ex;
     DevBuf<uint8_t> ptr;
     DevBuf<unsigned long long> k_hist;
     DevBuf<uint64_t> scratch_a, scratch_b, scratch_c;
@@ -94,7 +95,7 @@ struct pml_problem {
 
     TreeDev tree() const {
         return TreeDev{N, NI, parent.ptr, first_child.ptr, n_children.ptr, slot.ptr, int_nodes.ptr, dist.ptr,
-                       zc_index.ptr, fc_slot.ptr, nc_slot.ptr, pslot.ptr, n_root_slots};
+                       zc_index.ptr, fc_slot.ptr, nc_slot.ptr, pslot.ptr, n_root_slots, bu_desc.ptr, td_desc.ptr};
     }
     ZcDev zc() const { return ZcDev{zc_alt.ptr, zc_altflag.ptr, zc_initial.ptr, zc_hasinit.ptr, zc_touched.ptr}; }
     LaneDev lanes(int n_sets) const {
@@ -104,6 +105,8 @@ struct pml_problem {
 };
 
 namespace {
+
+const CoopSet *pick_coop(const pml_problem *p, int J);
 
 void run_root_loglik(pml_problem *p, const LaneDev &ln, const uint64_t *mask, int alter, int is_marginal) {
     p->ks->root_loglik(p->stream, p->tree(), p->zc(), ln, mask, alter, p->bu.ptr, p->bu_ex.ptr, p->roots.ptr,
@@ -142,9 +145,15 @@ void run_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marg
     BuArgs a{p->tree(), p->zc(), ln, mask, alter, p->bu.ptr, p->bu_ex.ptr, keep_ptr ? p->ptr.ptr : nullptr,
              p->err.ptr};
     const bool maxp = !is_marginal;
+    const CoopSet *coop = maxp ? nullptr : pick_coop(p, ln.J);
     for (int lvl = p->n_levels - 1; lvl >= 0; --lvl) {
         const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
         if (ns <= 0) continue;
+        if (coop) {
+            coop->bu(p->stream, a, s0, ns);
+            p->launches++;
+            continue;
+        }
         const int chunk = (int) std::max<long long>(1, kMaxItemsPerLaunch / ln.J);
         for (int off = 0; off < ns; off += chunk) {
             p->ks->bu(p->stream, a, maxp, s0 + off, std::min(chunk, ns - off));
@@ -201,6 +210,7 @@ int ensure_marginal_buffers(pml_problem *p, bool want_probs, bool want_node_lh) 
     if (!p->td_ex.ptr && p->NI) CUDA_TRY(p->td_ex.alloc((size_t) p->NI * p->C));
     if (want_probs && !p->probs.ptr) CUDA_TRY(p->probs.alloc((size_t) p->N * p->C * p->K));
     if (want_node_lh && !p->node_lh.ptr) CUDA_TRY(p->node_lh.alloc((size_t) p->N * p->C));
+    if (want_node_lh && !p->node_ex.ptr) CUDA_TRY(p->node_ex.alloc((size_t) p->N * p->C));
     if (!p->k_hist.ptr) CUDA_TRY(p->k_hist.alloc((size_t) p->C * (p->K + 1)));
     return PML_OK;
 }
@@ -211,15 +221,26 @@ void run_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_no
     cudaMemsetAsync(p->k_hist.ptr, 0, sizeof(unsigned long long) * p->C * (p->K + 1), p->stream);
     TdArgs a{p->tree(), p->zc(), ln, p->mask[PML_MASK_ANNOTATION].ptr, p->bu.ptr, p->bu_ex.ptr, p->td.ptr,
              p->td_ex.ptr, p->joint_state.ptr, force_joint, want_probs ? p->probs.ptr : nullptr,
-             want_node_lh ? p->node_lh.ptr : nullptr, p->mask[PML_MASK_MAP].ptr, p->mask[PML_MASK_MPPA].ptr,
+             want_node_lh ? p->node_lh.ptr : nullptr, p->node_ex.ptr, p->mask[PML_MASK_MAP].ptr, p->mask[PML_MASK_MPPA].ptr,
              p->k_hist.ptr, p->zc_lh.ptr, p->zc_k.ptr};
+    const CoopSet *coop = pick_coop(p, ln.C);
     for (int lvl = 0; lvl < p->n_levels; ++lvl) {
         const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
+        if (coop) {
+            coop->td(p->stream, a, n0, nn);
+            p->launches++;
+            continue;
+        }
         const int chunk = (int) std::max<long long>(1, kMaxItemsPerLaunch / ln.C);
         for (int off = 0; off < nn; off += chunk) {
             p->ks->td(p->stream, a, n0 + off, std::min(chunk, nn - off));
             p->launches++;
         }
+    }
+    if (coop && want_node_lh) {
+        const long long n = (long long) p->N * p->C;
+        log10_finish_kernel<<<grid_for(n), kBlock, 0, p->stream>>>(n, p->node_lh.ptr, p->node_ex.ptr);
+        p->launches++;
     }
 }
 
@@ -257,6 +278,54 @@ const KernelSet *kernel_set(int family, int kp) {
     return nullptr;
 }
 }  // namespace pml
+
+namespace pml {
+#define PML_CDECL(g, k, j) const CoopSet *pml_coop_##g##_##k##_##j();
+#define PML_CCASE(g, k, j) if (gg == g && kt == k && jt == j) return pml_coop_##g##_##k##_##j();
+#ifdef PML_ONLY_F81_20
+#define PML_COOP_ALL(X) X(4, 5, 0) X(4, 5, 8) X(2, 10, 8)
+#else
+#define PML_COOP_ALL(X) X(2, 2, 0) X(2, 3, 0) X(2, 4, 0) X(2, 5, 0) X(2, 6, 0) X(2, 8, 0) X(2, 10, 0) X(2, 12, 0) X(2, 16, 0) \
+                        X(4, 2, 0) X(4, 3, 0) X(4, 4, 0) X(4, 5, 0) X(4, 6, 0) X(4, 8, 0) X(4, 10, 0) X(4, 12, 0) X(4, 16, 0) \
+                        X(8, 2, 0) X(8, 3, 0) X(8, 4, 0) X(8, 5, 0) X(8, 6, 0) X(8, 8, 0) X(16, 2, 0) X(16, 3, 0) X(16, 4, 0) \
+                        X(32, 2, 0) X(4, 5, 8) X(2, 5, 16) X(2, 5, 8) X(4, 5, 4) X(2, 2, 16) X(2, 2, 8) X(2, 10, 8)
+#endif
+PML_COOP_ALL(PML_CDECL)
+const CoopSet *coop_set(int gg, int kt, int jt) {
+    PML_COOP_ALL(PML_CCASE)
+    return nullptr;
+}
+}  // namespace pml
+
+namespace {
+// Picks the cooperative configuration for K states and J lanes: G * J <= 32 threads per node, KT = the smallest
+// built size >= ceil(K / G); least padding first, then the larger group.  nullptr -> thread-per-item kernels.
+const CoopSet *pick_coop(const pml_problem *p, int J) {
+    static const bool disabled = getenv("PASTML_B200_NO_COOP") != nullptr;
+    if (disabled || p->kind != PML_MODEL_F81 || J > 16 || p->K < 3) return nullptr;
+    const int kts[] = {2, 3, 4, 5, 6, 8, 10, 12, 16};
+    const CoopSet *best = nullptr;
+    double best_score = 1e30;
+    static const int forced_g = getenv("PASTML_B200_COOP_G") ? atoi(getenv("PASTML_B200_COOP_G")) : 0;   // tuning aid
+    for (int g = 2; g <= 32 && g * J <= 32; g <<= 1) {
+        if (forced_g && g != forced_g) continue;
+        const int need = (p->K + g - 1) / g;
+        for (int kt : kts) {
+            if (kt < need) continue;
+            const CoopSet *cs = coop_set(g, kt, 0);
+            if (!cs) break;
+            if (g * kt == p->K) {   // a variant with compile-time lane count and state count, when built
+                const CoopSet *exact = coop_set(g, kt, J);
+                if (exact) cs = exact;
+            }
+            const double score = (double) (g * kt - p->K) / p->K + (kt < 3 ? 0.5 : 0.) + (kt > 8 ? 0.25 : 0.) - 1e-3 * g;
+            if (score < best_score) { best_score = score; best = cs; }
+            break;
+        }
+    }
+    return best;
+}
+}  // namespace
 
 // ====================================================================================== C ABI
 
@@ -428,6 +497,24 @@ int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dis
         PML_UPLOAD(p->nc_slot, ncs);
         PML_UPLOAD(p->pslot, ps);
         p->n_root_slots = int_level_ptr[1];
+        std::vector<int4> bd(2 * (size_t) NI), td((size_t) N);
+        for (int s = 0; s < NI; ++s) {
+            const int f = fcs[s], n = ncs[s];
+            const double d0 = dist[f], d1 = n > 1 ? dist[f + 1] : 0.;
+            bd[2 * s] = make_int4(f, n, slot[f], n > 1 ? slot[f + 1] : -1);
+            int4 w;
+            std::memcpy(&w.x, &d0, 8);
+            std::memcpy(&w.z, &d1, 8);
+            bd[2 * s + 1] = w;
+        }
+        for (int v = 0; v < N; ++v) {
+            int4 w = make_int4(ps[v], slot[v], 0, 0);
+            const double d = dist[v];
+            std::memcpy(&w.z, &d, 8);
+            td[v] = w;
+        }
+        PML_UPLOAD(p->bu_desc, bd);
+        PML_UPLOAD(p->td_desc, td);
     }
     PML_UPLOAD(p->zc_index, zc_index);
     PML_UPLOAD(p->roots, roots);

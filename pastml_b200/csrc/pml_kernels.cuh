@@ -42,6 +42,10 @@ struct TreeDev {
     const int *nc_slot;      // [NI] number of children of the slot's node
     const int *pslot;        // [N]  slot of the parent, -1 for roots
     int n_root_slots;        // internal roots occupy slots [0, n_root_slots)
+    const int4 *bu_desc;     // [NI][2] packed {first child, #children, slot of child 0, slot of child 1} +
+                             //         {dist of child 0, dist of child 1}: everything the bottom-up step needs to
+                             //         issue its vector loads after ONE dependent load
+    const int4 *td_desc;     // [N]     packed {parent slot, own slot, dist (2 words)} for the top-down step
 };
 
 struct ZcDev {              // zero-branch cluster table, rows x C
@@ -622,6 +626,7 @@ struct TdArgs {
     int force_joint;
     double *probs;              // [N][C][K] or null
     double *node_log10lh;       // [N][C] or null
+    int *node_ex;               // [N][C] exponent of the raw sums the cooperative kernel leaves in node_log10lh
     uint64_t *map_mask;         // [N][C]
     uint64_t *mppa_mask;        // [N][C]
     unsigned long long *k_hist; // [C][K+1]
@@ -1009,6 +1014,13 @@ static __global__ void init_masks_kernel(int N, int C, uint64_t kmask, const uin
     if (apply_default && !m) m = kmask;
     if (member_cn && member_cn[(size_t) c * N + node]) m |= kMemberFlag;
     base_nc[g] = m;
+}
+
+// node_log10lh holds sum of the node's marginal mantissas, node_ex its power-of-two exponent: take the logarithm
+// (all lanes busy, instead of one rank per group inside the sweep)
+static __global__ void log10_finish_kernel(long long n, double *v, const int *ex) {
+    const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) v[g] = log10(v[g]) + (double) ex[g] * 0.30102999566398119521;
 }
 
 static __global__ void strip_flag_kernel(long long n, uint64_t kmask, const uint64_t *in, uint64_t *out) {

@@ -28,4 +28,12 @@ inline unsigned grid_for(long long items) {
 // family: 0 = F81, 1 = HKY, 2 = EIG (PML_MODEL_*); returns nullptr when the combination is not built
 const KernelSet *kernel_set(int family, int kp);
 
+// Warp-cooperative F81 sweeps (pml_coop.cuh): G threads per (node, lane) item, KT states per thread.
+struct CoopSet {
+    void (*bu)(cudaStream_t, const BuArgs &, int slot_begin, int n_slots);
+    void (*td)(cudaStream_t, const TdArgs &, int node_begin, int n_nodes);
+    int G, KT, JT;   // JT > 0: built for exactly JT lanes and K == G * KT
+};
+const CoopSet *coop_set(int g, int kt, int jt);   // nullptr when not built
+
 }  // namespace pml

@@ -29,10 +29,22 @@ def build_variant(spec):
     for i, line in enumerate(lines):
         if 'Compiling entry function' in line and ('bu_level_kernelILi20ENS_7F81LaneELb0' in line or 'td_level' in line):
             info.append(('bu' if 'bu_level' in line else 'td') + ': ' + ' | '.join(x.replace('ptxas info    : ', '').strip() for x in lines[i + 2:i + 4]))
+    objs = [o1, o2]
+    for g, kt, jt in ((4, 5, 0), (4, 5, 8), (2, 10, 8)):
+        o3 = os.path.join(OUT, name + '_coop{}_{}_{}.o'.format(g, kt, jt))
+        objs.append(o3)
+        res = subprocess.run(['nvcc'] + FLAGS + defs + ['-Xptxas', '-v', '-DPML_G={}'.format(g), '-DPML_KT={}'.format(kt), '-DPML_JT={}'.format(jt),
+                                                        '-c', os.path.join(CSRC, 'pml_coop_inst.cu'), '-o', o3],
+                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, check=True)
+        lines = res.stdout.splitlines()
+        for i, line in enumerate(lines):
+            if 'Compiling entry function' in line and 'coop_kernel' in line:
+                info.append(('bu_coop' if 'bu_coop' in line else 'td_coop') + ' G={} KT={} JT={}: '.format(g, kt, jt) + ' | '.join(
+                    x.replace('ptxas info    : ', '').strip() for x in lines[i + 2:i + 4]))
     lib = os.path.join(OUT, 'lib_' + name + '.so')
-    subprocess.check_call(['nvcc', '--shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', lib, o1, o2])
-    os.remove(o1)
-    os.remove(o2)
+    subprocess.check_call(['nvcc', '--shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', lib] + objs)
+    for o in objs:
+        os.remove(o)
     return name, info
 
 
