@@ -106,7 +106,7 @@ class ClockSampler(object):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         self._thread = threading.Thread(target=self._run, daemon=True)

@@ -133,6 +133,10 @@ int pml_zero_likelihood_info(pml_problem *p, int32_t *column, int32_t *param_set
  * was fine.  out_pairs[n_lanes][2], lane = param_set * C + column. */
 int pml_zero_likelihood_all(pml_problem *p, int32_t *out_pairs, int32_t n_lanes);
 
+/* Device buffers of destroyed problems are kept in a per-process cache and reused by the next problem of the same
+ * shape (cudaMalloc/cudaFree of GBs cost more than the sweeps).  This returns the cached blocks to the driver. */
+int pml_trim_memory(void);
+
 /* Timing of the last call on this handle: device time between the first and last kernel of the call, measured
  * with CUDA events on the handle's stream (ms), and the number of kernels launched. */
 int pml_last_call_stats(pml_problem *p, double *device_ms, int64_t *kernel_launches);

@@ -4,6 +4,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -28,6 +30,92 @@ int fail(int code, const std::string &msg) {
             return fail(PML_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
     } while (0)
 
+// Device memory is recycled through a small per-process cache: creating and destroying problems of the same
+// shape (the end-to-end path, one problem per call) would otherwise spend longer in cudaMalloc / cudaFree than in
+// the kernels.  pml_trim_memory() returns the cached blocks to the driver.
+class DevicePool {
+    std::mutex mu_;
+    std::multimap<std::pair<int, size_t>, void *> free_;   // (device, bytes) -> block
+    size_t cached_ = 0;
+    static constexpr size_t kMaxCached = 48ull << 30;
+public:
+    cudaError_t get(size_t bytes, void **out) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            auto it = free_.find({dev, bytes});
+            if (it != free_.end()) {
+                *out = it->second;
+                free_.erase(it);
+                cached_ -= bytes;
+                return cudaSuccess;
+            }
+        }
+        cudaError_t rc = cudaMalloc(out, bytes);
+        if (rc != cudaSuccess) {   // give the cache back and retry once
+            trim();
+            cudaGetLastError();
+            rc = cudaMalloc(out, bytes);
+        }
+        return rc;
+    }
+    void put(void *ptr, size_t bytes) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lock(mu_);
+        if (bytes < (1u << 20) || cached_ + bytes > kMaxCached) { cudaFree(ptr); return; }
+        free_.insert({{dev, bytes}, ptr});
+        cached_ += bytes;
+    }
+    void trim() {
+        std::lock_guard<std::mutex> lock(mu_);
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (auto &kv : free_) { cudaSetDevice(kv.first.first); cudaFree(kv.second); }
+        cudaSetDevice(cur);
+        free_.clear();
+        cached_ = 0;
+    }
+};
+DevicePool g_pool;
+
+// Pinned host staging arena (cached, grown on demand) for the arrays pml_problem_create derives and uploads.
+struct HostStage {
+    std::mutex mu;
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    std::vector<std::pair<char *, size_t>> overflow;   // blocks taken after the arena filled up (kept until reset)
+    void reset(size_t at_least = 0) {
+        size_t want = std::max(used, at_least);
+        for (auto &b : overflow) { want += b.second; cudaFreeHost(b.first); }
+        overflow.clear();
+        if (want > cap) {   // regrow to what the previous call needed
+            if (base) cudaFreeHost(base);
+            base = nullptr;
+            cap = 0;
+            if (cudaHostAlloc((void **) &base, want + (want >> 3), cudaHostAllocDefault) == cudaSuccess) cap = want + (want >> 3);
+            else cudaGetLastError();
+        }
+        used = 0;
+    }
+    template <typename T>
+    T *take(size_t n) {
+        const size_t bytes = ((n * sizeof(T)) + 255) & ~size_t(255);
+        if (bytes == 0) return reinterpret_cast<T *>(base ? base : nullptr);
+        if (used + bytes <= cap) {
+            T *out = reinterpret_cast<T *>(base + used);
+            used += bytes;
+            return out;
+        }
+        char *blk = nullptr;
+        if (cudaHostAlloc((void **) &blk, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        overflow.push_back({blk, bytes});
+        return reinterpret_cast<T *>(blk);
+    }
+};
+HostStage g_stage;
+
 template <typename T>
 struct DevBuf {
     T *ptr = nullptr;
@@ -36,10 +124,10 @@ struct DevBuf {
         release();
         count = n;
         if (n == 0) return cudaSuccess;
-        return cudaMalloc((void **) &ptr, n * sizeof(T));
+        return g_pool.get(n * sizeof(T), (void **) &ptr);
     }
     void release() {
-        if (ptr) cudaFree(ptr);
+        if (ptr) g_pool.put(ptr, count * sizeof(T));
         ptr = nullptr;
         count = 0;
     }
@@ -212,6 +300,8 @@ int ensure_marginal_buffers(pml_problem *p, bool want_probs, bool want_node_lh) 
     if (want_node_lh && !p->node_lh.ptr) CUDA_TRY(p->node_lh.alloc((size_t) p->N * p->C));
     if (want_node_lh && !p->node_ex.ptr) CUDA_TRY(p->node_ex.alloc((size_t) p->N * p->C));
     if (!p->k_hist.ptr) CUDA_TRY(p->k_hist.alloc((size_t) p->C * (p->K + 1)));
+    if (!p->mask[PML_MASK_MAP].ptr) CUDA_TRY(p->mask[PML_MASK_MAP].alloc((size_t) p->N * p->C));
+    if (!p->mask[PML_MASK_MPPA].ptr) CUDA_TRY(p->mask[PML_MASK_MPPA].alloc((size_t) p->N * p->C));
     return PML_OK;
 }
 
@@ -242,6 +332,14 @@ void run_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_no
         log10_finish_kernel<<<grid_for(n), kBlock, 0, p->stream>>>(n, p->node_lh.ptr, p->node_ex.ptr);
         p->launches++;
     }
+}
+
+int ensure_joint_buffers(pml_problem *p) {
+    const size_t nc = (size_t) p->N * p->C;
+    if (!p->ptr.ptr) CUDA_TRY(p->ptr.alloc(nc * p->K));
+    if (!p->joint_state.ptr) CUDA_TRY(p->joint_state.alloc(nc));
+    if (!p->mask[PML_MASK_JOINT].ptr) CUDA_TRY(p->mask[PML_MASK_JOINT].alloc(nc));
+    return PML_OK;
 }
 
 int copy_masks_out(pml_problem *p, const uint64_t *dev, uint64_t *host) {
@@ -371,51 +469,89 @@ int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dis
     CUDA_TRY(cudaSetDevice(device));
 
     const int N = n_nodes, C = n_columns, K = n_states;
-    // ---- topology checks and derived arrays (level order: parents non-decreasing and before children)
-    std::vector<int> nch(N, 0), fch(N, 0), slot(N, -1), roots;
+    // ---- topology checks and derived arrays (level order: parents non-decreasing and before children), built
+    // straight into a cached pinned staging arena so that the uploads run at PCIe speed
+    std::lock_guard<std::mutex> stage_lock(g_stage.mu);
+    g_stage.reset((size_t) N * 80 + (1u << 16));   // upper bound of what the derived arrays need
+    int *nch = g_stage.take<int>(N), *fch = g_stage.take<int>(N), *slot = g_stage.take<int>(N);
+    int *zc_index = g_stage.take<int>(N), *ps = g_stage.take<int>(N);
+    if (!nch || !fch || !slot || !zc_index || !ps) return fail(PML_ERR_CUDA, "could not allocate pinned staging memory");
+    std::memset(nch, 0, sizeof(int) * (size_t) N);
+    int n_roots = 0;
+    bool any_zero = false;
     for (int v = 0; v < N; ++v) {
         const int q = parent[v];
         if (q >= v) return fail(PML_ERR_INVALID, "nodes are not in level order (a parent must precede its children)");
         if (v > 0 && q < parent[v - 1]) return fail(PML_ERR_INVALID, "nodes are not in level order (parents must be non-decreasing)");
-        if (q < 0) roots.push_back(v);
-        else nch[q]++;
+        if (q < 0) ++n_roots;
+        else {
+            nch[q]++;
+            any_zero |= (dist[v] == 0.);
+        }
     }
-    if (roots.empty() || roots.back() != (int) roots.size() - 1)
-        return fail(PML_ERR_INVALID, "roots must come first in level order");
+    if (n_roots < 1 || parent[n_roots - 1] >= 0) return fail(PML_ERR_INVALID, "roots must come first in level order");
+    std::vector<int> roots(n_roots);
+    for (int r = 0; r < n_roots; ++r) roots[r] = r;
+    int NI = 0;
     {
-        long long next = (long long) roots.size();
-        for (int v = 0; v < N; ++v) { fch[v] = (int) next; next += nch[v]; }
+        long long next = n_roots;
+        for (int v = 0; v < N; ++v) {
+            fch[v] = (int) next;
+            next += nch[v];
+            slot[v] = nch[v] ? NI++ : -1;
+        }
         if (next != N) return fail(PML_ERR_INVALID, "inconsistent parent array");
     }
-    std::vector<int> level_ptr{0, (int) roots.size()};
-    while (level_ptr.back() < N) {
-        const int lo = level_ptr[level_ptr.size() - 2], hi = level_ptr.back();
-        long long nxt = hi;
-        for (int v = lo; v < hi; ++v) nxt += nch[v];
-        if (nxt == hi) return fail(PML_ERR_INVALID, "disconnected nodes");
-        level_ptr.push_back((int) nxt);
+    int *int_nodes = g_stage.take<int>(NI), *fcs = g_stage.take<int>(NI), *ncs = g_stage.take<int>(NI);
+    int4 *bd = g_stage.take<int4>(2 * (size_t) NI), *tdd = g_stage.take<int4>(N);
+    if ((NI && (!int_nodes || !fcs || !ncs || !bd)) || !tdd)
+        return fail(PML_ERR_CUDA, "could not allocate pinned staging memory");
+    for (int v = 0; v < N; ++v) {
+        const int s = slot[v];
+        const int q = parent[v];
+        const int pq = q < 0 ? -1 : slot[q];
+        ps[v] = pq;
+        zc_index[v] = -1;
+        int4 w = make_int4(pq, s, 0, 0);
+        const double d = dist[v];
+        std::memcpy(&w.z, &d, 8);
+        tdd[v] = w;
+        if (s >= 0) {
+            const int f = fch[v], n = nch[v];
+            int_nodes[s] = v;
+            fcs[s] = f;
+            ncs[s] = n;
+            const double d0 = dist[f], d1 = n > 1 ? dist[f + 1] : 0.;
+            bd[2 * (size_t) s] = make_int4(f, n, slot[f], n > 1 ? slot[f + 1] : -1);
+            int4 l;
+            std::memcpy(&l.x, &d0, 8);
+            std::memcpy(&l.z, &d1, 8);
+            bd[2 * (size_t) s + 1] = l;
+        }
     }
-    std::vector<int> int_nodes;
-    int_nodes.reserve(N / 2 + 1);
-    for (int v = 0; v < N; ++v)
-        if (nch[v]) { slot[v] = (int) int_nodes.size(); int_nodes.push_back(v); }
-    const int NI = (int) int_nodes.size();
+    std::vector<int> level_ptr{0, n_roots};
+    while (level_ptr.back() < N) {
+        // the next level ends where parents stop falling into the current one: parent[] is sorted
+        const int hi = level_ptr.back();
+        const int nxt = (int) (std::lower_bound(parent + hi, parent + N, hi) - parent);
+        if (nxt == hi) return fail(PML_ERR_INVALID, "disconnected nodes");
+        level_ptr.push_back(nxt);
+    }
     const int n_levels = (int) level_ptr.size() - 1;
     std::vector<int> int_level_ptr(n_levels + 1, 0);
     for (int l = 0; l <= n_levels; ++l)
-        int_level_ptr[l] = (int) (std::lower_bound(int_nodes.begin(), int_nodes.end(), level_ptr[l]) - int_nodes.begin());
+        int_level_ptr[l] = (int) (std::lower_bound(int_nodes, int_nodes + NI, level_ptr[l]) - int_nodes);
 
     // ---- zero-branch clusters per column (get_zero_clusters_with_states, ml.py:321-349)
-    std::vector<int> top(N);
-    bool any_zero = false;
-    for (int v = 0; v < N; ++v) {
-        const int q = parent[v];
-        if (q >= 0 && dist[v] == 0.) { top[v] = top[q]; any_zero = true; }
-        else top[v] = v;
-    }
-    std::vector<int> cl_col, cl_ptr{0}, cl_mem, zc_index(N, -1), row_node;
-    std::vector<uint8_t> member((size_t) C * N, 0);
+    std::vector<int> cl_col, cl_ptr{0}, cl_mem, row_node;
+    std::vector<uint8_t> member;
     if (any_zero) {
+        std::vector<int> top(N);
+        for (int v = 0; v < N; ++v) {
+            const int q = parent[v];
+            top[v] = (q >= 0 && dist[v] == 0.) ? top[q] : v;
+        }
+        member.assign((size_t) C * N, 0);
         std::vector<int> cnt(N), start(N + 1), fill(N), order;
         for (int c = 0; c < C; ++c) {
             const uint8_t *hs = has_state + (size_t) c * N;
@@ -479,44 +615,28 @@ int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dis
     PML_TRY_FREE(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     PML_TRY_FREE(cudaEventCreate(&p->ev0));
     PML_TRY_FREE(cudaEventCreate(&p->ev1));
-    {
-        std::vector<int> par(parent, parent + N);
-        std::vector<double> dst(dist, dist + N);
-        PML_UPLOAD(p->parent, par);
-        PML_UPLOAD(p->dist, dst);
-    }
-    PML_UPLOAD(p->first_child, fch);
-    PML_UPLOAD(p->n_children, nch);
-    PML_UPLOAD(p->slot, slot);
-    PML_UPLOAD(p->int_nodes, int_nodes);
-    {
-        std::vector<int> fcs(NI), ncs(NI), ps(N);
-        for (int s = 0; s < NI; ++s) { fcs[s] = fch[int_nodes[s]]; ncs[s] = nch[int_nodes[s]]; }
-        for (int v = 0; v < N; ++v) ps[v] = parent[v] < 0 ? -1 : slot[parent[v]];
-        PML_UPLOAD(p->fc_slot, fcs);
-        PML_UPLOAD(p->nc_slot, ncs);
-        PML_UPLOAD(p->pslot, ps);
-        p->n_root_slots = int_level_ptr[1];
-        std::vector<int4> bd(2 * (size_t) NI), td((size_t) N);
-        for (int s = 0; s < NI; ++s) {
-            const int f = fcs[s], n = ncs[s];
-            const double d0 = dist[f], d1 = n > 1 ? dist[f + 1] : 0.;
-            bd[2 * s] = make_int4(f, n, slot[f], n > 1 ? slot[f + 1] : -1);
-            int4 w;
-            std::memcpy(&w.x, &d0, 8);
-            std::memcpy(&w.z, &d1, 8);
-            bd[2 * s + 1] = w;
-        }
-        for (int v = 0; v < N; ++v) {
-            int4 w = make_int4(ps[v], slot[v], 0, 0);
-            const double d = dist[v];
-            std::memcpy(&w.z, &d, 8);
-            td[v] = w;
-        }
-        PML_UPLOAD(p->bu_desc, bd);
-        PML_UPLOAD(p->td_desc, td);
-    }
-    PML_UPLOAD(p->zc_index, zc_index);
+#define PML_UPLOAD_RAW(buf, src, n)                                                                      \
+    do {                                                                                                 \
+        PML_TRY_FREE((buf).alloc((size_t) (n)));                                                         \
+        if ((n) > 0)                                                                                     \
+            PML_TRY_FREE(cudaMemcpyAsync((buf).ptr, (src), (size_t) (n) * sizeof(*(src)), cudaMemcpyHostToDevice, \
+                                         p->stream));                                                    \
+    } while (0)
+    PML_UPLOAD_RAW(p->parent, parent, N);
+    PML_UPLOAD_RAW(p->dist, dist, N);
+    PML_UPLOAD_RAW(p->first_child, fch, N);
+    PML_UPLOAD_RAW(p->n_children, nch, N);
+    PML_UPLOAD_RAW(p->slot, slot, N);
+    PML_UPLOAD_RAW(p->int_nodes, int_nodes, NI);
+    PML_UPLOAD_RAW(p->zc_index, zc_index, N);
+    PML_UPLOAD_RAW(p->fc_slot, fcs, NI);
+    PML_UPLOAD_RAW(p->nc_slot, ncs, NI);
+    PML_UPLOAD_RAW(p->pslot, ps, N);
+    PML_UPLOAD_RAW(p->bu_desc, bd, 2 * (size_t) NI);
+    PML_UPLOAD_RAW(p->td_desc, tdd, N);
+    p->n_root_slots = int_level_ptr[1];
+    PML_TRY_FREE(cudaStreamSynchronize(p->stream));   // the staging arena is reused by the next create
+#undef PML_UPLOAD_RAW
     PML_UPLOAD(p->roots, roots);
     PML_UPLOAD(p->cl_col, cl_col);
     PML_UPLOAD(p->cl_ptr, cl_ptr);
@@ -542,15 +662,17 @@ int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dis
     PML_TRY_FREE(cudaMemset(p->zc_lh.ptr, 0, rc * K * sizeof(double)));
 
     const size_t nc = (size_t) N * C;
-    for (int m = 0; m < 5; ++m) PML_TRY_FREE(p->mask[m].alloc(nc));
+    PML_TRY_FREE(p->mask[PML_MASK_ANNOTATION].alloc(nc));   // the other mask sets are allocated when first produced
     {
         // [C][N] -> [N][C] on the device
         DevBuf<uint64_t> tmp_mask;
         DevBuf<uint8_t> tmp_mem;
         PML_TRY_FREE(tmp_mask.alloc(nc));
-        PML_TRY_FREE(tmp_mem.alloc(nc));
-        PML_TRY_FREE(cudaMemcpy(tmp_mask.ptr, annot_mask, nc * sizeof(uint64_t), cudaMemcpyHostToDevice));
-        PML_TRY_FREE(cudaMemcpy(tmp_mem.ptr, member.data(), nc, cudaMemcpyHostToDevice));
+        PML_TRY_FREE(cudaMemcpyAsync(tmp_mask.ptr, annot_mask, nc * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
+        if (!member.empty()) {
+            PML_TRY_FREE(tmp_mem.alloc(nc));
+            PML_TRY_FREE(cudaMemcpyAsync(tmp_mem.ptr, member.data(), nc, cudaMemcpyHostToDevice, p->stream));
+        }
         init_masks_kernel<<<grid_for((long long) nc), kBlock, 0, p->stream>>>(N, C, p->kmask, tmp_mask.ptr, tmp_mem.ptr,
                                                                               p->mask[PML_MASK_ANNOTATION].ptr, 1);
         PML_TRY_FREE(cudaStreamSynchronize(p->stream));
@@ -562,8 +684,6 @@ int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dis
     PML_TRY_FREE(p->bu_ex.alloc(std::max<size_t>((size_t) NI * J, 1)));
     PML_TRY_FREE(p->err.alloc(2 * J));
     PML_TRY_FREE(p->out_lh.alloc(J));
-    PML_TRY_FREE(p->joint_state.alloc(nc));
-    PML_TRY_FREE(cudaMemset(p->joint_state.ptr, 0, nc * sizeof(int)));
 #undef PML_UPLOAD
 #undef PML_TRY_FREE
     *out = p;
@@ -599,9 +719,9 @@ int pml_loglik(pml_problem *p, const double *params, int32_t n_sets, int32_t mas
 int pml_joint(pml_problem *p, const double *params, double *out_loglh, int32_t *out_state) {
     if (!p || !params) return fail(PML_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(p->device));
-    const size_t nck = (size_t) p->N * p->C * p->K;
-    if (!p->ptr.ptr) CUDA_TRY(p->ptr.alloc(nck));
-    int rc = upload_params(p, params, 1);
+    int rc = ensure_joint_buffers(p);
+    if (rc) return rc;
+    rc = upload_params(p, params, 1);
     if (rc) return rc;
     CallTimer timer(p);
     const uint64_t *base = p->mask[PML_MASK_ANNOTATION].ptr;
@@ -788,6 +908,7 @@ int pml_set_custom_masks(pml_problem *p, const uint64_t *mask) {
     const size_t nc = (size_t) p->N * p->C;
     if (!p->scratch_a.ptr) CUDA_TRY(p->scratch_a.alloc(nc));
     if (!p->scratch_b.ptr) CUDA_TRY(p->scratch_b.alloc(nc));
+    if (!p->mask[PML_MASK_CUSTOM].ptr) CUDA_TRY(p->mask[PML_MASK_CUSTOM].alloc(nc));
     CUDA_TRY(cudaMemcpyAsync(p->scratch_a.ptr, mask, nc * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
     // member flags are taken from the annotation masks: [C][N] -> [N][C], then OR the flags in
     init_masks_kernel<<<grid_for((long long) nc), kBlock, 0, p->stream>>>(p->N, p->C, p->kmask, p->scratch_a.ptr, nullptr,
@@ -851,6 +972,11 @@ int pml_zero_likelihood_all(pml_problem *p, int32_t *out_pairs, int32_t n_lanes)
     return PML_OK;
 }
 
+int pml_trim_memory(void) {
+    g_pool.trim();
+    return PML_OK;
+}
+
 int pml_last_call_stats(pml_problem *p, double *device_ms, int64_t *kernel_launches) {
     if (!p) return fail(PML_ERR_INVALID, "null argument");
     if (device_ms) *device_ms = p->last_ms;
@@ -871,7 +997,7 @@ int pml_bench_pass(pml_problem *p, const double *params, int32_t n_sets, int32_t
         if (rc) return rc;
         if (force_joint && !p->joint_done) return fail(PML_ERR_INVALID, "call pml_joint first");
     }
-    if (which == 2 && !p->ptr.ptr) CUDA_TRY(p->ptr.alloc((size_t) p->N * p->C * p->K));
+    if (which == 2) { int r2 = ensure_joint_buffers(p); if (r2) return r2; }
     int rc = upload_params(p, params, n_sets);
     if (rc) return rc;
     const long long flush_n = 64LL << 20;   // 256 MiB of floats > 126 MB L2
