@@ -278,7 +278,9 @@ def run_b200(args):
     else:
         peak, peak_src = 6650., 'fallback (B200_PROFILING.md)'
     bu_bytes, td_bytes = algorithmic_bytes(flat, K, C)
-    sweeps = {'td_level_kernel': (td_bytes, td_ms, td_launches), 'bu_level_kernel': (bu_bytes, bu_ms, bu_launches)}
+    coop = C <= 16 and K >= 3 and not os.environ.get('PASTML_B200_NO_COOP')   # pick_coop() in pml_engine.cu
+    td_name, bu_name = ('td_coop_kernel', 'bu_coop_kernel') if coop else ('td_level_kernel', 'bu_level_kernel')
+    sweeps = {td_name: (td_bytes, td_ms, td_launches), bu_name: (bu_bytes, bu_ms, bu_launches)}
     dom = max(sweeps, key=lambda k: sweeps[k][1])
 
     def roof(name):

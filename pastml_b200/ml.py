@@ -113,9 +113,20 @@ def mask_to_sets(mask_column, states):
 
 # ---------------------------------------------------------------------------------------- lock-step objective
 
+def batched_gradients():
+    """L-BFGS-B differentiates the objective by forward differences (scipy's default, as in the reference).  scipy
+    hands the n_params perturbed points of one gradient to a map-like ``workers`` option; we evaluate them as
+    parameter sets of ONE device pass.  The points, their order and the values are those of the default path
+    (checked in tests), only the number of launch sequences changes.  PASTML_B200_BATCHED_FD=0 disables it."""
+    import os
+    return os.environ.get('PASTML_B200_BATCHED_FD', '1') != '0'
+
+
 class LockstepEvaluator(object):
     """Rendezvous of the per-column optimiser threads: when every column that is still being fitted has asked
-    for one objective value, a single batched pass evaluates all of them."""
+    for objective values, a single batched pass evaluates all of them.  A request is a list of parameter blocks
+    (one for a plain evaluation, n_params + 1 for the finite-difference batch of one L-BFGS-B gradient): the pass
+    runs max(len) parameter sets x all columns."""
 
     def __init__(self, batch):
         self.batch = batch
@@ -124,23 +135,38 @@ class LockstepEvaluator(object):
         self.pending = {}
         self.results = {}
         self.errors = {}
+        self.last_block = [m.engine_block() for m in batch.models]
         self.n_passes = 0
+        self.n_lane_evaluations = 0
 
     def _flush(self):
         cols = sorted(self.pending)
-        values, errs = self.batch.loglik_columns(cols)
+        n_sets = max(len(self.pending[c]) for c in cols)
+        params = np.empty((n_sets, self.batch.C, self.batch.problem.stride), dtype=np.float64)
+        for c in range(self.batch.C):
+            blocks = self.pending.get(c)
+            if blocks is None:
+                params[:, c, :] = self.last_block[c]
+            else:
+                for b in range(n_sets):
+                    params[b, c, :] = blocks[min(b, len(blocks) - 1)]
+                self.last_block[c] = blocks[-1]
+        values, errs = self.batch.loglik_sets(params, n_sets)
         self.n_passes += 1
         for c in cols:
-            self.results[c] = values[c]
-            if c in errs:
-                self.errors[c] = errs[c]
+            n = len(self.pending[c])
+            self.n_lane_evaluations += n
+            self.results[c] = [float(values[b, c]) for b in range(n)]
+            bad = [errs[(b, c)] for b in range(n) if (b, c) in errs]
+            if bad:
+                self.errors[c] = bad[0]
         self.pending.clear()
         self.cond.notify_all()
 
-    def evaluate(self, c):
-        """Log-likelihood of column c at its model's current parameters."""
+    def evaluate(self, c, blocks):
+        """Log-likelihoods of column c for the given parameter blocks."""
         with self.cond:
-            self.pending[c] = True
+            self.pending[c] = list(blocks)
             self.results.pop(c, None)
             if set(self.pending) >= self.active:
                 self._flush()
@@ -161,7 +187,9 @@ class LockstepEvaluator(object):
 class ColumnBatch(object):
     """Columns of one forest that share the model family and the number of states: one engine problem."""
 
-    def __init__(self, flat, characters, models, device=0):
+    def __init__(self, flat, characters, models, device=0, annot_mask=None, has_state=None):
+        """``annot_mask`` / ``has_state`` ([C][N]) may be given directly (array-native callers); otherwise they are
+        read from the node features named by ``characters``."""
         self.flat = flat
         self.characters = list(characters)
         self.models = list(models)
@@ -169,11 +197,15 @@ class ColumnBatch(object):
         m0 = self.models[0]
         self.K = len(m0.states)
         self.kind = m0.engine_kind
-        masks, has = zip(*(state_masks(flat, ch, list(m.states)) for ch, m in zip(self.characters, self.models)))
-        self.annot_mask = np.stack(masks)
-        self.has_state = np.stack(has)
-        self.problem = Problem(flat, self.K, self.kind, self.annot_mask, self.has_state, max_param_sets=1,
-                               device=device)
+        if annot_mask is None:
+            masks, has = zip(*(state_masks(flat, ch, list(m.states)) for ch, m in zip(self.characters, self.models)))
+            annot_mask, has_state = np.stack(masks), np.stack(has)
+        self.annot_mask = np.ascontiguousarray(annot_mask, dtype=np.uint64)
+        self.has_state = np.ascontiguousarray(has_state, dtype=np.uint8)
+        # capacity for the finite-difference batch of one gradient: every free parameter + the base point
+        self.max_sets = (1 + max(m.get_num_params() for m in self.models)) if batched_gradients() else 1
+        self.problem = Problem(flat, self.K, self.kind, self.annot_mask, self.has_state,
+                               max_param_sets=self.max_sets, device=device)
 
     def close(self):
         self.problem.close()
@@ -189,6 +221,12 @@ class ColumnBatch(object):
             'restrictions on these node states and/or use a smoothing factor (tau).'
             .format(names[parent], names[child], self.flat.dist[child]))
 
+    def loglik_sets(self, params, n_sets):
+        """(values [n_sets][C], {(set, column): PastMLLikelihoodError}) for n_sets parameter sets x all columns."""
+        values, bad = self.problem.loglik(params, n_sets, MASK_ANNOTATION, True, True, tolerate_zero=True)
+        errs = {(j // self.C, j % self.C): self._error_for(j % self.C, *pc) for j, pc in bad.items()}
+        return values, errs
+
     def loglik_columns(self, cols=None, mask_kind=MASK_ANNOTATION, is_marginal=True, alter=True):
         """({column: log-likelihood}, {column: PastMLLikelihoodError}) for one batched pass."""
         values, bad = self.problem.loglik(self.params(), 1, mask_kind, is_marginal, alter, tolerate_zero=True)
@@ -199,10 +237,11 @@ class ColumnBatch(object):
 
 # ---------------------------------------------------------------------------------------- parameter fit
 
-def optimize_likelihood_params(evaluate, observed_frequencies, model):
+def optimize_likelihood_params(evaluate, observed_frequencies, model, evaluate_many=None):
     """One stage of the fit for one column (``ml.py:174-237``): L-BFGS-B from the current parameters, then from the
     observed frequencies, then from uniform random points, returning at the first successful run that is not worse
-    than the better starting point.  ``evaluate()`` returns the log-likelihood at the model's current parameters."""
+    than the better starting point.  ``evaluate()`` returns the log-likelihood at the model's current parameters;
+    ``evaluate_many(blocks)`` (optional) the log-likelihoods for several parameter blocks in one device pass."""
     bounds = model.get_bounds()
 
     def get_v(ps):
@@ -211,6 +250,30 @@ def optimize_likelihood_params(evaluate, observed_frequencies, model):
         model.set_params_from_optimised(ps)
         res = evaluate()
         return np.inf if pd.isnull(res) else -res
+
+    def get_v_many(_fun, points):
+        # scipy's finite-difference driver maps the objective over the perturbed points of one gradient: same points,
+        # same order as its sequential loop (the model ends up at the last one, as it would there)
+        points = list(points)
+        blocks, ok = [], []
+        for ps in points:
+            if np.any(pd.isnull(ps)):
+                ok.append(False)
+                continue
+            model.set_params_from_optimised(ps)
+            blocks.append(model.engine_block())
+            ok.append(True)
+        values = iter(evaluate_many(blocks) if blocks else [])
+        out = []
+        for good in ok:
+            if not good:
+                out.append(np.nan)
+            else:
+                res = next(values)
+                out.append(np.inf if pd.isnull(res) else -res)
+        return out
+
+    options = {'workers': get_v_many} if evaluate_many is not None else {}
 
     if np.any(observed_frequencies <= 0):
         observed_frequencies = np.maximum(observed_frequencies, 1e-10)
@@ -232,7 +295,7 @@ def optimize_likelihood_params(evaluate, observed_frequencies, model):
             vs = x0_EFT
         else:
             vs = np.random.uniform(bounds[:, 0], bounds[:, 1])
-        fres = minimize(get_v, x0=vs, method='L-BFGS-B', bounds=bounds)
+        fres = minimize(get_v, x0=vs, method='L-BFGS-B', bounds=bounds, options=options)
         if fres.success and not np.any(np.isnan(fres.x)):
             if -fres.fun >= best_log_lh:
                 model.set_params_from_optimised(fres.x)
@@ -241,7 +304,7 @@ def optimize_likelihood_params(evaluate, observed_frequencies, model):
     return best_log_lh
 
 
-def _fit_one(evaluate, character, model, observed_frequencies):
+def _fit_one(evaluate, character, model, observed_frequencies, evaluate_many=None):
     """optimise_likelihood for one column (``ml.py:865-920``) given its objective."""
     logger = logging.getLogger('pastml')
     likelihood = evaluate()
@@ -260,7 +323,7 @@ def _fit_one(evaluate, character, model, observed_frequencies):
               'https://github.com/evolbioinfo/pastml/issues'.format(character)
     if not model.basic_params_fixed():
         model.fix_extra_params()
-        likelihood = optimize_likelihood_params(evaluate, observed_frequencies, model)
+        likelihood = optimize_likelihood_params(evaluate, observed_frequencies, model, evaluate_many)
         if np.isnan(likelihood) or likelihood == -np.inf:
             raise PastMLLikelihoodError(failure)
         model.unfix_extra_params()
@@ -268,7 +331,7 @@ def _fit_one(evaluate, character, model, observed_frequencies):
             logger.debug('Pre-optimised basic parameters for {}:\n{}\tlog likelihood:\t{:.6f}.'
                          .format(character, model._print_basic_parameters(), likelihood))
     if not model.extra_params_fixed():
-        likelihood = optimize_likelihood_params(evaluate, observed_frequencies, model)
+        likelihood = optimize_likelihood_params(evaluate, observed_frequencies, model, evaluate_many)
         if np.isnan(likelihood) or likelihood == -np.inf:
             raise PastMLLikelihoodError(failure)
     logger.debug('Optimised parameters for {}:\n{}\tlog likelihood:\t{:.6f}'
@@ -284,7 +347,10 @@ def fit_batch(batch, observed_frequencies):
 
     def work(c):
         try:
-            out[c] = _fit_one(lambda: ev.evaluate(c), batch.characters[c], batch.models[c], observed_frequencies[c])
+            model = batch.models[c]
+            many = (lambda blocks: ev.evaluate(c, blocks)) if batch.max_sets > 1 else None
+            out[c] = _fit_one(lambda: ev.evaluate(c, [model.engine_block()])[0], batch.characters[c], model,
+                              observed_frequencies[c], many)
         except BaseException as e:  # re-raised in the caller's thread
             failures[c] = e
         finally:

@@ -117,7 +117,9 @@ def test_columns_and_parameter_sets_batched():
 
 
 @pytest.mark.parametrize('n_tips,K,C,kind', [(3000, 10, 4, 'yule'), (2000, 20, 3, 'coalescent'), (1500, 3, 8, 'yule'),
-                                            (1000, 30, 2, 'yule')])
+                                            (1000, 30, 2, 'yule'), (2000, 20, 8, 'yule'), (600, 45, 2, 'yule'),
+                                            (400, 62, 1, 'coalescent'), (800, 12, 20, 'yule'), (700, 5, 1, 'yule'),
+                                            (900, 2, 16, 'coalescent')])
 def test_synthetic_against_oracle(n_tips, K, C, kind):
     from pastml_b200.engine import Problem, MASK_MAP, MASK_MPPA, pack_params
     from pastml_b200 import synth
