@@ -53,6 +53,19 @@ struct GroupOps {
     }
 };
 
+// 1 / x for a normal positive x: hardware approximation (2^-23) + two Newton steps, ~1 ulp.  The fused top-down
+// step divides K values per (node, lane) item; __drcp_rn's exact rounding and special-case handling cost three
+// times as many instructions and buy nothing at the 1e-10 tolerance.  Tiny or huge x take the exact path.
+__device__ __forceinline__ double fast_rcp(double x) {
+    if (!(x > 0x1p-900 && x < 0x1p+900)) return __drcp_rn(x);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double t = fma(-x, r, 1.);
+    r = fma(r, t, r);
+    t = fma(-x, r, 1.);
+    return fma(r, t, r);
+}
+
 struct CoopLane {   // where a thread sits: which node of the warp's batch, which lane (column), which rank
     int sub, r, j, c, npw;
     bool lane_on;
@@ -198,9 +211,9 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kerne
             double m0 = 0., m1 = 0.;
 #pragma unroll
             for (int i = 0; i < KT; ++i) {
-                acc[i] *= fmax(fma(e0, in0[i], b0), 0.);
+                acc[i] *= fma(e0, in0[i], b0);   // >= 0, the reference's np.maximum(., 0) is a no-op here
                 m0 = fmax(m0, acc[i]);
-                acc[i] *= fmax(fma(e1, in1[i], b1), 0.);
+                acc[i] *= fma(e1, in1[i], b1);
                 m1 = fmax(m1, acc[i]);
             }
             m1 = grp.max(m1);
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kerne
                 double mx = 0.;
 #pragma unroll
                 for (int i = 0; i < KT; ++i) {
-                    if (valid) acc[i] *= fmax(fma(e, in[i], b), 0.);
+                    if (valid) acc[i] *= fma(e, in[i], b);
                     mx = fmax(mx, acc[i]);
                 }
                 mx = grp.max(mx);
@@ -332,8 +345,8 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) td_coop_kerne
         double q[KT];
 #pragma unroll
         for (int i = 0; i < KT; ++i) {
-            const double cv = fmax(fma(e, Lc[i], ome * s), 0.);
-            q[i] = (cv > 0.) ? X[i] * __drcp_rn(cv) : X[i];
+            const double cv = fma(e, Lc[i], ome * s);   // >= 0: e in [0, 1] and the inputs are non-negative
+            q[i] = (cv > 0.) ? X[i] * fast_rcp(cv) : X[i];
         }
         double s2 = 0.;
 #pragma unroll
@@ -355,7 +368,7 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) td_coop_kerne
         double tdv[KT];
 #pragma unroll
         for (int i = 0; i < KT; ++i)
-            tdv[i] = PML_VALID(i) ? fmax(fma(e, q[i], ome * s2), 0.) * scale : 0.;   // ml.py:288-289
+            tdv[i] = PML_VALID(i) ? fma(e, q[i], ome * s2) * scale : 0.;   // ml.py:288-289 (already >= 0)
         if (has_parent) {
             if (cs >= 0) {
                 if (on) {

@@ -1,6 +1,7 @@
 // Host side of the pastml_b200 engine: problem handles, level-synchronous launch sequences, the C ABI declared
 // in include/pastml_b200.h.  Built by nvcc for sm_100a only (see pastml_b200/build.py).
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -180,6 +181,8 @@ struct pml_problem {
     double last_ms = 0.;
     long long last_launches = 0, launches = 0;
     const KernelSet *ks = nullptr;
+    struct GraphEntry { cudaGraphExec_t exec; long long launches; };
+    std::map<std::array<long long, 6>, GraphEntry> graphs;
 
     TreeDev tree() const {
         return TreeDev{N, NI, parent.ptr, first_child.ptr, n_children.ptr, slot.ptr, int_nodes.ptr, dist.ptr,
@@ -225,7 +228,7 @@ int upload_params(pml_problem *p, const double *params, int n_sets) {
 }
 
 // the bottom-up sweep on resident params/masks; leaves out_lh on the device
-void run_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marginal, int alter, bool keep_ptr) {
+void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marginal, int alter, bool keep_ptr) {
     const LaneDev ln = p->lanes(n_sets);
     if (alter) run_alter(p, mask);
     fill_int_kernel<<<grid_for(2LL * ln.J), kBlock, 0, p->stream>>>(2LL * ln.J, -1, p->err.ptr);
@@ -249,6 +252,50 @@ void run_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marg
         }
     }
     run_root_loglik(p, ln, mask, alter, is_marginal);
+}
+
+void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh);
+
+// Launch sequences are captured once into CUDA graphs (one per distinct combination of arguments) and replayed:
+// a sweep is ~55 dependent launches, half of them over levels too narrow to hide the launch latency.
+// PASTML_B200_NO_GRAPH=1 launches the kernels directly (ncu captures, debugging).
+template <class F>
+void run_graphed(pml_problem *p, const std::array<long long, 6> &key, F enqueue) {
+    static const bool disabled = getenv("PASTML_B200_NO_GRAPH") != nullptr;
+    if (disabled) { enqueue(); return; }
+    auto it = p->graphs.find(key);
+    if (it == p->graphs.end()) {
+        const long long l0 = p->launches;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        bool ok = cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            enqueue();
+            ok = cudaStreamEndCapture(p->stream, &graph) == cudaSuccess && graph != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        const long long n = p->launches - l0;
+        p->launches = l0;
+        if (!ok) {   // capture not possible: fall back to direct launches for this handle
+            cudaGetLastError();
+            enqueue();
+            return;
+        }
+        it = p->graphs.emplace(key, pml_problem::GraphEntry{exec, n}).first;
+    }
+    cudaGraphLaunch(it->second.exec, p->stream);
+    p->launches += it->second.launches;
+}
+
+void run_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marginal, int alter, bool keep_ptr) {
+    run_graphed(p, {0, n_sets, (long long) (uintptr_t) mask, is_marginal, alter, keep_ptr ? 1 : 0},
+                [&]() { enqueue_bottom_up(p, n_sets, mask, is_marginal, alter, keep_ptr); });
+}
+
+void run_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh) {
+    run_graphed(p, {1, force_joint, want_probs ? 1 : 0, want_node_lh ? 1 : 0, 0, 0},
+                [&]() { enqueue_top_down(p, force_joint, want_probs, want_node_lh); });
 }
 
 int fetch_loglik(pml_problem *p, int n_sets, double *out) {
@@ -306,7 +353,7 @@ int ensure_marginal_buffers(pml_problem *p, bool want_probs, bool want_node_lh) 
 }
 
 // the fused top-down sweep on resident bottom-up state
-void run_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh) {
+void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh) {
     const LaneDev ln = p->lanes(1);
     cudaMemsetAsync(p->k_hist.ptr, 0, sizeof(unsigned long long) * p->C * (p->K + 1), p->stream);
     TdArgs a{p->tree(), p->zc(), ln, p->mask[PML_MASK_ANNOTATION].ptr, p->bu.ptr, p->bu_ex.ptr, p->td.ptr,
@@ -694,6 +741,8 @@ void pml_problem_destroy(pml_problem *p) {
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
+    for (auto &kv : p->graphs) cudaGraphExecDestroy(kv.second.exec);
+    p->graphs.clear();
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) cudaStreamDestroy(p->stream);
