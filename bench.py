@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument('--tree', default='yule', choices=['yule', 'coalescent'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--no-fit', action='store_true')
     ap.add_argument('--sweeps-only', action='store_true', help='development: print the sweep timings and exit')
     return ap.parse_args()
 
@@ -212,11 +213,8 @@ def run_b200(args):
         print('sweeps step_ms={:.3f} min={:.3f} bu_ms={:.3f} td_ms={:.3f} launches={} lib={}'.format(
             avg_ms, min_ms, bu_ms, td_ms, launches, os.environ.get('PASTML_B200_LIB', 'default')))
         return
-    step_ms = avg_ms
-    if dist is not None:
-        t = torch.tensor([step_ms], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms = float(t.item())
+    from pastml_b200.parallel import max_over_ranks
+    step_ms = max_over_ranks(avg_ms, device='cuda')
     value = node_states * world / (step_ms * 1e-3)
 
     # ---- end to end through the C ABI with pinned host buffers
@@ -262,14 +260,35 @@ def run_b200(args):
     for _ in range(args.e2e_steps):
         e2e_step()
     barrier()
-    e2e_dt = (time.perf_counter() - t0) / args.e2e_steps
-    if dist is not None:
-        t = torch.tensor([e2e_dt], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
+    e2e_dt = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps, device='cuda')
     e2e_value = node_states * world / e2e_dt
     h2d = h_parent.nbytes + h_dist.nbytes + h_masks.nbytes + h_has.nbytes + params.nbytes
     d2h = h_probs.nbytes + h_map.nbytes + h_mppa.nbytes + h_lh.nbytes + h_hist.nbytes
+
+    # ---- ML-fit wall time: the full two-stage L-BFGS-B fit of all columns (host optimiser, device objective)
+    ml_fit = None
+    if not args.no_fit:
+        from pastml_b200.annotation import ForestStats
+        from pastml_b200.ml import ColumnBatch, fit_batch
+        from pastml_b200.models import F81Model
+        fs = ForestStats(flat=flat)
+        names = np.array(['s{:02d}'.format(i) for i in range(K)])
+        obs = []
+        for c in range(C):
+            f = np.bincount(np.log2(masks[c][flat.is_tip].astype(np.float64)).astype(int), minlength=K).astype(np.float64)
+            obs.append(f / f.sum())
+        models = [F81Model(states=names, forest_stats=fs, character='c{}'.format(c)) for c in range(C)]
+        batch = ColumnBatch(flat, ['c{}'.format(c) for c in range(C)], models, device=local_rank, annot_mask=masks,
+                            has_state=has)
+        barrier()
+        t0 = time.perf_counter()
+        _, passes = fit_batch(batch, obs)
+        barrier()
+        fit_s = max_over_ranks(time.perf_counter() - t0, device='cuda')
+        batch.close()
+        ml_fit = {'seconds': fit_s, 'device_passes': int(passes),
+                  'what': 'two-stage L-BFGS-B fit of sf + {} frequencies for all {} columns of this rank in lock step, '
+                          'finite-difference gradients batched as parameter sets'.format(K - 1, C)}
 
     # ---- roofline of the dominant kernel family (per-level launches of one templated kernel)
     peaks_path = os.path.join(REPO, 'MEASURED_PEAKS.json')
@@ -283,11 +302,19 @@ def run_b200(args):
     sweeps = {td_name: (td_bytes, td_ms, td_launches), bu_name: (bu_bytes, bu_ms, bu_launches)}
     dom = max(sweeps, key=lambda k: sweeps[k][1])
 
+    # measured DRAM traffic of one sweep (ncu dram__bytes_read/write.sum over all its launches), when the committed
+    # capture matches this workload
+    traffic = {}
+    tpath = os.path.join(REPO, 'profiles', 'r1_i_dram_traffic.json')
+    if os.path.exists(tpath) and (args.tips, K, C, args.tree) == (1_000_000, 20, 8, 'yule'):
+        traffic = {k: v['dram_bytes_total'] for k, v in json.load(open(tpath))['kernels'].items()}
+
     def roof(name):
         b, ms, n = sweeps[name]
         ach = b / (ms * 1e-3) / 1e9
         return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                'traffic': None, 'algorithmic_bytes_per_sweep': int(b), 'launches_per_sweep': int(n),
+                'traffic': traffic.get(name), 'traffic_source': 'profiles/r1_i_dram_traffic.json (per sweep)' if name in traffic else None,
+                'algorithmic_bytes_per_sweep': int(b), 'launches_per_sweep': int(n),
                 'avg_launch_us': ms * 1e3 / max(n, 1), 'sweep_ms': ms, 'peak_source': peak_src}
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -300,7 +327,7 @@ def run_b200(args):
             'gpu_launches': int(launches * args.steps),
             'roofline': roof(dom), 'roofline_other': roof([k for k in sweeps if k != dom][0]),
             'min_ms_per_step': min_ms, 'wall_s_timed_region': wall,
-            'bu_objective_ms': bu_ms, 'bu_node_states_per_s': node_states / (bu_ms * 1e-3)}
+            'bu_objective_ms': bu_ms, 'bu_node_states_per_s': node_states / (bu_ms * 1e-3), 'ml_fit': ml_fit}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
