@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--no-fit', action='store_true')
+    ap.add_argument('--sharding', default='batch', choices=['batch', 'subtree'],
+                    help='batch: every GPU owns an independent (tree x columns) batch (weak scaling, default); '
+                         'subtree: ONE tree is cut into clades spread over the GPUs, one all-gather per sweep (strong)')
     ap.add_argument('--sweeps-only', action='store_true', help='development: print the sweep timings and exit')
     return ap.parse_args()
 
@@ -171,6 +174,61 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ B200 arm
+
+def run_subtree_sharded(args):
+    """One tree for all the GPUs: every rank prunes its clades, the clade-root vectors are all-gathered (NCCL), every
+    rank finishes the replicated top of the tree and sweeps back down into its own clades."""
+    import torch
+    import torch.distributed as dist
+    from pastml_b200.parallel import max_over_ranks
+    from pastml_b200.sharded import SubtreePlan, ShardedProblem, all_gather_partials
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    flat, masks, has, pis, sfs, params = make_workload(args, 0)     # the SAME tree on every rank
+    K, C = args.states, args.columns
+    plan = SubtreePlan(flat, world)
+    sp = ShardedProblem(plan, rank, K, 0, masks, has, device=local_rank)
+
+    def step():
+        vec, ex = sp.local_root_partials(params)
+        gathered = all_gather_partials(vec, ex, plan, rank)
+        vec, ex = sp.assemble(gathered)
+        return sp.marginal(params, vec, ex, want_probs=False, reuse_bottom_up=True)
+
+    for _ in range(max(args.warmup, 3)):
+        top, mine = step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    with ClockSampler(local_rank) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            top, mine = step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = (time.perf_counter() - t0) / args.steps
+    dt = max_over_ranks(dt, device='cuda')
+    node_states = flat.n_nodes * K * C
+    line = {'metric': METRIC, 'value': node_states / dt, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, flat),
+            'clocks': clocks.summary(), 'loglh_column0': float(top['loglh'][0]),
+            'sharding': {'kind': 'subtree', 'cut_level': int(plan.cut_level), 'clades': int(len(plan.boundary)),
+                         'top_nodes': int(plan.n_top), 'nodes_per_rank': [int(len(n)) for n in plan.nodes],
+                         'exchange': 'one all_gather_into_tensor of {} x (K+1) x C doubles per step'.format(
+                             max(len(p) for p in plan.roots_pos))},
+            'timing': 'host wall clock around K steps (the exchange goes through the host), max over ranks',
+            'gpu_launches': None}
+    line['config']['sharding'] = 'one tree cut into clades over the GPUs (subtree sharding)'
+    sp.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
 
 def run_b200(args):
     import torch
@@ -348,5 +406,7 @@ if __name__ == '__main__':
     a = parse_args()
     if a.impl == 'reference':
         run_reference(a)
+    elif a.sharding == 'subtree' and int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        run_subtree_sharded(a)
     else:
         run_b200(a)

@@ -56,6 +56,8 @@ typedef struct pml_problem pml_problem;
 #define PML_PARS_DOWNPASS 2
 #define PML_PARS_DELTRAN 4
 
+#define PML_REUSE_BOTTOM_UP 2
+
 /* error codes */
 #define PML_OK 0
 #define PML_ERR_INVALID 1
@@ -97,7 +99,9 @@ int pml_joint(pml_problem *p, const double *params, double *out_loglh, int32_t *
 
 /* Marginal reconstruction (ml.py:697-714, 735-742): bottom-up, top-down, marginal likelihoods,
  * probabilities, MAP and MPPA state selection, fused in one level-synchronous sweep.
- *   force_joint        MPPA keeps room for the JOINT state (needs a previous pml_joint call)
+ *   force_joint        bit 0: MPPA keeps room for the JOINT state (needs a previous pml_joint call);
+ *                      bit 1 (PML_REUSE_BOTTOM_UP): the bottom-up state of the immediately preceding pml_loglik call
+ *                      (same parameters, one set, annotation masks, marginal, alter) is reused instead of recomputed
  *   out_loglh[C]       marginal log-likelihood                                     (may be NULL)
  *   out_probs[N][C][K] marginal probabilities, ml.py:486-502                        (may be NULL)
  *   out_node_log10lh[N][C]  log10 of the node's total marginal likelihood = log10(sum LIKELIHOOD) -
@@ -132,6 +136,23 @@ int pml_zero_likelihood_info(pml_problem *p, int32_t *column, int32_t *param_set
 /* After PML_ERR_ZERO_LIKELIHOOD from pml_loglik: (parent, child) of every lane of that call, -1 where the lane
  * was fine.  out_pairs[n_lanes][2], lane = param_set * C + column. */
 int pml_zero_likelihood_all(pml_problem *p, int32_t *out_pairs, int32_t n_lanes);
+
+/* ---- Subtree sharding of one big tree: a tree is cut at a depth level; every GPU owns the
+ * clades below the cut as a forest, the part above the cut ("top tree") is replicated and sees the clade roots as
+ * tips whose bottom-up vectors are supplied from outside.  One exchange per sweep: the clade-root vectors (all-gather
+ * between the GPUs, done by the caller), and the top-down vectors handed back to the clade roots.
+ *   pml_get_root_partials  after pml_loglik on a clade forest: bottom-up vectors of its roots,
+ *                          out_vec[T][K][J] mantissas, out_ex[T][J] power-of-two exponents (J = n_sets * C)
+ *   pml_set_tip_partials   on the top tree: attach such vectors to the n listed tips (same set on every call)
+ *   pml_get_tip_td         after pml_marginal on the top tree: top-down vectors computed for those tips,
+ *                          out_vec[n][K][C], out_ex[n][C]
+ *   pml_set_root_td        on a clade forest before pml_marginal: top-down vectors arriving at its roots
+ *                          (vec[T][K][C], ex[T][C]) instead of the all-ones vector of a true root (ml.py:274-277) */
+int pml_get_root_partials(pml_problem *p, int32_t n_sets, double *out_vec, int32_t *out_ex);
+int pml_set_tip_partials(pml_problem *p, int32_t n, const int32_t *nodes, const double *vec, const int32_t *ex,
+                         int32_t n_sets);
+int pml_get_tip_td(pml_problem *p, double *out_vec, int32_t *out_ex);
+int pml_set_root_td(pml_problem *p, const double *vec, const int32_t *ex);
 
 /* Device buffers of destroyed problems are kept in a per-process cache and reused by the next problem of the same
  * shape (cudaMalloc/cudaFree of GBs cost more than the sweeps).  This returns the cached blocks to the driver. */

@@ -13,7 +13,8 @@ LIB_PATH = os.environ.get('PASTML_B200_LIB') or os.path.join(HERE, 'libpastml_b2
 EXPORTS = ['pml_last_error', 'pml_version', 'pml_device_count', 'pml_param_stride', 'pml_problem_create',
            'pml_problem_destroy', 'pml_loglik', 'pml_joint', 'pml_marginal', 'pml_mppa_finalize', 'pml_parsimony',
            'pml_set_custom_masks', 'pml_get_masks', 'pml_get_initial', 'pml_zero_likelihood_info',
-           'pml_zero_likelihood_all', 'pml_trim_memory',
+           'pml_zero_likelihood_all', 'pml_trim_memory', 'pml_get_root_partials', 'pml_set_tip_partials',
+           'pml_get_tip_td', 'pml_set_root_td',
            'pml_last_call_stats', 'pml_bench_pass']
 
 PML_OK, PML_ERR_INVALID, PML_ERR_CUDA, PML_ERR_ZERO_LIKELIHOOD, PML_ERR_NO_DEVICE = 0, 1, 2, 3, 4
@@ -68,6 +69,14 @@ def load():
     lib.pml_zero_likelihood_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.pml_zero_likelihood_all.restype = C.c_int
     lib.pml_zero_likelihood_all.argtypes = [vp, vp, i32]
+    lib.pml_get_root_partials.restype = C.c_int
+    lib.pml_get_root_partials.argtypes = [vp, i32, vp, vp]
+    lib.pml_set_tip_partials.restype = C.c_int
+    lib.pml_set_tip_partials.argtypes = [vp, i32, vp, vp, vp, i32]
+    lib.pml_get_tip_td.restype = C.c_int
+    lib.pml_get_tip_td.argtypes = [vp, vp, vp]
+    lib.pml_set_root_td.restype = C.c_int
+    lib.pml_set_root_td.argtypes = [vp, vp, vp]
     lib.pml_trim_memory.restype = C.c_int
     lib.pml_trim_memory.argtypes = []
     lib.pml_last_call_stats.restype = C.c_int

@@ -122,16 +122,26 @@ __device__ __forceinline__ int exponent_rescale(double (&v)[KT], double vmax, bo
 
 // K and J are passed explicitly so that the instantiations with compile-time K / J fold the address arithmetic
 template <int KT, int G, bool KX>
-__device__ __forceinline__ int coop_load(const TreeDev &t, const ZcDev &zc, const LaneDev &ln, const uint64_t *mask,
-                                         const double *bu, const int *bu_ex, int node, int cs, int r, int j, int c,
-                                         bool use_alt, double (&in)[KT], int K, int J) {
+__device__ __forceinline__ int coop_load(const TreeDev &t, const ZcDev &zc, const ExtDev &ext, const LaneDev &ln,
+                                         const uint64_t *mask, const double *bu, const int *bu_ex, int node, int cs,
+                                         int r, int j, int c, bool use_alt, double (&in)[KT], int K, int J) {
     if (cs >= 0) {
         const double *src = bu + ((size_t) (cs * K + r) * J + j);
 #pragma unroll
         for (int i = 0; i < KT; ++i) in[i] = PML_VALID(i) ? src[(G * i) * J] : 0.;
         return bu_ex[(size_t) cs * J + j];
     }
-    const uint64_t m = eff_mask(mask, t, zc, ln.C, node, c, use_alt, ln.kmask) >> r;
+    const uint64_t raw = mask[(size_t) node * ln.C + c];
+    if (raw & kExtFlag) {   // a clade root cut off by subtree sharding: its vector comes from the ExtDev tables
+        const int e = ext.index[node];
+        const double *src = ext.bu + ((size_t) (e * K + r) * J + j);
+#pragma unroll
+        for (int i = 0; i < KT; ++i) in[i] = PML_VALID(i) ? src[(G * i) * J] : 0.;
+        return ext.bu_ex[(size_t) e * J + j];
+    }
+    uint64_t m = raw;
+    if (use_alt && (m & kMemberFlag)) m = zc.alt[(size_t) t.zc_index[node] * ln.C + c];
+    m = (m & ln.kmask) >> r;
 #pragma unroll
     for (int i = 0; i < KT; ++i) in[i] = bit_as_double(m, G * i);
     return 0;
@@ -198,8 +208,8 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kerne
             double in0[KT], in1[KT];
             const int cs0 = d_top.z, cs1 = d_top.w;
             const double dmine = (r & 1) ? __hiloint2double(d_len.w, d_len.z) : __hiloint2double(d_len.y, d_len.x);
-            ex += coop_load<KT, G, KX>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, fc, cs0, r, j, c, use_alt, in0, K, J);
-            ex += coop_load<KT, G, KX>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, cs1, r, j, c, use_alt, in1, K, J);
+            ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc, cs0, r, j, c, use_alt, in0, K, J);
+            ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, cs1, r, j, c, use_alt, in1, K, J);
             const double emine = mu_inf ? 0. : exp(-mu * ((dmine + tau) * tauf * sf));
             const double e0 = grp.from_rank(emine, 0), e1 = grp.from_rank(emine, 1);
             double s0 = 0., s1 = 0.;
@@ -228,7 +238,7 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kerne
                 const bool valid = q < nc;
                 const int ch = fc + (valid ? q : 0);
                 double in[KT];
-                const int exc = coop_load<KT, G, KX>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, ch, a.t.slot[ch], r, j, c,
+                const int exc = coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, ch, a.t.slot[ch], r, j, c,
                                                  use_alt, in, K, J);
                 const double e = mu_inf ? 0. : exp(-mu * ((a.t.dist[ch] + tau) * tauf * sf));
                 double s = 0.;
@@ -308,7 +318,7 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) td_coop_kerne
         const size_t nc = (size_t) node * C + c;
 
         double Lc[KT], X[KT];
-        const int exc = coop_load<KT, G, KX>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, node, cs, r, c, c, use_alt, Lc, K, C);
+        const int exc = coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, node, cs, r, c, c, use_alt, Lc, K, C);
         const uint64_t base_mask = a.mask[nc];
         const uint64_t flag = base_mask & kMemberFlag;
         const uint64_t allowed = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
@@ -327,7 +337,18 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) td_coop_kerne
 #pragma unroll
                 for (int i = 0; i < KT; ++i) X[i] *= PML_VALID(i) ? src2[(G * i) * C] : 0.;
                 pex += a.td_ex[(size_t) ps * C + c];
+            } else if (a.ext.root_td) {   // child of a clade root: the root's top-down vector came from above the cut
+                const int rn = a.t.int_nodes[ps];
+                const double *src2 = a.ext.root_td + ((size_t) (rn * K + r) * C + c);
+#pragma unroll
+                for (int i = 0; i < KT; ++i) X[i] *= PML_VALID(i) ? src2[(G * i) * C] : 0.;
+                pex += a.ext.root_td_ex[(size_t) rn * C + c];
             }
+        } else if (a.ext.root_td) {   // a clade root: its top-down vector arrives from above the cut
+            const double *src = a.ext.root_td + ((size_t) (node * K + r) * C + c);
+#pragma unroll
+            for (int i = 0; i < KT; ++i) X[i] = PML_VALID(i) ? src[(G * i) * C] : 0.;
+            ex_total += a.ext.root_td_ex[(size_t) node * C + c];
         } else {
 #pragma unroll
             for (int i = 0; i < KT; ++i) X[i] = 1.;
@@ -379,6 +400,16 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) td_coop_kerne
                     if (r == 0) a.td_ex[(size_t) cs * C + c] = qex;
                 }
             }
+            else if (base_mask & kExtFlag) {   // hand the vector to the clade below the cut
+                if (on) {
+                    const int e_row = a.ext.index[node];
+                    double *dst = a.ext.td + ((size_t) (e_row * K + r) * C + c);
+#pragma unroll
+                    for (int i = 0; i < KT; ++i)
+                        if (PML_VALID(i)) dst[(G * i) * C] = tdv[i];
+                    if (r == 0) a.ext.td_ex[(size_t) e_row * C + c] = qex;
+                }
+            }
             ex_total = qex + exc;
         }
         // marginal likelihood vector (ml.py:454-465): L * TD * pi * allowed
@@ -387,7 +418,7 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) td_coop_kerne
         const uint64_t allowed_r = allowed >> r;
 #pragma unroll
         for (int i = 0; i < KT; ++i) {
-            const double tdi = has_parent ? tdv[i] : 1.;
+            const double tdi = has_parent ? tdv[i] : X[i];   // roots: all ones, or the vector from above the cut
             m[i] = ((allowed_r >> (G * i)) & 1ULL) ? Lc[i] * tdi * pi[i] : 0.;
             sum += m[i];
         }

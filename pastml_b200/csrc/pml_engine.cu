@@ -188,6 +188,15 @@ struct pml_problem {
         return TreeDev{N, NI, parent.ptr, first_child.ptr, n_children.ptr, slot.ptr, int_nodes.ptr, dist.ptr,
                        zc_index.ptr, fc_slot.ptr, nc_slot.ptr, pslot.ptr, n_root_slots, bu_desc.ptr, td_desc.ptr};
     }
+    // subtree sharding: external tip vectors / root top-down vectors
+    int n_ext = 0, ext_sets = 0;
+    bool have_root_td = false;
+    DevBuf<int> ext_index, ext_bu_ex, ext_td_ex, root_td_ex, ext_nodes;
+    DevBuf<double> ext_bu, ext_td, root_td;
+    ExtDev ext() const {
+        return ExtDev{ext_index.ptr, ext_bu.ptr, ext_bu_ex.ptr, ext_td.ptr, ext_td_ex.ptr,
+                      have_root_td ? root_td.ptr : nullptr, root_td_ex.ptr};
+    }
     ZcDev zc() const { return ZcDev{zc_alt.ptr, zc_altflag.ptr, zc_initial.ptr, zc_hasinit.ptr, zc_touched.ptr}; }
     LaneDev lanes(int n_sets) const {
         return LaneDev{C, n_sets * C, K, stride, params.ptr, kmask, FastDiv::make((unsigned) (n_sets * C)),
@@ -233,7 +242,7 @@ void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_
     if (alter) run_alter(p, mask);
     fill_int_kernel<<<grid_for(2LL * ln.J), kBlock, 0, p->stream>>>(2LL * ln.J, -1, p->err.ptr);
     p->launches++;
-    BuArgs a{p->tree(), p->zc(), ln, mask, alter, p->bu.ptr, p->bu_ex.ptr, keep_ptr ? p->ptr.ptr : nullptr,
+    BuArgs a{p->tree(), p->zc(), p->ext(), ln, mask, alter, p->bu.ptr, p->bu_ex.ptr, keep_ptr ? p->ptr.ptr : nullptr,
              p->err.ptr};
     const bool maxp = !is_marginal;
     const CoopSet *coop = maxp ? nullptr : pick_coop(p, ln.J);
@@ -289,12 +298,12 @@ void run_graphed(pml_problem *p, const std::array<long long, 6> &key, F enqueue)
 }
 
 void run_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marginal, int alter, bool keep_ptr) {
-    run_graphed(p, {0, n_sets, (long long) (uintptr_t) mask, is_marginal, alter, keep_ptr ? 1 : 0},
+    run_graphed(p, {0, n_sets, (long long) (uintptr_t) mask, is_marginal, alter, (keep_ptr ? 1 : 0) + 2 * p->n_ext},
                 [&]() { enqueue_bottom_up(p, n_sets, mask, is_marginal, alter, keep_ptr); });
 }
 
 void run_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh) {
-    run_graphed(p, {1, force_joint, want_probs ? 1 : 0, want_node_lh ? 1 : 0, 0, 0},
+    run_graphed(p, {1, force_joint, want_probs ? 1 : 0, want_node_lh ? 1 : 0, p->n_ext, p->have_root_td ? 1 : 0},
                 [&]() { enqueue_top_down(p, force_joint, want_probs, want_node_lh); });
 }
 
@@ -356,7 +365,7 @@ int ensure_marginal_buffers(pml_problem *p, bool want_probs, bool want_node_lh) 
 void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh) {
     const LaneDev ln = p->lanes(1);
     cudaMemsetAsync(p->k_hist.ptr, 0, sizeof(unsigned long long) * p->C * (p->K + 1), p->stream);
-    TdArgs a{p->tree(), p->zc(), ln, p->mask[PML_MASK_ANNOTATION].ptr, p->bu.ptr, p->bu_ex.ptr, p->td.ptr,
+    TdArgs a{p->tree(), p->zc(), p->ext(), ln, p->mask[PML_MASK_ANNOTATION].ptr, p->bu.ptr, p->bu_ex.ptr, p->td.ptr,
              p->td_ex.ptr, p->joint_state.ptr, force_joint, want_probs ? p->probs.ptr : nullptr,
              want_node_lh ? p->node_lh.ptr : nullptr, p->node_ex.ptr, p->mask[PML_MASK_MAP].ptr, p->mask[PML_MASK_MPPA].ptr,
              p->k_hist.ptr, p->zc_lh.ptr, p->zc_k.ptr};
@@ -798,6 +807,10 @@ int pml_joint(pml_problem *p, const double *params, double *out_loglh, int32_t *
 int pml_marginal(pml_problem *p, const double *params, int32_t force_joint, double *out_loglh, double *out_probs,
                  double *out_node_log10lh, uint64_t *out_map_mask, uint64_t *out_mppa_mask, int64_t *out_k_hist) {
     if (!p || !params) return fail(PML_ERR_INVALID, "null argument");
+    // bit 1 of force_joint (PML_REUSE_BOTTOM_UP): the bottom-up state left by the previous pml_loglik call (one
+    // parameter set, annotation masks, marginal, alter) is still current -- skip recomputing it
+    const bool reuse_bu = (force_joint & 2) != 0;
+    force_joint &= 1;
     if (force_joint && !p->joint_done)
         return fail(PML_ERR_INVALID, "force_joint needs the JOINT states: call pml_joint first");
     CUDA_TRY(cudaSetDevice(p->device));
@@ -807,7 +820,7 @@ int pml_marginal(pml_problem *p, const double *params, int32_t force_joint, doub
     if (rc) return rc;
     CallTimer timer(p);
     // ml.py:700-706: allowed states are re-initialised and altered, then BU(alter=False), TD, marginals
-    run_bottom_up(p, 1, p->mask[PML_MASK_ANNOTATION].ptr, 1, 1, false);
+    if (!reuse_bu) run_bottom_up(p, 1, p->mask[PML_MASK_ANNOTATION].ptr, 1, 1, false);
     run_top_down(p, force_joint, out_probs != nullptr, out_node_log10lh != nullptr);
     // remember the '.initial' state MAP saw: pml_mppa_finalize needs it
     if (p->n_rows) {
@@ -1018,6 +1031,92 @@ int pml_zero_likelihood_all(pml_problem *p, int32_t *out_pairs, int32_t n_lanes)
         out_pairs[2 * j] = have ? p->h_err[2 * j] : -1;
         out_pairs[2 * j + 1] = have ? p->h_err[2 * j + 1] : -1;
     }
+    return PML_OK;
+}
+
+int pml_get_root_partials(pml_problem *p, int32_t n_sets, double *out_vec, int32_t *out_ex) {
+    if (!p || !out_vec || !out_ex) return fail(PML_ERR_INVALID, "null argument");
+    if (n_sets < 1 || n_sets > p->B) return fail(PML_ERR_INVALID, "bad n_sets");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const LaneDev ln = p->lanes(n_sets);
+    const size_t nv = (size_t) p->n_roots * p->K * ln.J, ne = (size_t) p->n_roots * ln.J;
+    DevBuf<double> vec;
+    DevBuf<int> ex;
+    CUDA_TRY(vec.alloc(nv));
+    CUDA_TRY(ex.alloc(ne));
+    root_partials_kernel<<<grid_for((long long) ne), kBlock, 0, p->stream>>>(
+        p->tree(), p->zc(), ln, p->mask[PML_MASK_ANNOTATION].ptr, 1, p->bu.ptr, p->bu_ex.ptr, p->n_roots, vec.ptr, ex.ptr);
+    p->launches++;
+    CUDA_TRY(cudaMemcpyAsync(out_vec, vec.ptr, nv * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(out_ex, ex.ptr, ne * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    CUDA_TRY(cudaGetLastError());
+    return PML_OK;
+}
+
+int pml_set_tip_partials(pml_problem *p, int32_t n, const int32_t *nodes, const double *vec, const int32_t *ex,
+                         int32_t n_sets) {
+    if (!p || !nodes || !vec || !ex || n < 1) return fail(PML_ERR_INVALID, "bad argument");
+    if (n_sets < 1 || n_sets > p->B) return fail(PML_ERR_INVALID, "bad n_sets");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const int J = n_sets * p->C;
+    if (p->n_ext != n) {
+        // first call (or a different cut): validate and mark the tips
+        std::vector<int> slot_host(p->N);
+        CUDA_TRY(cudaMemcpy(slot_host.data(), p->slot.ptr, sizeof(int) * p->N, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; ++i)
+            if (nodes[i] < 0 || nodes[i] >= p->N || slot_host[nodes[i]] >= 0)
+                return fail(PML_ERR_INVALID, "external partials can only be attached to tips");
+        if (p->n_ext) return fail(PML_ERR_INVALID, "the set of external tips cannot change on a handle");
+        CUDA_TRY(p->ext_index.alloc(p->N));
+        CUDA_TRY(cudaMemsetAsync(p->ext_index.ptr, 0xff, sizeof(int) * p->N, p->stream));
+        CUDA_TRY(p->ext_nodes.alloc(n));
+        CUDA_TRY(cudaMemcpyAsync(p->ext_nodes.ptr, nodes, sizeof(int) * n, cudaMemcpyHostToDevice, p->stream));
+        mark_ext_kernel<<<grid_for((long long) n * p->C), kBlock, 0, p->stream>>>(
+            n, p->ext_nodes.ptr, p->C, p->mask[PML_MASK_ANNOTATION].ptr, p->ext_index.ptr);
+        p->launches++;
+        CUDA_TRY(p->ext_td.alloc((size_t) n * p->K * p->C));
+        CUDA_TRY(p->ext_td_ex.alloc((size_t) n * p->C));
+        p->n_ext = n;
+    }
+    if (p->ext_sets != n_sets) {
+        CUDA_TRY(p->ext_bu.alloc((size_t) n * p->K * J));
+        CUDA_TRY(p->ext_bu_ex.alloc((size_t) n * J));
+        p->ext_sets = n_sets;
+        for (auto &kv : p->graphs) cudaGraphExecDestroy(kv.second.exec);   // the tables moved: re-capture
+        p->graphs.clear();
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->ext_bu.ptr, vec, sizeof(double) * (size_t) n * p->K * J, cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->ext_bu_ex.ptr, ex, sizeof(int) * (size_t) n * J, cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    CUDA_TRY(cudaGetLastError());
+    return PML_OK;
+}
+
+int pml_get_tip_td(pml_problem *p, double *out_vec, int32_t *out_ex) {
+    if (!p || !out_vec || !out_ex) return fail(PML_ERR_INVALID, "null argument");
+    if (!p->n_ext || !p->marginal_done) return fail(PML_ERR_INVALID, "needs external tips and a marginal sweep");
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(cudaMemcpyAsync(out_vec, p->ext_td.ptr, sizeof(double) * (size_t) p->n_ext * p->K * p->C,
+                             cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(out_ex, p->ext_td_ex.ptr, sizeof(int) * (size_t) p->n_ext * p->C, cudaMemcpyDeviceToHost,
+                             p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return PML_OK;
+}
+
+int pml_set_root_td(pml_problem *p, const double *vec, const int32_t *ex) {
+    if (!p || !vec || !ex) return fail(PML_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const size_t nv = (size_t) p->n_roots * p->K * p->C, ne = (size_t) p->n_roots * p->C;
+    if (!p->root_td.ptr) {
+        CUDA_TRY(p->root_td.alloc(nv));
+        CUDA_TRY(p->root_td_ex.alloc(ne));
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->root_td.ptr, vec, nv * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->root_td_ex.ptr, ex, ne * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    p->have_root_td = true;
     return PML_OK;
 }
 

@@ -17,6 +17,8 @@
 namespace pml {
 
 constexpr uint64_t kMemberFlag = 1ULL << 63;  // (node, column) belongs to a zero-branch cluster (see alter_kernel)
+constexpr uint64_t kExtFlag = 1ULL << 62;     // tip whose bottom-up vector is supplied from outside (a clade cut off by
+                                              // subtree sharding): see ExtDev
 #ifndef PML_BLOCK
 #define PML_BLOCK 128
 #endif
@@ -146,6 +148,19 @@ __device__ __forceinline__ double vec_max(const double (&v)[KP]) {
 // a warp read consecutive words.  A lane model exposes: branch(dist) -> Branch, matvec(out = max(P(t) in, 0)),
 // maxvec(out_i = max_j P_ij in_j with the first argmax), pi(k).  Entries k >= K of every register vector are zero
 // and stay zero, so arithmetic runs unguarded over the padded length KP and only memory accesses are guarded.
+
+// Subtree sharding: when one big tree is cut into clades owned by different GPUs, the part of
+// the tree above the cut sees every clade root as a tip whose bottom-up vector comes from another problem (possibly
+// another GPU, after an all-gather), and every clade forest sees top-down vectors arriving at its roots.
+struct ExtDev {
+    const int *index;       // [N] tip node -> row of the tables below (valid where the mask carries kExtFlag)
+    const double *bu;       // [rows][K][J] bottom-up mantissas of the external tips
+    const int *bu_ex;       // [rows][J]
+    double *td;             // [rows][K][C] top-down vectors computed for the external tips (output of the sweep)
+    int *td_ex;             // [rows][C]
+    const double *root_td;  // [T][K][C] top-down vectors arriving at the roots, or null (roots start from all ones)
+    const int *root_td_ex;  // [T][C]
+};
 
 struct LaneSmem {
     const double *s;   // staged fields of this lane: field f at s[f * J]
@@ -426,6 +441,7 @@ static __global__ void alter_kernel(int n_clusters, const int *cl_col, const int
 struct BuArgs {
     TreeDev t;
     ZcDev zc;
+    ExtDev ext;
     LaneDev ln;
     const uint64_t *mask;   // [N][C]
     int alter;              // apply the cluster table where the lane's tau == 0
@@ -438,9 +454,9 @@ struct BuArgs {
 // loads the K-vector of a child: a stored mantissa vector for internal nodes, the allowed-state mask for tips
 // (tips: BOTTOM_UP_LIKELIHOOD = allowed states, SF = 0)
 template <int KP>
-__device__ __forceinline__ int load_child(const TreeDev &t, const ZcDev &zc, const LaneDev &ln, const uint64_t *mask,
-                                          const double *bu, const int *bu_ex, int ch, int j, int c, bool use_alt,
-                                          double (&in)[KP], uint64_t &tip_mask) {
+__device__ __forceinline__ int load_child(const TreeDev &t, const ZcDev &zc, const ExtDev &ext, const LaneDev &ln,
+                                          const uint64_t *mask, const double *bu, const int *bu_ex, int ch, int j, int c,
+                                          bool use_alt, double (&in)[KP], uint64_t &tip_mask) {
     const int cs = t.slot[ch];
     if (cs >= 0) {
         const double *src = bu + ((size_t) cs * ln.K) * ln.J + j;
@@ -448,6 +464,14 @@ __device__ __forceinline__ int load_child(const TreeDev &t, const ZcDev &zc, con
         for (int k = 0; k < KP; ++k) in[k] = (k < ln.K) ? src[(size_t) k * ln.J] : 0.;
         tip_mask = 0ULL;
         return bu_ex[(size_t) cs * ln.J + j];
+    }
+    if (mask[(size_t) ch * ln.C + c] & kExtFlag) {   // a clade root cut off by subtree sharding
+        const int e = ext.index[ch];
+        const double *src = ext.bu + ((size_t) e * ln.K) * ln.J + j;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) in[k] = (k < ln.K) ? src[(size_t) k * ln.J] : 0.;
+        tip_mask = ln.kmask;
+        return ext.bu_ex[(size_t) e * ln.J + j];
     }
     tip_mask = eff_mask(mask, t, zc, ln.C, ch, c, use_alt, ln.kmask);
 #pragma unroll
@@ -485,8 +509,8 @@ __global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_BU_MINB : 1)) bu_level
             double in0[KP], in1[KP];
             uint64_t tm;
             const double d0 = a.t.dist[fc], d1 = a.t.dist[fc + 1];
-            ex += load_child<KP>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, fc, j, c, use_alt, in0, tm);
-            ex += load_child<KP>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, j, c, use_alt, in1, tm);
+            ex += load_child<KP>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc, j, c, use_alt, in0, tm);
+            ex += load_child<KP>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, j, c, use_alt, in1, tm);
             const typename Lane<KP>::Branch b0 = lane.branch(d0, K), b1 = lane.branch(d1, K);
             lane.mul_matvec(b0, in0, acc, K);
             const double vmax0 = vec_max<KP>(acc);
@@ -501,7 +525,7 @@ __global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_BU_MINB : 1)) bu_level
                 const typename Lane<KP>::Branch br = lane.branch(a.t.dist[ch], K);
                 double in[KP];
                 uint64_t tm;
-                ex += load_child<KP>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, ch, j, c, use_alt, in, tm);
+                ex += load_child<KP>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, ch, j, c, use_alt, in, tm);
                 if (MAXP) {
                     double v[KP];
                     uint8_t arg[KP];
@@ -616,6 +640,7 @@ static __global__ void joint_trace_kernel(JointArgs a, int node_begin, int n_nod
 struct TdArgs {
     TreeDev t;
     ZcDev zc;
+    ExtDev ext;
     LaneDev ln;                 // J == C (one parameter set)
     const uint64_t *mask;       // annotation masks
     const double *bu;
@@ -760,13 +785,20 @@ __global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_TD_MINB : 1)) td_level
 
         double Lc[KP], X[KP];
         uint64_t mc;
-        const int exc = load_child<KP>(a.t, a.zc, a.ln, a.mask, a.bu, a.bu_ex, node, c, c, use_alt, Lc, mc);
+        const int exc = load_child<KP>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, node, c, c, use_alt, Lc, mc);
         if (cs >= 0) mc = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
         int ex_total;
         if (ps < 0) {
-#pragma unroll
-            for (int k = 0; k < KP; ++k) X[k] = Lc[k];   // TD(root) = 1
             ex_total = exc;
+            if (a.ext.root_td) {   // a clade root: its top-down vector arrives from the part of the tree above the cut
+                const double *src = a.ext.root_td + ((size_t) node * K) * C + c;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) X[k] = (k < K) ? Lc[k] * src[(size_t) k * C] : 0.;
+                ex_total += a.ext.root_td_ex[(size_t) node * C + c];
+            } else {
+#pragma unroll
+                for (int k = 0; k < KP; ++k) X[k] = Lc[k];   // TD(root) = 1
+            }
         } else {
             // parent part of the node's top-down vector: TD_p * L_p, divided below by the node's own contribution
             {
@@ -780,6 +812,12 @@ __global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_TD_MINB : 1)) td_level
 #pragma unroll
                 for (int k = 0; k < KP; ++k) X[k] *= (k < K) ? src[(size_t) k * C] : 0.;
                 pex += a.td_ex[(size_t) ps * C + c];
+            } else if (a.ext.root_td) {   // child of a clade root: the root's top-down vector came from above the cut
+                const int rn = a.t.int_nodes[ps];
+                const double *src = a.ext.root_td + ((size_t) rn * K) * C + c;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) X[k] *= (k < K) ? src[(size_t) k * C] : 0.;
+                pex += a.ext.root_td_ex[(size_t) rn * C + c];
             }
             const typename Lane<KP>::Branch br = lane.branch(a.t.dist[node], K);
             double q[KP];
@@ -795,6 +833,13 @@ __global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_TD_MINB : 1)) td_level
                 for (int k = 0; k < KP; ++k)
                     if (k < K) dst[(size_t) k * C] = X[k];
                 a.td_ex[(size_t) cs * C + c] = qex;
+            } else if (a.mask[(size_t) node * C + c] & kExtFlag) {   // hand the vector to the clade below the cut
+                const int e = a.ext.index[node];
+                double *dst = a.ext.td + ((size_t) e * K) * C + c;
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+                    if (k < K) dst[(size_t) k * C] = X[k];
+                a.ext.td_ex[(size_t) e * C + c] = qex;
             }
 #pragma unroll
             for (int k = 0; k < KP; ++k) X[k] *= Lc[k];
@@ -1021,6 +1066,30 @@ static __global__ void init_masks_kernel(int N, int C, uint64_t kmask, const uin
 static __global__ void log10_finish_kernel(long long n, double *v, const int *ex) {
     const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     if (g < n) v[g] = log10(v[g]) + (double) ex[g] * 0.30102999566398119521;
+}
+
+// marks the listed tips as external (their vectors live in the ExtDev tables) in every column
+static __global__ void mark_ext_kernel(int n, const int *nodes, int C, uint64_t *mask, int *ext_index) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n * C) return;
+    const int i = g / C, c = g % C;
+    mask[(size_t) nodes[i] * C + c] |= kExtFlag;
+    if (c == 0) ext_index[nodes[i]] = i;
+}
+
+// gathers the bottom-up vectors of the roots: [T][K][J] mantissas and [T][J] exponents (tip roots: their masks)
+static __global__ void root_partials_kernel(TreeDev t, ZcDev zc, LaneDev ln, const uint64_t *mask, int alter,
+                                            const double *bu, const int *bu_ex, int n_roots, double *out,
+                                            int *out_ex) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_roots * ln.J) return;
+    const int node = g / ln.J, j = g % ln.J, c = j % ln.C;
+    const int s = t.slot[node];
+    const double *p = ln.params + (size_t) j * ln.stride;
+    const uint64_t m = (s >= 0) ? 0ULL : eff_mask(mask, t, zc, ln.C, node, c, alter && p[1] == 0., ln.kmask);
+    for (int k = 0; k < ln.K; ++k)
+        out[((size_t) node * ln.K + k) * ln.J + j] = (s >= 0) ? bu[((size_t) s * ln.K + k) * ln.J + j] : bit_as_double(m, k);
+    out_ex[(size_t) node * ln.J + j] = (s >= 0) ? bu_ex[(size_t) s * ln.J + j] : 0;
 }
 
 static __global__ void strip_flag_kernel(long long n, uint64_t kmask, const uint64_t *in, uint64_t *out) {

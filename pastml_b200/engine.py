@@ -133,7 +133,10 @@ class Problem(object):
         self._check(self.lib.pml_joint(self._h, _p(params), _p(lh), _p(states)))
         return lh, states
 
-    def marginal(self, params, force_joint=True, want_probs=True, want_node_lh=False, want_masks=True):
+    def marginal(self, params, force_joint=True, want_probs=True, want_node_lh=False, want_masks=True,
+                 reuse_bottom_up=False):
+        """``reuse_bottom_up``: the bottom-up state of the immediately preceding ``loglik(params)`` call (one set,
+        annotation masks, marginal, alter) is reused instead of recomputed."""
         params = self._params(params, 1)
         lh = np.empty(self.C, dtype=np.float64)
         probs = np.empty((self.N, self.C, self.K), dtype=np.float64) if want_probs else None
@@ -141,7 +144,8 @@ class Problem(object):
         map_mask = np.empty((self.N, self.C), dtype=np.uint64) if want_masks else None
         mppa_mask = np.empty((self.N, self.C), dtype=np.uint64) if want_masks else None
         k_hist = np.empty((self.C, self.K + 1), dtype=np.int64)
-        self._check(self.lib.pml_marginal(self._h, _p(params), 1 if force_joint else 0, _p(lh), _p(probs),
+        self._check(self.lib.pml_marginal(self._h, _p(params), (1 if force_joint else 0) | (2 if reuse_bottom_up else 0),
+                                          _p(lh), _p(probs),
                                           _p(node_lh), _p(map_mask), _p(mppa_mask), _p(k_hist)))
         return dict(loglh=lh, probs=probs, node_log10lh=node_lh, map_mask=map_mask, mppa_mask=mppa_mask,
                     k_hist=k_hist)
@@ -177,6 +181,39 @@ class Problem(object):
         init = np.empty((self.N, self.C), dtype=np.uint64)
         self._check(self.lib.pml_get_initial(self._h, _p(has), _p(init)))
         return has, init
+
+    # ------------------------------------------------------------------ subtree sharding hooks
+    def root_partials(self, n_sets=1):
+        """Bottom-up vectors of the roots after a loglik pass: (vec [T][K][J], ex [T][J])."""
+        T, J = len(self.flat.roots), n_sets * self.C
+        vec = np.empty((T, self.K, J), dtype=np.float64)
+        ex = np.empty((T, J), dtype=np.int32)
+        self._check(self.lib.pml_get_root_partials(self._h, n_sets, _p(vec), _p(ex)))
+        return vec, ex
+
+    def set_tip_partials(self, nodes, vec, ex, n_sets=1):
+        nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+        vec = np.ascontiguousarray(vec, dtype=np.float64)
+        ex = np.ascontiguousarray(ex, dtype=np.int32)
+        if vec.shape != (len(nodes), self.K, n_sets * self.C) or ex.shape != (len(nodes), n_sets * self.C):
+            raise ValueError('external partials must be [n][K][J] and [n][J]')
+        self._check(self.lib.pml_set_tip_partials(self._h, len(nodes), _p(nodes), _p(vec), _p(ex), n_sets))
+        self._n_ext = len(nodes)
+
+    def tip_td(self):
+        n = self._n_ext
+        vec = np.empty((n, self.K, self.C), dtype=np.float64)
+        ex = np.empty((n, self.C), dtype=np.int32)
+        self._check(self.lib.pml_get_tip_td(self._h, _p(vec), _p(ex)))
+        return vec, ex
+
+    def set_root_td(self, vec, ex):
+        T = len(self.flat.roots)
+        vec = np.ascontiguousarray(vec, dtype=np.float64)
+        ex = np.ascontiguousarray(ex, dtype=np.int32)
+        if vec.shape != (T, self.K, self.C) or ex.shape != (T, self.C):
+            raise ValueError('root top-down vectors must be [T][K][C] and [T][C]')
+        self._check(self.lib.pml_set_root_td(self._h, _p(vec), _p(ex)))
 
     def last_call_stats(self):
         ms, n = C.c_double(), C.c_int64()

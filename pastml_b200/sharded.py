@@ -1,0 +1,192 @@
+"""Subtree sharding of ONE big tree across GPUs (second case).
+
+The tree is cut at a depth level with enough clades; each rank owns a balanced set of clades as a forest problem,
+and the part of the tree above the cut (the "top tree", a few thousand nodes at most) is replicated on every rank,
+seeing the clade roots as tips whose bottom-up vectors come from outside.  One exchange per sweep:
+
+  bottom-up:  every rank prunes its clades  ->  ALL-GATHER of the clade-root vectors ((K + 1) numbers per lane and
+              clade)  ->  every rank finishes the top tree redundantly, so every rank holds the log-likelihood;
+  top-down:   every rank runs the top tree's top-down sweep itself (it has all the inputs), which leaves the
+              top-down vectors of the clade roots; each rank hands its own to its clade forest and continues
+              downwards -- no second collective.
+
+Only marginal passes are sharded (objective evaluations and the BU + TD / marginal / MAP / MPPA pipeline without
+the forced joint state); the exchange payload is tiny (latency-, not bandwidth-bound), so it travels as one
+``all_gather`` of a padded tensor (NCCL on the GPU box, gloo in CPU tests).
+"""
+import numpy as np
+
+from pastml_b200.engine import Problem
+from pastml_b200.tree import FlatForest
+
+
+class SubtreePlan(object):
+    """Where a single tree is cut and who owns which clade.
+
+    Attributes: ``cut_level``, ``n_top`` (the top tree is nodes [0, n_top) of the flat order, unchanged),
+    ``boundary`` (ids of the clade roots = internal nodes of the cut level; tips of the top tree),
+    ``owner_of_clade`` [len(boundary)], and per rank ``nodes[r]`` (global ids of its forest in level order),
+    ``roots_pos[r]`` (positions of its clade roots inside ``boundary``).
+    """
+
+    def __init__(self, flat, world_size, clades_per_rank=8):
+        if flat.n_trees != 1:
+            raise ValueError('subtree sharding takes one tree (forests shard by tree)')
+        self.flat = flat
+        self.world = int(world_size)
+        want = self.world * clades_per_rank
+        internal = flat.n_children > 0
+        cut = None
+        best = (0, None)
+        for lvl in range(1, flat.n_levels):
+            lo, hi = flat.level_ptr[lvl], flat.level_ptr[lvl + 1]
+            n_int = int(internal[lo:hi].sum())
+            # a zero-length branch across the cut would split a zero-branch cluster between problems
+            ok = not np.any((flat.dist[lo:hi] == 0) & internal[lo:hi])
+            if ok and n_int > best[0]:
+                best = (n_int, lvl)
+            if ok and n_int >= want:
+                cut = lvl
+                break
+        if cut is None:
+            cut = best[1]
+        if cut is None or best[0] < self.world:
+            raise ValueError('the tree has no level with enough clades to shard over {} ranks'.format(self.world))
+        self.cut_level = cut
+        lo, hi = flat.level_ptr[cut], flat.level_ptr[cut + 1]
+        self.n_top = int(hi)
+        self.boundary = (np.arange(lo, hi)[internal[lo:hi]]).astype(np.int32)
+
+        # subtree sizes, accumulated level by level from the bottom
+        size = np.ones(flat.n_nodes, dtype=np.int64)
+        for lvl in range(flat.n_levels - 1, 0, -1):
+            a, b = flat.level_ptr[lvl], flat.level_ptr[lvl + 1]
+            np.add.at(size, flat.parent[a:b], size[a:b])
+        # longest-processing-time assignment of clades to ranks
+        order = np.argsort(-size[self.boundary], kind='stable')
+        load = np.zeros(self.world, dtype=np.int64)
+        self.owner_of_clade = np.zeros(len(self.boundary), dtype=np.int32)
+        for i in order:
+            r = int(np.argmin(load))
+            self.owner_of_clade[i] = r
+            load[r] += size[self.boundary[i]]
+        self.load = load
+
+        # owner of every node below the cut
+        owner = np.full(flat.n_nodes, -1, dtype=np.int32)
+        owner[self.boundary] = self.owner_of_clade
+        for lvl in range(cut + 1, flat.n_levels):
+            a, b = flat.level_ptr[lvl], flat.level_ptr[lvl + 1]
+            owner[a:b] = owner[flat.parent[a:b]]
+        self.nodes, self.roots_pos, self._forests = [], [], [None] * self.world
+        for r in range(self.world):
+            ids = np.flatnonzero(owner == r).astype(np.int64)   # increasing id = level order of the forest
+            self.nodes.append(ids)
+            self.roots_pos.append(np.flatnonzero(self.owner_of_clade == r).astype(np.int64))
+
+    def top_forest(self):
+        """The replicated part: nodes above and at the cut, in their original order."""
+        return FlatForest(self.flat.parent[:self.n_top], self.flat.dist[:self.n_top])
+
+    def clade_forest(self, rank):
+        """The rank's clades as a level-ordered forest (roots = its clade roots, in boundary order)."""
+        if self._forests[rank] is None:
+            ids = self.nodes[rank]
+            new_id = np.full(self.flat.n_nodes, -1, dtype=np.int64)
+            new_id[ids] = np.arange(len(ids))
+            par = self.flat.parent[ids].astype(np.int64)
+            is_root = np.isin(ids, self.boundary)
+            new_par = np.where(is_root, -1, new_id[np.where(is_root, 0, par)]).astype(np.int32)
+            self._forests[rank] = FlatForest(new_par, self.flat.dist[ids])
+        return self._forests[rank]
+
+
+class ShardedProblem(object):
+    """One rank's share of a sharded tree: its clade forest and the replicated top tree, both on one device."""
+
+    def __init__(self, plan, rank, n_states, model_kind, annot_mask, has_state, max_param_sets=1, device=0):
+        self.plan, self.rank = plan, rank
+        annot_mask = np.atleast_2d(annot_mask)
+        has_state = np.atleast_2d(has_state)
+        ids = plan.nodes[rank]
+        self.clades = Problem(plan.clade_forest(rank), n_states, model_kind, annot_mask[:, ids], has_state[:, ids],
+                              max_param_sets=max_param_sets, device=device)
+        self.top = Problem(plan.top_forest(), n_states, model_kind, annot_mask[:, :plan.n_top],
+                           has_state[:, :plan.n_top], max_param_sets=max_param_sets, device=device)
+        self.K, self.C = int(n_states), annot_mask.shape[0]
+
+    def close(self):
+        self.clades.close()
+        self.top.close()
+
+    # ---- bottom-up
+    def local_root_partials(self, params, n_sets=1):
+        """Prunes this rank's clades; returns (vec [n_mine][K][J], ex [n_mine][J])."""
+        self.clades.loglik(params, n_sets=n_sets, tolerate_zero=True)
+        return self.clades.root_partials(n_sets)
+
+    def assemble(self, gathered):
+        """[(vec, ex) of rank 0, of rank 1, ...] -> arrays in boundary order."""
+        n = len(self.plan.boundary)
+        J = gathered[0][0].shape[2]
+        vec = np.empty((n, self.K, J), dtype=np.float64)
+        ex = np.empty((n, J), dtype=np.int32)
+        for r, (v, e) in enumerate(gathered):
+            pos = self.plan.roots_pos[r]
+            vec[pos] = v[:len(pos)]
+            ex[pos] = e[:len(pos)]
+        return vec, ex
+
+    def finish_loglik(self, params, vec, ex, n_sets=1):
+        """Log-likelihoods [n_sets][C] of the whole tree given all clade-root vectors."""
+        self.top.set_tip_partials(self.plan.boundary, vec, ex, n_sets)
+        return self.top.loglik(params, n_sets=n_sets)
+
+    # ---- fused top-down sweep
+    def marginal(self, params, vec, ex, want_probs=True, reuse_bottom_up=False):
+        """Top tree sweep on every rank, then this rank's clades.  Returns the rank's pieces: dictionaries for the
+        top tree (node ids [0, n_top)) and for its clade forest (global node ids in ``plan.nodes[rank]``)."""
+        self.top.set_tip_partials(self.plan.boundary, vec, ex, 1)
+        top = self.top.marginal(params, force_joint=False, want_probs=want_probs)
+        td_vec, td_ex = self.top.tip_td()
+        pos = self.plan.roots_pos[self.rank]
+        self.clades.set_root_td(td_vec[pos], td_ex[pos])
+        # the clades' bottom-up state is the one local_root_partials() just computed
+        mine = self.clades.marginal(params, force_joint=False, want_probs=want_probs, reuse_bottom_up=reuse_bottom_up)
+        return top, mine
+
+
+def all_gather_partials(vec, ex, plan, rank):
+    """All ranks' (vec, ex), exchanged with one all_gather of a padded tensor (torch.distributed must be
+    initialised; the backend decides the transport: NCCL over NVLink on the GPU box, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    n_max = max(len(p) for p in plan.roots_pos)
+    K, J = vec.shape[1], vec.shape[2]
+    use_cuda = dist.get_backend() == 'nccl'
+    payload = np.zeros((n_max, K + 1, J), dtype=np.float64)
+    payload[:len(vec), :K, :] = vec
+    payload[:len(ex), K, :] = ex          # exponents travel as doubles (exact for |ex| < 2^53)
+    t = torch.from_numpy(payload)
+    if use_cuda:
+        t = t.cuda()
+    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    out = out.cpu().numpy()
+    gathered = []
+    for r in range(world):
+        n = len(plan.roots_pos[r])
+        gathered.append((np.ascontiguousarray(out[r, :n, :K, :]), np.ascontiguousarray(out[r, :n, K, :]).astype(np.int32)))
+    return gathered
+
+
+def merge_outputs(plan, per_rank, key, n_nodes):
+    """Stitches per-rank [n_local][C](...) outputs into one [N][C](...) array (top tree from rank 0)."""
+    top0, _ = per_rank[0]
+    sample = top0[key]
+    out = np.empty((n_nodes,) + sample.shape[1:], dtype=sample.dtype)
+    out[:plan.n_top] = sample
+    for r, (_, mine) in enumerate(per_rank):
+        out[plan.nodes[r]] = mine[key]
+    return out

@@ -1,0 +1,77 @@
+"""Subtree sharding of one tree: the plan (CPU) and, on a GPU, equality with the unsharded engine when the ranks are
+simulated one after the other on one device."""
+import numpy as np
+import pytest
+
+
+def _tree(n_tips, seed, kind='yule'):
+    from pastml_b200 import synth
+    rng = np.random.default_rng(seed)
+    return (synth.yule_tree if kind == 'yule' else synth.coalescent_tree)(n_tips, rng), rng
+
+
+@pytest.mark.parametrize('world', [2, 3, 8])
+def test_plan_partitions_the_tree(world):
+    from pastml_b200.sharded import SubtreePlan
+    flat, _ = _tree(3000, 11)
+    plan = SubtreePlan(flat, world)
+    covered = np.concatenate([plan.nodes[r] for r in range(world)] + [np.arange(plan.n_top)])
+    # every node is in the top tree or in exactly one clade forest; the clade roots are in both
+    counts = np.bincount(covered, minlength=flat.n_nodes)
+    assert np.all(counts[plan.boundary] == 2)
+    rest = np.ones(flat.n_nodes, dtype=bool)
+    rest[plan.boundary] = False
+    assert np.all(counts[rest] == 1)
+    assert plan.load.max() <= 1.5 * plan.load.mean() + flat.n_nodes / (4 * world)
+    top = plan.top_forest()
+    assert np.array_equal(top.parent, flat.parent[:plan.n_top])
+    for r in range(world):
+        f = plan.clade_forest(r)
+        ids = plan.nodes[r]
+        assert f.n_trees == len(plan.roots_pos[r])
+        assert np.array_equal(ids[:f.n_trees], plan.boundary[plan.roots_pos[r]])
+        inner = f.parent >= 0
+        assert np.array_equal(ids[f.parent[inner]], flat.parent[ids[inner]])
+        assert np.array_equal(f.dist, flat.dist[ids])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n_tips,K,C,world,kind', [(4000, 20, 8, 2, 'yule'), (3000, 7, 3, 3, 'coalescent'),
+                                                  (2500, 12, 20, 4, 'yule')])
+def test_sharded_equals_unsharded(n_tips, K, C, world, kind):
+    from pastml_b200 import synth
+    from pastml_b200.engine import Problem, pack_params
+    from pastml_b200.sharded import SubtreePlan, ShardedProblem, merge_outputs
+    flat, rng = _tree(n_tips, 100 + n_tips + K, kind)
+    masks, has, pis, sfs = synth.simulate_tip_masks(flat, K, C, rng, missing=0.05)
+    params = np.stack([pack_params(0, K, sfs[c], 0., 1., pis[c]) for c in range(C)])
+    sets = np.stack([params, params])
+    sets[1, :, 0] *= 1.3
+    whole = Problem(flat, K, 0, masks, has, max_param_sets=2)
+    want_lh = whole.loglik(sets, n_sets=2)
+    want = whole.marginal(params, force_joint=False)
+    whole.close()
+
+    plan = SubtreePlan(flat, world, clades_per_rank=4)
+    ranks = [ShardedProblem(plan, r, K, 0, masks, has, max_param_sets=2) for r in range(world)]
+    # objective: every rank prunes its clades, the vectors are exchanged, every rank finishes the top tree
+    gathered = [sp.local_root_partials(sets, n_sets=2) for sp in ranks]
+    for sp in ranks:
+        vec, ex = sp.assemble(gathered)
+        got = sp.finish_loglik(sets, vec, ex, n_sets=2)
+        np.testing.assert_allclose(got, want_lh, rtol=1e-12, atol=0)
+    # fused sweep
+    gathered = [sp.local_root_partials(params) for sp in ranks]
+    pieces = []
+    for sp in ranks:
+        vec, ex = sp.assemble(gathered)
+        pieces.append(sp.marginal(params, vec, ex))
+    for key in ('probs', 'map_mask', 'mppa_mask'):
+        got = merge_outputs(plan, pieces, key, flat.n_nodes)
+        if key == 'probs':
+            np.testing.assert_allclose(got, want[key], rtol=0, atol=1e-12)
+        else:
+            assert np.array_equal(got, want[key]), key
+    np.testing.assert_allclose(pieces[0][0]['loglh'], want['loglh'], rtol=1e-12)
+    for sp in ranks:
+        sp.close()
