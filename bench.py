@@ -197,7 +197,7 @@ def run_subtree_sharded(args):
         vec, ex = sp.local_root_partials(params)
         gathered = all_gather_partials(vec, ex, plan, rank)
         vec, ex = sp.assemble(gathered)
-        return sp.marginal(params, vec, ex, want_probs=False, reuse_bottom_up=True)
+        return sp.marginal(params, vec, ex, want_probs=False, want_masks=False, reuse_bottom_up=True)
 
     for _ in range(max(args.warmup, 3)):
         top, mine = step()
@@ -224,6 +224,12 @@ def run_subtree_sharded(args):
             'gpu_launches': None}
     line['config']['sharding'] = 'one tree cut into clades over the GPUs (subtree sharding)'
     sp.close()
+    if rank == 0:   # outside the timed region: the same tree, unsharded, on this GPU
+        from pastml_b200.engine import Problem
+        whole = Problem(flat, K, 0, masks, has, device=local_rank)
+        ref = whole.loglik(params)[0]
+        whole.close()
+        line['check_max_rel_dev_loglh_vs_unsharded'] = float(np.max(np.abs(top['loglh'] - ref) / np.abs(ref)))
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

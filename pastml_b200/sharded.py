@@ -143,16 +143,17 @@ class ShardedProblem(object):
         return self.top.loglik(params, n_sets=n_sets)
 
     # ---- fused top-down sweep
-    def marginal(self, params, vec, ex, want_probs=True, reuse_bottom_up=False):
+    def marginal(self, params, vec, ex, want_probs=True, reuse_bottom_up=False, want_masks=True):
         """Top tree sweep on every rank, then this rank's clades.  Returns the rank's pieces: dictionaries for the
         top tree (node ids [0, n_top)) and for its clade forest (global node ids in ``plan.nodes[rank]``)."""
         self.top.set_tip_partials(self.plan.boundary, vec, ex, 1)
-        top = self.top.marginal(params, force_joint=False, want_probs=want_probs)
+        top = self.top.marginal(params, force_joint=False, want_probs=want_probs, want_masks=want_masks)
         td_vec, td_ex = self.top.tip_td()
         pos = self.plan.roots_pos[self.rank]
         self.clades.set_root_td(td_vec[pos], td_ex[pos])
         # the clades' bottom-up state is the one local_root_partials() just computed
-        mine = self.clades.marginal(params, force_joint=False, want_probs=want_probs, reuse_bottom_up=reuse_bottom_up)
+        mine = self.clades.marginal(params, force_joint=False, want_probs=want_probs, want_masks=want_masks,
+                                    reuse_bottom_up=reuse_bottom_up)
         return top, mine
 
 
@@ -171,9 +172,9 @@ def all_gather_partials(vec, ex, plan, rank):
     t = torch.from_numpy(payload)
     if use_cuda:
         t = t.cuda()
-    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-    dist.all_gather_into_tensor(out, t)
-    out = out.cpu().numpy()
+    out = torch.empty((world * n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t)   # concatenated along dim 0: the form both NCCL and gloo accept
+    out = out.cpu().numpy().reshape((world, n_max) + tuple(t.shape[1:]))
     gathered = []
     for r in range(world):
         n = len(plan.roots_pos[r])

@@ -64,3 +64,45 @@ def test_two_gloo_ranks_shard_columns(tmp_path):
         assert o['merged'] == ['c0', 'c1', 'c2', 'c3', 'c4']
         assert o['owners'] == [0, 0, 0, 1, 1]
         assert o['slowest'] == 2.0
+
+
+SHARD_WORKER = textwrap.dedent("""
+    import os, sys, json
+    sys.path.insert(0, {repo!r})
+    import numpy as np
+    import torch.distributed as dist
+    from pastml_b200 import synth
+    from pastml_b200.sharded import SubtreePlan, all_gather_partials
+    dist.init_process_group('gloo', rank=int(os.environ['RANK']), world_size=int(os.environ['WORLD_SIZE']))
+    rank = dist.get_rank()
+    flat = synth.yule_tree(500, np.random.default_rng(3))
+    plan = SubtreePlan(flat, 2, clades_per_rank=3)
+    K, J = 4, 3
+    n = len(plan.roots_pos[rank])
+    # a recognisable payload: clade-root id in the mantissas, rank in the exponents
+    vec = np.zeros((n, K, J)) + plan.boundary[plan.roots_pos[rank]][:, None, None]
+    ex = np.full((n, J), rank - 7, dtype=np.int32)
+    got = all_gather_partials(vec, ex, plan, rank)
+    ok = all(np.all(got[r][0] == plan.boundary[plan.roots_pos[r]][:, None, None]) and np.all(got[r][1] == r - 7)
+             and got[r][0].shape == (len(plan.roots_pos[r]), K, J) for r in range(2))
+    print(json.dumps(dict(rank=rank, ok=bool(ok), clades=[len(p) for p in plan.roots_pos])))
+    dist.destroy_process_group()
+""")
+
+
+@pytest.mark.timeout(180)
+def test_two_gloo_ranks_exchange_clade_root_partials(tmp_path):
+    """The one collective of the subtree-sharded path (all-gather of clade-root vectors) over gloo."""
+    import json
+    script = tmp_path / 'shard_worker.py'
+    script.write_text(SHARD_WORKER.format(repo=REPO))
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE='2', MASTER_ADDR='127.0.0.1', MASTER_PORT='29618')
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    for p in procs:
+        out, err = p.communicate(timeout=170)
+        assert p.returncode == 0, err[-2000:]
+        res = json.loads(out.strip().splitlines()[-1])
+        assert res['ok'] and sum(res['clades']) >= 6
