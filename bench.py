@@ -197,7 +197,8 @@ def run_subtree_sharded(args):
         vec, ex = sp.local_root_partials(params)
         gathered = all_gather_partials(vec, ex, plan, rank)
         vec, ex = sp.assemble(gathered)
-        return sp.marginal(params, vec, ex, want_probs=False, want_masks=False, reuse_bottom_up=True)
+        return sp.marginal(params, vec, ex, want_probs=False, want_masks=False, reuse_bottom_up=True,
+                           results_on_device=True)   # same device work as the N = 1 step: probabilities are written
 
     for _ in range(max(args.warmup, 3)):
         top, mine = step()

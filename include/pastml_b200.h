@@ -57,6 +57,7 @@ typedef struct pml_problem pml_problem;
 #define PML_PARS_DELTRAN 4
 
 #define PML_REUSE_BOTTOM_UP 2
+#define PML_RESULTS_ON_DEVICE 4
 
 /* error codes */
 #define PML_OK 0
@@ -101,7 +102,9 @@ int pml_joint(pml_problem *p, const double *params, double *out_loglh, int32_t *
  * probabilities, MAP and MPPA state selection, fused in one level-synchronous sweep.
  *   force_joint        bit 0: MPPA keeps room for the JOINT state (needs a previous pml_joint call);
  *                      bit 1 (PML_REUSE_BOTTOM_UP): the bottom-up state of the immediately preceding pml_loglik call
- *                      (same parameters, one set, annotation masks, marginal, alter) is reused instead of recomputed
+ *                      (same parameters, one set, annotation masks, marginal, alter) is reused instead of recomputed;
+ *                      bit 2 (PML_RESULTS_ON_DEVICE): probabilities / node log-likelihoods are computed into the
+ *                      handle's device buffers even when the host pointers are NULL
  *   out_loglh[C]       marginal log-likelihood                                     (may be NULL)
  *   out_probs[N][C][K] marginal probabilities, ml.py:486-502                        (may be NULL)
  *   out_node_log10lh[N][C]  log10 of the node's total marginal likelihood = log10(sum LIKELIHOOD) -

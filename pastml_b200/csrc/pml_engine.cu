@@ -810,18 +810,22 @@ int pml_marginal(pml_problem *p, const double *params, int32_t force_joint, doub
     // bit 1 of force_joint (PML_REUSE_BOTTOM_UP): the bottom-up state left by the previous pml_loglik call (one
     // parameter set, annotation masks, marginal, alter) is still current -- skip recomputing it
     const bool reuse_bu = (force_joint & 2) != 0;
+    // bit 2 (PML_RESULTS_ON_DEVICE): probabilities and node log-likelihoods are computed and kept in the handle's
+    // device buffers even though no host pointer is given (device-resident timing of the full sweep)
+    const bool on_device = (force_joint & 4) != 0;
     force_joint &= 1;
     if (force_joint && !p->joint_done)
         return fail(PML_ERR_INVALID, "force_joint needs the JOINT states: call pml_joint first");
     CUDA_TRY(cudaSetDevice(p->device));
-    int rc = ensure_marginal_buffers(p, out_probs != nullptr, out_node_log10lh != nullptr);
+    const bool do_probs = out_probs != nullptr || on_device, do_node_lh = out_node_log10lh != nullptr || on_device;
+    int rc = ensure_marginal_buffers(p, do_probs, do_node_lh);
     if (rc) return rc;
     rc = upload_params(p, params, 1);
     if (rc) return rc;
     CallTimer timer(p);
     // ml.py:700-706: allowed states are re-initialised and altered, then BU(alter=False), TD, marginals
     if (!reuse_bu) run_bottom_up(p, 1, p->mask[PML_MASK_ANNOTATION].ptr, 1, 1, false);
-    run_top_down(p, force_joint, out_probs != nullptr, out_node_log10lh != nullptr);
+    run_top_down(p, force_joint, do_probs, do_node_lh);
     // remember the '.initial' state MAP saw: pml_mppa_finalize needs it
     if (p->n_rows) {
         cudaMemcpyAsync(p->zc_prev_initial.ptr, p->zc_initial.ptr, sizeof(uint64_t) * (size_t) p->n_rows * p->C,

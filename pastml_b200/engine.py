@@ -134,7 +134,7 @@ class Problem(object):
         return lh, states
 
     def marginal(self, params, force_joint=True, want_probs=True, want_node_lh=False, want_masks=True,
-                 reuse_bottom_up=False):
+                 reuse_bottom_up=False, results_on_device=False):
         """``reuse_bottom_up``: the bottom-up state of the immediately preceding ``loglik(params)`` call (one set,
         annotation masks, marginal, alter) is reused instead of recomputed."""
         params = self._params(params, 1)
@@ -144,7 +144,7 @@ class Problem(object):
         map_mask = np.empty((self.N, self.C), dtype=np.uint64) if want_masks else None
         mppa_mask = np.empty((self.N, self.C), dtype=np.uint64) if want_masks else None
         k_hist = np.empty((self.C, self.K + 1), dtype=np.int64)
-        self._check(self.lib.pml_marginal(self._h, _p(params), (1 if force_joint else 0) | (2 if reuse_bottom_up else 0),
+        self._check(self.lib.pml_marginal(self._h, _p(params), (1 if force_joint else 0) | (2 if reuse_bottom_up else 0) | (4 if results_on_device else 0),
                                           _p(lh), _p(probs),
                                           _p(node_lh), _p(map_mask), _p(mppa_mask), _p(k_hist)))
         return dict(loglh=lh, probs=probs, node_log10lh=node_lh, map_mask=map_mask, mppa_mask=mppa_mask,

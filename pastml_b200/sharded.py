@@ -143,17 +143,19 @@ class ShardedProblem(object):
         return self.top.loglik(params, n_sets=n_sets)
 
     # ---- fused top-down sweep
-    def marginal(self, params, vec, ex, want_probs=True, reuse_bottom_up=False, want_masks=True):
+    def marginal(self, params, vec, ex, want_probs=True, reuse_bottom_up=False, want_masks=True,
+                 results_on_device=False):
         """Top tree sweep on every rank, then this rank's clades.  Returns the rank's pieces: dictionaries for the
         top tree (node ids [0, n_top)) and for its clade forest (global node ids in ``plan.nodes[rank]``)."""
         self.top.set_tip_partials(self.plan.boundary, vec, ex, 1)
-        top = self.top.marginal(params, force_joint=False, want_probs=want_probs, want_masks=want_masks)
+        top = self.top.marginal(params, force_joint=False, want_probs=want_probs, want_masks=want_masks,
+                                results_on_device=results_on_device)
         td_vec, td_ex = self.top.tip_td()
         pos = self.plan.roots_pos[self.rank]
         self.clades.set_root_td(td_vec[pos], td_ex[pos])
         # the clades' bottom-up state is the one local_root_partials() just computed
         mine = self.clades.marginal(params, force_joint=False, want_probs=want_probs, want_masks=want_masks,
-                                    reuse_bottom_up=reuse_bottom_up)
+                                    reuse_bottom_up=reuse_bottom_up, results_on_device=results_on_device)
         return top, mine
 
 
