@@ -14,36 +14,40 @@ namespace pml {
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kCoopBlock = 128;
 
-template <int G>
+// Reductions over the G threads that share one (node, lane) item.  Lane layout inside a warp:
+// lane = sub * (G * J) + r * J + j.  When J is a power of two (PJ) the partner of a butterfly step is
+// lane ^ (step * J): SHFL.BFLY does the address arithmetic for free; otherwise the partner lane is computed.
+template <int G, bool PJ>
 struct GroupOps {
     static constexpr int kSteps = (G >= 32) ? 5 : (G >= 16) ? 4 : (G >= 8) ? 3 : (G >= 4) ? 2 : (G >= 2) ? 1 : 0;
     int lane, r, J;
-    int pl[kSteps > 0 ? kSteps : 1];   // partner lane of every butterfly step
-    __device__ __forceinline__ GroupOps(int lane_, int r_, int J_) : lane(lane_), r(r_), J(J_) {
-#pragma unroll
-        for (int q = 0; q < kSteps; ++q) pl[q] = lane + ((r ^ (1 << q)) - r) * J;
+    __device__ __forceinline__ GroupOps(int lane_, int r_, int J_) : lane(lane_), r(r_), J(J_) {}
+    template <class T>
+    __device__ __forceinline__ T xchg(T v, int q) const {
+        if (PJ) return __shfl_xor_sync(kFullMask, v, (1 << q) * J);
+        return __shfl_sync(kFullMask, v, lane + ((r ^ (1 << q)) - r) * J);
     }
     __device__ __forceinline__ double sum(double v) const {
 #pragma unroll
-        for (int q = 0; q < kSteps; ++q) v += __shfl_sync(kFullMask, v, pl[q]);
+        for (int q = 0; q < kSteps; ++q) v += xchg(v, q);
         return v;
     }
     __device__ __forceinline__ double max(double v) const {
 #pragma unroll
-        for (int q = 0; q < kSteps; ++q) v = fmax(v, __shfl_sync(kFullMask, v, pl[q]));
+        for (int q = 0; q < kSteps; ++q) v = fmax(v, xchg(v, q));
         return v;
     }
     __device__ __forceinline__ unsigned long long bit_or(unsigned long long v) const {
 #pragma unroll
-        for (int q = 0; q < kSteps; ++q) v |= __shfl_sync(kFullMask, v, pl[q]);
+        for (int q = 0; q < kSteps; ++q) v |= xchg(v, q);
         return v;
     }
     // arg max with the reference's tie rule (first index): larger value wins, equal values -> smaller index
     __device__ __forceinline__ void argmax(double &v, int &k) const {
 #pragma unroll
         for (int q = 0; q < kSteps; ++q) {
-            const double ov = __shfl_sync(kFullMask, v, pl[q]);
-            const int ok = __shfl_sync(kFullMask, k, pl[q]);
+            const double ov = xchg(v, q);
+            const int ok = xchg(k, q);
             if (ov > v || (ov == v && ok < k)) { v = ov; k = ok; }
         }
     }
@@ -52,6 +56,33 @@ struct GroupOps {
         return __shfl_sync(kFullMask, v, lane + (src - r) * J);
     }
 };
+
+// exp(x) for x <= 0 (every use here is exp(-mu t), t >= 0): Cody-Waite reduction x = n ln2 + r, |r| <= ln2 / 2,
+// degree-13 Taylor polynomial (truncation 4e-18), exact scaling by 2^n through the exponent field.  About a third
+// of the instructions of the library exp (no special-case paths: results below 2^-1021 flush to zero).
+__device__ __forceinline__ double exp_nonpos(double x) {
+    if (!(x > -708.)) return (x != x) ? x : 0.;
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);   // round(x / ln2) in the low mantissa bits
+    const int n = __double2loint(t);
+    const double nf = t - 6755399441055744.0;
+    double r = fma(nf, -6.93147180369123816490e-01, x);
+    r = fma(nf, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);          // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);         // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);         // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);        // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);          // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);         // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);         // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);         // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);        // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);        // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.);
+    p = fma(p, r, 1.);
+    return __hiloint2double(__double2hiint(p) + n * 1048576, __double2loint(p));
+}
 
 // 1 / x for a normal positive x: hardware approximation (2^-23) + two Newton steps, ~1 ulp.  The fused top-down
 // step divides K values per (node, lane) item; __drcp_rn's exact rounding and special-case handling cost three
@@ -157,7 +188,7 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kerne
     stage_params(s_par, a.ln, 4 + K);
     const CoopLane cl = coop_lane<G>(J, C);
     const int r = cl.r, j = cl.j, c = cl.c;
-    const GroupOps<G> grp((int) (threadIdx.x & 31), r, J);
+    const GroupOps<G, (JT > 0 && (JT & (JT - 1)) == 0)> grp((int) (threadIdx.x & 31), r, J);
     const double sf = s_par[j], tau = s_par[J + j], tauf = s_par[2 * J + j], mu = s_par[3 * J + j];
     double pi[KT];
 #pragma unroll
@@ -210,7 +241,7 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kerne
             const double dmine = (r & 1) ? __hiloint2double(d_len.w, d_len.z) : __hiloint2double(d_len.y, d_len.x);
             ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc, cs0, r, j, c, use_alt, in0, K, J);
             ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, cs1, r, j, c, use_alt, in1, K, J);
-            const double emine = mu_inf ? 0. : exp(-mu * ((dmine + tau) * tauf * sf));
+            const double emine = mu_inf ? 0. : exp_nonpos(-mu * ((dmine + tau) * tauf * sf));
             const double e0 = grp.from_rank(emine, 0), e1 = grp.from_rank(emine, 1);
             double s0 = 0., s1 = 0.;
 #pragma unroll
@@ -240,7 +271,7 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kerne
                 double in[KT];
                 const int exc = coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, ch, a.t.slot[ch], r, j, c,
                                                  use_alt, in, K, J);
-                const double e = mu_inf ? 0. : exp(-mu * ((a.t.dist[ch] + tau) * tauf * sf));
+                const double e = mu_inf ? 0. : exp_nonpos(-mu * ((a.t.dist[ch] + tau) * tauf * sf));
                 double s = 0.;
 #pragma unroll
                 for (int i = 0; i < KT; ++i) s = fma(pi[i], in[i], s);
@@ -286,7 +317,7 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) td_coop_kerne
     stage_params(s_par, a.ln, nf);
     const CoopLane cl = coop_lane<G>(C, C);
     const int r = cl.r, c = cl.j;
-    const GroupOps<G> grp((int) (threadIdx.x & 31), r, C);
+    const GroupOps<G, (JT > 0 && (JT & (JT - 1)) == 0)> grp((int) (threadIdx.x & 31), r, C);
     const double sf = s_par[c], tau = s_par[C + c], tauf = s_par[2 * C + c], mu = s_par[3 * C + c];
     double pi[KT];
 #pragma unroll
@@ -355,7 +386,7 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) td_coop_kerne
         }
         // the branch above the node: rank 0 evaluates the exponential for its group
         double e = 0.;
-        if (r == 0 && !mu_inf) e = exp(-mu * ((__hiloint2double(desc.w, desc.z) + tau) * tauf * sf));
+        if (r == 0 && !mu_inf) e = exp_nonpos(-mu * ((__hiloint2double(desc.w, desc.z) + tau) * tauf * sf));
         e = grp.from_rank(e, 0);
         const double ome = 1. - e;
         // node_contribution = P L_node (ml.py:280); q = TD_p L_p / contribution, contribution <= 0 -> 1 (ml.py:281-283)
