@@ -11,7 +11,9 @@ of the marginal probabilities, MAP/MPPA masks and the k histogram, every step.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--tips T] [--states K] [--columns C]
 
 With --gpus N > 1 the driver launches one rank per GPU through torchrun; every rank owns an independent
-(tree x columns) batch of the same shape (weak scaling, no data-path collective).
+(tree x columns) batch of the same shape (weak scaling, no data-path collective).  ``--sharding subtree`` instead
+cuts ONE tree into clades spread over the ranks, with one NCCL all-gather of clade-root vectors per step (strong
+scaling; pastml_b200/sharded.py).
 """
 import argparse
 import json
