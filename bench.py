@@ -227,6 +227,29 @@ def run_subtree_sharded(args):
             'gpu_launches': None}
     line['config']['sharding'] = 'one tree cut into clades over the GPUs (subtree sharding)'
     sp.close()
+    if not args.no_fit:
+        # the full ML fit of the 8 columns on the sharded tree: every rank runs the same host optimiser on values that
+        # are identical on all ranks, one all-gather per objective batch
+        from pastml_b200.annotation import ForestStats
+        from pastml_b200.ml import fit_batch
+        from pastml_b200.models import F81Model
+        from pastml_b200.sharded import ShardedColumnBatch
+        fs = ForestStats(flat=flat)
+        names = np.array(['s{:02d}'.format(i) for i in range(K)])
+        obs = []
+        for c in range(C):
+            f = np.bincount(np.log2(masks[c][flat.is_tip].astype(np.float64)).astype(int), minlength=K).astype(np.float64)
+            obs.append(f / f.sum())
+        models = [F81Model(states=names, forest_stats=fs, character='c{}'.format(c)) for c in range(C)]
+        batch = ShardedColumnBatch(plan, rank, ['c{}'.format(c) for c in range(C)], models, masks, has, device=local_rank)
+        dist.barrier()
+        t0 = time.perf_counter()
+        lhs, passes = fit_batch(batch, obs)
+        dist.barrier()
+        fit_s = max_over_ranks(time.perf_counter() - t0, device='cuda')
+        batch.close()
+        line['ml_fit'] = {'seconds': fit_s, 'device_passes': int(passes), 'loglh_column0': float(lhs[0]),
+                          'what': 'two-stage L-BFGS-B fit of all {} columns of the ONE sharded tree'.format(C)}
     if rank == 0:   # outside the timed region: the same tree, unsharded, on this GPU
         from pastml_b200.engine import Problem
         whole = Problem(flat, K, 0, masks, has, device=local_rank)

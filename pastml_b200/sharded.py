@@ -193,3 +193,35 @@ def merge_outputs(plan, per_rank, key, n_nodes):
     for r, (_, mine) in enumerate(per_rank):
         out[plan.nodes[r]] = mine[key]
     return out
+
+
+class ShardedColumnBatch(object):
+    """Drop-in for :class:`pastml_b200.ml.ColumnBatch` inside the lock-step fit when ONE tree is sharded by subtree:
+    every objective evaluation is clades bottom-up -> all-gather -> top tree, and returns the same values on every
+    rank (the top tree is finished redundantly from identical inputs), so the ranks' host optimisers stay in step
+    without any further communication."""
+
+    def __init__(self, plan, rank, characters, models, annot_mask, has_state, device=0, gather=None):
+        from pastml_b200.ml import batched_gradients
+        self.plan, self.rank = plan, rank
+        self.flat = plan.flat
+        self.characters, self.models = list(characters), list(models)
+        self.C = len(self.characters)
+        self.K = len(self.models[0].states)
+        self.kind = self.models[0].engine_kind
+        self.max_sets = (1 + max(m.get_num_params() for m in self.models)) if batched_gradients() else 1
+        self.sp = ShardedProblem(plan, rank, self.K, self.kind, annot_mask, has_state, max_param_sets=self.max_sets,
+                                 device=device)
+        self.problem = self.sp.top          # LockstepEvaluator reads .stride from here
+        self.gather = gather or (lambda vec, ex: all_gather_partials(vec, ex, plan, rank))
+
+    def close(self):
+        self.sp.close()
+
+    def params(self):
+        return np.stack([m.engine_block() for m in self.models])
+
+    def loglik_sets(self, params, n_sets):
+        vec, ex = self.sp.local_root_partials(params, n_sets)
+        vec, ex = self.sp.assemble(self.gather(vec, ex))
+        return self.sp.finish_loglik(params, vec, ex, n_sets), {}

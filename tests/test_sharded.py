@@ -75,3 +75,33 @@ def test_sharded_equals_unsharded(n_tips, K, C, world, kind):
     np.testing.assert_allclose(pieces[0][0]['loglh'], want['loglh'], rtol=1e-12)
     for sp in ranks:
         sp.close()
+
+
+@pytest.mark.gpu
+def test_fit_on_a_sharded_tree_matches_the_plain_fit():
+    """The lock-step fit driven by the sharded objective (one rank owning all clades: the exchange is the identity)
+    gives what the plain ColumnBatch gives."""
+    from pastml_b200 import synth
+    from pastml_b200.annotation import ForestStats
+    from pastml_b200.ml import ColumnBatch, fit_batch
+    from pastml_b200.models import F81Model
+    from pastml_b200.sharded import SubtreePlan, ShardedColumnBatch
+    flat, rng = _tree(3000, 77)
+    K, C = 6, 3
+    masks, has, pis, sfs = synth.simulate_tip_masks(flat, K, C, rng)
+    fs = ForestStats(flat=flat)
+    states = np.array(['s%d' % i for i in range(K)])
+    obs = [np.full(K, 1. / K)] * C
+
+    def models():
+        return [F81Model(states=states, forest_stats=fs, character='c%d' % c) for c in range(C)]
+
+    plain = ColumnBatch(flat, ['c0', 'c1', 'c2'], models(), annot_mask=masks, has_state=has)
+    want, _ = fit_batch(plain, obs)
+    plain.close()
+    plan = SubtreePlan(flat, 1, clades_per_rank=6)
+    ms = models()
+    sharded = ShardedColumnBatch(plan, 0, ['c0', 'c1', 'c2'], ms, masks, has, gather=lambda vec, ex: [(vec, ex)])
+    got, _ = fit_batch(sharded, obs)
+    sharded.close()
+    np.testing.assert_allclose(got, want, rtol=1e-9)
