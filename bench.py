@@ -219,7 +219,7 @@ def run_subtree_sharded(args):
             'warmup': max(args.warmup, 3), 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, flat),
             'clocks': clocks.summary(), 'loglh_column0': float(top['loglh'][0]),
-            'sharding': {'kind': 'subtree', 'cut_level': int(plan.cut_level), 'clades': int(len(plan.boundary)),
+            'sharding': {'kind': 'subtree', 'top_levels': int(plan.top_forest().n_levels), 'clades': int(len(plan.boundary)),
                          'top_nodes': int(plan.n_top), 'nodes_per_rank': [int(len(n)) for n in plan.nodes],
                          'exchange': 'one all_gather_into_tensor of {} x (K+1) x C doubles per step'.format(
                              max(len(p) for p in plan.roots_pos))},

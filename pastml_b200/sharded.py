@@ -23,45 +23,62 @@ from pastml_b200.tree import FlatForest
 class SubtreePlan(object):
     """Where a single tree is cut and who owns which clade.
 
-    Attributes: ``cut_level``, ``n_top`` (the top tree is nodes [0, n_top) of the flat order, unchanged),
-    ``boundary`` (ids of the clade roots = internal nodes of the cut level; tips of the top tree),
-    ``owner_of_clade`` [len(boundary)], and per rank ``nodes[r]`` (global ids of its forest in level order),
-    ``roots_pos[r]`` (positions of its clade roots inside ``boundary``).
+    The cut follows the sizes, not a depth level: starting from the root, the largest remaining clade is split into
+    its children until no clade is larger than ``N / (world * clades_per_rank)`` (Yule / coalescent trees are
+    unbalanced: one child of the root may hold half of the tips).  A clade root is never placed below a zero-length
+    branch, which would split a zero-branch cluster between two problems.
+
+    Attributes: ``top_ids`` (global ids of the replicated top tree, increasing = level order), ``boundary`` (global ids
+    of the clade roots, which are tips of the top tree), ``boundary_top`` (their ids inside the top tree),
+    ``owner_of_clade`` [len(boundary)], and per rank ``nodes[r]`` (global ids of its forest in the forest's level
+    order), ``roots_pos[r]`` (positions of its clade roots inside ``boundary``).
     """
 
     def __init__(self, flat, world_size, clades_per_rank=8):
+        import heapq
         if flat.n_trees != 1:
             raise ValueError('subtree sharding takes one tree (forests shard by tree)')
         self.flat = flat
         self.world = int(world_size)
-        want = self.world * clades_per_rank
+        n = flat.n_nodes
         internal = flat.n_children > 0
-        cut = None
-        best = (0, None)
-        for lvl in range(1, flat.n_levels):
-            lo, hi = flat.level_ptr[lvl], flat.level_ptr[lvl + 1]
-            n_int = int(internal[lo:hi].sum())
-            # a zero-length branch across the cut would split a zero-branch cluster between problems
-            ok = not np.any((flat.dist[lo:hi] == 0) & internal[lo:hi])
-            if ok and n_int > best[0]:
-                best = (n_int, lvl)
-            if ok and n_int >= want:
-                cut = lvl
-                break
-        if cut is None:
-            cut = best[1]
-        if cut is None or best[0] < self.world:
-            raise ValueError('the tree has no level with enough clades to shard over {} ranks'.format(self.world))
-        self.cut_level = cut
-        lo, hi = flat.level_ptr[cut], flat.level_ptr[cut + 1]
-        self.n_top = int(hi)
-        self.boundary = (np.arange(lo, hi)[internal[lo:hi]]).astype(np.int32)
-
         # subtree sizes, accumulated level by level from the bottom
-        size = np.ones(flat.n_nodes, dtype=np.int64)
+        size = np.ones(n, dtype=np.int64)
         for lvl in range(flat.n_levels - 1, 0, -1):
             a, b = flat.level_ptr[lvl], flat.level_ptr[lvl + 1]
             np.add.at(size, flat.parent[a:b], size[a:b])
+        target = max(n // (self.world * clades_per_rank), 1)
+        in_top = np.zeros(n, dtype=bool)
+        heap = [(-int(size[0]), 0)] if internal[0] else []
+        in_top[0] = True
+        final = []
+        while heap:
+            neg, v = heapq.heappop(heap)
+            must_split = flat.dist[v] == 0 or v == 0
+            enough = len(final) + len(heap) + 1 >= self.world
+            if -neg <= target and enough and not must_split:
+                final.append(v)
+                continue
+            # v stays in the top tree as an internal node; its children become candidates (or top-tree tips)
+            fc, nc = int(flat.first_child[v]), int(flat.n_children[v])
+            splittable = any(internal[c] for c in range(fc, fc + nc))
+            if not splittable and not must_split and enough:
+                final.append(v)
+                continue
+            in_top[fc:fc + nc] = True
+            for c in range(fc, fc + nc):
+                if internal[c]:
+                    heapq.heappush(heap, (-int(size[c]), c))
+        if len(final) < self.world:
+            raise ValueError('the tree cannot be cut into {} clades'.format(self.world))
+        self.boundary = np.array(sorted(final), dtype=np.int32)
+        self.top_ids = np.flatnonzero(in_top).astype(np.int64)
+        top_pos = np.full(n, -1, dtype=np.int64)
+        top_pos[self.top_ids] = np.arange(len(self.top_ids))
+        self.boundary_top = top_pos[self.boundary].astype(np.int32)
+        self._top_pos = top_pos
+        self.n_top = len(self.top_ids)
+
         # longest-processing-time assignment of clades to ranks
         order = np.argsort(-size[self.boundary], kind='stable')
         load = np.zeros(self.world, dtype=np.int64)
@@ -72,21 +89,29 @@ class SubtreePlan(object):
             load[r] += size[self.boundary[i]]
         self.load = load
 
-        # owner of every node below the cut
-        owner = np.full(flat.n_nodes, -1, dtype=np.int32)
+        # owner and depth-below-its-clade-root of every node below the cut
+        owner = np.full(n, -1, dtype=np.int32)
+        rel_depth = np.zeros(n, dtype=np.int32)
         owner[self.boundary] = self.owner_of_clade
-        for lvl in range(cut + 1, flat.n_levels):
+        for lvl in range(1, flat.n_levels):
             a, b = flat.level_ptr[lvl], flat.level_ptr[lvl + 1]
-            owner[a:b] = owner[flat.parent[a:b]]
+            par = flat.parent[a:b]
+            inherit = (owner[par] >= 0) & (owner[a:b] < 0)
+            idx = np.arange(a, b)[inherit]
+            owner[idx] = owner[flat.parent[idx]]
+            rel_depth[idx] = rel_depth[flat.parent[idx]] + 1
         self.nodes, self.roots_pos, self._forests = [], [], [None] * self.world
         for r in range(self.world):
-            ids = np.flatnonzero(owner == r).astype(np.int64)   # increasing id = level order of the forest
+            ids = np.flatnonzero(owner == r).astype(np.int64)
+            ids = ids[np.lexsort((ids, rel_depth[ids]))]      # the forest's own level order: (depth in clade, id)
             self.nodes.append(ids)
             self.roots_pos.append(np.flatnonzero(self.owner_of_clade == r).astype(np.int64))
 
     def top_forest(self):
-        """The replicated part: nodes above and at the cut, in their original order."""
-        return FlatForest(self.flat.parent[:self.n_top], self.flat.dist[:self.n_top])
+        """The replicated part: everything above the cut plus the clade roots (as tips), in increasing id."""
+        par = self.flat.parent[self.top_ids].astype(np.int64)
+        new_par = np.where(par < 0, -1, self._top_pos[np.maximum(par, 0)]).astype(np.int32)
+        return FlatForest(new_par, self.flat.dist[self.top_ids])
 
     def clade_forest(self, rank):
         """The rank's clades as a level-ordered forest (roots = its clade roots, in boundary order)."""
@@ -111,8 +136,8 @@ class ShardedProblem(object):
         ids = plan.nodes[rank]
         self.clades = Problem(plan.clade_forest(rank), n_states, model_kind, annot_mask[:, ids], has_state[:, ids],
                               max_param_sets=max_param_sets, device=device)
-        self.top = Problem(plan.top_forest(), n_states, model_kind, annot_mask[:, :plan.n_top],
-                           has_state[:, :plan.n_top], max_param_sets=max_param_sets, device=device)
+        self.top = Problem(plan.top_forest(), n_states, model_kind, annot_mask[:, plan.top_ids],
+                           has_state[:, plan.top_ids], max_param_sets=max_param_sets, device=device)
         self.K, self.C = int(n_states), annot_mask.shape[0]
 
     def close(self):
@@ -139,15 +164,15 @@ class ShardedProblem(object):
 
     def finish_loglik(self, params, vec, ex, n_sets=1):
         """Log-likelihoods [n_sets][C] of the whole tree given all clade-root vectors."""
-        self.top.set_tip_partials(self.plan.boundary, vec, ex, n_sets)
+        self.top.set_tip_partials(self.plan.boundary_top, vec, ex, n_sets)
         return self.top.loglik(params, n_sets=n_sets)
 
     # ---- fused top-down sweep
     def marginal(self, params, vec, ex, want_probs=True, reuse_bottom_up=False, want_masks=True,
                  results_on_device=False):
         """Top tree sweep on every rank, then this rank's clades.  Returns the rank's pieces: dictionaries for the
-        top tree (node ids [0, n_top)) and for its clade forest (global node ids in ``plan.nodes[rank]``)."""
-        self.top.set_tip_partials(self.plan.boundary, vec, ex, 1)
+        top tree (global node ids ``plan.top_ids``) and for its clade forest (global node ids in ``plan.nodes[rank]``)."""
+        self.top.set_tip_partials(self.plan.boundary_top, vec, ex, 1)
         top = self.top.marginal(params, force_joint=False, want_probs=want_probs, want_masks=want_masks,
                                 results_on_device=results_on_device)
         td_vec, td_ex = self.top.tip_td()
@@ -189,7 +214,7 @@ def merge_outputs(plan, per_rank, key, n_nodes):
     top0, _ = per_rank[0]
     sample = top0[key]
     out = np.empty((n_nodes,) + sample.shape[1:], dtype=sample.dtype)
-    out[:plan.n_top] = sample
+    out[plan.top_ids] = sample
     for r, (_, mine) in enumerate(per_rank):
         out[plan.nodes[r]] = mine[key]
     return out
