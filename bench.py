@@ -247,8 +247,9 @@ def run_subtree_sharded(args):
         lhs, passes = fit_batch(batch, obs)
         dist.barrier()
         fit_s = max_over_ranks(time.perf_counter() - t0, device='cuda')
+        phases = dict(batch.phase_seconds)
         batch.close()
-        line['ml_fit'] = {'seconds': fit_s, 'device_passes': int(passes), 'loglh_column0': float(lhs[0]),
+        line['ml_fit'] = {'seconds': fit_s, 'device_passes': int(passes), 'loglh_column0': float(lhs[0]), 'phases_rank0': phases,
                           'what': 'two-stage L-BFGS-B fit of all {} columns of the ONE sharded tree'.format(C)}
     if rank == 0:   # outside the timed region: the same tree, unsharded, on this GPU
         from pastml_b200.engine import Problem

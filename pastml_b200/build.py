@@ -32,7 +32,8 @@ INSTANCES = [(0, k) for k in (2, 4, 8, 12, 16, 20, 24, 32, 48, 62)] + [(1, 4)] +
 # (G, KT) of the warp-cooperative F81 sweeps; keep in sync with PML_COOP_ALL in pml_engine.cu
 COOP_INSTANCES = [(2, k, 0) for k in (2, 3, 4, 5, 6, 8, 10, 12, 16)] + [(4, k, 0) for k in (2, 3, 4, 5, 6, 8, 10, 12, 16)] + \
                  [(8, k, 0) for k in (2, 3, 4, 5, 6, 8)] + [(16, k, 0) for k in (2, 3, 4)] + [(32, 2, 0)] + \
-                 [(4, 5, 8), (2, 5, 16), (2, 5, 8), (4, 5, 4), (2, 2, 16), (2, 2, 8), (2, 10, 8)]   # compile-time lanes / K
+                 [(4, 5, 8), (2, 5, 16), (2, 5, 8), (4, 5, 4), (2, 2, 16), (2, 2, 8), (2, 10, 8),
+                  (4, 3, 8), (4, 4, 8), (4, 2, 8), (2, 3, 8), (2, 4, 8), (4, 6, 8), (4, 8, 8), (2, 6, 8)]   # compile-time lanes / K
 
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2']

@@ -180,23 +180,40 @@ __device__ __forceinline__ int coop_load(const TreeDev &t, const ZcDev &zc, cons
 
 // ------------------------------------------------------------------------------------------ bottom-up
 
-// JT > 0: the number of lanes J is the compile-time constant JT; KX: K == G * KT exactly
-template <int KT, int G, int JT, bool KX>
+// JT > 0: the number of lanes J is the compile-time constant JT; KX: K == G * KT exactly.
+// TILED: the pass has more lanes than one warp batch can take (many parameter sets x columns, the batched
+// finite-difference objective): blockIdx.y selects a tile of JT consecutive lanes, memory keeps its full leading
+// dimension `ld` = total lanes.
+template <int KT, int G, int JT, bool KX, bool TILED>
 __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kernel(BuArgs a, int slot_begin, int n_slots) {
     extern __shared__ double s_par[];
     const int J = JT ? JT : a.ln.J, K = KX ? G * KT : a.ln.K, C = a.ln.C;
-    stage_params(s_par, a.ln, 4 + K);
+    const int ld = TILED ? a.ln.J : J;                 // leading dimension of bu / bu_ex / ext tables
+    const int j0 = TILED ? (int) blockIdx.y * J : 0;   // first lane of this block's tile
+    {
+        // stage the tile's lane parameters, transposed to [field][lane]
+        const int total = (4 + K) * J;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int f = i / J, jj = i - f * J;
+            s_par[i] = a.ln.params[(size_t) (j0 + jj) * a.ln.stride + f];
+        }
+        __syncthreads();
+    }
     const CoopLane cl = coop_lane<G>(J, C);
-    const int r = cl.r, j = cl.j, c = cl.c;
+    const int r = cl.r;
+    const int j = j0 + cl.j;                 // lane index in memory
+    const int c = TILED ? j % C : cl.c;
     const GroupOps<G, (JT > 0 && (JT & (JT - 1)) == 0)> grp((int) (threadIdx.x & 31), r, J);
-    const double sf = s_par[j], tau = s_par[J + j], tauf = s_par[2 * J + j], mu = s_par[3 * J + j];
+    const int jl = cl.j;                     // lane index inside the tile (shared-memory column)
+    const double sf = s_par[jl], tau = s_par[J + jl], tauf = s_par[2 * J + jl], mu = s_par[3 * J + jl];
     double pi[KT];
 #pragma unroll
-    for (int i = 0; i < KT; ++i) pi[i] = PML_VALID(i) ? s_par[(4 + r + G * i) * J + j] : 0.;
+    for (int i = 0; i < KT; ++i) pi[i] = PML_VALID(i) ? s_par[(4 + r + G * i) * J + jl] : 0.;
     const bool use_alt = a.alter && tau == 0.;
     const bool mu_inf = isinf(mu);
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    (void) jl;
 
     // the loop is software-pipelined by one step: the packed descriptor (and node id) of the next batch is requested
     // before the current batch is processed, so that only the vector loads remain on the dependent path
@@ -239,8 +256,8 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kerne
             double in0[KT], in1[KT];
             const int cs0 = d_top.z, cs1 = d_top.w;
             const double dmine = (r & 1) ? __hiloint2double(d_len.w, d_len.z) : __hiloint2double(d_len.y, d_len.x);
-            ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc, cs0, r, j, c, use_alt, in0, K, J);
-            ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, cs1, r, j, c, use_alt, in1, K, J);
+            ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc, cs0, r, j, c, use_alt, in0, K, ld);
+            ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, cs1, r, j, c, use_alt, in1, K, ld);
             const double emine = mu_inf ? 0. : exp_nonpos(-mu * ((dmine + tau) * tauf * sf));
             const double e0 = grp.from_rank(emine, 0), e1 = grp.from_rank(emine, 1);
             double s0 = 0., s1 = 0.;
@@ -270,7 +287,7 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kerne
                 const int ch = fc + (valid ? q : 0);
                 double in[KT];
                 const int exc = coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, ch, a.t.slot[ch], r, j, c,
-                                                 use_alt, in, K, J);
+                                                 use_alt, in, K, ld);
                 const double e = mu_inf ? 0. : exp_nonpos(-mu * ((a.t.dist[ch] + tau) * tauf * sf));
                 double s = 0.;
 #pragma unroll
@@ -295,11 +312,11 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kerne
             if (bad_child >= 0 && r == 0) {   // all entries zero: PastMLLikelihoodError of ml.py:139-145
                 if (atomicCAS(a.err + 2 * j, -1, node) == -1) a.err[2 * j + 1] = bad_child;
             }
-            double *dst = a.bu + ((size_t) (slot * K + r) * J + j);
+            double *dst = a.bu + ((size_t) (slot * K + r) * ld + j);
 #pragma unroll
             for (int i = 0; i < KT; ++i)
-                if (PML_VALID(i)) dst[(G * i) * J] = acc[i];
-            if (r == 0) a.bu_ex[(size_t) slot * J + j] = ex;
+                if (PML_VALID(i)) dst[(G * i) * ld] = acc[i];
+            if (r == 0) a.bu_ex[(size_t) slot * ld + j] = ex;
         }
     }
 }

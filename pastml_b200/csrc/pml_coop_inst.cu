@@ -29,10 +29,20 @@ unsigned coop_grid(int n, int lanes) {
 }
 
 void bu_launch(cudaStream_t st, const BuArgs &a, int s0, int ns) {
+    if (JT > 0 && a.ln.J > JT) {
+        // more lanes than the compile-time tile: one grid row per tile of JT lanes
+        const int tiles = a.ln.J / JT;
+        const size_t sh = sizeof(double) * (4 + a.ln.K) * JT;
+        unsigned gx = coop_grid(ns, JT);
+        const unsigned per_row = (148u * PML_COOP_GRID + tiles - 1) / tiles;
+        if (gx > per_row) gx = per_row;
+        bu_coop_kernel<KT, G, JT, KX, true><<<dim3(gx, tiles), kCoopBlock, sh, st>>>(a, s0, ns);
+        return;
+    }
     const size_t sh = sizeof(double) * (4 + a.ln.K) * a.ln.J;
     if (sh > 48 * 1024)
-        cudaFuncSetAttribute(bu_coop_kernel<KT, G, JT, KX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
-    bu_coop_kernel<KT, G, JT, KX><<<coop_grid(ns, a.ln.J), kCoopBlock, sh, st>>>(a, s0, ns);
+        cudaFuncSetAttribute(bu_coop_kernel<KT, G, JT, KX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+    bu_coop_kernel<KT, G, JT, KX, false><<<coop_grid(ns, a.ln.J), kCoopBlock, sh, st>>>(a, s0, ns);
 }
 
 void td_launch(cudaStream_t st, const TdArgs &a, int n0, int nn) {

@@ -442,7 +442,8 @@ namespace pml {
 #define PML_COOP_ALL(X) X(2, 2, 0) X(2, 3, 0) X(2, 4, 0) X(2, 5, 0) X(2, 6, 0) X(2, 8, 0) X(2, 10, 0) X(2, 12, 0) X(2, 16, 0) \
                         X(4, 2, 0) X(4, 3, 0) X(4, 4, 0) X(4, 5, 0) X(4, 6, 0) X(4, 8, 0) X(4, 10, 0) X(4, 12, 0) X(4, 16, 0) \
                         X(8, 2, 0) X(8, 3, 0) X(8, 4, 0) X(8, 5, 0) X(8, 6, 0) X(8, 8, 0) X(16, 2, 0) X(16, 3, 0) X(16, 4, 0) \
-                        X(32, 2, 0) X(4, 5, 8) X(2, 5, 16) X(2, 5, 8) X(4, 5, 4) X(2, 2, 16) X(2, 2, 8) X(2, 10, 8)
+                        X(32, 2, 0) X(4, 5, 8) X(2, 5, 16) X(2, 5, 8) X(4, 5, 4) X(2, 2, 16) X(2, 2, 8) X(2, 10, 8) \
+                        X(4, 3, 8) X(4, 4, 8) X(4, 2, 8) X(2, 3, 8) X(2, 4, 8) X(4, 6, 8) X(4, 8, 8) X(2, 6, 8)
 #endif
 PML_COOP_ALL(PML_CDECL)
 const CoopSet *coop_set(int gg, int kt, int jt) {
@@ -456,7 +457,17 @@ namespace {
 // built size >= ceil(K / G); least padding first, then the larger group.  nullptr -> thread-per-item kernels.
 const CoopSet *pick_coop(const pml_problem *p, int J) {
     static const bool disabled = getenv("PASTML_B200_NO_COOP") != nullptr;
-    if (disabled || p->kind != PML_MODEL_F81 || J > 16 || p->K < 3) return nullptr;
+    if (disabled || p->kind != PML_MODEL_F81 || p->K < 3) return nullptr;
+    if (J > 16) {
+        // many lanes (parameter sets x columns): tiles of 8 lanes through the compile-time variants, when they fit
+        if (J % 8) return nullptr;
+        for (int g = 4; g >= 2; g >>= 1)
+            if (p->K % g == 0) {
+                const CoopSet *cs = coop_set(g, p->K / g, 8);
+                if (cs) return cs;
+            }
+        return nullptr;
+    }
     const int kts[] = {2, 3, 4, 5, 6, 8, 10, 12, 16};
     const CoopSet *best = nullptr;
     double best_score = 1e30;
@@ -1083,13 +1094,13 @@ int pml_set_tip_partials(pml_problem *p, int32_t n, const int32_t *nodes, const 
         CUDA_TRY(p->ext_td_ex.alloc((size_t) n * p->C));
         p->n_ext = n;
     }
-    if (p->ext_sets != n_sets) {
-        CUDA_TRY(p->ext_bu.alloc((size_t) n * p->K * J));
-        CUDA_TRY(p->ext_bu_ex.alloc((size_t) n * J));
-        p->ext_sets = n_sets;
-        for (auto &kv : p->graphs) cudaGraphExecDestroy(kv.second.exec);   // the tables moved: re-capture
-        p->graphs.clear();
+    if (!p->ext_bu.ptr) {
+        // sized for the handle's capacity of parameter sets once, so that the tables never move (the captured
+        // launch graphs keep pointing at them) whatever n_sets the following calls use
+        CUDA_TRY(p->ext_bu.alloc((size_t) n * p->K * p->B * p->C));
+        CUDA_TRY(p->ext_bu_ex.alloc((size_t) n * p->B * p->C));
     }
+    p->ext_sets = n_sets;
     CUDA_TRY(cudaMemcpyAsync(p->ext_bu.ptr, vec, sizeof(double) * (size_t) n * p->K * J, cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaMemcpyAsync(p->ext_bu_ex.ptr, ex, sizeof(int) * (size_t) n * J, cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));

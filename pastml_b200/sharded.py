@@ -239,6 +239,7 @@ class ShardedColumnBatch(object):
                                  device=device)
         self.problem = self.sp.top          # LockstepEvaluator reads .stride from here
         self.gather = gather or (lambda vec, ex: all_gather_partials(vec, ex, plan, rank))
+        self.phase_seconds = {}
 
     def close(self):
         self.sp.close()
@@ -247,6 +248,15 @@ class ShardedColumnBatch(object):
         return np.stack([m.engine_block() for m in self.models])
 
     def loglik_sets(self, params, n_sets):
+        import time
+        t0 = time.perf_counter()
         vec, ex = self.sp.local_root_partials(params, n_sets)
-        vec, ex = self.sp.assemble(self.gather(vec, ex))
-        return self.sp.finish_loglik(params, vec, ex, n_sets), {}
+        t1 = time.perf_counter()
+        gathered = self.gather(vec, ex)
+        t2 = time.perf_counter()
+        vec, ex = self.sp.assemble(gathered)
+        out = self.sp.finish_loglik(params, vec, ex, n_sets)
+        t3 = time.perf_counter()
+        for key, dt in (('clades_bottom_up_s', t1 - t0), ('exchange_s', t2 - t1), ('top_tree_s', t3 - t2)):
+            self.phase_seconds[key] = self.phase_seconds.get(key, 0.) + dt
+        return out, {}

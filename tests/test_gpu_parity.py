@@ -164,3 +164,31 @@ def test_zero_likelihood_is_reported():
         pb.loglik(params, alter=False)
     assert (e.value.parent, e.value.child) == (0, 2)
     pb.close()
+
+
+@pytest.mark.parametrize('K,C,B', [(20, 8, 3), (10, 16, 5), (12, 8, 4)])
+def test_many_parameter_sets_tiled(K, C, B):
+    """More than 16 lanes (parameter sets x columns): the cooperative bottom-up kernel runs one grid row per tile of 8
+    lanes; every (set, column) must equal the single-set evaluation and the oracle."""
+    from pastml_b200.engine import Problem, pack_params
+    from pastml_b200 import synth
+    from oracle import cpu_oracle
+    rng = np.random.default_rng(50 + K + C)
+    flat = synth.yule_tree(1500, rng)
+    masks, has, pis, sfs = synth.simulate_tip_masks(flat, K, C, rng, missing=0.05)
+    base = np.stack([pack_params(0, K, sfs[c], 0., 1., pis[c]) for c in range(C)])
+    sets = np.stack([base] * B)
+    for b in range(B):
+        sets[b, :, 0] *= 1. + 0.17 * b
+    pb = Problem(flat, K, 0, masks, has, max_param_sets=B)
+    got = pb.loglik(sets, n_sets=B)
+    for b in range(B):
+        one = pb.loglik(sets[b], n_sets=1)[0]
+        np.testing.assert_allclose(got[b], one, rtol=1e-13)
+    pb.close()
+    full = np.uint64((1 << K) - 1)
+    tree = cpu_oracle.OracleTree(flat)
+    for b, c in ((B - 1, 0), (1, C - 1)):
+        model = cpu_oracle.OracleModel(0, pis[c], float(sets[b, c, 0]))
+        want = cpu_oracle.loglikelihood(tree, model, np.where(masks[c] == 0, full, masks[c]), has[c])
+        assert got[b, c] == pytest.approx(want, rel=LH_RTOL)
