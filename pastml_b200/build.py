@@ -21,7 +21,9 @@ LIB_PATH = os.path.join(HERE, LIB_NAME)
 ENGINE_SRC = os.path.join(CSRC, 'pml_engine.cu')
 INST_SRC = os.path.join(CSRC, 'pml_inst.cu')
 COOP_SRC = os.path.join(CSRC, 'pml_coop_inst.cu')
-HEADERS = [os.path.join(CSRC, 'pml_kernels.cuh'), os.path.join(CSRC, 'pml_coop.cuh'), os.path.join(CSRC, 'pml_launch.h'),
+TPI_SRC = os.path.join(CSRC, 'pml_tpi.cu')
+HEADERS = [os.path.join(CSRC, 'pml_kernels.cuh'), os.path.join(CSRC, 'pml_coop.cuh'), os.path.join(CSRC, 'pml_tpi.cuh'),
+           os.path.join(CSRC, 'pml_launch.h'),
            os.path.join(os.path.dirname(HERE), 'include', 'pastml_b200.h')]
 
 # (family, KP): 0 = F81/JC/EFT, 1 = HKY, 2 = eigen-decomposition models (CUSTOM_RATES, JTT); keep in sync with
@@ -78,6 +80,7 @@ def build(force=False, verbose=False, jobs=None):
             os.remove(os.path.join(OBJ_DIR, f))
     flags = ' '.join(NVCC_FLAGS)
     tasks = [(ENGINE_SRC, os.path.join(OBJ_DIR, 'pml_engine.o'), [], _digest([ENGINE_SRC] + HEADERS, flags))]
+    tasks.append((TPI_SRC, os.path.join(OBJ_DIR, 'pml_tpi.o'), [], _digest([TPI_SRC] + HEADERS, flags)))
     inst_digest = _digest([INST_SRC] + HEADERS, flags)
     for fam, kp in INSTANCES:
         tasks.append((INST_SRC, os.path.join(OBJ_DIR, 'pml_inst_{}_{}.o'.format(fam, kp)),
@@ -88,7 +91,10 @@ def build(force=False, verbose=False, jobs=None):
                       ['-DPML_G={}'.format(g), '-DPML_KT={}'.format(kt), '-DPML_JT={}'.format(jt)], coop_digest))
     jobs = jobs or max(1, min(len(tasks), os.cpu_count() or 1))
     # biggest instantiations first so that they do not end up alone at the tail
-    tasks.sort(key=lambda t: -int(t[2][1].split('=')[1]) * (1 if 'PML_KP' in t[2][1] else 0) if t[2] else 0)
+    def weight(t):
+        kp = [d for d in t[2] if d.startswith('-DPML_KP=')]
+        return -int(kp[0].split('=')[1]) if kp else 0
+    tasks.sort(key=weight)
     with ThreadPoolExecutor(max_workers=jobs) as pool:
         rebuilt = list(pool.map(lambda t: _compile(nvcc, t[0], t[1], t[2], t[3], verbose), tasks))
     if any(rebuilt) or not os.path.exists(LIB_PATH):

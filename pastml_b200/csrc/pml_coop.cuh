@@ -97,6 +97,46 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return fma(r, t, r);
 }
 
+// ------------------------------------------------------------------------------------------ TMA staging
+//
+// The TMA variants of the sweeps (template flag TMA) take the K-vectors of the NEXT node of a warp's queue with bulk
+// asynchronous copies (cp.async.bulk, global -> shared, completion counted on a per-warp mbarrier) while the warp
+// computes the current node out of registers: on the [slot][k][lane] layout the whole vector of a node for all the
+// lanes is ONE contiguous run (K * J * 8 bytes, 1 280 B for K = 20 x 8 lanes), so a step needs 2-3 copies issued by
+// one thread instead of 2-3 x KT dependent loads in every thread, and no vector load is left on the dependent path.
+// One staging slot per warp: it is drained into registers at the top of the step and refilled right away.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__host__ __device__ constexpr int round16(int x) { return (x + 15) & ~15; }
+
+// dynamic shared memory of the TMA variants (host side of the layout the kernels carve up)
+__host__ __device__ constexpr int bu_tma_sub_bytes(int K, int J) { return 2 * (K * J * 8 + J * 4); }
+__host__ __device__ constexpr int td_tma_sub_bytes(int K, int C) { return 3 * (K * C * 8 + C * 4); }
+inline size_t bu_tma_smem(int K, int J, int G) {
+    return (size_t) round16((4 + K) * J * 8) + (size_t) (kCoopBlock / 32) * (32 / (G * J)) * bu_tma_sub_bytes(K, J) + 8 * (kCoopBlock / 32);
+}
+inline size_t td_tma_smem(int K, int C, int G) {
+    return (size_t) round16((4 + K) * C * 8 + C * (K + 1) * 4) + (size_t) (kCoopBlock / 32) * (32 / (G * C)) * td_tma_sub_bytes(K, C) +
+           8 * (kCoopBlock / 32);
+}
+
 struct CoopLane {   // where a thread sits: which node of the warp's batch, which lane (column), which rank
     int sub, r, j, c, npw;
     bool lane_on;
@@ -109,6 +149,15 @@ struct CoopLane {   // where a thread sits: which node of the warp's batch, whic
 // resident blocks per SM the kernels are compiled for: 64 registers per thread up to 5 states per thread (measured
 // best for K = 20: more warps in flight beat the few spills), fewer blocks when a thread holds more states
 constexpr int coop_min_blocks(int kt) { return kt <= 5 ? PML_COOP_MINB : kt <= 8 ? 5 : 3; }
+// the TMA variants keep the next batch's descriptors and mask words in registers and do not need as many warps to
+// cover the memory latency (the copies run ahead of the arithmetic): fewer resident blocks, more registers each
+#ifndef PML_TMA_MINB
+#define PML_TMA_MINB 5
+#endif
+#ifndef PML_TMA_MINB_WIDE
+#define PML_TMA_MINB_WIDE 4
+#endif
+constexpr int coop_min_blocks(int kt, bool tma) { return tma ? (kt <= 5 ? PML_TMA_MINB : kt <= 8 ? 4 : PML_TMA_MINB_WIDE) : coop_min_blocks(kt); }
 
 template <int G>
 __device__ __forceinline__ CoopLane coop_lane(int J, int C) {
@@ -180,16 +229,44 @@ __device__ __forceinline__ int coop_load(const TreeDev &t, const ZcDev &zc, cons
 
 // ------------------------------------------------------------------------------------------ bottom-up
 
+// effective allowed-state mask from the raw annotation word (eff_mask with the word already loaded)
+__device__ __forceinline__ uint64_t eff_from_raw(uint64_t raw, const TreeDev &t, const ZcDev &zc, int C, int node, int c,
+                                                 bool use_alt, uint64_t kmask) {
+    if (use_alt && (raw & kMemberFlag)) raw = zc.alt[(size_t) t.zc_index[node] * C + c];
+    return raw & kmask;
+}
+
 // JT > 0: the number of lanes J is the compile-time constant JT; KX: K == G * KT exactly.
 // TILED: the pass has more lanes than one warp batch can take (many parameter sets x columns, the batched
 // finite-difference objective): blockIdx.y selects a tile of JT consecutive lanes, memory keeps its full leading
 // dimension `ld` = total lanes.
-template <int KT, int G, int JT, bool KX, bool TILED>
-__global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kernel(BuArgs a, int slot_begin, int n_slots) {
+// TMA: the children's vectors of the next node are staged in shared memory by bulk asynchronous copies (see above);
+// needs JT > 0, KX, no external (subtree-sharding) tables.
+template <int KT, int G, int JT, bool KX, bool TILED, bool TMA = false>
+__global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT, TMA)) bu_coop_kernel(BuArgs a, int slot_begin, int n_slots) {
     extern __shared__ double s_par[];
+    static_assert(!TMA || (JT > 0 && KX && (32 % (G * (JT ? JT : 1))) == 0), "TMA staging needs compile-time lanes");
     const int J = JT ? JT : a.ln.J, K = KX ? G * KT : a.ln.K, C = a.ln.C;
     const int ld = TILED ? a.ln.J : J;                 // leading dimension of bu / bu_ex / ext tables
     const int j0 = TILED ? (int) blockIdx.y * J : 0;   // first lane of this block's tile
+    const CoopLane cl = coop_lane<G>(J, C);
+    constexpr int VB = G * KT * (JT ? JT : 1) * 8, EB = (JT ? JT : 1) * 4;   // bytes of one staged vector / exponent row
+    uint32_t bar = 0, stage = 0, phase = 0;
+    const double *st_vec = nullptr;
+    if constexpr (TMA) {
+        unsigned char *st_base = reinterpret_cast<unsigned char *>(s_par) + round16((4 + K) * J * 8);
+        constexpr int sub_bytes = bu_tma_sub_bytes(G * KT, JT);
+        constexpr int npw = 32 / (G * JT);
+        const int warp = threadIdx.x >> 5;
+        unsigned char *mine = st_base + (warp * npw + cl.sub) * sub_bytes;
+        bar = smem_addr(st_base + (kCoopBlock / 32) * npw * sub_bytes + 8 * warp);
+        stage = smem_addr(mine);
+        st_vec = reinterpret_cast<const double *>(mine);
+        if ((threadIdx.x & 31) == 0) {
+            mbar_init(bar, npw);
+            mbar_fence_init();
+        }
+    }
     {
         // stage the tile's lane parameters, transposed to [field][lane]
         const int total = (4 + K) * J;
@@ -199,7 +276,6 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kerne
         }
         __syncthreads();
     }
-    const CoopLane cl = coop_lane<G>(J, C);
     const int r = cl.r;
     const int j = j0 + cl.j;                 // lane index in memory
     const int c = TILED ? j % C : cl.c;
@@ -213,51 +289,136 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kerne
     const bool mu_inf = isinf(mu);
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    (void) jl;
 
-    // the loop is software-pipelined by one step: the packed descriptor (and node id) of the next batch is requested
-    // before the current batch is processed, so that only the vector loads remain on the dependent path
+    // the loop is software-pipelined: the packed descriptor (and node id) of the next batch is requested before the
+    // current batch is processed, so that only the vector loads remain on the dependent path -- and with TMA not
+    // even those: the copies for batch i + 1 are issued at the top of batch i, the descriptor of batch i + 2 and the
+    // mask words of batch i + 1 are requested right after
     const int stride = n_warps * cl.npw;
     int base = warp_global * cl.npw;
     int4 nx_top = make_int4(0, 0, 0, 0), nx_len = make_int4(0, 0, 0, 0);
     int nx_node = 0;
+    int4 cu_top = make_int4(0, 0, 0, 0), cu_len = make_int4(0, 0, 0, 0);   // TMA: the batch whose copies are in flight
+    int cu_node = 0;
+    uint64_t cu_mo = 0, cu_m0 = 0, cu_m1 = 0;                                // TMA: its mask words (own, tip children)
+    auto load_desc = [&](int b, int4 &top, int4 &len, int &node) {
+        const int sl = b + cl.sub;
+        const size_t slot = (size_t) slot_begin + ((cl.lane_on && sl < n_slots) ? sl : b);
+        top = a.t.bu_desc[2 * slot];
+        len = a.t.bu_desc[2 * slot + 1];
+        node = a.t.int_nodes[slot];
+    };
+    auto load_masks = [&](const int4 &top, int node, uint64_t &mo, uint64_t &m0, uint64_t &m1) {
+        mo = a.mask[(size_t) node * C + c];
+        m0 = (top.z < 0) ? a.mask[(size_t) top.x * C + c] : 0ULL;
+        m1 = (top.w < 0 && top.y == 2) ? a.mask[(size_t) (top.x + 1) * C + c] : 0ULL;
+    };
+    // the copies of one batch: one thread per node arms the barrier; untiled, the same thread issues one copy per
+    // child vector (contiguous for all the lanes); tiled, the rows of the tile are spread over the node's threads
+    auto issue = [&](const int4 &top) {
+        const int li = cl.r * J + cl.j;
+        const bool bin = top.y == 2;
+        const int cs0 = top.z, cs1 = top.w;
+        if (li == 0) mbar_arrive_expect(bar, bin ? ((cs0 >= 0 ? VB + EB : 0) + (cs1 >= 0 ? VB + EB : 0)) : 0);
+        if (TILED) __syncwarp();
+        if (!bin) return;
+        if (!TILED) {
+            if (li == 0) {
+                if (cs0 >= 0) {
+                    bulk_g2s(stage, a.bu + (size_t) cs0 * K * J, VB, bar);
+                    bulk_g2s(stage + 2 * VB, a.bu_ex + (size_t) cs0 * J, EB, bar);
+                }
+                if (cs1 >= 0) {
+                    bulk_g2s(stage + VB, a.bu + (size_t) cs1 * K * J, VB, bar);
+                    bulk_g2s(stage + 2 * VB + EB, a.bu_ex + (size_t) cs1 * J, EB, bar);
+                }
+            }
+        } else {
+            for (int k = li; k <= K; k += G * J) {
+                if (k < K) {
+                    if (cs0 >= 0) bulk_g2s(stage + k * J * 8, a.bu + ((size_t) (cs0 * K + k) * ld + j0), J * 8, bar);
+                    if (cs1 >= 0) bulk_g2s(stage + VB + k * J * 8, a.bu + ((size_t) (cs1 * K + k) * ld + j0), J * 8, bar);
+                } else {
+                    if (cs0 >= 0) bulk_g2s(stage + 2 * VB, a.bu_ex + ((size_t) cs0 * ld + j0), EB, bar);
+                    if (cs1 >= 0) bulk_g2s(stage + 2 * VB + EB, a.bu_ex + ((size_t) cs1 * ld + j0), EB, bar);
+                }
+            }
+        }
+    };
     if (base < n_slots) {
-        const int sl = base + cl.sub;
-        const size_t slot = (size_t) slot_begin + ((cl.lane_on && sl < n_slots) ? sl : base);
-        nx_top = a.t.bu_desc[2 * slot];
-        nx_len = a.t.bu_desc[2 * slot + 1];
-        nx_node = a.t.int_nodes[slot];
+        if constexpr (TMA) {
+            load_desc(base, cu_top, cu_len, cu_node);
+            issue(cu_top);
+            load_masks(cu_top, cu_node, cu_mo, cu_m0, cu_m1);
+            if (base + stride < n_slots) load_desc(base + stride, nx_top, nx_len, nx_node);
+        } else {
+            load_desc(base, nx_top, nx_len, nx_node);
+        }
     }
     for (; base < n_slots; base += stride) {
         const int sl = base + cl.sub;
         const bool on = cl.lane_on && sl < n_slots;
         const int slot = slot_begin + (on ? sl : base);
-        const int4 d_top = nx_top, d_len = nx_len;
-        const int node = nx_node;
-        if (base + stride < n_slots) {
-            const int nsl = base + stride + cl.sub;
-            const size_t nslot = (size_t) slot_begin + ((cl.lane_on && nsl < n_slots) ? nsl : base + stride);
-            nx_top = a.t.bu_desc[2 * nslot];
-            nx_len = a.t.bu_desc[2 * nslot + 1];
-            nx_node = a.t.int_nodes[nslot];
-        }
+        const int4 d_top = TMA ? cu_top : nx_top, d_len = TMA ? cu_len : nx_len;
+        const int node = TMA ? cu_node : nx_node;
+        const uint64_t raw_own = cu_mo, raw0 = cu_m0, raw1 = cu_m1;
         const int fc = d_top.x, nc = d_top.y;
+        const bool all_bin = __all_sync(kFullMask, nc == 2);
+        double in0[KT], in1[KT];
+        int ex = 0;
+        if constexpr (TMA) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            if (all_bin) {
+                const int cs0 = d_top.z, cs1 = d_top.w;
+                if (cs0 >= 0) {
+#pragma unroll
+                    for (int i = 0; i < KT; ++i) in0[i] = st_vec[(r + G * i) * J + jl];
+                    ex += reinterpret_cast<const int *>(st_vec + 2 * (VB / 8))[jl];
+                } else {
+                    const uint64_t m = eff_from_raw(raw0, a.t, a.zc, C, fc, c, use_alt, a.ln.kmask) >> r;
+#pragma unroll
+                    for (int i = 0; i < KT; ++i) in0[i] = bit_as_double(m, G * i);
+                }
+                if (cs1 >= 0) {
+#pragma unroll
+                    for (int i = 0; i < KT; ++i) in1[i] = st_vec[VB / 8 + (r + G * i) * J + jl];
+                    ex += reinterpret_cast<const int *>(st_vec + 2 * (VB / 8))[J + jl];
+                } else {
+                    const uint64_t m = eff_from_raw(raw1, a.t, a.zc, C, fc + 1, c, use_alt, a.ln.kmask) >> r;
+#pragma unroll
+                    for (int i = 0; i < KT; ++i) in1[i] = bit_as_double(m, G * i);
+                }
+            }
+            __syncwarp();
+            if (base + stride < n_slots) {
+                issue(nx_top);
+                cu_top = nx_top;
+                cu_len = nx_len;
+                cu_node = nx_node;
+                load_masks(cu_top, cu_node, cu_mo, cu_m0, cu_m1);
+                if (base + 2 * stride < n_slots) load_desc(base + 2 * stride, nx_top, nx_len, nx_node);
+            }
+        } else {
+            if (base + stride < n_slots) load_desc(base + stride, nx_top, nx_len, nx_node);
+        }
         double acc[KT];
         {
-            const uint64_t m = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask) >> r;
+            const uint64_t m = (TMA ? eff_from_raw(raw_own, a.t, a.zc, C, node, c, use_alt, a.ln.kmask)
+                                    : eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask)) >> r;
 #pragma unroll
             for (int i = 0; i < KT; ++i) acc[i] = bit_as_double(m, G * i);   // 10 ** log10(allowed), ml.py:127
         }
-        int ex = 0;
         int bad_child = -1;
-        if (__all_sync(kFullMask, nc == 2)) {
+        if (all_bin) {
             // binary nodes: both children's vectors are requested before any arithmetic; rank 0 and rank 1 of the
             // group evaluate one exp each and hand it to the others
-            double in0[KT], in1[KT];
-            const int cs0 = d_top.z, cs1 = d_top.w;
             const double dmine = (r & 1) ? __hiloint2double(d_len.w, d_len.z) : __hiloint2double(d_len.y, d_len.x);
-            ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc, cs0, r, j, c, use_alt, in0, K, ld);
-            ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, cs1, r, j, c, use_alt, in1, K, ld);
+            if constexpr (!TMA) {
+                const int cs0 = d_top.z, cs1 = d_top.w;
+                ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc, cs0, r, j, c, use_alt, in0, K, ld);
+                ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, cs1, r, j, c, use_alt, in1, K, ld);
+            }
             const double emine = mu_inf ? 0. : exp_nonpos(-mu * ((dmine + tau) * tauf * sf));
             const double e0 = grp.from_rank(emine, 0), e1 = grp.from_rank(emine, 1);
             double s0 = 0., s1 = 0.;
@@ -323,16 +484,36 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kerne
 
 // ------------------------------------------------------------------------------------------ top-down sweep
 
-// node-centric fused top-down / marginal / MAP / MPPA step (see td_level_kernel) with the K-vector split over G threads
-template <int KT, int G, int JT, bool KX>
-__global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) td_coop_kernel(TdArgs a, int node_begin, int n_nodes) {
+// node-centric fused top-down / marginal / MAP / MPPA step (see td_level_kernel) with the K-vector split over G threads.
+// TMA: the node's own bottom-up vector and its parent's bottom-up and top-down vectors are staged one step ahead by
+// bulk copies (three contiguous K * C * 8-byte runs), the mask word and the joint state are prefetched in registers.
+template <int KT, int G, int JT, bool KX, bool TMA = false>
+__global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT, TMA)) td_coop_kernel(TdArgs a, int node_begin, int n_nodes) {
     extern __shared__ double s_par[];
+    static_assert(!TMA || (JT > 0 && KX && (32 % (G * (JT ? JT : 1))) == 0), "TMA staging needs compile-time lanes");
     const int C = JT ? JT : a.ln.C, K = KX ? G * KT : a.ln.K;
     const int nf = 4 + K;
     unsigned int *sh_hist = reinterpret_cast<unsigned int *>(s_par + (size_t) nf * C);   // [C][K+1]
     for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x) sh_hist[i] = 0u;
-    stage_params(s_par, a.ln, nf);
     const CoopLane cl = coop_lane<G>(C, C);
+    constexpr int VB = G * KT * (JT ? JT : 1) * 8, EB = (JT ? JT : 1) * 4;   // bytes of one staged vector / exponent row
+    uint32_t bar = 0, stage = 0, phase = 0;
+    const double *st_vec = nullptr;
+    if constexpr (TMA) {
+        unsigned char *st_base = reinterpret_cast<unsigned char *>(s_par) + round16(nf * C * 8 + C * (K + 1) * 4);
+        constexpr int sub_bytes = td_tma_sub_bytes(G * KT, JT);
+        constexpr int npw = 32 / (G * JT);
+        const int warp = threadIdx.x >> 5;
+        unsigned char *mine = st_base + (warp * npw + cl.sub) * sub_bytes;
+        bar = smem_addr(st_base + (kCoopBlock / 32) * npw * sub_bytes + 8 * warp);
+        stage = smem_addr(mine);
+        st_vec = reinterpret_cast<const double *>(mine);
+        if ((threadIdx.x & 31) == 0) {
+            mbar_init(bar, npw);
+            mbar_fence_init();
+        }
+    }
+    stage_params(s_par, a.ln, nf);
     const int r = cl.r, c = cl.j;
     const GroupOps<G, (JT > 0 && (JT & (JT - 1)) == 0)> grp((int) (threadIdx.x & 31), r, C);
     const double sf = s_par[c], tau = s_par[C + c], tauf = s_par[2 * C + c], mu = s_par[3 * C + c];
@@ -344,63 +525,140 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) td_coop_kerne
     const bool fj = a.force_joint != 0;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_root_slots = a.t.n_root_slots;
 
     const int stride = n_warps * cl.npw;
     int base = warp_global * cl.npw;
     int4 nx_desc = make_int4(-1, -1, 0, 0);
+    int4 cu_desc = make_int4(-1, -1, 0, 0);   // TMA: the batch whose copies are in flight
+    uint64_t cu_raw = 0;                      // TMA: its mask word
+    int cu_js = 0;                            //      and joint state
+    auto node_of = [&](int b) {
+        const int nd = b + cl.sub;
+        return node_begin + ((cl.lane_on && nd < n_nodes) ? nd : b);
+    };
+    // the copies of one batch, issued by one thread per node: own vector (internal nodes), parent's bottom-up vector,
+    // parent's top-down vector (parents that are not roots), each with its exponent row
+    auto issue = [&](const int4 &d) {
+        if (cl.r != 0 || cl.j != 0) return;
+        const int ps = d.x, cs = d.y;
+        const bool ptd = ps >= n_root_slots;
+        mbar_arrive_expect(bar, (cs >= 0 ? VB + EB : 0) + (ps >= 0 ? VB + EB : 0) + (ptd ? VB + EB : 0));
+        if (cs >= 0) {
+            bulk_g2s(stage, a.bu + (size_t) cs * K * C, VB, bar);
+            bulk_g2s(stage + 3 * VB, a.bu_ex + (size_t) cs * C, EB, bar);
+        }
+        if (ps >= 0) {
+            bulk_g2s(stage + VB, a.bu + (size_t) ps * K * C, VB, bar);
+            bulk_g2s(stage + 3 * VB + EB, a.bu_ex + (size_t) ps * C, EB, bar);
+        }
+        if (ptd) {
+            bulk_g2s(stage + 2 * VB, a.td + (size_t) ps * K * C, VB, bar);
+            bulk_g2s(stage + 3 * VB + 2 * EB, a.td_ex + (size_t) ps * C, EB, bar);
+        }
+    };
     if (base < n_nodes) {
-        const int nd = base + cl.sub;
-        nx_desc = a.t.td_desc[node_begin + ((cl.lane_on && nd < n_nodes) ? nd : base)];
+        if constexpr (TMA) {
+            const int n0 = node_of(base);
+            cu_desc = a.t.td_desc[n0];
+            issue(cu_desc);
+            cu_raw = a.mask[(size_t) n0 * C + c];
+            if (fj) cu_js = a.joint_state[(size_t) n0 * C + c];
+            if (base + stride < n_nodes) nx_desc = a.t.td_desc[node_of(base + stride)];
+        } else {
+            nx_desc = a.t.td_desc[node_of(base)];
+        }
     }
     for (; base < n_nodes; base += stride) {
         const int nd = base + cl.sub;
         const bool on = cl.lane_on && nd < n_nodes;
         const int node = node_begin + (on ? nd : base);
-        const int4 desc = nx_desc;   // {parent slot, own slot, dist}
-        if (base + stride < n_nodes) {
-            const int nnd = base + stride + cl.sub;
-            nx_desc = a.t.td_desc[node_begin + ((cl.lane_on && nnd < n_nodes) ? nnd : base + stride)];
-        }
+        const int4 desc = TMA ? cu_desc : nx_desc;   // {parent slot, own slot, dist}
+        const uint64_t raw_mask = cu_raw;
+        const int js_pre = cu_js;
         const int ps = desc.x;
         const int cs = desc.y;
         const size_t nc = (size_t) node * C + c;
+        const bool has_parent = ps >= 0;
 
         double Lc[KT], X[KT];
-        const int exc = coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, node, cs, r, c, c, use_alt, Lc, K, C);
-        const uint64_t base_mask = a.mask[nc];
-        const uint64_t flag = base_mask & kMemberFlag;
-        const uint64_t allowed = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
-        int ex_total = exc;
-        const bool has_parent = ps >= 0;
-        // parent part of the node's top-down vector: TD_p * L_p (all ones above a root, ml.py:274-277)
-        int pex = 0;
-        if (has_parent) {
-            const size_t off = (size_t) (ps * K + r) * C + c;
-            const double *src = a.bu + off;
+        int exc = 0, pex = 0, ex_total;
+        uint64_t base_mask, allowed;
+        if constexpr (TMA) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            base_mask = raw_mask;
+            allowed = eff_from_raw(raw_mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
+            const int *st_ex = reinterpret_cast<const int *>(st_vec + 3 * (VB / 8));
+            if (cs >= 0) {
 #pragma unroll
-            for (int i = 0; i < KT; ++i) X[i] = PML_VALID(i) ? src[(G * i) * C] : 0.;
-            pex = a.bu_ex[(size_t) ps * C + c];
-            if (ps >= a.t.n_root_slots) {
-                const double *src2 = a.td + off;
+                for (int i = 0; i < KT; ++i) Lc[i] = st_vec[(r + G * i) * C + c];
+                exc = st_ex[c];
+            } else {   // a tip: its vector is its allowed-state mask
+                const uint64_t m = allowed >> r;
 #pragma unroll
-                for (int i = 0; i < KT; ++i) X[i] *= PML_VALID(i) ? src2[(G * i) * C] : 0.;
-                pex += a.td_ex[(size_t) ps * C + c];
-            } else if (a.ext.root_td) {   // child of a clade root: the root's top-down vector came from above the cut
-                const int rn = a.t.int_nodes[ps];
-                const double *src2 = a.ext.root_td + ((size_t) (rn * K + r) * C + c);
-#pragma unroll
-                for (int i = 0; i < KT; ++i) X[i] *= PML_VALID(i) ? src2[(G * i) * C] : 0.;
-                pex += a.ext.root_td_ex[(size_t) rn * C + c];
+                for (int i = 0; i < KT; ++i) Lc[i] = bit_as_double(m, G * i);
             }
-        } else if (a.ext.root_td) {   // a clade root: its top-down vector arrives from above the cut
-            const double *src = a.ext.root_td + ((size_t) (node * K + r) * C + c);
+            ex_total = exc;
+            // parent part of the node's top-down vector: TD_p * L_p (all ones above a root, ml.py:274-277)
+            if (has_parent) {
 #pragma unroll
-            for (int i = 0; i < KT; ++i) X[i] = PML_VALID(i) ? src[(G * i) * C] : 0.;
-            ex_total += a.ext.root_td_ex[(size_t) node * C + c];
+                for (int i = 0; i < KT; ++i) X[i] = st_vec[VB / 8 + (r + G * i) * C + c];
+                pex = st_ex[C + c];
+                if (ps >= n_root_slots) {
+#pragma unroll
+                    for (int i = 0; i < KT; ++i) X[i] *= st_vec[2 * (VB / 8) + (r + G * i) * C + c];
+                    pex += st_ex[2 * C + c];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < KT; ++i) X[i] = 1.;
+            }
+            __syncwarp();
+            if (base + stride < n_nodes) {
+                issue(nx_desc);
+                cu_desc = nx_desc;
+                const int n1 = node_of(base + stride);
+                cu_raw = a.mask[(size_t) n1 * C + c];
+                if (fj) cu_js = a.joint_state[(size_t) n1 * C + c];
+                if (base + 2 * stride < n_nodes) nx_desc = a.t.td_desc[node_of(base + 2 * stride)];
+            }
         } else {
+            if (base + stride < n_nodes) nx_desc = a.t.td_desc[node_of(base + stride)];
+            exc = coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, node, cs, r, c, c, use_alt, Lc, K, C);
+            base_mask = a.mask[nc];
+            allowed = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
+            ex_total = exc;
+            // parent part of the node's top-down vector: TD_p * L_p (all ones above a root, ml.py:274-277)
+            if (has_parent) {
+                const size_t off = (size_t) (ps * K + r) * C + c;
+                const double *src = a.bu + off;
 #pragma unroll
-            for (int i = 0; i < KT; ++i) X[i] = 1.;
+                for (int i = 0; i < KT; ++i) X[i] = PML_VALID(i) ? src[(G * i) * C] : 0.;
+                pex = a.bu_ex[(size_t) ps * C + c];
+                if (ps >= n_root_slots) {
+                    const double *src2 = a.td + off;
+#pragma unroll
+                    for (int i = 0; i < KT; ++i) X[i] *= PML_VALID(i) ? src2[(G * i) * C] : 0.;
+                    pex += a.td_ex[(size_t) ps * C + c];
+                } else if (a.ext.root_td) {   // child of a clade root: the root's top-down vector came from above the cut
+                    const int rn = a.t.int_nodes[ps];
+                    const double *src2 = a.ext.root_td + ((size_t) (rn * K + r) * C + c);
+#pragma unroll
+                    for (int i = 0; i < KT; ++i) X[i] *= PML_VALID(i) ? src2[(G * i) * C] : 0.;
+                    pex += a.ext.root_td_ex[(size_t) rn * C + c];
+                }
+            } else if (a.ext.root_td) {   // a clade root: its top-down vector arrives from above the cut
+                const double *src = a.ext.root_td + ((size_t) (node * K + r) * C + c);
+#pragma unroll
+                for (int i = 0; i < KT; ++i) X[i] = PML_VALID(i) ? src[(G * i) * C] : 0.;
+                ex_total += a.ext.root_td_ex[(size_t) node * C + c];
+            } else {
+#pragma unroll
+                for (int i = 0; i < KT; ++i) X[i] = 1.;
+            }
         }
+        const uint64_t flag = base_mask & kMemberFlag;
         // the branch above the node: rank 0 evaluates the exponential for its group
         double e = 0.;
         if (r == 0 && !mu_inf) e = exp_nonpos(-mu * ((__hiloint2double(desc.w, desc.z) + tau) * tauf * sf));
@@ -448,7 +706,7 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) td_coop_kerne
                     if (r == 0) a.td_ex[(size_t) cs * C + c] = qex;
                 }
             }
-            else if (base_mask & kExtFlag) {   // hand the vector to the clade below the cut
+            else if (!TMA && (base_mask & kExtFlag)) {   // hand the vector to the clade below the cut
                 if (on) {
                     const int e_row = a.ext.index[node];
                     double *dst = a.ext.td + ((size_t) (e_row * K + r) * C + c);
@@ -517,7 +775,7 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) td_coop_kerne
         for (int i = 0; i < KT; ++i)
             if (PML_VALID(i) && m[i] > bv) { bv = m[i]; best = r + G * i; }
         grp.argmax(bv, best);
-        const int ji = fj ? a.joint_state[nc] : best;
+        const int ji = fj ? (TMA ? js_pre : a.joint_state[nc]) : best;
         // MPPA (ml.py:539-572), see mppa_select in pml_kernels.cuh for the derivation
         int best_k = 1;
         uint64_t sel = 1ULL << best;

@@ -20,12 +20,25 @@ constexpr size_t kMaxDynSmem = 200 * 1024;
 #define PML_COOP_GRID 8
 #endif
 
-unsigned coop_grid(int n, int lanes) {
+unsigned coop_grid(int n, int lanes, int blocks_per_sm = PML_COOP_GRID) {
     const int per_block = (kCoopBlock / 32) * (32 / (G * lanes));
     long long g = ((long long) n + per_block - 1) / per_block;
-    const long long cap = 148LL * PML_COOP_GRID;   // one resident wave; the kernels loop (and prefetch) beyond it
+    const long long cap = 148LL * blocks_per_sm;   // one resident wave; the kernels loop (and prefetch) beyond it
     if (g > cap) g = cap;
     return (unsigned) (g < 1 ? 1 : g);
+}
+
+// shared memory the TMA variants need per SM for their resident blocks, as a carve-out percentage (set once)
+template <class Kernel>
+void prefer_smem(Kernel kernel, size_t per_block, bool &done) {
+    if (done) return;
+    done = true;
+    const size_t per_sm = (per_block + 1024) * coop_min_blocks(KT, true);   // + 1 KB reserved per block
+    int pct = (int) ((per_sm * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (per_block > 48 * 1024)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
 }
 
 void bu_launch(cudaStream_t st, const BuArgs &a, int s0, int ns) {
@@ -51,6 +64,34 @@ void td_launch(cudaStream_t st, const TdArgs &a, int n0, int nn) {
         cudaFuncSetAttribute(td_coop_kernel<KT, G, JT, KX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
     td_coop_kernel<KT, G, JT, KX><<<coop_grid(nn, a.ln.C), kCoopBlock, sh, st>>>(a, n0, nn);
 }
+
+#if PML_JT > 0
+constexpr int kTmaBlocks = coop_min_blocks(KT, true);   // persistent grid: one resident wave
+// TMA-staged variants (compile-time lanes, K == G * KT, no external tables): see pml_coop.cuh
+void bu_tma_launch(cudaStream_t st, const BuArgs &a, int s0, int ns) {
+    const size_t sh = bu_tma_smem(G * KT, JT, G);
+    if (a.ln.J > JT) {
+        static bool done = false;
+        prefer_smem(bu_coop_kernel<KT, G, JT, KX, true, true>, sh, done);
+        const int tiles = a.ln.J / JT;
+        unsigned gx = coop_grid(ns, JT, kTmaBlocks);
+        const unsigned per_row = (148u * kTmaBlocks + tiles - 1) / tiles;
+        if (gx > per_row) gx = per_row;
+        bu_coop_kernel<KT, G, JT, KX, true, true><<<dim3(gx, tiles), kCoopBlock, sh, st>>>(a, s0, ns);
+        return;
+    }
+    static bool done = false;
+    prefer_smem(bu_coop_kernel<KT, G, JT, KX, false, true>, sh, done);
+    bu_coop_kernel<KT, G, JT, KX, false, true><<<coop_grid(ns, JT, kTmaBlocks), kCoopBlock, sh, st>>>(a, s0, ns);
+}
+
+void td_tma_launch(cudaStream_t st, const TdArgs &a, int n0, int nn) {
+    const size_t sh = td_tma_smem(G * KT, JT, G);
+    static bool done = false;
+    prefer_smem(td_coop_kernel<KT, G, JT, KX, true>, sh, done);
+    td_coop_kernel<KT, G, JT, KX, true><<<coop_grid(nn, JT, kTmaBlocks), kCoopBlock, sh, st>>>(a, n0, nn);
+}
+#endif
 }  // namespace
 
 #define PML_CS_NAME3(g, k, j) pml_coop_##g##_##k##_##j
@@ -58,7 +99,11 @@ void td_launch(cudaStream_t st, const TdArgs &a, int n0, int nn) {
 #define PML_CS_NAME PML_CS_NAME2(PML_G, PML_KT, PML_JT)
 
 const CoopSet *PML_CS_NAME() {
-    static const CoopSet cs = {bu_launch, td_launch, G, KT, JT};
+#if PML_JT > 0
+    static const CoopSet cs = {bu_launch, td_launch, G, KT, JT, bu_tma_launch, td_tma_launch};
+#else
+    static const CoopSet cs = {bu_launch, td_launch, G, KT, JT, nullptr, nullptr};
+#endif
     return &cs;
 }
 

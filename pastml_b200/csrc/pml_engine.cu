@@ -206,7 +206,15 @@ struct pml_problem {
 
 namespace {
 
-const CoopSet *pick_coop(const pml_problem *p, int J);
+const CoopSet *pick_coop(const pml_problem *p, int J, bool wide = false);
+inline bool tpi_enabled() {   // PASTML_B200_NO_TPI=1: the cooperative kernels instead (A/B measurements)
+    static const bool off = getenv("PASTML_B200_NO_TPI") != nullptr;
+    return !off;
+}
+inline bool tma_enabled() {   // PASTML_B200_NO_TMA=1: the register-path cooperative kernels (A/B measurements)
+    static const bool off = getenv("PASTML_B200_NO_TMA") != nullptr;
+    return !off;
+}
 
 void run_root_loglik(pml_problem *p, const LaneDev &ln, const uint64_t *mask, int alter, int is_marginal) {
     p->ks->root_loglik(p->stream, p->tree(), p->zc(), ln, mask, alter, p->bu.ptr, p->bu_ex.ptr, p->roots.ptr,
@@ -246,11 +254,20 @@ void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_
              p->err.ptr};
     const bool maxp = !is_marginal;
     const CoopSet *coop = maxp ? nullptr : pick_coop(p, ln.J);
+    // bulk-copy staging of the child vectors: needs the compile-time variants and no external (sharding) tips
+    const bool bu_tma = coop && coop->bu_tma && !p->ext_index.ptr && tma_enabled();
+    // thread-per-item sweep with TMA-staged child vectors (F81 family, sum-product mode, no external tips)
+    const int tpi_jt = (!maxp && p->kind == PML_MODEL_F81 && !p->ext_index.ptr && tpi_enabled()) ? tpi_tile_lanes(p->K, ln.J) : 0;
     for (int lvl = p->n_levels - 1; lvl >= 0; --lvl) {
         const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
         if (ns <= 0) continue;
+        if (tpi_jt) {
+            tpi_bu_launch(tpi_jt, p->stream, a, s0, ns);
+            p->launches++;
+            continue;
+        }
         if (coop) {
-            coop->bu(p->stream, a, s0, ns);
+            (bu_tma ? coop->bu_tma : coop->bu)(p->stream, a, s0, ns);
             p->launches++;
             continue;
         }
@@ -369,11 +386,13 @@ void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool wan
              p->td_ex.ptr, p->joint_state.ptr, force_joint, want_probs ? p->probs.ptr : nullptr,
              want_node_lh ? p->node_lh.ptr : nullptr, p->node_ex.ptr, p->mask[PML_MASK_MAP].ptr, p->mask[PML_MASK_MPPA].ptr,
              p->k_hist.ptr, p->zc_lh.ptr, p->zc_k.ptr};
-    const CoopSet *coop = pick_coop(p, ln.C);
+    const bool tma_ok = !p->ext_index.ptr && !p->have_root_td && tma_enabled();
+    const CoopSet *coop = pick_coop(p, ln.C, tma_ok && !getenv("PASTML_B200_COOP_G"));
+    const bool td_tma = coop && coop->td_tma && !p->ext_index.ptr && !p->have_root_td && tma_enabled();
     for (int lvl = 0; lvl < p->n_levels; ++lvl) {
         const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
         if (coop) {
-            coop->td(p->stream, a, n0, nn);
+            (td_tma ? coop->td_tma : coop->td)(p->stream, a, n0, nn);
             p->launches++;
             continue;
         }
@@ -455,7 +474,7 @@ const CoopSet *coop_set(int gg, int kt, int jt) {
 namespace {
 // Picks the cooperative configuration for K states and J lanes: G * J <= 32 threads per node, KT = the smallest
 // built size >= ceil(K / G); least padding first, then the larger group.  nullptr -> thread-per-item kernels.
-const CoopSet *pick_coop(const pml_problem *p, int J) {
+const CoopSet *pick_coop(const pml_problem *p, int J, bool wide) {
     static const bool disabled = getenv("PASTML_B200_NO_COOP") != nullptr;
     if (disabled || p->kind != PML_MODEL_F81 || p->K < 3) return nullptr;
     if (J > 16) {
@@ -468,6 +487,11 @@ const CoopSet *pick_coop(const pml_problem *p, int J) {
             }
         return nullptr;
     }
+    if (wide && p->K % 2 == 0 && p->K / 2 <= 10) {
+        // the TMA-staged top-down sweep runs best with two threads per item (measured: K = 20, 2.50 against 2.59 ms)
+        const CoopSet *cs = coop_set(2, p->K / 2, J);
+        if (cs && cs->td_tma) return cs;
+    }
     const int kts[] = {2, 3, 4, 5, 6, 8, 10, 12, 16};
     const CoopSet *best = nullptr;
     double best_score = 1e30;
@@ -478,11 +502,11 @@ const CoopSet *pick_coop(const pml_problem *p, int J) {
         for (int kt : kts) {
             if (kt < need) continue;
             const CoopSet *cs = coop_set(g, kt, 0);
-            if (!cs) break;
             if (g * kt == p->K) {   // a variant with compile-time lane count and state count, when built
                 const CoopSet *exact = coop_set(g, kt, J);
                 if (exact) cs = exact;
             }
+            if (!cs) break;
             const double score = (double) (g * kt - p->K) / p->K + (kt < 3 ? 0.5 : 0.) + (kt > 8 ? 0.25 : 0.) - 1e-3 * g;
             if (score < best_score) { best_score = score; best = cs; }
             break;

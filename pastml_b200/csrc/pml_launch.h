@@ -33,7 +33,14 @@ struct CoopSet {
     void (*bu)(cudaStream_t, const BuArgs &, int slot_begin, int n_slots);
     void (*td)(cudaStream_t, const TdArgs &, int node_begin, int n_nodes);
     int G, KT, JT;   // JT > 0: built for exactly JT lanes and K == G * KT
+    // TMA-staged variants of the same sweeps (JT > 0 only; problems without external tables), else nullptr
+    void (*bu_tma)(cudaStream_t, const BuArgs &, int slot_begin, int n_slots);
+    void (*td_tma)(cudaStream_t, const TdArgs &, int node_begin, int n_nodes);
 };
 const CoopSet *coop_set(int g, int kt, int jt);   // nullptr when not built
+
+// Thread-per-item F81 bottom-up sweep with TMA-staged operands (pml_tpi.cuh)
+int tpi_tile_lanes(int K, int J);   // lanes per tile for a pass with J lanes, 0 = not applicable
+void tpi_bu_launch(int jt, cudaStream_t, const BuArgs &, int slot_begin, int n_slots);
 
 }  // namespace pml
