@@ -200,7 +200,7 @@ struct pml_problem {
     ZcDev zc() const { return ZcDev{zc_alt.ptr, zc_altflag.ptr, zc_initial.ptr, zc_hasinit.ptr, zc_touched.ptr}; }
     LaneDev lanes(int n_sets) const {
         return LaneDev{C, n_sets * C, K, stride, params.ptr, kmask, FastDiv::make((unsigned) (n_sets * C)),
-                       FastDiv::make((unsigned) C)};
+                       FastDiv::make((unsigned) C), 0};
     }
 };
 
@@ -245,8 +245,19 @@ int upload_params(pml_problem *p, const double *params, int n_sets) {
 }
 
 // the bottom-up sweep on resident params/masks; leaves out_lh on the device
+// lanes per tile of the TMA-staged bottom-up sweep for a sum-product pass with J lanes, 0 = other kernels
+// (the tile-major layout only for passes with several parameter sets: the top-down sweep, which always runs on one
+// set, reads the plain layout)
+int bu_tile_lanes(const pml_problem *p, int J) {
+    if (p->kind != PML_MODEL_F81 || p->ext_index.ptr || !tpi_enabled()) return 0;
+    const int jt = tpi_tile_lanes(p->K, J);
+    return (jt == J || J > p->C) ? jt : 0;
+}
+
 void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marginal, int alter, bool keep_ptr) {
-    const LaneDev ln = p->lanes(n_sets);
+    LaneDev ln = p->lanes(n_sets);
+    const int tpi_jt = is_marginal ? bu_tile_lanes(p, ln.J) : 0;
+    ln.jt = tpi_jt;
     if (alter) run_alter(p, mask);
     fill_int_kernel<<<grid_for(2LL * ln.J), kBlock, 0, p->stream>>>(2LL * ln.J, -1, p->err.ptr);
     p->launches++;
@@ -257,7 +268,6 @@ void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_
     // bulk-copy staging of the child vectors: needs the compile-time variants and no external (sharding) tips
     const bool bu_tma = coop && coop->bu_tma && !p->ext_index.ptr && tma_enabled();
     // thread-per-item sweep with TMA-staged child vectors (F81 family, sum-product mode, no external tips)
-    const int tpi_jt = (!maxp && p->kind == PML_MODEL_F81 && !p->ext_index.ptr && tpi_enabled()) ? tpi_tile_lanes(p->K, ln.J) : 0;
     for (int lvl = p->n_levels - 1; lvl >= 0; --lvl) {
         const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
         if (ns <= 0) continue;
@@ -1077,7 +1087,8 @@ int pml_get_root_partials(pml_problem *p, int32_t n_sets, double *out_vec, int32
     if (!p || !out_vec || !out_ex) return fail(PML_ERR_INVALID, "null argument");
     if (n_sets < 1 || n_sets > p->B) return fail(PML_ERR_INVALID, "bad n_sets");
     CUDA_TRY(cudaSetDevice(p->device));
-    const LaneDev ln = p->lanes(n_sets);
+    LaneDev ln = p->lanes(n_sets);
+    ln.jt = bu_tile_lanes(p, ln.J);   // the layout the last sum-product pass with this many lanes left behind
     const size_t nv = (size_t) p->n_roots * p->K * ln.J, ne = (size_t) p->n_roots * ln.J;
     DevBuf<double> vec;
     DevBuf<int> ex;

@@ -79,7 +79,18 @@ struct LaneDev {
     const double *params;    // [J][stride]
     uint64_t kmask;          // (1 << K) - 1
     FastDiv divJ, divC;
+    int jt;                  // 0: bottom-up vectors laid out [slot][k][J]; else tile-major [slot][J / jt][k][jt]
+                             // (passes of the TMA-staged bottom-up sweep with more lanes than one tile)
 };
+
+// index of state k, lane j of a slot's bottom-up vector in the layout of this pass
+__device__ __forceinline__ size_t bu_at(const LaneDev &ln, int slot, int k, int j) {
+    if (ln.jt > 0 && ln.jt < ln.J) {
+        const int t = j / ln.jt, jl = j - t * ln.jt;
+        return (((size_t) slot * (ln.J / ln.jt) + t) * ln.K + k) * ln.jt + jl;
+    }
+    return ((size_t) slot * ln.K + k) * ln.J + j;
+}
 
 // Launches cover at most this many (node, lane) items, so that item indices fit 31 bits
 constexpr long long kMaxItemsPerLaunch = 1LL << 30;
@@ -574,7 +585,7 @@ static __global__ void root_loglik_kernel(TreeDev t, ZcDev zc, LaneDev ln, const
         if (s >= 0) ex = bu_ex[(size_t) s * J + j];
         const uint64_t m = (s >= 0) ? 0ULL : eff_mask(mask, t, zc, ln.C, node, c, use_alt, ln.kmask);
         for (int k = 0; k < K; ++k) {
-            const double l = (s >= 0) ? bu[((size_t) s * K + k) * J + j] : bit_as_double(m, k);
+            const double l = (s >= 0) ? bu[bu_at(ln, s, k, j)] : bit_as_double(m, k);
             const double x = l * p[4 + k];
             acc = is_marginal ? acc + x : fmax(acc, x);
         }
@@ -1088,7 +1099,7 @@ static __global__ void root_partials_kernel(TreeDev t, ZcDev zc, LaneDev ln, con
     const double *p = ln.params + (size_t) j * ln.stride;
     const uint64_t m = (s >= 0) ? 0ULL : eff_mask(mask, t, zc, ln.C, node, c, alter && p[1] == 0., ln.kmask);
     for (int k = 0; k < ln.K; ++k)
-        out[((size_t) node * ln.K + k) * ln.J + j] = (s >= 0) ? bu[((size_t) s * ln.K + k) * ln.J + j] : bit_as_double(m, k);
+        out[((size_t) node * ln.K + k) * ln.J + j] = (s >= 0) ? bu[bu_at(ln, s, k, j)] : bit_as_double(m, k);
     out_ex[(size_t) node * ln.J + j] = (s >= 0) ? bu_ex[(size_t) s * ln.J + j] : 0;
 }
 

@@ -37,7 +37,9 @@ void bu_launch_t(cudaStream_t st, const BuArgs &a, int s0, int ns) {
 int tpi_tile_lanes(int K, int J) {
     if (K < 2 || K > 62) return 0;
     for (int jt : {32, 16, 8, 4})
-        if (J == jt) return jt;   // one tile; passes with more lanes need the tile-major layout
+        if (J == jt) return jt;   // one tile: the plain layout
+    if (J % 8 == 0) return 8;     // more lanes (parameter sets x columns): tiles of 8 lanes, tile-major layout
+    if (J % 4 == 0) return 4;
     return 0;
 }
 
