@@ -29,6 +29,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
+TRAFFIC_FILE = 'r1_l_dram_traffic.json'   # ncu capture of one step of the default workload with the current kernels
 METRIC = 'mppa_node_states_per_s'
 UNIT = 'node-states/s'
 
@@ -176,6 +177,39 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ B200 arm
+
+def full_ml_acr(flat, masks, has, cols, K, device, sync):
+    """(fit seconds, reconstruction seconds, device passes, log-likelihood of the first column) of the ML ACR of the
+    given columns: the call sequence of ml_acr (ml.py:640-750) on array-native inputs, outputs left on the device."""
+    from pastml_b200.annotation import ForestStats
+    from pastml_b200.engine import MASK_MAP, MASK_MPPA
+    from pastml_b200.ml import ColumnBatch, fit_batch
+    from pastml_b200.models import F81Model
+    fs = ForestStats(flat=flat)
+    names = np.array(['s{:02d}'.format(i) for i in range(K)])
+    obs = []
+    for c in cols:
+        f = np.bincount(np.log2(masks[c][flat.is_tip].astype(np.float64)).astype(int), minlength=K).astype(np.float64)
+        obs.append(f / f.sum())
+    models = [F81Model(states=names, forest_stats=fs, character='c{}'.format(c)) for c in cols]
+    batch = ColumnBatch(flat, ['c{}'.format(c) for c in cols], models, device=device,
+                        annot_mask=np.ascontiguousarray(masks[cols]), has_state=np.ascontiguousarray(has[cols]))
+    sync()
+    t0 = time.perf_counter()
+    lhs, passes = fit_batch(batch, obs)
+    t1 = time.perf_counter()
+    params = batch.params()
+    pb = batch.problem
+    pb.joint(params, want_states=False)
+    pb.marginal(params, force_joint=True, want_probs=False, want_masks=False, results_on_device=True)
+    pb.loglik(params, mask_kind=MASK_MAP)
+    pb.mppa_finalize(force_joint=True, want_masks=False)
+    pb.loglik(params, mask_kind=MASK_MPPA)
+    sync()
+    t2 = time.perf_counter()
+    batch.close()
+    return t1 - t0, t2 - t1, passes, float(lhs[0])
+
 
 def run_subtree_sharded(args):
     """One tree for all the GPUs: every rank prunes its clades, the clade-root vectors are all-gathered (NCCL), every
@@ -356,30 +390,39 @@ def run_b200(args):
     h2d = h_parent.nbytes + h_dist.nbytes + h_masks.nbytes + h_has.nbytes + params.nbytes
     d2h = h_probs.nbytes + h_map.nbytes + h_mppa.nbytes + h_lh.nbytes + h_hist.nbytes
 
-    # ---- ML-fit wall time: the full two-stage L-BFGS-B fit of all columns (host optimiser, device objective)
+    # ---- ML-fit wall time (metric ii): two-stage L-BFGS-B fit of every column (host optimiser, device objective)
+    # + JOINT + marginal + MAP + MPPA + the restricted-likelihood passes, results left on the device
     ml_fit = None
     if not args.no_fit:
-        from pastml_b200.annotation import ForestStats
-        from pastml_b200.ml import ColumnBatch, fit_batch
-        from pastml_b200.models import F81Model
-        fs = ForestStats(flat=flat)
-        names = np.array(['s{:02d}'.format(i) for i in range(K)])
-        obs = []
-        for c in range(C):
-            f = np.bincount(np.log2(masks[c][flat.is_tip].astype(np.float64)).astype(int), minlength=K).astype(np.float64)
-            obs.append(f / f.sum())
-        models = [F81Model(states=names, forest_stats=fs, character='c{}'.format(c)) for c in range(C)]
-        batch = ColumnBatch(flat, ['c{}'.format(c) for c in range(C)], models, device=local_rank, annot_mask=masks,
-                            has_state=has)
         barrier()
-        t0 = time.perf_counter()
-        _, passes = fit_batch(batch, obs)
+        fit_s, rec_s, passes, lh0 = full_ml_acr(flat, masks, has, list(range(C)), K, local_rank, torch.cuda.synchronize)
         barrier()
-        fit_s = max_over_ranks(time.perf_counter() - t0, device='cuda')
-        batch.close()
-        ml_fit = {'seconds': fit_s, 'device_passes': int(passes),
-                  'what': 'two-stage L-BFGS-B fit of sf + {} frequencies for all {} columns of this rank in lock step, '
-                          'finite-difference gradients batched as parameter sets'.format(K - 1, C)}
+        fit_s = max_over_ranks(fit_s, device='cuda')
+        rec_s = max_over_ranks(rec_s, device='cuda')
+        ml_fit = {'seconds': fit_s + rec_s, 'fit_seconds': fit_s, 'reconstruction_seconds': rec_s, 'device_passes': int(passes),
+                  'what': 'two-stage L-BFGS-B fit of sf + {} frequencies for all {} columns of this rank in lock step '
+                          '(finite-difference gradients batched as parameter sets), then JOINT + marginal + MAP + MPPA + '
+                          'restricted-likelihood passes'.format(K - 1, C)}
+        if world > 1:
+            # strong scaling of the same job: the C columns of ONE tree (rank 0's workload) spread over the GPUs --
+            # columns are independent, so there is no exchange; the slowest rank sets the time
+            from pastml_b200.parallel import partition
+            flat0, masks0, has0 = (flat, masks, has) if rank == 0 else make_workload(args, 0)[:3]
+            lo, hi = partition(C, world, rank)
+            mine = list(range(lo, hi))
+            barrier()
+            if mine:
+                f1, r1, p1, _ = full_ml_acr(flat0, masks0, has0, mine, K, local_rank, torch.cuda.synchronize)
+            else:
+                f1 = r1 = 0.
+                p1 = 0
+            barrier()
+            tot = max_over_ranks(f1 + r1, device='cuda')
+            ml_fit['one_tree_columns_sharded'] = {
+                'seconds': tot, 'columns_per_rank': [partition(C, world, r)[1] - partition(C, world, r)[0] for r in range(world)],
+                'device_passes_rank0': int(p1),
+                'what': 'the {} columns of rank 0\'s tree fitted and reconstructed on {} GPUs, columns partitioned over the '
+                        'ranks (independent, no exchange), max over ranks'.format(C, world)}
 
     # ---- roofline of the dominant kernel family (per-level launches of one templated kernel)
     peaks_path = os.path.join(REPO, 'MEASURED_PEAKS.json')
@@ -388,15 +431,18 @@ def run_b200(args):
     else:
         peak, peak_src = 6650., 'fallback (B200_PROFILING.md)'
     bu_bytes, td_bytes = algorithmic_bytes(flat, K, C)
-    coop = C <= 16 and K >= 3 and not os.environ.get('PASTML_B200_NO_COOP')   # pick_coop() in pml_engine.cu
-    td_name, bu_name = ('td_coop_kernel', 'bu_coop_kernel') if coop else ('td_level_kernel', 'bu_level_kernel')
+    # names of the kernels the engine picks for this shape (enqueue_bottom_up / enqueue_top_down in pml_engine.cu)
+    coop = C <= 16 and K >= 3 and not os.environ.get('PASTML_B200_NO_COOP')
+    td_name = 'td_coop_kernel' if coop else 'td_level_kernel'
+    bu_name = 'bu_tpi_kernel' if (C in (4, 8, 16, 32) and not os.environ.get('PASTML_B200_NO_TPI')) else \
+        ('bu_coop_kernel' if coop else 'bu_level_kernel')
     sweeps = {td_name: (td_bytes, td_ms, td_launches), bu_name: (bu_bytes, bu_ms, bu_launches)}
     dom = max(sweeps, key=lambda k: sweeps[k][1])
 
     # measured DRAM traffic of one sweep (ncu dram__bytes_read/write.sum over all its launches), when the committed
     # capture matches this workload
     traffic = {}
-    tpath = os.path.join(REPO, 'profiles', 'r1_i_dram_traffic.json')
+    tpath = os.path.join(REPO, 'profiles', TRAFFIC_FILE)
     if os.path.exists(tpath) and (args.tips, K, C, args.tree) == (1_000_000, 20, 8, 'yule'):
         traffic = {k: v['dram_bytes_total'] for k, v in json.load(open(tpath))['kernels'].items()}
 
@@ -404,7 +450,7 @@ def run_b200(args):
         b, ms, n = sweeps[name]
         ach = b / (ms * 1e-3) / 1e9
         return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                'traffic': traffic.get(name), 'traffic_source': 'profiles/r1_i_dram_traffic.json (per sweep)' if name in traffic else None,
+                'traffic': traffic.get(name), 'traffic_source': 'profiles/{} (per sweep)'.format(TRAFFIC_FILE) if name in traffic else None,
                 'algorithmic_bytes_per_sweep': int(b), 'launches_per_sweep': int(n),
                 'avg_launch_us': ms * 1e3 / max(n, 1), 'sweep_ms': ms, 'peak_source': peak_src}
 
@@ -436,6 +482,8 @@ def run_b200(args):
 
 
 if __name__ == '__main__':
+    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION / INFO) off it
+    os.environ['NCCL_DEBUG'] = os.environ.get('PASTML_B200_NCCL_DEBUG', 'WARN')
     a = parse_args()
     if a.impl == 'reference':
         run_reference(a)

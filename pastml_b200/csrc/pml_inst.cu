@@ -35,7 +35,7 @@ void allow_big_smem(Kern kern, size_t bytes) {
 
 void bu_launch(cudaStream_t st, const BuArgs &a, bool maxp, int s0, int ns) {
     const long long items = (long long) ns * a.ln.J;
-    const size_t sh = sizeof(double) * staged_fields(kFamily, a.ln.K) * a.ln.J;
+    const size_t sh = sizeof(double) * staged_doubles(kFamily, a.ln.K, a.ln.J);
     if (maxp) {
         allow_big_smem(bu_level_kernel<KP, TheLane, true>, sh);
         bu_level_kernel<KP, TheLane, true><<<grid_for(items), kBlock, sh, st>>>(a, s0, ns);
@@ -53,7 +53,7 @@ void root_launch(cudaStream_t st, const TreeDev &t, const ZcDev &zc, const LaneD
 }
 
 size_t td_smem(const TdArgs &a) {
-    return sizeof(double) * staged_fields(kFamily, a.ln.K) * a.ln.C + sizeof(unsigned) * a.ln.C * (a.ln.K + 1);
+    return sizeof(double) * staged_doubles(kFamily, a.ln.K, a.ln.C) + sizeof(unsigned) * a.ln.C * (a.ln.K + 1);
 }
 
 void td_launch(cudaStream_t st, const TdArgs &a, int s0, int ns) {

@@ -179,14 +179,40 @@ struct LaneSmem {
     __device__ __forceinline__ double f(int i) const { return s[i * J]; }
 };
 
-// number of leading parameter fields staged in shared memory
+// number of leading parameter fields staged in shared memory ([field][lane])
 __host__ __device__ inline int staged_fields(int family, int K) { return family == 1 ? 8 : 4 + K; }
 
-__device__ __forceinline__ void stage_params(double *smem, const LaneDev &ln, int nf) {
+// The eigen-decomposition models also stage the eigenvalues and both matrices (2 K + 2 K^2 doubles per lane, 6.6 KB for
+// K = 20) when they fit: every matrix element is read once per matrix-vector product, by all the nodes a warp holds
+// for that lane.  Lane-major ([lane][element], so that the unrolled products keep immediate offsets), lane stride
+// = 1 mod 16 doubles: the 8 or 16 lanes of a warp fall into distinct banks.
+constexpr size_t kEigStageBytes = 160 * 1024;
+__host__ __device__ inline int eig_elements(int K) { return 2 * K + 2 * K * K; }
+__host__ __device__ inline int eig_lane_stride(int K) {
+    const int n = eig_elements(K);
+    return n + (17 - n % 16) % 16;
+}
+__host__ __device__ inline bool eig_staged(int family, int K, int J) {
+    return family == 2 && ((size_t) staged_fields(family, K) + eig_lane_stride(K)) * J * sizeof(double) <= kEigStageBytes;
+}
+// doubles of the staging area of a block
+__host__ __device__ inline size_t staged_doubles(int family, int K, int J) {
+    return (size_t) staged_fields(family, K) * J + (eig_staged(family, K, J) ? (size_t) eig_lane_stride(K) * J : 0);
+}
+
+__device__ __forceinline__ void stage_params(double *smem, const LaneDev &ln, int nf, bool with_eig = false) {
     const int total = nf * ln.J;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int f = i / ln.J, j = i - f * ln.J;
         smem[i] = ln.params[(size_t) j * ln.stride + f];
+    }
+    if (with_eig) {   // [lane][d, A, A^-1] behind the fields
+        const int ne = eig_elements(ln.K), ls = eig_lane_stride(ln.K);
+        double *dst = smem + total;
+        for (int i = threadIdx.x; i < ne * ln.J; i += blockDim.x) {
+            const int j = i / ne, e = i - j * ne;
+            dst[(size_t) j * ls + e] = ln.params[(size_t) j * ln.stride + 4 + ln.K + e];
+        }
     }
     __syncthreads();
 }
@@ -198,7 +224,7 @@ struct F81Lane {  // F81 / JC / EFT: P_ij = (1 - e) pi_j + delta_ij e, e = exp(-
     double sf, tau, tauf, mu;
     struct Branch { double e, ome; };
 
-    __device__ __forceinline__ void init(const LaneSmem &l, const double *, int) {
+    __device__ __forceinline__ void init(const LaneSmem &l, const double *, int, const double *) {
         sm = l;
         sf = l.f(0); tau = l.f(1); tauf = l.f(2); mu = l.f(3);
     }
@@ -266,7 +292,7 @@ struct HKYLane {  // HKY85 closed form, states A, C, G, T  (HKYModel.py:44-82); 
     double p4[4];
     struct Branch { double P[4][4]; };
 
-    __device__ __forceinline__ void init(const LaneSmem &l, const double *, int) {
+    __device__ __forceinline__ void init(const LaneSmem &l, const double *, int, const double *) {
         sm = l;
         sf = l.f(0); tau = l.f(1); tauf = l.f(2); kappa = l.f(3);
 #pragma unroll
@@ -335,13 +361,13 @@ struct EigLane {  // CUSTOM_RATES / JTT: P = A diag(exp(d t')) A^-1  (generator.
     static constexpr int family = 2;
     LaneSmem sm;
     double sf, tau, tauf;
-    const double *d, *A, *Ainv;  // this lane's eigen-decomposition in global memory (read-only path)
+    const double *d, *A, *Ainv;  // this lane's eigen-decomposition: staged in shared memory, else in the parameter block
     struct Branch { double ed[KP]; };
 
-    __device__ __forceinline__ void init(const LaneSmem &l, const double *gp, int K) {
+    __device__ __forceinline__ void init(const LaneSmem &l, const double *gp, int K, const double *staged) {
         sm = l;
         sf = l.f(0); tau = l.f(1); tauf = l.f(2);
-        d = gp + 4 + K;
+        d = staged ? staged : gp + 4 + K;
         A = d + K;
         Ainv = A + K * K;
     }
@@ -350,7 +376,7 @@ struct EigLane {  // CUSTOM_RATES / JTT: P = A diag(exp(d t')) A^-1  (generator.
         const double t = (dist + tau) * tauf * sf;
         Branch b;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) b.ed[k] = (k < K) ? exp(__ldg(d + k) * t) : 0.;
+        for (int k = 0; k < KP; ++k) b.ed[k] = (k < K) ? exp(d[k] * t) : 0.;
         return b;
     }
     // out = A (ed o (A^-1 in)): 2 K^2 fused multiply-adds instead of forming P (2 K^3)
@@ -362,7 +388,7 @@ struct EigLane {  // CUSTOM_RATES / JTT: P = A diag(exp(d t')) A^-1  (generator.
             if (m < K) {
 #pragma unroll
                 for (int j = 0; j < KP; ++j)
-                    if (j < K) s = fma(__ldg(Ainv + m * K + j), in[j], s);
+                    if (j < K) s = fma(Ainv[m * K + j], in[j], s);
             }
             w[m] = s * b.ed[m];
         }
@@ -372,7 +398,7 @@ struct EigLane {  // CUSTOM_RATES / JTT: P = A diag(exp(d t')) A^-1  (generator.
             if (i < K) {
 #pragma unroll
                 for (int m = 0; m < KP; ++m)
-                    if (m < K) s = fma(__ldg(A + i * K + m), w[m], s);
+                    if (m < K) s = fma(A[i * K + m], w[m], s);
             }
             out[i] = fmax(s, 0.);
         }
@@ -389,7 +415,7 @@ struct EigLane {  // CUSTOM_RATES / JTT: P = A diag(exp(d t')) A^-1  (generator.
         for (int i = 0; i < K; ++i) {
             double row[KP];
 #pragma unroll
-            for (int m = 0; m < KP; ++m) row[m] = (m < K) ? __ldg(A + i * K + m) * b.ed[m] : 0.;
+            for (int m = 0; m < KP; ++m) row[m] = (m < K) ? A[i * K + m] * b.ed[m] : 0.;
             double best = -CUDART_INF;
             int bi = 0;
 #pragma unroll 1
@@ -397,7 +423,7 @@ struct EigLane {  // CUSTOM_RATES / JTT: P = A diag(exp(d t')) A^-1  (generator.
                 double s = 0.;
 #pragma unroll
                 for (int m = 0; m < KP; ++m)
-                    if (m < K) s = fma(row[m], __ldg(Ainv + m * K + j), s);
+                    if (m < K) s = fma(row[m], Ainv[m * K + j], s);
                 double inj = 0.;
 #pragma unroll
                 for (int q = 0; q < KP; ++q) inj = (q == j) ? in[q] : inj;
@@ -495,7 +521,9 @@ template <int KP, template <int> class Lane, bool MAXP>
 __global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_BU_MINB : 1)) bu_level_kernel(BuArgs a, int slot_begin, int n_slots) {
     extern __shared__ double s_par[];
     const int J = a.ln.J, K = a.ln.K, C = a.ln.C;
-    stage_params(s_par, a.ln, staged_fields(Lane<KP>::family, K));
+    const int nf = staged_fields(Lane<KP>::family, K);
+    const bool with_eig = eig_staged(Lane<KP>::family, K, J);
+    stage_params(s_par, a.ln, nf, with_eig);
     const unsigned n_items = (unsigned) n_slots * (unsigned) J;
     for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n_items; g += gridDim.x * blockDim.x) {
         const unsigned sl = a.ln.divJ.div(g);
@@ -503,7 +531,8 @@ __global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_BU_MINB : 1)) bu_level
         const int j = (int) (g - sl * (unsigned) J);
         const int c = j - (int) a.ln.divC.div((unsigned) j) * C;
         Lane<KP> lane;
-        lane.init(LaneSmem{s_par + j, J}, a.ln.params + (size_t) j * a.ln.stride, K);
+        lane.init(LaneSmem{s_par + j, J}, a.ln.params + (size_t) j * a.ln.stride, K,
+                  with_eig ? s_par + (size_t) nf * J + (size_t) j * eig_lane_stride(K) : nullptr);
         const bool use_alt = a.alter && lane.tau == 0.;
         const int fc = a.t.fc_slot[slot], nc = a.t.nc_slot[slot];
         const int node = a.t.int_nodes[slot];
@@ -780,16 +809,18 @@ __global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_TD_MINB : 1)) td_level
     extern __shared__ double s_par[];
     const int C = a.ln.C, K = a.ln.K;
     const int nf = staged_fields(Lane<KP>::family, K);
-    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(s_par + (size_t) nf * C);   // [C][K+1]
+    const bool with_eig = eig_staged(Lane<KP>::family, K, C);
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(s_par + staged_doubles(Lane<KP>::family, K, C));   // [C][K+1]
     for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x) sh_hist[i] = 0u;
-    stage_params(s_par, a.ln, nf);
+    stage_params(s_par, a.ln, nf, with_eig);
     const unsigned n_items = (unsigned) n_nodes * (unsigned) C;
     for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n_items; g += gridDim.x * blockDim.x) {
         const unsigned nd = a.ln.divC.div(g);
         const int node = node_begin + (int) nd;
         const int c = (int) (g - nd * (unsigned) C);
         Lane<KP> lane;
-        lane.init(LaneSmem{s_par + c, C}, a.ln.params + (size_t) c * a.ln.stride, K);
+        lane.init(LaneSmem{s_par + c, C}, a.ln.params + (size_t) c * a.ln.stride, K,
+                  with_eig ? s_par + (size_t) nf * C + (size_t) c * eig_lane_stride(K) : nullptr);
         const bool use_alt = lane.tau == 0.;   // ml.py:702-703
         const int ps = a.t.pslot[node];
         const int cs = a.t.slot[node];

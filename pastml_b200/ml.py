@@ -122,6 +122,21 @@ def batched_gradients():
     return os.environ.get('PASTML_B200_BATCHED_FD', '1') != '0'
 
 
+def padded_sets(n_sets, n_columns):
+    """Number of parameter sets a batched pass is run with: the engine's TMA-staged bottom-up sweep takes lanes
+    (sets x columns) in tiles of 8 (or 4), so a multi-set pass is padded with copies of its last set when that costs
+    at most a quarter more lanes.  Single-set passes are left alone."""
+    if n_sets <= 1:
+        return n_sets
+    for tile in (8, 4):
+        n = n_sets
+        while (n * n_columns) % tile:
+            n += 1
+        if 4 * n <= 5 * n_sets:
+            return n
+    return n_sets
+
+
 class LockstepEvaluator(object):
     """Rendezvous of the per-column optimiser threads: when every column that is still being fitted has asked
     for objective values, a single batched pass evaluates all of them.  A request is a list of parameter blocks
@@ -141,7 +156,7 @@ class LockstepEvaluator(object):
 
     def _flush(self):
         cols = sorted(self.pending)
-        n_sets = max(len(self.pending[c]) for c in cols)
+        n_sets = min(padded_sets(max(len(self.pending[c]) for c in cols), self.batch.C), self.batch.max_sets)
         params = np.empty((n_sets, self.batch.C, self.batch.problem.stride), dtype=np.float64)
         for c in range(self.batch.C):
             blocks = self.pending.get(c)
@@ -203,7 +218,7 @@ class ColumnBatch(object):
         self.annot_mask = np.ascontiguousarray(annot_mask, dtype=np.uint64)
         self.has_state = np.ascontiguousarray(has_state, dtype=np.uint8)
         # capacity for the finite-difference batch of one gradient: every free parameter + the base point
-        self.max_sets = (1 + max(m.get_num_params() for m in self.models)) if batched_gradients() else 1
+        self.max_sets = padded_sets(1 + max(m.get_num_params() for m in self.models), self.C) if batched_gradients() else 1
         self.problem = Problem(flat, self.K, self.kind, self.annot_mask, self.has_state,
                                max_param_sets=self.max_sets, device=device)
 

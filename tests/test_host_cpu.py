@@ -89,3 +89,19 @@ def test_newick_round_trip_and_naming():
     assert [n.name for n in again.traverse()] == [n.name for n in t.traverse()]
     collapse_zero_branches([t])
     assert sum(1 for _ in t.traverse()) == 9
+
+
+def test_padded_sets():
+    """Multi-set passes are padded to lane tiles of 8 (or 4) when that costs at most a quarter more lanes."""
+    from pastml_b200.ml import padded_sets
+    assert padded_sets(1, 1) == 1 and padded_sets(1, 8) == 1
+    assert padded_sets(21, 8) == 21          # 168 lanes: already whole tiles
+    assert padded_sets(21, 1) == 24
+    assert padded_sets(2, 1) == 2            # padding 2 -> 4 would double the work
+    assert padded_sets(21, 2) == 24
+    assert padded_sets(11, 16) == 11
+    assert padded_sets(5, 3) == 5            # 15 lanes -> 24 is too expensive, -> 16 is not a multiple of 3
+    for n in range(1, 40):
+        for c in range(1, 20):
+            p = padded_sets(n, c)
+            assert n <= p <= 1.25 * n + 1e-9
