@@ -22,6 +22,7 @@ ENGINE_SRC = os.path.join(CSRC, 'pml_engine.cu')
 INST_SRC = os.path.join(CSRC, 'pml_inst.cu')
 COOP_SRC = os.path.join(CSRC, 'pml_coop_inst.cu')
 TPI_SRC = os.path.join(CSRC, 'pml_tpi.cu')
+MMA_SRC = os.path.join(CSRC, 'pml_mma.cu')
 HEADERS = [os.path.join(CSRC, 'pml_kernels.cuh'), os.path.join(CSRC, 'pml_coop.cuh'), os.path.join(CSRC, 'pml_tpi.cuh'),
            os.path.join(CSRC, 'pml_launch.h'),
            os.path.join(os.path.dirname(HERE), 'include', 'pastml_b200.h')]
@@ -81,6 +82,7 @@ def build(force=False, verbose=False, jobs=None):
     flags = ' '.join(NVCC_FLAGS)
     tasks = [(ENGINE_SRC, os.path.join(OBJ_DIR, 'pml_engine.o'), [], _digest([ENGINE_SRC] + HEADERS, flags))]
     tasks.append((TPI_SRC, os.path.join(OBJ_DIR, 'pml_tpi.o'), [], _digest([TPI_SRC] + HEADERS, flags)))
+    tasks.append((MMA_SRC, os.path.join(OBJ_DIR, 'pml_mma.o'), [], _digest([MMA_SRC] + HEADERS, flags)))
     inst_digest = _digest([INST_SRC] + HEADERS, flags)
     for fam, kp in INSTANCES:
         tasks.append((INST_SRC, os.path.join(OBJ_DIR, 'pml_inst_{}_{}.o'.format(fam, kp)),

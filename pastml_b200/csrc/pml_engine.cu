@@ -189,6 +189,7 @@ struct pml_problem {
                        zc_index.ptr, fc_slot.ptr, nc_slot.ptr, pslot.ptr, n_root_slots, bu_desc.ptr, td_desc.ptr};
     }
     // subtree sharding: external tip vectors / root top-down vectors
+    bool eig_shared = false;   // EIG: every lane of the uploaded parameters carries the same d, A, A^-1
     int n_ext = 0, ext_sets = 0;
     bool have_root_td = false;
     DevBuf<int> ext_index, ext_bu_ex, ext_td_ex, root_td_ex, ext_nodes;
@@ -240,6 +241,15 @@ int upload_params(pml_problem *p, const double *params, int n_sets) {
         for (int c = 0; c < p->C; ++c)
             if (params[((size_t) b * p->C + c) * p->stride + 1] == 0.) rec[c] = 1;
     CUDA_TRY(cudaMemcpyAsync(p->record_col.ptr, rec.data(), p->C, cudaMemcpyHostToDevice, p->stream));
+    if (p->kind == PML_MODEL_EIG) {
+        // do all the lanes share one eigen-decomposition (JTT with its fixed frequencies)?  Then the products of a
+        // node are GEMMs against the same matrices and the bottom-up sweep can run on the tensor cores
+        const size_t off = 4 + (size_t) p->K, len = (size_t) p->stride - off;
+        bool same = true;
+        for (size_t j = 1; same && j < (size_t) n_sets * p->C; ++j)
+            same = std::memcmp(params + off, params + j * p->stride + off, len * sizeof(double)) == 0;
+        p->eig_shared = same;
+    }
     CUDA_TRY(cudaStreamSynchronize(p->stream));   // rec is a stack-local host buffer
     return PML_OK;
 }
@@ -266,11 +276,19 @@ void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_
     const bool maxp = !is_marginal;
     const CoopSet *coop = maxp ? nullptr : pick_coop(p, ln.J);
     // bulk-copy staging of the child vectors: needs the compile-time variants and no external (sharding) tips
+    static const bool no_mma = getenv("PASTML_B200_NO_MMA") != nullptr;
+    const bool mma = !maxp && p->kind == PML_MODEL_EIG && p->eig_shared && !p->ext_index.ptr && !no_mma &&
+                     mma_bu_applicable(p->K, ln.J);
     const bool bu_tma = coop && coop->bu_tma && !p->ext_index.ptr && tma_enabled();
     // thread-per-item sweep with TMA-staged child vectors (F81 family, sum-product mode, no external tips)
     for (int lvl = p->n_levels - 1; lvl >= 0; --lvl) {
         const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
         if (ns <= 0) continue;
+        if (mma) {
+            mma_bu_launch(p->stream, a, s0, ns);
+            p->launches++;
+            continue;
+        }
         if (tpi_jt) {
             tpi_bu_launch(tpi_jt, p->stream, a, s0, ns);
             p->launches++;

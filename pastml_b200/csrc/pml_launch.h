@@ -43,4 +43,8 @@ const CoopSet *coop_set(int g, int kt, int jt);   // nullptr when not built
 int tpi_tile_lanes(int K, int J);   // lanes per tile for a pass with J lanes, 0 = not applicable
 void tpi_bu_launch(int jt, cudaStream_t, const BuArgs &, int slot_begin, int n_slots);
 
+// Bottom-up sweep of the eigen-decomposition models on the FP64 tensor cores (pml_mma.cu): lanes share one decomposition
+bool mma_bu_applicable(int K, int J);
+void mma_bu_launch(cudaStream_t, const BuArgs &, int slot_begin, int n_slots);
+
 }  // namespace pml

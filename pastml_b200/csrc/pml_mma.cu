@@ -1,0 +1,204 @@
+// Bottom-up sweep of the eigen-decomposition models (JTT, CUSTOM_RATES) on the FP64 tensor cores.
+//
+// P(t) L = A (exp(d t') o (A^-1 L)) (generator.py:54-65) costs 2 K^2 fused multiply-adds per (branch, lane); when
+// all the lanes share one decomposition (JTT with its fixed frequencies: the columns differ only in the scaling
+// factor, which enters through exp(d t')), the two products of a node are small GEMMs against the SAME matrices:
+// [K x K] . [K x 8 lanes].  One warp takes one (node, tile of 8 lanes): the child's vector, [k][lane] in memory, is
+// exactly the col-major B operand of mma.sync.m8n8k4 (one coalesced 256-byte load per step of 4 states), the
+// matrices sit in registers as A fragments (2 x ceil(K/8) x ceil(K/4) doubles per thread), the accumulators are
+// the 8 x 8 D tiles.  Between the two products the D tiles are scaled by exp(d_m t'_n) and turned into B fragments
+// through a 1.5 KB shared-memory slot per warp.
+//
+// Used for K <= 24, lanes a multiple of 8, sum-product mode, no external (subtree-sharding) tips; everything else
+// takes the thread-per-item kernels of pml_kernels.cuh.
+#include "pml_coop.cuh"
+#include "pml_launch.h"
+
+namespace pml {
+namespace {
+
+constexpr int kMmaKP = 24;            // largest padded state count: 3 row tiles of 8, 6 steps of 4
+constexpr int kMmaBlock = 128;
+constexpr int kMmaMinBlocks = 4;
+
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// group-wide maximum over the 8 row groups of a D tile column (lanes that differ in bits 2..4)
+__device__ __forceinline__ double colmax(double v) {
+    v = fmax(v, __shfl_xor_sync(kFullMask, v, 4));
+    v = fmax(v, __shfl_xor_sync(kFullMask, v, 8));
+    return fmax(v, __shfl_xor_sync(kFullMask, v, 16));
+}
+
+// MT row tiles of 8 states, KS steps of 4 states: the smallest pair that covers K (all-zero tiles are not issued)
+template <int MT, int KS>
+__global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) bu_mma_kernel(BuArgs a, int slot_begin, int n_slots) {
+    __shared__ __align__(16) double s_w[kMmaBlock / 32][kMmaKP * 8];
+    const int K = a.ln.K, J = a.ln.J, C = a.ln.C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t4 = lane & 3;   // D tile: row g, columns 2 t4, 2 t4 + 1; A: (g, t4); B: (t4, g)
+    const int tiles = J >> 3;
+    double *sw = s_w[warp];
+
+    // the shared decomposition, from lane 0's parameter block: A fragments of A^-1 and of A, this thread's eigenvalues
+    const double *dv = a.ln.params + 4 + K, *Am = dv + K, *Ai = Am + (size_t) K * K;
+    double f_inv[MT][KS], f_a[MT][KS], dm[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int row = 8 * mt + g;
+        dm[mt] = (row < K) ? dv[row] : 0.;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const int col = 4 * s + t4;
+            const bool in = row < K && col < K;
+            f_inv[mt][s] = in ? Ai[row * K + col] : 0.;
+            f_a[mt][s] = in ? Am[row * K + col] : 0.;
+        }
+    }
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const long long n_items = (long long) n_slots * tiles;
+    for (long long w = warp_global; w < n_items; w += n_warps) {
+        const int sl = (int) (w / tiles), tile = (int) (w - (long long) sl * tiles);
+        const int slot = slot_begin + sl;
+        const int j0 = tile * 8;
+        const int jb = j0 + g;              // the lane this thread feeds as B operand
+        const int jd = j0 + 2 * t4;         // the two lanes of this thread's D elements: jd, jd + 1
+        const int cb = jb % C, cd0 = jd % C, cd1 = (jd + 1) % C;
+        const double *p0 = a.ln.params + (size_t) jd * a.ln.stride, *p1 = p0 + a.ln.stride;
+        const double sf0 = p0[0], tau0 = p0[1], tf0 = p0[2], sf1 = p1[0], tau1 = p1[1], tf1 = p1[2];
+        const bool alt_b = a.alter && a.ln.params[(size_t) jb * a.ln.stride + 1] == 0.;
+        const int4 top = a.t.bu_desc[2 * (size_t) slot], len = a.t.bu_desc[2 * (size_t) slot + 1];
+        const int node = a.t.int_nodes[slot];
+        const int fc = top.x, nc = top.y;
+        double acc[MT][2];
+        {
+            const uint64_t m0 = eff_mask(a.mask, a.t, a.zc, C, node, cd0, a.alter && tau0 == 0., a.ln.kmask);
+            const uint64_t m1 = eff_mask(a.mask, a.t, a.zc, C, node, cd1, a.alter && tau1 == 0., a.ln.kmask);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {   // 10 ** log10(allowed), ml.py:127
+                acc[mt][0] = (8 * mt + g < K) ? bit_as_double(m0, 8 * mt + g) : 0.;
+                acc[mt][1] = (8 * mt + g < K) ? bit_as_double(m1, 8 * mt + g) : 0.;
+            }
+        }
+        int ex0 = 0, ex1 = 0, bad0 = -1, bad1 = -1;
+        for (int q = 0; q < nc; ++q) {
+            const int ch = fc + q;
+            const int cs = (q == 0) ? top.z : (q == 1) ? top.w : a.t.slot[ch];
+            const double dist = (q == 0) ? __hiloint2double(len.y, len.x) : (q == 1) ? __hiloint2double(len.w, len.z) : a.t.dist[ch];
+            // the child's vector as B fragments: states 4 s + t4 of lane jb
+            double lf[KS];
+            if (cs >= 0) {
+                const double *src = a.bu + (size_t) cs * K * J + jb;
+#pragma unroll
+                for (int s = 0; s < KS; ++s) lf[s] = (4 * s + t4 < K) ? src[(size_t) (4 * s + t4) * J] : 0.;
+            } else {
+                const uint64_t m = eff_mask(a.mask, a.t, a.zc, C, ch, cb, alt_b, a.ln.kmask);
+#pragma unroll
+                for (int s = 0; s < KS; ++s) lf[s] = bit_as_double(m, 4 * s + t4);
+            }
+            // W = A^-1 L
+            double wv[MT][2];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                wv[mt][0] = wv[mt][1] = 0.;
+#pragma unroll
+                for (int s = 0; s < KS; ++s) dmma(wv[mt][0], wv[mt][1], f_inv[mt][s], lf[s]);
+            }
+            // W o exp(d t'), handed over as B fragments through the warp's shared-memory slot
+            const double t0 = (dist + tau0) * tf0 * sf0, t1 = (dist + tau1) * tf1 * sf1;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const bool in = 8 * mt + g < K;
+                const double e0 = in ? exp_nonpos(dm[mt] * t0) : 0., e1 = in ? exp_nonpos(dm[mt] * t1) : 0.;
+                *reinterpret_cast<double2 *>(sw + (8 * mt + g) * 8 + 2 * t4) = make_double2(wv[mt][0] * e0, wv[mt][1] * e1);
+            }
+            __syncwarp();
+            double bf[KS];
+#pragma unroll
+            for (int s = 0; s < KS; ++s) bf[s] = sw[(4 * s + t4) * 8 + g];
+            __syncwarp();
+            // V = A (W o exp(d t')); acc *= max(V, 0)
+            double m0 = 0., m1 = 0.;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                double v0 = 0., v1 = 0.;
+#pragma unroll
+                for (int s = 0; s < KS; ++s) dmma(v0, v1, f_a[mt][s], bf[s]);
+                acc[mt][0] *= fmax(v0, 0.);
+                acc[mt][1] *= fmax(v1, 0.);
+                m0 = fmax(m0, acc[mt][0]);
+                m1 = fmax(m1, acc[mt][1]);
+            }
+            m0 = colmax(m0);
+            m1 = colmax(m1);
+            if (cs >= 0) {
+                ex0 += a.bu_ex[(size_t) cs * J + jd];
+                ex1 += a.bu_ex[(size_t) cs * J + jd + 1];
+            }
+            if (m0 == 0. && bad0 < 0) bad0 = ch;
+            if (m1 == 0. && bad1 < 0) bad1 = ch;
+            // keep the vectors in range (same policy as rescale<> of the thread-per-item kernels), lane by lane
+            if (m0 > 0. && !isinf(m0)) {
+                int e = exponent_of(m0);
+                if (e < -kKeep || e > kKeep) {
+                    int extra = 0;
+                    double lift = 1.;
+                    if (e == -1023) { lift = 0x1p+200; e = exponent_of(m0 * 0x1p+200); extra = -200; }
+                    const double s1 = pow2(-(e / 2)), s2 = pow2(-(e - e / 2));
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) acc[mt][0] = ((acc[mt][0] * lift) * s1) * s2;
+                    ex0 += e + extra;
+                }
+            }
+            if (m1 > 0. && !isinf(m1)) {
+                int e = exponent_of(m1);
+                if (e < -kKeep || e > kKeep) {
+                    int extra = 0;
+                    double lift = 1.;
+                    if (e == -1023) { lift = 0x1p+200; e = exponent_of(m1 * 0x1p+200); extra = -200; }
+                    const double s1 = pow2(-(e / 2)), s2 = pow2(-(e - e / 2));
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) acc[mt][1] = ((acc[mt][1] * lift) * s1) * s2;
+                    ex1 += e + extra;
+                }
+            }
+        }
+        // the D tiles are the node's vector: rows = states, two adjacent lanes per thread
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int row = 8 * mt + g;
+            if (row < K) *reinterpret_cast<double2 *>(a.bu + ((size_t) slot * K + row) * J + jd) = make_double2(acc[mt][0], acc[mt][1]);
+        }
+        if (g == 0) {
+            a.bu_ex[(size_t) slot * J + jd] = ex0;
+            a.bu_ex[(size_t) slot * J + jd + 1] = ex1;
+            // all entries zero: PastMLLikelihoodError of ml.py:139-145
+            if (bad0 >= 0 && atomicCAS(a.err + 2 * jd, -1, node) == -1) a.err[2 * jd + 1] = bad0;
+            if (bad1 >= 0 && atomicCAS(a.err + 2 * (jd + 1), -1, node) == -1) a.err[2 * (jd + 1) + 1] = bad1;
+        }
+    }
+}
+
+}  // namespace
+
+bool mma_bu_applicable(int K, int J) { return K >= 2 && K <= kMmaKP && J >= 8 && J % 8 == 0; }
+
+void mma_bu_launch(cudaStream_t st, const BuArgs &a, int s0, int ns) {
+    const long long items = (long long) ns * (a.ln.J / 8);
+    long long g = (items + kMmaBlock / 32 - 1) / (kMmaBlock / 32);
+    const long long cap = 148LL * kMmaMinBlocks;   // persistent grid
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    const int K = a.ln.K;
+    if (K <= 8) bu_mma_kernel<1, 2><<<(unsigned) g, kMmaBlock, 0, st>>>(a, s0, ns);
+    else if (K <= 16) bu_mma_kernel<2, 4><<<(unsigned) g, kMmaBlock, 0, st>>>(a, s0, ns);
+    else if (K <= 20) bu_mma_kernel<3, 5><<<(unsigned) g, kMmaBlock, 0, st>>>(a, s0, ns);
+    else bu_mma_kernel<3, 6><<<(unsigned) g, kMmaBlock, 0, st>>>(a, s0, ns);
+}
+
+}  // namespace pml

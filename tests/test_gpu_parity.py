@@ -192,3 +192,45 @@ def test_many_parameter_sets_tiled(K, C, B):
         model = cpu_oracle.OracleModel(0, pis[c], float(sets[b, c, 0]))
         want = cpu_oracle.loglikelihood(tree, model, np.where(masks[c] == 0, full, masks[c]), has[c])
         assert got[b, c] == pytest.approx(want, rel=LH_RTOL)
+
+
+@pytest.mark.parametrize('n_tips,C,kind', [(1500, 8, 'yule'), (800, 16, 'coalescent')])
+def test_jtt_columns_on_tensor_cores(n_tips, C, kind):
+    """JTT on several columns (one shared eigen-decomposition, lanes a multiple of 8): the bottom-up sweep runs as
+    FP64 tensor-core GEMMs (pml_mma.cu); log-likelihoods and marginal probabilities against the oracle, and two
+    parameter sets in one pass."""
+    from pastml_b200.annotation import ForestStats
+    from pastml_b200.engine import Problem
+    from pastml_b200.models import JTTModel
+    from pastml_b200 import synth
+    from oracle import cpu_oracle
+    rng = np.random.default_rng(77 + n_tips)
+    flat = synth.yule_tree(n_tips, rng) if kind == 'yule' else synth.coalescent_tree(n_tips, rng)
+    K = 20
+    masks, has, pis, sfs = synth.simulate_tip_masks(flat, K, C, rng, missing=0.05)
+    fs = ForestStats(flat=flat)
+    models = [JTTModel(forest_stats=fs, sf=float(sfs[c])) for c in range(C)]
+    params = np.stack([m.engine_block() for m in models])
+    pb = Problem(flat, K, models[0].engine_kind, masks, has, max_param_sets=2)
+    lh = pb.loglik(params)[0]
+    res = pb.marginal(params, force_joint=False)
+    sets = np.stack([params, params])
+    sets[1, :, 0] *= 1.3
+    lh2 = pb.loglik(sets, n_sets=2)
+    pb.close()
+    full = np.uint64((1 << K) - 1)
+    tree = cpu_oracle.OracleTree(flat)
+    for c in range(C):
+        m = models[c]
+        kw = dict(d=np.real(m.D_DIAGONAL), A=np.real(m.A), Ainv=np.real(m.A_INV))
+        om = cpu_oracle.OracleModel(2, m.frequencies, float(m.sf), **kw)
+        allowed = np.where(masks[c] == 0, full, masks[c])
+        want = cpu_oracle.loglikelihood(tree, om, allowed, has[c])
+        assert lh[c] == pytest.approx(want, rel=LH_RTOL)
+        assert lh2[0, c] == pytest.approx(want, rel=LH_RTOL)
+        om2 = cpu_oracle.OracleModel(2, m.frequencies, float(m.sf) * 1.3, **kw)
+        assert lh2[1, c] == pytest.approx(cpu_oracle.loglikelihood(tree, om2, allowed, has[c]), rel=LH_RTOL)
+        if c in (0, C - 1):
+            ref = cpu_oracle.ml_acr_fixed(flat, om, masks[c], has[c], method='MAP', force_joint=False)
+            np.testing.assert_allclose(res['probs'][:, c, :], ref['marginal_probabilities'], rtol=0, atol=PROB_ATOL)
+            assert np.array_equal(res['map_mask'][:, c], ref['map_mask'])
