@@ -174,6 +174,25 @@ int pml_last_call_stats(pml_problem *p, double *device_ms, int64_t *kernel_launc
 int pml_bench_pass(pml_problem *p, const double *params, int32_t n_sets, int32_t which, int32_t n_iter,
                    int32_t flush_l2, double *avg_ms, double *min_ms, int64_t *kernel_launches);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Array-native newick ingest (host only; no GPU needed).  Replaces pastml.tree.read_forest / read_tree and the ete3
+ * traversal for large trees (pastml/tree.py:176-222): every ';'-terminated tree of the text becomes part of ONE
+ * forest numbered in level order (all roots, then all depth-1 nodes, ...; children left to right) -- the node index
+ * space of pml_problem_create.  Labels of internal nodes are names (ete3 format 1), a missing branch length is 1.0
+ * (0 for a root), negative lengths become 0 (tree.py:194-198), [comments] are skipped.
+ * pml_newick_name_nodes applies pastml.tree.name_tree (tree.py:76-105) to every tree (use_tree_suffix: "_<tree>"
+ * suffixes for forests of several trees).  pml_newick_fill copies parent[N], dist[N] and, when both are given, the
+ * names as a concatenated byte buffer with name_offsets[N + 1]. */
+typedef struct pml_newick pml_newick;
+const char *pml_newick_last_error(void);
+int pml_newick_parse(const char *text, int64_t len, pml_newick **out);
+int64_t pml_newick_num_nodes(const pml_newick *nw);
+int64_t pml_newick_num_trees(const pml_newick *nw);
+int64_t pml_newick_names_bytes(const pml_newick *nw);
+int pml_newick_name_nodes(pml_newick *nw, int use_tree_suffix);
+int pml_newick_fill(const pml_newick *nw, int32_t *parent, double *dist, int64_t *name_offsets, char *names);
+void pml_newick_free(pml_newick *nw);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,9 @@ EXPORTS = ['pml_last_error', 'pml_version', 'pml_device_count', 'pml_param_strid
            'pml_set_custom_masks', 'pml_get_masks', 'pml_get_initial', 'pml_zero_likelihood_info',
            'pml_zero_likelihood_all', 'pml_trim_memory', 'pml_get_root_partials', 'pml_set_tip_partials',
            'pml_get_tip_td', 'pml_set_root_td',
-           'pml_last_call_stats', 'pml_bench_pass']
+           'pml_last_call_stats', 'pml_bench_pass',
+           'pml_newick_last_error', 'pml_newick_parse', 'pml_newick_num_nodes', 'pml_newick_num_trees',
+           'pml_newick_names_bytes', 'pml_newick_name_nodes', 'pml_newick_fill', 'pml_newick_free']
 
 PML_OK, PML_ERR_INVALID, PML_ERR_CUDA, PML_ERR_ZERO_LIKELIHOOD, PML_ERR_NO_DEVICE = 0, 1, 2, 3, 4
 MODEL_F81, MODEL_HKY, MODEL_EIG = 0, 1, 2
@@ -73,6 +75,23 @@ def load():
     lib.pml_get_root_partials.argtypes = [vp, i32, vp, vp]
     lib.pml_set_tip_partials.restype = C.c_int
     lib.pml_set_tip_partials.argtypes = [vp, i32, vp, vp, vp, i32]
+    i64 = C.c_int64
+    lib.pml_newick_last_error.restype = C.c_char_p
+    lib.pml_newick_last_error.argtypes = []
+    lib.pml_newick_parse.restype = C.c_int
+    lib.pml_newick_parse.argtypes = [C.c_char_p, i64, C.POINTER(vp)]
+    lib.pml_newick_num_nodes.restype = i64
+    lib.pml_newick_num_nodes.argtypes = [vp]
+    lib.pml_newick_num_trees.restype = i64
+    lib.pml_newick_num_trees.argtypes = [vp]
+    lib.pml_newick_names_bytes.restype = i64
+    lib.pml_newick_names_bytes.argtypes = [vp]
+    lib.pml_newick_name_nodes.restype = C.c_int
+    lib.pml_newick_name_nodes.argtypes = [vp, C.c_int]
+    lib.pml_newick_fill.restype = C.c_int
+    lib.pml_newick_fill.argtypes = [vp, vp, vp, vp, vp]
+    lib.pml_newick_free.restype = None
+    lib.pml_newick_free.argtypes = [vp]
     lib.pml_get_tip_td.restype = C.c_int
     lib.pml_get_tip_td.argtypes = [vp, vp, vp]
     lib.pml_set_root_td.restype = C.c_int

@@ -23,6 +23,7 @@ INST_SRC = os.path.join(CSRC, 'pml_inst.cu')
 COOP_SRC = os.path.join(CSRC, 'pml_coop_inst.cu')
 TPI_SRC = os.path.join(CSRC, 'pml_tpi.cu')
 MMA_SRC = os.path.join(CSRC, 'pml_mma.cu')
+NEWICK_SRC = os.path.join(CSRC, 'pml_newick.cpp')
 HEADERS = [os.path.join(CSRC, 'pml_kernels.cuh'), os.path.join(CSRC, 'pml_coop.cuh'), os.path.join(CSRC, 'pml_tpi.cuh'),
            os.path.join(CSRC, 'pml_launch.h'),
            os.path.join(os.path.dirname(HERE), 'include', 'pastml_b200.h')]
@@ -83,6 +84,7 @@ def build(force=False, verbose=False, jobs=None):
     tasks = [(ENGINE_SRC, os.path.join(OBJ_DIR, 'pml_engine.o'), [], _digest([ENGINE_SRC] + HEADERS, flags))]
     tasks.append((TPI_SRC, os.path.join(OBJ_DIR, 'pml_tpi.o'), [], _digest([TPI_SRC] + HEADERS, flags)))
     tasks.append((MMA_SRC, os.path.join(OBJ_DIR, 'pml_mma.o'), [], _digest([MMA_SRC] + HEADERS, flags)))
+    tasks.append((NEWICK_SRC, os.path.join(OBJ_DIR, 'pml_newick.o'), [], _digest([NEWICK_SRC, HEADERS[-1]], flags)))
     inst_digest = _digest([INST_SRC] + HEADERS, flags)
     for fam, kp in INSTANCES:
         tasks.append((INST_SRC, os.path.join(OBJ_DIR, 'pml_inst_{}_{}.o'.format(fam, kp)),

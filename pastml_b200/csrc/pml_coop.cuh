@@ -670,10 +670,32 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT, TMA)) td_coop_
         for (int i = 0; i < KT; ++i) s = fma(pi[i], Lc[i], s);
         s = grp.sum(s);
         double q[KT];
+        {
+            // the reciprocals: the range check of fast_rcp is hoisted out of the loop (one vote per warp instead of a
+            // branch per element); tiny / huge contributions take the exact path for the whole batch
+            const double os = ome * s;
+            bool plain = true;
 #pragma unroll
-        for (int i = 0; i < KT; ++i) {
-            const double cv = fma(e, Lc[i], ome * s);   // >= 0: e in [0, 1] and the inputs are non-negative
-            q[i] = (cv > 0.) ? X[i] * fast_rcp(cv) : X[i];
+            for (int i = 0; i < KT; ++i) {
+                q[i] = fma(e, Lc[i], os);   // >= 0: e in [0, 1] and the inputs are non-negative
+                plain = plain && (!(q[i] > 0.) || (q[i] > 0x1p-900 && q[i] < 0x1p+900));
+            }
+            if (__all_sync(kFullMask, plain)) {
+#pragma unroll
+                for (int i = 0; i < KT; ++i) {
+                    const double cv = q[i];
+                    double rr;
+                    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rr) : "d"(cv));
+                    double tt = fma(-cv, rr, 1.);
+                    rr = fma(rr, tt, rr);
+                    tt = fma(-cv, rr, 1.);
+                    rr = fma(rr, tt, rr);
+                    q[i] = (cv > 0.) ? X[i] * rr : X[i];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < KT; ++i) q[i] = (q[i] > 0.) ? X[i] * fast_rcp(q[i]) : X[i];
+            }
         }
         double s2 = 0.;
 #pragma unroll

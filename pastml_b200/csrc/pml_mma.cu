@@ -19,12 +19,45 @@ namespace {
 
 constexpr int kMmaKP = 24;            // largest padded state count: 3 row tiles of 8, 6 steps of 4
 constexpr int kMmaBlock = 128;
-constexpr int kMmaMinBlocks = 4;
+#ifndef PML_MMA_MINB
+#define PML_MMA_MINB 4
+#endif
+constexpr int kMmaMinBlocks = PML_MMA_MINB;
 
 __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
+}
+
+// exp_nonpos (pml_coop.cuh) on N arguments at once: the Horner steps run across the arguments, so that each of the 14
+// coefficients is materialised once per batch instead of once per exponential
+template <int N>
+__device__ __forceinline__ void exp_nonpos_n(const double (&x)[N], double (&y)[N]) {
+    double r[N], p[N];
+    int n[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double t = fma(x[i], 1.4426950408889634074, 6755399441055744.0);
+        n[i] = __double2loint(t);
+        const double nf = t - 6755399441055744.0;
+        r[i] = fma(nf, -6.93147180369123816490e-01, x[i]);
+        r[i] = fma(nf, -1.90821492927058770002e-10, r[i]);
+        p[i] = 1.6059043836821613e-10;
+    }
+    const double c[13] = {2.08767569878681e-09, 2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
+                          2.48015873015873e-05, 1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03,
+                          4.1666666666666664e-02, 1.6666666666666666e-01, 0.5, 1., 1.};
+#pragma unroll
+    for (int k = 0; k < 13; ++k) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = fma(p[i], r[i], c[k]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double v = __hiloint2double(__double2hiint(p[i]) + n[i] * 1048576, __double2loint(p[i]));
+        y[i] = (x[i] > -708.) ? v : ((x[i] != x[i]) ? x[i] : 0.);
+    }
 }
 
 // group-wide maximum over the 8 row groups of a D tile column (lanes that differ in bits 2..4)
@@ -62,9 +95,26 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) bu_mma_kernel(BuArgs
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const long long n_items = (long long) n_slots * tiles;
+    // the packed descriptor (and node id) of the next item is requested before the current one is processed
+    int4 nx_top = make_int4(0, 0, 0, 0), nx_len = nx_top;
+    int nx_node = 0;
+    if (warp_global < n_items) {
+        const size_t s0 = (size_t) slot_begin + (size_t) (warp_global / tiles);
+        nx_top = a.t.bu_desc[2 * s0];
+        nx_len = a.t.bu_desc[2 * s0 + 1];
+        nx_node = a.t.int_nodes[s0];
+    }
     for (long long w = warp_global; w < n_items; w += n_warps) {
         const int sl = (int) (w / tiles), tile = (int) (w - (long long) sl * tiles);
         const int slot = slot_begin + sl;
+        const int4 top = nx_top, len = nx_len;
+        const int node = nx_node;
+        if (w + n_warps < n_items) {
+            const size_t s1 = (size_t) slot_begin + (size_t) ((w + n_warps) / tiles);
+            nx_top = a.t.bu_desc[2 * s1];
+            nx_len = a.t.bu_desc[2 * s1 + 1];
+            nx_node = a.t.int_nodes[s1];
+        }
         const int j0 = tile * 8;
         const int jb = j0 + g;              // the lane this thread feeds as B operand
         const int jd = j0 + 2 * t4;         // the two lanes of this thread's D elements: jd, jd + 1
@@ -72,8 +122,6 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) bu_mma_kernel(BuArgs
         const double *p0 = a.ln.params + (size_t) jd * a.ln.stride, *p1 = p0 + a.ln.stride;
         const double sf0 = p0[0], tau0 = p0[1], tf0 = p0[2], sf1 = p1[0], tau1 = p1[1], tf1 = p1[2];
         const bool alt_b = a.alter && a.ln.params[(size_t) jb * a.ln.stride + 1] == 0.;
-        const int4 top = a.t.bu_desc[2 * (size_t) slot], len = a.t.bu_desc[2 * (size_t) slot + 1];
-        const int node = a.t.int_nodes[slot];
         const int fc = top.x, nc = top.y;
         double acc[MT][2];
         {
@@ -111,11 +159,17 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) bu_mma_kernel(BuArgs
             }
             // W o exp(d t'), handed over as B fragments through the warp's shared-memory slot
             const double t0 = (dist + tau0) * tf0 * sf0, t1 = (dist + tau1) * tf1 * sf1;
+            {
+                double xs[2 * MT], es[2 * MT];
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const bool in = 8 * mt + g < K;
-                const double e0 = in ? exp_nonpos(dm[mt] * t0) : 0., e1 = in ? exp_nonpos(dm[mt] * t1) : 0.;
-                *reinterpret_cast<double2 *>(sw + (8 * mt + g) * 8 + 2 * t4) = make_double2(wv[mt][0] * e0, wv[mt][1] * e1);
+                for (int mt = 0; mt < MT; ++mt) {   // rows >= K carry d = 0 and W = 0
+                    xs[2 * mt] = dm[mt] * t0;
+                    xs[2 * mt + 1] = dm[mt] * t1;
+                }
+                exp_nonpos_n<2 * MT>(xs, es);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+                    *reinterpret_cast<double2 *>(sw + (8 * mt + g) * 8 + 2 * t4) = make_double2(wv[mt][0] * es[2 * mt], wv[mt][1] * es[2 * mt + 1]);
             }
             __syncwarp();
             double bf[KS];

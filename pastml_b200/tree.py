@@ -737,6 +737,42 @@ def flatten_forest(forest):
     return FlatForest(np.asarray(parent, dtype=np.int32), dist, nodes=nodes)
 
 
+def read_forest_flat(tree_path_or_newick, name_nodes=True):
+    """Array-native ingest for large trees: parses the newick file (or string) with the engine library's C++ parser
+    (``csrc/pml_newick.cpp``; same rules as :func:`read_forest` / ``pastml.tree.read_forest``,
+    ``/root/reference/pastml/tree.py:176-222``) straight into a level-ordered :class:`FlatForest`, without building a
+    Python object per node.  ``name_nodes`` applies :func:`name_tree`'s rule (``tree.py:76-105``).  NHX annotations are
+    skipped: annotate through the mask arrays (``ml.ColumnBatch(annot_mask=...)``)."""
+    import ctypes as C
+    import os
+    from pastml_b200 import _lib
+    lib = _lib.load()
+    text = tree_path_or_newick
+    if isinstance(text, str) and os.path.exists(text):
+        with open(text, 'rb') as f:
+            data = f.read()
+    else:
+        data = text.encode() if isinstance(text, str) else bytes(text)
+    handle = C.c_void_p()
+    if lib.pml_newick_parse(data, len(data), C.byref(handle)) != 0:
+        raise ValueError('Could not read the tree: {}. Is it a valid newick?'.format(lib.pml_newick_last_error().decode()))
+    try:
+        if name_nodes:
+            lib.pml_newick_name_nodes(handle, 1)
+        n = lib.pml_newick_num_nodes(handle)
+        parent = np.empty(n, dtype=np.int32)
+        dist = np.empty(n, dtype=np.float64)
+        offsets = np.empty(n + 1, dtype=np.int64)
+        buf = np.empty(max(1, lib.pml_newick_names_bytes(handle)), dtype=np.uint8)
+        lib.pml_newick_fill(handle, parent.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p),
+                            offsets.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p))
+    finally:
+        lib.pml_newick_free(handle)
+    raw = buf.tobytes()
+    names = np.array([raw[offsets[i]:offsets[i + 1]].decode() for i in range(n)], dtype=object)
+    return FlatForest(parent, dist, names=names)
+
+
 def forest_from_arrays(parent, dist, names=None):
     """Builds :class:`Tree` objects from level-ordered arrays (the inverse of :func:`flatten_forest`);
     returns the list of roots."""

@@ -105,3 +105,93 @@ def test_padded_sets():
         for c in range(1, 20):
             p = padded_sets(n, c)
             assert n <= p <= 1.25 * n + 1e-9
+
+
+# ------------------------------------------------------------------ array-native newick ingest (csrc/pml_newick.cpp)
+
+def _python_flat(text, name=True):
+    """The Python path: read_tree per ';'-separated tree + negative lengths to zero + name_tree + flatten_forest."""
+    from pastml_b200 import tree as T
+    roots = [T.read_tree(nwk + ';') for nwk in text.replace('\n', '').split(';')[:-1] if nwk.strip()]
+    for i, root in enumerate(roots):
+        for node in root.traverse():
+            if node.dist < 0:
+                node.dist = 0
+        if name:
+            T.name_tree(root, suffix='_{}'.format(i) if len(roots) > 1 else '')
+    flat = T.flatten_forest(roots)
+    return flat, [n.name for n in flat.nodes]
+
+
+def _random_newick(rng, n_tips, named_internal=0.5, dup=False):
+    from pastml_b200 import tree as T
+    nodes = [T.Tree(name='x{}'.format(i) if not dup else 'same') for i in range(n_tips)]
+    k = 0
+    while len(nodes) > 1:
+        m = min(len(nodes), int(rng.integers(2, 5)))
+        idx = sorted(rng.choice(len(nodes), size=m, replace=False))[::-1]
+        parent = T.Tree(name='in{}'.format(k) if rng.random() < named_internal else '')
+        k += 1
+        for i in idx:
+            ch = nodes.pop(i)
+            ch.dist = float(np.round(rng.exponential(1.), 6)) if rng.random() < 0.9 else 0.
+            ch.up = parent
+            parent.children.append(ch)
+        nodes.append(parent)
+    return nodes[0].write(format=1)
+
+
+@pytest.mark.parametrize('text', [
+    "((A:1,B:2)ab:0.5,(C:-1,'D d':3)[&&NHX:x=1]:4,E)r;",
+    "(A,B,(C,D));",
+    "A;",
+    "A:1.5;",
+    "((a:1,b:1):1,(a:1,c:1):2);\n(x:1,(y:2,z:3)w:1)top:7;",
+    "( A : 1 , B : 2e-3 ) ;",
+    "((A:1,B:1)0.9:1,C:2);",
+])
+def test_newick_ingest_matches_python_reader(text):
+    from pastml_b200 import tree as T
+    for name in (False, True):
+        want, want_names = _python_flat(text, name)
+        got = T.read_forest_flat(text, name_nodes=name)
+        assert np.array_equal(got.parent, want.parent)
+        assert np.array_equal(got.dist, want.dist)
+        assert list(got.names) == want_names
+
+
+def test_newick_ingest_random_trees_and_naming_rules():
+    from pastml_b200 import tree as T
+    rng = np.random.default_rng(11)
+    for trial in range(12):
+        text = _random_newick(rng, int(rng.integers(2, 60)), named_internal=rng.random(), dup=trial % 4 == 3)
+        if trial % 3 == 2:
+            text += '\n' + _random_newick(rng, 7)
+        want, want_names = _python_flat(text)
+        got = T.read_forest_flat(text)
+        assert np.array_equal(got.parent, want.parent)
+        assert np.allclose(got.dist, want.dist, rtol=0, atol=0)
+        assert list(got.names) == want_names
+        assert len(set(got.names[got.tree_id == 0])) == int((got.tree_id == 0).sum())
+
+
+def test_newick_ingest_golden_trees_round_trip():
+    """Every fixture tree, written to newick from its arrays, comes back with the same level-ordered arrays."""
+    from helpers import Golden, golden_names
+    from pastml_b200 import tree as T
+    for name in golden_names()[:8]:
+        g = Golden(name)
+        roots = T.forest_from_arrays(g['parent'], g['dist'], g['names'])
+        text = '\n'.join(r.write(format=1) for r in roots)
+        got = T.read_forest_flat(text, name_nodes=False)
+        assert np.array_equal(got.parent, g['parent'])
+        np.testing.assert_allclose(got.dist, g['dist'], rtol=1e-6)   # write() prints 6 significant digits
+        keep = g['parent'] >= 0   # like ete3, write() leaves the root's name out
+        assert list(got.names[keep]) == [str(x) for x in g['names'][keep]]
+
+
+@pytest.mark.parametrize('text', ["((A,B);", "(A,B));", "(A,B)C)D;", "", "   ", "(A:x,B);", "(A,'B);"])
+def test_newick_ingest_errors(text):
+    from pastml_b200 import tree as T
+    with pytest.raises(ValueError):
+        T.read_forest_flat(text)
