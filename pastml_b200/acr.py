@@ -147,3 +147,10 @@ def acr(forest, df=None, columns=None, column2states=None, prediction_method=MPP
         else:
             acr_results.append(r)
     return acr_results
+
+
+def pastml_pipeline(*args, **kwargs):
+    """``pastml.acr.pastml_pipeline`` lives here in the reference; the implementation is in
+    :mod:`pastml_b200.pipeline` (imported lazily: it builds on :func:`acr`)."""
+    from pastml_b200.pipeline import pastml_pipeline as run
+    return run(*args, **kwargs)
