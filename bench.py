@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument('--columns', type=int, default=8)
     ap.add_argument('--tree', default='yule', choices=['yule', 'coalescent'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-fit', action='store_true')
     ap.add_argument('--sharding', default='batch', choices=['batch', 'subtree'],
                     help='batch: every GPU owns an independent (tree x columns) batch (weak scaling, default); '
@@ -382,8 +382,11 @@ def run_b200(args):
     e2e_step()
     barrier()
     t0 = time.perf_counter()
+    e2e_each = []
     for _ in range(args.e2e_steps):
+        t1 = time.perf_counter()
         e2e_step()
+        e2e_each.append(time.perf_counter() - t1)
     barrier()
     e2e_dt = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps, device='cuda')
     e2e_value = node_states * world / e2e_dt
@@ -459,7 +462,7 @@ def run_b200(args):
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, flat),
             'clocks': clocks.summary(),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                    'ms_per_step': e2e_dt * 1e3, 'steps': args.e2e_steps,
+                    'ms_per_step': e2e_dt * 1e3, 'steps': args.e2e_steps, 'min_ms_per_step_rank0': min(e2e_each) * 1e3,
                     'what': 'pml_problem_create + pml_marginal (all outputs to pinned host memory) + destroy'},
             'gpu_launches': int(launches * args.steps),
             'roofline': roof(dom), 'roofline_other': roof([k for k in sweeps if k != dom][0]),

@@ -207,7 +207,7 @@ struct pml_problem {
 
 namespace {
 
-const CoopSet *pick_coop(const pml_problem *p, int J, bool wide = false);
+const CoopSet *pick_coop(const pml_problem *p, int J, bool wide = false, bool allow_tiled = true);
 inline bool tpi_enabled() {   // PASTML_B200_NO_TPI=1: the cooperative kernels instead (A/B measurements)
     static const bool off = getenv("PASTML_B200_NO_TPI") != nullptr;
     return !off;
@@ -415,7 +415,7 @@ void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool wan
              want_node_lh ? p->node_lh.ptr : nullptr, p->node_ex.ptr, p->mask[PML_MASK_MAP].ptr, p->mask[PML_MASK_MPPA].ptr,
              p->k_hist.ptr, p->zc_lh.ptr, p->zc_k.ptr};
     const bool tma_ok = !p->ext_index.ptr && !p->have_root_td && tma_enabled();
-    const CoopSet *coop = pick_coop(p, ln.C, tma_ok && !getenv("PASTML_B200_COOP_G"));
+    const CoopSet *coop = pick_coop(p, ln.C, tma_ok && !getenv("PASTML_B200_COOP_G"), false);
     const bool td_tma = coop && coop->td_tma && !p->ext_index.ptr && !p->have_root_td && tma_enabled();
     for (int lvl = 0; lvl < p->n_levels; ++lvl) {
         const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
@@ -502,12 +502,13 @@ const CoopSet *coop_set(int gg, int kt, int jt) {
 namespace {
 // Picks the cooperative configuration for K states and J lanes: G * J <= 32 threads per node, KT = the smallest
 // built size >= ceil(K / G); least padding first, then the larger group.  nullptr -> thread-per-item kernels.
-const CoopSet *pick_coop(const pml_problem *p, int J, bool wide) {
+const CoopSet *pick_coop(const pml_problem *p, int J, bool wide, bool allow_tiled) {
     static const bool disabled = getenv("PASTML_B200_NO_COOP") != nullptr;
     if (disabled || p->kind != PML_MODEL_F81 || p->K < 3) return nullptr;
     if (J > 16) {
         // many lanes (parameter sets x columns): tiles of 8 lanes through the compile-time variants, when they fit
-        if (J % 8) return nullptr;
+        // (bottom-up sweep only: the top-down kernels take all the columns of a node in one warp batch)
+        if (!allow_tiled || J % 8) return nullptr;
         for (int g = 4; g >= 2; g >>= 1)
             if (p->K % g == 0) {
                 const CoopSet *cs = coop_set(g, p->K / g, 8);

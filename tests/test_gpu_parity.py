@@ -119,7 +119,8 @@ def test_columns_and_parameter_sets_batched():
 @pytest.mark.parametrize('n_tips,K,C,kind', [(3000, 10, 4, 'yule'), (2000, 20, 3, 'coalescent'), (1500, 3, 8, 'yule'),
                                             (1000, 30, 2, 'yule'), (2000, 20, 8, 'yule'), (600, 45, 2, 'yule'),
                                             (400, 62, 1, 'coalescent'), (800, 12, 20, 'yule'), (700, 5, 1, 'yule'),
-                                            (900, 2, 16, 'coalescent')])
+                                            (900, 2, 16, 'coalescent'), (700, 10, 8, 'yule'), (600, 16, 8, 'coalescent'),
+                                            (500, 5, 8, 'yule'), (400, 40, 8, 'yule'), (500, 6, 32, 'yule')])
 def test_synthetic_against_oracle(n_tips, K, C, kind):
     from pastml_b200.engine import Problem, MASK_MAP, MASK_MPPA, pack_params
     from pastml_b200 import synth
@@ -166,7 +167,7 @@ def test_zero_likelihood_is_reported():
     pb.close()
 
 
-@pytest.mark.parametrize('K,C,B', [(20, 8, 3), (10, 16, 5), (12, 8, 4)])
+@pytest.mark.parametrize('K,C,B', [(20, 8, 3), (10, 16, 5), (12, 8, 4), (6, 4, 3), (20, 8, 21), (7, 3, 4)])
 def test_many_parameter_sets_tiled(K, C, B):
     """More than 16 lanes (parameter sets x columns): the cooperative bottom-up kernel runs one grid row per tile of 8
     lanes; every (set, column) must equal the single-set evaluation and the oracle."""
