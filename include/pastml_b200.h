@@ -157,6 +157,15 @@ int pml_set_tip_partials(pml_problem *p, int32_t n, const int32_t *nodes, const 
 int pml_get_tip_td(pml_problem *p, double *out_vec, int32_t *out_ex);
 int pml_set_root_td(pml_problem *p, const double *vec, const int32_t *ex);
 
+/* The optimiser's objective over an explicit list of lanes (replaces the n_sets x all-columns grid of pml_loglik when
+ * only some columns are still being fitted, ml.py:202-208): lane i evaluates column lane_columns[i] with the parameter
+ * block params[i][stride]; annotation masks, sum-product, alteration on.  n_lanes must be a multiple of 4 (pad with
+ * copies of a lane) and at most max_param_sets * C.  Available when pml_supports_lane_lists() is non-zero (F81 family,
+ * no external tables).  Zero-likelihood lanes are reported like pml_loglik (pml_zero_likelihood_all: one pair per lane). */
+int pml_supports_lane_lists(pml_problem *p);
+int pml_loglik_lanes(pml_problem *p, const double *params, const int32_t *lane_columns, int32_t n_lanes,
+                     double *out_loglh);
+
 /* Device buffers of destroyed problems are kept in a per-process cache and reused by the next problem of the same
  * shape (cudaMalloc/cudaFree of GBs cost more than the sweeps).  This returns the cached blocks to the driver. */
 int pml_trim_memory(void);

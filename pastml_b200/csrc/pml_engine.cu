@@ -189,6 +189,7 @@ struct pml_problem {
                        zc_index.ptr, fc_slot.ptr, nc_slot.ptr, pslot.ptr, n_root_slots, bu_desc.ptr, td_desc.ptr};
     }
     // subtree sharding: external tip vectors / root top-down vectors
+    DevBuf<int> lane_col;      // explicit column per lane (pml_loglik_lanes), B * C entries, allocated on first use
     bool eig_shared = false;   // EIG: every lane of the uploaded parameters carries the same d, A, A^-1
     int n_ext = 0, ext_sets = 0;
     bool have_root_td = false;
@@ -201,7 +202,7 @@ struct pml_problem {
     ZcDev zc() const { return ZcDev{zc_alt.ptr, zc_altflag.ptr, zc_initial.ptr, zc_hasinit.ptr, zc_touched.ptr}; }
     LaneDev lanes(int n_sets) const {
         return LaneDev{C, n_sets * C, K, stride, params.ptr, kmask, FastDiv::make((unsigned) (n_sets * C)),
-                       FastDiv::make((unsigned) C), 0};
+                       FastDiv::make((unsigned) C), 0, nullptr};
     }
 };
 
@@ -264,9 +265,16 @@ int bu_tile_lanes(const pml_problem *p, int J) {
     return (jt == J || J > p->C) ? jt : 0;
 }
 
-void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marginal, int alter, bool keep_ptr) {
+// n_lanes > 0: the pass runs over an explicit list of n_lanes lanes (p->lane_col) instead of n_sets x all columns
+void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marginal, int alter, bool keep_ptr,
+                       int n_lanes = 0) {
     LaneDev ln = p->lanes(n_sets);
-    const int tpi_jt = is_marginal ? bu_tile_lanes(p, ln.J) : 0;
+    if (n_lanes > 0) {
+        ln.J = n_lanes;
+        ln.divJ = FastDiv::make((unsigned) n_lanes);
+        ln.lane_col = p->lane_col.ptr;
+    }
+    const int tpi_jt = n_lanes > 0 ? tpi_tile_lanes(p->K, n_lanes) : (is_marginal ? bu_tile_lanes(p, ln.J) : 0);
     ln.jt = tpi_jt;
     if (alter) run_alter(p, mask);
     fill_int_kernel<<<grid_for(2LL * ln.J), kBlock, 0, p->stream>>>(2LL * ln.J, -1, p->err.ptr);
@@ -342,9 +350,11 @@ void run_graphed(pml_problem *p, const std::array<long long, 6> &key, F enqueue)
     p->launches += it->second.launches;
 }
 
-void run_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marginal, int alter, bool keep_ptr) {
-    run_graphed(p, {0, n_sets, (long long) (uintptr_t) mask, is_marginal, alter, (keep_ptr ? 1 : 0) + 2 * p->n_ext},
-                [&]() { enqueue_bottom_up(p, n_sets, mask, is_marginal, alter, keep_ptr); });
+void run_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marginal, int alter, bool keep_ptr,
+                   int n_lanes = 0) {
+    run_graphed(p, {n_lanes > 0 ? 2 : 0, n_lanes > 0 ? n_lanes : n_sets, (long long) (uintptr_t) mask, is_marginal, alter,
+                    (keep_ptr ? 1 : 0) + 2 * p->n_ext},
+                [&]() { enqueue_bottom_up(p, n_sets, mask, is_marginal, alter, keep_ptr, n_lanes); });
 }
 
 void run_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh) {
@@ -352,8 +362,8 @@ void run_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_no
                 [&]() { enqueue_top_down(p, force_joint, want_probs, want_node_lh); });
 }
 
-int fetch_loglik(pml_problem *p, int n_sets, double *out) {
-    const int J = n_sets * p->C;
+int fetch_loglik(pml_problem *p, int n_sets, double *out, int n_lanes = 0) {
+    const int J = n_lanes > 0 ? n_lanes : n_sets * p->C;
     p->h_out.resize(J);
     p->h_err.resize(2 * (size_t) J);
     CUDA_TRY(cudaMemcpyAsync(p->h_out.data(), p->out_lh.ptr, J * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
@@ -836,6 +846,42 @@ int pml_loglik(pml_problem *p, const double *params, int32_t n_sets, int32_t mas
     timer.stop();
     CUDA_TRY(cudaGetLastError());
     return fetch_loglik(p, n_sets, out_loglh);
+}
+
+int pml_supports_lane_lists(pml_problem *p) {
+    return p && p->kind == PML_MODEL_F81 && !p->ext_index.ptr && tpi_enabled() && p->K >= 2;
+}
+
+int pml_loglik_lanes(pml_problem *p, const double *params, const int32_t *lane_columns, int32_t n_lanes,
+                     double *out_loglh) {
+    if (!p || !params || !lane_columns) return fail(PML_ERR_INVALID, "null argument");
+    if (!pml_supports_lane_lists(p)) return fail(PML_ERR_INVALID, "lane lists need the TMA-staged bottom-up sweep (F81 family)");
+    if (n_lanes < 1 || n_lanes > p->B * p->C) return fail(PML_ERR_INVALID, "n_lanes exceeds the capacity given at creation");
+    if (!tpi_tile_lanes(p->K, n_lanes)) return fail(PML_ERR_INVALID, "the number of lanes must be a multiple of 4");
+    CUDA_TRY(cudaSetDevice(p->device));
+    if (!p->lane_col.ptr) CUDA_TRY(p->lane_col.alloc((size_t) p->B * p->C));
+    std::vector<uint8_t> rec(p->C, 0);
+    for (int j = 0; j < n_lanes; ++j) {
+        const int c = lane_columns[j];
+        if (c < 0 || c >= p->C) return fail(PML_ERR_INVALID, "lane column out of range");
+        if (params[(size_t) j * p->stride + 1] == 0.) rec[c] = 1;
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->params.ptr, params, (size_t) n_lanes * p->stride * sizeof(double), cudaMemcpyHostToDevice,
+                             p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->lane_col.ptr, lane_columns, (size_t) n_lanes * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->record_col.ptr, rec.data(), p->C, cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));   // rec is a stack-local host buffer
+    CallTimer timer(p);
+    run_bottom_up(p, 1, p->mask[PML_MASK_ANNOTATION].ptr, 1, 1, false, n_lanes);
+    timer.stop();
+    CUDA_TRY(cudaGetLastError());
+    const int rc = fetch_loglik(p, 1, out_loglh, n_lanes);
+    if (rc == PML_ERR_ZERO_LIKELIHOOD) {   // (column, lane) of the first failing lane
+        const int j = p->zero_info[1] * p->C + p->zero_info[0];
+        p->zero_info[0] = lane_columns[j];
+        p->zero_info[1] = j;
+    }
+    return rc;
 }
 
 int pml_joint(pml_problem *p, const double *params, double *out_loglh, int32_t *out_state) {

@@ -81,7 +81,11 @@ struct LaneDev {
     FastDiv divJ, divC;
     int jt;                  // 0: bottom-up vectors laid out [slot][k][J]; else tile-major [slot][J / jt][k][jt]
                              // (passes of the TMA-staged bottom-up sweep with more lanes than one tile)
+    const int *lane_col;     // null: lane j works on column j % C; else an explicit column per lane (objective passes
+                             // over the columns that are still being fitted, pml_loglik_lanes)
 };
+
+__device__ __forceinline__ int lane_column(const LaneDev &ln, int j) { return ln.lane_col ? ln.lane_col[j] : j % ln.C; }
 
 // index of state k, lane j of a slot's bottom-up vector in the layout of this pass
 __device__ __forceinline__ size_t bu_at(const LaneDev &ln, int slot, int k, int j) {
@@ -602,7 +606,7 @@ static __global__ void root_loglik_kernel(TreeDev t, ZcDev zc, LaneDev ln, const
                                           int is_marginal, double *out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ln.J) return;
-    const int K = ln.K, J = ln.J, c = j % ln.C;
+    const int K = ln.K, J = ln.J, c = lane_column(ln, j);
     const double *p = ln.params + (size_t) j * ln.stride;
     const bool use_alt = alter && p[1] == 0.;
     double total = 0.;

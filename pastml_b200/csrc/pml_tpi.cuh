@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(PML_TPI_BLOCK, PML_TPI_BU_MINB) bu_tpi_kernel(
     const int T = gridDim.y, tile = blockIdx.y, j0 = tile * JT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / JT, jl = lane - sub * JT;
-    const int j = j0 + jl, c = j % C;
+    const int j = j0 + jl, c = lane_column(a.ln, j);
     const int VB = K * JT * 8, EB = JT * 4, sub_bytes = 2 * (VB + EB);
     unsigned char *st_base = reinterpret_cast<unsigned char *>(s_par) + round16((4 + K) * JT * 8);
     unsigned char *mine = st_base + (size_t) (warp * NPW + sub) * sub_bytes;

@@ -126,6 +126,29 @@ class Problem(object):
             self._check(rc)
         return out, bad
 
+    def supports_lane_lists(self):
+        return bool(self.lib.pml_supports_lane_lists(self._h))
+
+    def loglik_lanes(self, params, lane_columns):
+        """The objective for an explicit list of lanes: lane i = column ``lane_columns[i]`` with the parameter block
+        ``params[i]``; returns (values [n_lanes], {lane: (parent, child)} for zero-likelihood lanes).  The number of
+        lanes must be a multiple of 4 (pad with copies of a lane)."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        cols = np.ascontiguousarray(lane_columns, dtype=np.int32)
+        n = len(cols)
+        if params.shape != (n, self.stride):
+            raise ValueError('params must be [n_lanes][{}]'.format(self.stride))
+        out = np.empty(n, dtype=np.float64)
+        rc = self.lib.pml_loglik_lanes(self._h, _p(params), _p(cols), n, _p(out))
+        bad = {}
+        if rc == _lib.PML_ERR_ZERO_LIKELIHOOD:
+            pairs = np.empty((n, 2), dtype=np.int32)
+            self._check(self.lib.pml_zero_likelihood_all(self._h, _p(pairs), n))
+            bad = {int(j): (int(pairs[j, 0]), int(pairs[j, 1])) for j in np.flatnonzero(pairs[:, 0] >= 0)}
+        else:
+            self._check(rc)
+        return out, bad
+
     def joint(self, params, want_states=True):
         params = self._params(params, 1)
         lh = np.empty(self.C, dtype=np.float64)

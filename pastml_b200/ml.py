@@ -156,6 +156,17 @@ class LockstepEvaluator(object):
 
     def _flush(self):
         cols = sorted(self.pending)
+        n_lanes = sum(len(self.pending[c]) for c in cols)
+        n_lanes = 4 if n_lanes <= 4 else 8 * ((n_lanes + 7) // 8)
+        if self.batch.lane_lists and n_lanes <= self.batch.max_sets * self.batch.C:
+            self._flush_lanes(cols)
+        else:
+            self._flush_grid(cols)
+        self.pending.clear()
+        self.cond.notify_all()
+
+    def _flush_grid(self, cols):
+        """One pass over (parameter sets) x (all columns): columns without a request ride along on their last block."""
         n_sets = min(padded_sets(max(len(self.pending[c]) for c in cols), self.batch.C), self.batch.max_sets)
         params = np.empty((n_sets, self.batch.C, self.batch.problem.stride), dtype=np.float64)
         for c in range(self.batch.C):
@@ -175,8 +186,30 @@ class LockstepEvaluator(object):
             bad = [errs[(b, c)] for b in range(n) if (b, c) in errs]
             if bad:
                 self.errors[c] = bad[0]
-        self.pending.clear()
-        self.cond.notify_all()
+
+    def _flush_lanes(self, cols):
+        """One pass over exactly the requested (column, parameter block) lanes."""
+        lane_cols, blocks = [], []
+        for c in cols:
+            for block in self.pending[c]:
+                lane_cols.append(c)
+                blocks.append(block)
+            self.last_block[c] = self.pending[c][-1]
+        n = len(lane_cols)
+        padded = 4 if n <= 4 else 8 * ((n + 7) // 8)
+        lane_cols += [lane_cols[-1]] * (padded - n)
+        blocks += [blocks[-1]] * (padded - n)
+        values, errs = self.batch.loglik_lanes(np.asarray(blocks, dtype=np.float64), lane_cols)
+        self.n_passes += 1
+        at = 0
+        for c in cols:
+            k = len(self.pending[c])
+            self.n_lane_evaluations += k
+            self.results[c] = [float(values[at + b]) for b in range(k)]
+            bad = [errs[at + b] for b in range(k) if at + b in errs]
+            if bad:
+                self.errors[c] = bad[0]
+            at += k
 
     def evaluate(self, c, blocks):
         """Log-likelihoods of column c for the given parameter blocks."""
@@ -219,8 +252,17 @@ class ColumnBatch(object):
         self.has_state = np.ascontiguousarray(has_state, dtype=np.uint8)
         # capacity for the finite-difference batch of one gradient: every free parameter + the base point
         self.max_sets = padded_sets(1 + max(m.get_num_params() for m in self.models), self.C) if batched_gradients() else 1
+        self.batched_fd = self.max_sets > 1
+        if self.max_sets * self.C < 4:
+            self.max_sets = -(-4 // self.C)   # room for the smallest lane-list pass (4 lanes)
         self.problem = Problem(flat, self.K, self.kind, self.annot_mask, self.has_state,
                                max_param_sets=self.max_sets, device=device)
+        # every objective pass of the fit runs over exactly the requested (column, parameter block) lanes (engine:
+        # pml_loglik_lanes): columns that have finished no longer cost anything, and the base point and the perturbed
+        # points of a finite difference go through the same kernel, lane by lane.  PASTML_B200_LANE_LISTS=0 keeps the
+        # (sets x all columns) grid
+        import os
+        self.lane_lists = os.environ.get('PASTML_B200_LANE_LISTS', '1') != '0' and self.problem.supports_lane_lists()
 
     def close(self):
         self.problem.close()
@@ -240,6 +282,12 @@ class ColumnBatch(object):
         """(values [n_sets][C], {(set, column): PastMLLikelihoodError}) for n_sets parameter sets x all columns."""
         values, bad = self.problem.loglik(params, n_sets, MASK_ANNOTATION, True, True, tolerate_zero=True)
         errs = {(j // self.C, j % self.C): self._error_for(j % self.C, *pc) for j, pc in bad.items()}
+        return values, errs
+
+    def loglik_lanes(self, params, lane_columns):
+        """(values [n_lanes], {lane: PastMLLikelihoodError}) for an explicit list of (column, parameter block) lanes."""
+        values, bad = self.problem.loglik_lanes(params, lane_columns)
+        errs = {j: self._error_for(lane_columns[j], *pc) for j, pc in bad.items()}
         return values, errs
 
     def loglik_columns(self, cols=None, mask_kind=MASK_ANNOTATION, is_marginal=True, alter=True):
@@ -363,7 +411,7 @@ def fit_batch(batch, observed_frequencies):
     def work(c):
         try:
             model = batch.models[c]
-            many = (lambda blocks: ev.evaluate(c, blocks)) if batch.max_sets > 1 else None
+            many = (lambda blocks: ev.evaluate(c, blocks)) if batch.batched_fd else None
             out[c] = _fit_one(lambda: ev.evaluate(c, [model.engine_block()])[0], batch.characters[c], model,
                               observed_frequencies[c], many)
         except BaseException as e:  # re-raised in the caller's thread

@@ -235,6 +235,8 @@ class ShardedColumnBatch(object):
         self.K = len(self.models[0].states)
         self.kind = self.models[0].engine_kind
         self.max_sets = (1 + max(m.get_num_params() for m in self.models)) if batched_gradients() else 1
+        self.lane_lists = False   # the sharded objective always runs the (sets x columns) grid
+        self.batched_fd = self.max_sets > 1
         self.sp = ShardedProblem(plan, rank, self.K, self.kind, annot_mask, has_state, max_param_sets=self.max_sets,
                                  device=device)
         self.problem = self.sp.top          # LockstepEvaluator reads .stride from here

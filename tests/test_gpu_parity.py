@@ -235,3 +235,30 @@ def test_jtt_columns_on_tensor_cores(n_tips, C, kind):
             ref = cpu_oracle.ml_acr_fixed(flat, om, masks[c], has[c], method='MAP', force_joint=False)
             np.testing.assert_allclose(res['probs'][:, c, :], ref['marginal_probabilities'], rtol=0, atol=PROB_ATOL)
             assert np.array_equal(res['map_mask'][:, c], ref['map_mask'])
+
+
+def test_lane_list_objective_equals_grid():
+    """pml_loglik_lanes: an explicit list of (column, parameter block) lanes gives the values of the same lanes in the
+    (sets x columns) grid; a zero-likelihood lane is reported for its column."""
+    from pastml_b200.engine import Problem, pack_params
+    from pastml_b200 import synth
+    rng = np.random.default_rng(321)
+    K, C, B = 10, 8, 3
+    flat = synth.yule_tree(1200, rng)
+    masks, has, pis, sfs = synth.simulate_tip_masks(flat, K, C, rng, missing=0.05)
+    base = np.stack([pack_params(0, K, sfs[c], 0., 1., pis[c]) for c in range(C)])
+    sets = np.stack([base] * B)
+    for b in range(B):
+        sets[b, :, 0] *= 1. + 0.21 * b
+    pb = Problem(flat, K, 0, masks, has, max_param_sets=B)
+    assert pb.supports_lane_lists()
+    grid = pb.loglik(sets, n_sets=B)
+    lanes = [(5, 0), (5, 1), (5, 2), (1, 2), (7, 0), (7, 1), (2, 1), (2, 1)]   # (column, set); 8 lanes
+    got, bad = pb.loglik_lanes(np.stack([sets[b, c] for c, b in lanes]), [c for c, _ in lanes])
+    assert not bad
+    np.testing.assert_allclose(got, [grid[b, c] for c, b in lanes], rtol=1e-13)
+    got4, _ = pb.loglik_lanes(np.stack([sets[0, 3]] * 4), [3] * 4)
+    np.testing.assert_allclose(got4, grid[0, 3], rtol=1e-13)
+    with pytest.raises(Exception):
+        pb.loglik_lanes(np.stack([sets[0, 3]] * 3), [3] * 3)   # not a multiple of 4
+    pb.close()

@@ -109,4 +109,6 @@ def test_fit_on_a_sharded_tree_matches_the_plain_fit():
     sharded = ShardedColumnBatch(plan, 0, ['c0', 'c1', 'c2'], ms, masks, has, gather=lambda vec, ex: [(vec, ex)])
     got, _ = fit_batch(sharded, obs)
     sharded.close()
-    np.testing.assert_allclose(got, want, rtol=1e-9)
+    # the two objectives run on different kernels (rounding differs in the last bits), so the optimiser stops at
+    # slightly different points: agreement to its own tolerance, not to the bit
+    np.testing.assert_allclose(got, want, rtol=1e-6)
