@@ -1,4 +1,5 @@
 // Host-side launcher of the thread-per-item, TMA-staged F81 bottom-up sweep (pml_tpi.cuh).
+#include <cstdlib>
 #include "pml_tpi.cuh"
 #include "pml_launch.h"
 
@@ -38,8 +39,11 @@ int tpi_tile_lanes(int K, int J) {
     if (K < 2 || K > 62) return 0;
     for (int jt : {32, 16, 8, 4})
         if (J == jt) return jt;   // one tile: the plain layout
-    if (J % 8 == 0) return 8;     // more lanes (parameter sets x columns): tiles of 8 lanes, tile-major layout
-    if (J % 4 == 0) return 4;
+    // more lanes (parameter sets x columns): the widest tile that divides them, tile-major layout -- a wider tile
+    // shares a node's descriptor, mask words and bulk copies between more lanes
+    static const int max_tile = getenv("PASTML_B200_TPI_MAX_TILE") ? atoi(getenv("PASTML_B200_TPI_MAX_TILE")) : 32;
+    for (int jt : {32, 16, 8, 4})
+        if (jt <= max_tile && J % jt == 0) return jt;
     return 0;
 }
 
