@@ -388,7 +388,10 @@ def run_b200(args):
         e2e_step()
         e2e_each.append(time.perf_counter() - t1)
     barrier()
-    e2e_dt = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps, device='cuda')
+    e2e_mean = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps, device='cuda')
+    # the steps are PCIe- and host-bound and the box's other tenants show up as outliers of 2-5x: the median step
+    # time (max over ranks) is reported, the mean is given beside it
+    e2e_dt = max_over_ranks(float(np.median(e2e_each)), device='cuda')
     e2e_value = node_states * world / e2e_dt
     h2d = h_parent.nbytes + h_dist.nbytes + h_masks.nbytes + h_has.nbytes + params.nbytes
     d2h = h_probs.nbytes + h_map.nbytes + h_mppa.nbytes + h_lh.nbytes + h_hist.nbytes
@@ -462,8 +465,8 @@ def run_b200(args):
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, flat),
             'clocks': clocks.summary(),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                    'ms_per_step': e2e_dt * 1e3, 'steps': args.e2e_steps, 'min_ms_per_step_rank0': min(e2e_each) * 1e3,
-                    'what': 'pml_problem_create + pml_marginal (all outputs to pinned host memory) + destroy'},
+                    'ms_per_step': e2e_dt * 1e3, 'mean_ms_per_step': e2e_mean * 1e3, 'steps': args.e2e_steps, 'min_ms_per_step_rank0': min(e2e_each) * 1e3, 'each_ms_rank0': [round(x * 1e3, 2) for x in e2e_each],
+                    'what': 'pml_problem_create + pml_marginal (all outputs to pinned host memory) + destroy; median over the steps'},
             'gpu_launches': int(launches * args.steps),
             'roofline': roof(dom), 'roofline_other': roof([k for k in sweeps if k != dom][0]),
             'min_ms_per_step': min_ms, 'wall_s_timed_region': wall,
