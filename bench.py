@@ -34,6 +34,16 @@ METRIC = 'mppa_node_states_per_s'
 UNIT = 'node-states/s'
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Prints the one JSON line of the contract on the process's real stdout."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -173,7 +183,7 @@ def run_reference(args):
             'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0, 'host_cores': cores}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------ B200 arm
@@ -294,7 +304,7 @@ def run_subtree_sharded(args):
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
 
 
 def run_b200(args):
@@ -484,12 +494,15 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
 
 
 if __name__ == '__main__':
-    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION / INFO) off it
-    os.environ['NCCL_DEBUG'] = os.environ.get('PASTML_B200_NCCL_DEBUG', 'WARN')
+    # stdout carries exactly one JSON line: native libraries (NCCL's version banner) write to file descriptor 1 behind
+    # Python's back, so the descriptor is pointed at stderr for the run and the line goes to a duplicate of the real one
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     a = parse_args()
     if a.impl == 'reference':
         run_reference(a)
