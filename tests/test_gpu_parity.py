@@ -167,7 +167,7 @@ def test_zero_likelihood_is_reported():
     pb.close()
 
 
-@pytest.mark.parametrize('K,C,B', [(20, 8, 3), (10, 16, 5), (12, 8, 4), (6, 4, 3), (20, 8, 21), (7, 3, 4)])
+@pytest.mark.parametrize('K,C,B', [(20, 8, 3), (10, 16, 5), (12, 8, 4), (6, 4, 3), (20, 8, 21), (7, 3, 4), (10, 16, 4), (5, 8, 20)])
 def test_many_parameter_sets_tiled(K, C, B):
     """More than 16 lanes (parameter sets x columns): the cooperative bottom-up kernel runs one grid row per tile of 8
     lanes; every (set, column) must equal the single-set evaluation and the oracle."""
