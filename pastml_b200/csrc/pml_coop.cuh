@@ -127,11 +127,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 __host__ __device__ constexpr int round16(int x) { return (x + 15) & ~15; }
 
 // dynamic shared memory of the TMA variants (host side of the layout the kernels carve up)
-__host__ __device__ constexpr int bu_tma_sub_bytes(int K, int J) { return 2 * (K * J * 8 + J * 4); }
 __host__ __device__ constexpr int td_tma_sub_bytes(int K, int C) { return 3 * (K * C * 8 + C * 4); }
-inline size_t bu_tma_smem(int K, int J, int G) {
-    return (size_t) round16((4 + K) * J * 8) + (size_t) (kCoopBlock / 32) * (32 / (G * J)) * bu_tma_sub_bytes(K, J) + 8 * (kCoopBlock / 32);
-}
 inline size_t td_tma_smem(int K, int C, int G) {
     return (size_t) round16((4 + K) * C * 8 + C * (K + 1) * 4) + (size_t) (kCoopBlock / 32) * (32 / (G * C)) * td_tma_sub_bytes(K, C) +
            8 * (kCoopBlock / 32);
@@ -237,36 +233,16 @@ __device__ __forceinline__ uint64_t eff_from_raw(uint64_t raw, const TreeDev &t,
 }
 
 // JT > 0: the number of lanes J is the compile-time constant JT; KX: K == G * KT exactly.
-// TILED: the pass has more lanes than one warp batch can take (many parameter sets x columns, the batched
-// finite-difference objective): blockIdx.y selects a tile of JT consecutive lanes, memory keeps its full leading
-// dimension `ld` = total lanes.
-// TMA: the children's vectors of the next node are staged in shared memory by bulk asynchronous copies (see above);
-// needs JT > 0, KX, no external (subtree-sharding) tables.
-template <int KT, int G, int JT, bool KX, bool TILED, bool TMA = false>
-__global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT, TMA)) bu_coop_kernel(BuArgs a, int slot_begin, int n_slots) {
+// TILED: the pass has more lanes than one warp batch can take (many parameter sets x columns): blockIdx.y selects a
+// tile of JT consecutive lanes, memory keeps its full leading dimension `ld` = total lanes.
+// (Problems without external tables take the TMA-staged thread-per-item sweep of pml_tpi.cuh instead; this kernel
+// serves the subtree-sharded problems and the lane counts the staged sweep does not tile.)
+template <int KT, int G, int JT, bool KX, bool TILED>
+__global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kernel(BuArgs a, int slot_begin, int n_slots) {
     extern __shared__ double s_par[];
-    static_assert(!TMA || (JT > 0 && KX && (32 % (G * (JT ? JT : 1))) == 0), "TMA staging needs compile-time lanes");
     const int J = JT ? JT : a.ln.J, K = KX ? G * KT : a.ln.K, C = a.ln.C;
     const int ld = TILED ? a.ln.J : J;                 // leading dimension of bu / bu_ex / ext tables
     const int j0 = TILED ? (int) blockIdx.y * J : 0;   // first lane of this block's tile
-    const CoopLane cl = coop_lane<G>(J, C);
-    constexpr int VB = G * KT * (JT ? JT : 1) * 8, EB = (JT ? JT : 1) * 4;   // bytes of one staged vector / exponent row
-    uint32_t bar = 0, stage = 0, phase = 0;
-    const double *st_vec = nullptr;
-    if constexpr (TMA) {
-        unsigned char *st_base = reinterpret_cast<unsigned char *>(s_par) + round16((4 + K) * J * 8);
-        constexpr int sub_bytes = bu_tma_sub_bytes(G * KT, JT);
-        constexpr int npw = 32 / (G * JT);
-        const int warp = threadIdx.x >> 5;
-        unsigned char *mine = st_base + (warp * npw + cl.sub) * sub_bytes;
-        bar = smem_addr(st_base + (kCoopBlock / 32) * npw * sub_bytes + 8 * warp);
-        stage = smem_addr(mine);
-        st_vec = reinterpret_cast<const double *>(mine);
-        if ((threadIdx.x & 31) == 0) {
-            mbar_init(bar, npw);
-            mbar_fence_init();
-        }
-    }
     {
         // stage the tile's lane parameters, transposed to [field][lane]
         const int total = (4 + K) * J;
@@ -276,6 +252,7 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT, TMA)) bu_coop_
         }
         __syncthreads();
     }
+    const CoopLane cl = coop_lane<G>(J, C);
     const int r = cl.r;
     const int j = j0 + cl.j;                 // lane index in memory
     const int c = TILED ? j % C : cl.c;
@@ -290,17 +267,12 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT, TMA)) bu_coop_
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
 
-    // the loop is software-pipelined: the packed descriptor (and node id) of the next batch is requested before the
-    // current batch is processed, so that only the vector loads remain on the dependent path -- and with TMA not
-    // even those: the copies for batch i + 1 are issued at the top of batch i, the descriptor of batch i + 2 and the
-    // mask words of batch i + 1 are requested right after
+    // the loop is software-pipelined by one step: the packed descriptor (and node id) of the next batch is requested
+    // before the current batch is processed, so that only the vector loads remain on the dependent path
     const int stride = n_warps * cl.npw;
     int base = warp_global * cl.npw;
     int4 nx_top = make_int4(0, 0, 0, 0), nx_len = make_int4(0, 0, 0, 0);
     int nx_node = 0;
-    int4 cu_top = make_int4(0, 0, 0, 0), cu_len = make_int4(0, 0, 0, 0);   // TMA: the batch whose copies are in flight
-    int cu_node = 0;
-    uint64_t cu_mo = 0, cu_m0 = 0, cu_m1 = 0;                                // TMA: its mask words (own, tip children)
     auto load_desc = [&](int b, int4 &top, int4 &len, int &node) {
         const int sl = b + cl.sub;
         const size_t slot = (size_t) slot_begin + ((cl.lane_on && sl < n_slots) ? sl : b);
@@ -308,117 +280,31 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT, TMA)) bu_coop_
         len = a.t.bu_desc[2 * slot + 1];
         node = a.t.int_nodes[slot];
     };
-    auto load_masks = [&](const int4 &top, int node, uint64_t &mo, uint64_t &m0, uint64_t &m1) {
-        mo = a.mask[(size_t) node * C + c];
-        m0 = (top.z < 0) ? a.mask[(size_t) top.x * C + c] : 0ULL;
-        m1 = (top.w < 0 && top.y == 2) ? a.mask[(size_t) (top.x + 1) * C + c] : 0ULL;
-    };
-    // the copies of one batch: one thread per node arms the barrier; untiled, the same thread issues one copy per
-    // child vector (contiguous for all the lanes); tiled, the rows of the tile are spread over the node's threads
-    auto issue = [&](const int4 &top) {
-        const int li = cl.r * J + cl.j;
-        const bool bin = top.y == 2;
-        const int cs0 = top.z, cs1 = top.w;
-        if (li == 0) mbar_arrive_expect(bar, bin ? ((cs0 >= 0 ? VB + EB : 0) + (cs1 >= 0 ? VB + EB : 0)) : 0);
-        if (TILED) __syncwarp();
-        if (!bin) return;
-        if (!TILED) {
-            if (li == 0) {
-                if (cs0 >= 0) {
-                    bulk_g2s(stage, a.bu + (size_t) cs0 * K * J, VB, bar);
-                    bulk_g2s(stage + 2 * VB, a.bu_ex + (size_t) cs0 * J, EB, bar);
-                }
-                if (cs1 >= 0) {
-                    bulk_g2s(stage + VB, a.bu + (size_t) cs1 * K * J, VB, bar);
-                    bulk_g2s(stage + 2 * VB + EB, a.bu_ex + (size_t) cs1 * J, EB, bar);
-                }
-            }
-        } else {
-            for (int k = li; k <= K; k += G * J) {
-                if (k < K) {
-                    if (cs0 >= 0) bulk_g2s(stage + k * J * 8, a.bu + ((size_t) (cs0 * K + k) * ld + j0), J * 8, bar);
-                    if (cs1 >= 0) bulk_g2s(stage + VB + k * J * 8, a.bu + ((size_t) (cs1 * K + k) * ld + j0), J * 8, bar);
-                } else {
-                    if (cs0 >= 0) bulk_g2s(stage + 2 * VB, a.bu_ex + ((size_t) cs0 * ld + j0), EB, bar);
-                    if (cs1 >= 0) bulk_g2s(stage + 2 * VB + EB, a.bu_ex + ((size_t) cs1 * ld + j0), EB, bar);
-                }
-            }
-        }
-    };
-    if (base < n_slots) {
-        if constexpr (TMA) {
-            load_desc(base, cu_top, cu_len, cu_node);
-            issue(cu_top);
-            load_masks(cu_top, cu_node, cu_mo, cu_m0, cu_m1);
-            if (base + stride < n_slots) load_desc(base + stride, nx_top, nx_len, nx_node);
-        } else {
-            load_desc(base, nx_top, nx_len, nx_node);
-        }
-    }
+    if (base < n_slots) load_desc(base, nx_top, nx_len, nx_node);
     for (; base < n_slots; base += stride) {
         const int sl = base + cl.sub;
         const bool on = cl.lane_on && sl < n_slots;
         const int slot = slot_begin + (on ? sl : base);
-        const int4 d_top = TMA ? cu_top : nx_top, d_len = TMA ? cu_len : nx_len;
-        const int node = TMA ? cu_node : nx_node;
-        const uint64_t raw_own = cu_mo, raw0 = cu_m0, raw1 = cu_m1;
+        const int4 d_top = nx_top, d_len = nx_len;
+        const int node = nx_node;
+        if (base + stride < n_slots) load_desc(base + stride, nx_top, nx_len, nx_node);
         const int fc = d_top.x, nc = d_top.y;
-        const bool all_bin = __all_sync(kFullMask, nc == 2);
-        double in0[KT], in1[KT];
-        int ex = 0;
-        if constexpr (TMA) {
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-            if (all_bin) {
-                const int cs0 = d_top.z, cs1 = d_top.w;
-                if (cs0 >= 0) {
-#pragma unroll
-                    for (int i = 0; i < KT; ++i) in0[i] = st_vec[(r + G * i) * J + jl];
-                    ex += reinterpret_cast<const int *>(st_vec + 2 * (VB / 8))[jl];
-                } else {
-                    const uint64_t m = eff_from_raw(raw0, a.t, a.zc, C, fc, c, use_alt, a.ln.kmask) >> r;
-#pragma unroll
-                    for (int i = 0; i < KT; ++i) in0[i] = bit_as_double(m, G * i);
-                }
-                if (cs1 >= 0) {
-#pragma unroll
-                    for (int i = 0; i < KT; ++i) in1[i] = st_vec[VB / 8 + (r + G * i) * J + jl];
-                    ex += reinterpret_cast<const int *>(st_vec + 2 * (VB / 8))[J + jl];
-                } else {
-                    const uint64_t m = eff_from_raw(raw1, a.t, a.zc, C, fc + 1, c, use_alt, a.ln.kmask) >> r;
-#pragma unroll
-                    for (int i = 0; i < KT; ++i) in1[i] = bit_as_double(m, G * i);
-                }
-            }
-            __syncwarp();
-            if (base + stride < n_slots) {
-                issue(nx_top);
-                cu_top = nx_top;
-                cu_len = nx_len;
-                cu_node = nx_node;
-                load_masks(cu_top, cu_node, cu_mo, cu_m0, cu_m1);
-                if (base + 2 * stride < n_slots) load_desc(base + 2 * stride, nx_top, nx_len, nx_node);
-            }
-        } else {
-            if (base + stride < n_slots) load_desc(base + stride, nx_top, nx_len, nx_node);
-        }
         double acc[KT];
         {
-            const uint64_t m = (TMA ? eff_from_raw(raw_own, a.t, a.zc, C, node, c, use_alt, a.ln.kmask)
-                                    : eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask)) >> r;
+            const uint64_t m = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask) >> r;
 #pragma unroll
             for (int i = 0; i < KT; ++i) acc[i] = bit_as_double(m, G * i);   // 10 ** log10(allowed), ml.py:127
         }
+        int ex = 0;
         int bad_child = -1;
-        if (all_bin) {
+        if (__all_sync(kFullMask, nc == 2)) {
             // binary nodes: both children's vectors are requested before any arithmetic; rank 0 and rank 1 of the
             // group evaluate one exp each and hand it to the others
+            double in0[KT], in1[KT];
+            const int cs0 = d_top.z, cs1 = d_top.w;
             const double dmine = (r & 1) ? __hiloint2double(d_len.w, d_len.z) : __hiloint2double(d_len.y, d_len.x);
-            if constexpr (!TMA) {
-                const int cs0 = d_top.z, cs1 = d_top.w;
-                ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc, cs0, r, j, c, use_alt, in0, K, ld);
-                ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, cs1, r, j, c, use_alt, in1, K, ld);
-            }
+            ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc, cs0, r, j, c, use_alt, in0, K, ld);
+            ex += coop_load<KT, G, KX>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, cs1, r, j, c, use_alt, in1, K, ld);
             const double emine = mu_inf ? 0. : exp_nonpos(-mu * ((dmine + tau) * tauf * sf));
             const double e0 = grp.from_rank(emine, 0), e1 = grp.from_rank(emine, 1);
             double s0 = 0., s1 = 0.;

@@ -67,24 +67,7 @@ void td_launch(cudaStream_t st, const TdArgs &a, int n0, int nn) {
 
 #if PML_JT > 0
 constexpr int kTmaBlocks = coop_min_blocks(KT, true);   // persistent grid: one resident wave
-// TMA-staged variants (compile-time lanes, K == G * KT, no external tables): see pml_coop.cuh
-void bu_tma_launch(cudaStream_t st, const BuArgs &a, int s0, int ns) {
-    const size_t sh = bu_tma_smem(G * KT, JT, G);
-    if (a.ln.J > JT) {
-        static bool done = false;
-        prefer_smem(bu_coop_kernel<KT, G, JT, KX, true, true>, sh, done);
-        const int tiles = a.ln.J / JT;
-        unsigned gx = coop_grid(ns, JT, kTmaBlocks);
-        const unsigned per_row = (148u * kTmaBlocks + tiles - 1) / tiles;
-        if (gx > per_row) gx = per_row;
-        bu_coop_kernel<KT, G, JT, KX, true, true><<<dim3(gx, tiles), kCoopBlock, sh, st>>>(a, s0, ns);
-        return;
-    }
-    static bool done = false;
-    prefer_smem(bu_coop_kernel<KT, G, JT, KX, false, true>, sh, done);
-    bu_coop_kernel<KT, G, JT, KX, false, true><<<coop_grid(ns, JT, kTmaBlocks), kCoopBlock, sh, st>>>(a, s0, ns);
-}
-
+// TMA-staged top-down sweep (compile-time lanes, K == G * KT, no external tables): see pml_coop.cuh
 void td_tma_launch(cudaStream_t st, const TdArgs &a, int n0, int nn) {
     const size_t sh = td_tma_smem(G * KT, JT, G);
     static bool done = false;
@@ -100,9 +83,9 @@ void td_tma_launch(cudaStream_t st, const TdArgs &a, int n0, int nn) {
 
 const CoopSet *PML_CS_NAME() {
 #if PML_JT > 0
-    static const CoopSet cs = {bu_launch, td_launch, G, KT, JT, bu_tma_launch, td_tma_launch};
+    static const CoopSet cs = {bu_launch, td_launch, G, KT, JT, td_tma_launch};
 #else
-    static const CoopSet cs = {bu_launch, td_launch, G, KT, JT, nullptr, nullptr};
+    static const CoopSet cs = {bu_launch, td_launch, G, KT, JT, nullptr};
 #endif
     return &cs;
 }

@@ -283,11 +283,9 @@ void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_
              p->err.ptr};
     const bool maxp = !is_marginal;
     const CoopSet *coop = maxp ? nullptr : pick_coop(p, ln.J);
-    // bulk-copy staging of the child vectors: needs the compile-time variants and no external (sharding) tips
     static const bool no_mma = getenv("PASTML_B200_NO_MMA") != nullptr;
     const bool mma = !maxp && p->kind == PML_MODEL_EIG && p->eig_shared && !p->ext_index.ptr && !no_mma &&
                      mma_bu_applicable(p->K, ln.J);
-    const bool bu_tma = coop && coop->bu_tma && !p->ext_index.ptr && tma_enabled();
     // thread-per-item sweep with TMA-staged child vectors (F81 family, sum-product mode, no external tips)
     for (int lvl = p->n_levels - 1; lvl >= 0; --lvl) {
         const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
@@ -303,7 +301,7 @@ void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_
             continue;
         }
         if (coop) {
-            (bu_tma ? coop->bu_tma : coop->bu)(p->stream, a, s0, ns);
+            coop->bu(p->stream, a, s0, ns);
             p->launches++;
             continue;
         }

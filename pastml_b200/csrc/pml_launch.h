@@ -33,8 +33,7 @@ struct CoopSet {
     void (*bu)(cudaStream_t, const BuArgs &, int slot_begin, int n_slots);
     void (*td)(cudaStream_t, const TdArgs &, int node_begin, int n_nodes);
     int G, KT, JT;   // JT > 0: built for exactly JT lanes and K == G * KT
-    // TMA-staged variants of the same sweeps (JT > 0 only; problems without external tables), else nullptr
-    void (*bu_tma)(cudaStream_t, const BuArgs &, int slot_begin, int n_slots);
+    // TMA-staged variant of the top-down sweep (JT > 0 only; problems without external tables), else nullptr
     void (*td_tma)(cudaStream_t, const TdArgs &, int node_begin, int n_nodes);
 };
 const CoopSet *coop_set(int g, int kt, int jt);   // nullptr when not built

@@ -263,8 +263,8 @@ class ColumnBatch(object):
         # capacity for the finite-difference batch of one gradient: every free parameter + the base point
         self.max_sets = padded_sets(1 + max(m.get_num_params() for m in self.models), self.C) if batched_gradients() else 1
         self.batched_fd = self.max_sets > 1
-        if self.max_sets * self.C < 4:
-            self.max_sets = -(-4 // self.C)   # room for the smallest lane-list pass (4 lanes)
+        # room for the largest lane-list pass: every column asking for a full gradient, padded to whole lane tiles
+        self.max_sets = max(self.max_sets, -(-lane_list_size(self.max_sets * self.C) // self.C))
         self.problem = Problem(flat, self.K, self.kind, self.annot_mask, self.has_state,
                                max_param_sets=self.max_sets, device=device)
         # every objective pass of the fit runs over exactly the requested (column, parameter block) lanes (engine:

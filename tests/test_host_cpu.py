@@ -195,3 +195,74 @@ def test_newick_ingest_errors(text):
     from pastml_b200 import tree as T
     with pytest.raises(ValueError):
         T.read_forest_flat(text)
+
+
+# ------------------------------------------------------------------ lock-step fit on a stand-in objective (no GPU)
+
+class _FakeProblem(object):
+    stride = 4 + 3
+
+
+class _FakeBatch(object):
+    """Stands in for ColumnBatch: the 'log-likelihood' of column c is a concave function of (sf, pi) with its maximum
+    at a column-specific point, so that the columns need different numbers of L-BFGS-B iterations."""
+
+    def __init__(self, models, lane_lists):
+        self.models = models
+        self.C = len(models)
+        self.characters = ['c%d' % c for c in range(self.C)]
+        self.problem = _FakeProblem()
+        self.lane_lists = lane_lists
+        self.batched_fd = True
+        from pastml_b200.ml import padded_sets, lane_list_size
+        self.max_sets = padded_sets(1 + max(m.get_num_params() for m in models), self.C)
+        self.max_sets = max(self.max_sets, -(-lane_list_size(self.max_sets * self.C) // self.C))   # as ColumnBatch
+        self.lanes_evaluated = 0
+        self.calls = []
+
+    @staticmethod
+    def _value(c, block):
+        sf, pi = block[0], block[4:7]
+        target = np.array([.2 + .05 * c, .5 - .03 * c, .3 - .02 * c])
+        return -100. * (c + 1) * (np.log(sf) - np.log(0.5 + c)) ** 2 - 50. * ((pi - target) ** 2).sum() - 10.
+
+    def loglik_sets(self, params, n_sets):
+        self.calls.append(('grid', n_sets * self.C))
+        self.lanes_evaluated += n_sets * self.C
+        return np.array([[self._value(c, params[b, c]) for c in range(self.C)] for b in range(n_sets)]), {}
+
+    def loglik_lanes(self, params, lane_columns):
+        assert len(lane_columns) % 4 == 0 and len(lane_columns) <= self.max_sets * self.C
+        self.calls.append(('lanes', len(lane_columns)))
+        self.lanes_evaluated += len(lane_columns)
+        return np.array([self._value(c, params[i]) for i, c in enumerate(lane_columns)]), {}
+
+
+def _fake_fit(lane_lists, C=8):
+    from pastml_b200.annotation import ForestStats
+    from pastml_b200.ml import fit_batch
+    from pastml_b200.models import F81Model
+    from pastml_b200.tree import FlatForest
+    flat = FlatForest(np.array([-1, 0, 0, 1, 1], dtype=np.int32), np.array([0., 1., 2., 1., 1.]))
+    fs = ForestStats(flat=flat)
+    models = [F81Model(states=np.array(['a', 'b', 'c']), forest_stats=fs, character='c%d' % c) for c in range(C)]
+    batch = _FakeBatch(models, lane_lists)
+    out, passes = fit_batch(batch, [np.full(3, 1. / 3)] * C)
+    return out, passes, batch, models
+
+
+def test_lockstep_fit_lane_lists_match_the_grid():
+    """The lock-step fit with lane-list passes reaches the values of the (sets x columns) grid -- same requests, same
+    answers -- while evaluating fewer lanes once columns start to finish; every pass is padded to whole lane tiles."""
+    from pastml_b200.ml import lane_list_size
+    assert [lane_list_size(n) for n in (1, 4, 5, 8, 9, 63, 64, 65, 147)] == [4, 4, 8, 8, 16, 64, 64, 96, 160]
+    grid_out, grid_passes, grid_batch, grid_models = _fake_fit(False)
+    lane_out, lane_passes, lane_batch, lane_models = _fake_fit(True)
+    assert lane_passes == grid_passes
+    np.testing.assert_allclose(lane_out, grid_out, rtol=0, atol=0)
+    for a, b in zip(grid_models, lane_models):
+        assert a.sf == b.sf and np.array_equal(a.frequencies, b.frequencies)
+    assert all(kind == 'lanes' for kind, _ in lane_batch.calls) and all(kind == 'grid' for kind, _ in grid_batch.calls)
+    assert lane_batch.lanes_evaluated < grid_batch.lanes_evaluated
+    for c, m in enumerate(lane_models):   # the optimum of the stand-in objective
+        assert m.sf == pytest.approx(0.5 + c, rel=1e-3)
