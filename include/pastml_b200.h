@@ -133,6 +133,13 @@ int pml_get_masks(pml_problem *p, int32_t mask_kind, uint64_t *out_mask);
  * out_initial[N][C]. */
 int pml_get_initial(pml_problem *p, uint8_t *out_has, uint64_t *out_initial);
 
+/* The bottom-up state left by the last single-set sum-product pass (pml_loglik with n_sets = 1, or pml_marginal): the
+ * mantissa vectors out_vec[NI][K][C] and exponents out_ex[NI][C] of the internal nodes (slot order = internal nodes by
+ * increasing node index; a tip's vector is its allowed-state mask), the allowed-state masks in force during that
+ * pass out_allowed[N][C] (after the zero-branch alteration) and out_altered[N][C] = 1 where the alteration changed
+ * the node's mask.  Input of marginal_counts (ml.py:753-862). */
+int pml_get_bottom_up(pml_problem *p, double *out_vec, int32_t *out_ex, uint64_t *out_allowed, uint8_t *out_altered);
+
 /* After PML_ERR_ZERO_LIKELIHOOD: first failing (column, parameter set, parent node, child node). */
 int pml_zero_likelihood_info(pml_problem *p, int32_t *column, int32_t *param_set, int32_t *parent, int32_t *child);
 

@@ -15,7 +15,7 @@ EXPORTS = ['pml_last_error', 'pml_version', 'pml_device_count', 'pml_param_strid
            'pml_set_custom_masks', 'pml_get_masks', 'pml_get_initial', 'pml_zero_likelihood_info',
            'pml_zero_likelihood_all', 'pml_trim_memory', 'pml_get_root_partials', 'pml_set_tip_partials',
            'pml_get_tip_td', 'pml_set_root_td',
-           'pml_last_call_stats', 'pml_bench_pass', 'pml_supports_lane_lists', 'pml_loglik_lanes',
+           'pml_last_call_stats', 'pml_bench_pass', 'pml_supports_lane_lists', 'pml_loglik_lanes', 'pml_get_bottom_up',
            'pml_newick_last_error', 'pml_newick_parse', 'pml_newick_num_nodes', 'pml_newick_num_trees',
            'pml_newick_names_bytes', 'pml_newick_name_nodes', 'pml_newick_fill', 'pml_newick_free']
 
@@ -57,6 +57,8 @@ def load():
     lib.pml_supports_lane_lists.argtypes = [vp]
     lib.pml_loglik_lanes.restype = C.c_int
     lib.pml_loglik_lanes.argtypes = [vp, vp, vp, i32, vp]
+    lib.pml_get_bottom_up.restype = C.c_int
+    lib.pml_get_bottom_up.argtypes = [vp, vp, vp, vp, vp]
     lib.pml_joint.restype = C.c_int
     lib.pml_joint.argtypes = [vp, vp, vp, vp]
     lib.pml_marginal.restype = C.c_int

@@ -1127,6 +1127,35 @@ int pml_get_initial(pml_problem *p, uint8_t *out_has, uint64_t *out_initial) {
     return PML_OK;
 }
 
+int pml_get_bottom_up(pml_problem *p, double *out_vec, int32_t *out_ex, uint64_t *out_allowed, uint8_t *out_altered) {
+    if (!p || !out_vec || !out_ex || !out_allowed || !out_altered) return fail(PML_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    const size_t nc = (size_t) p->N * p->C;
+    if (p->NI) {
+        CUDA_TRY(cudaMemcpy(out_vec, p->bu.ptr, sizeof(double) * (size_t) p->NI * p->K * p->C, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(out_ex, p->bu_ex.ptr, sizeof(int) * (size_t) p->NI * p->C, cudaMemcpyDeviceToHost));
+    }
+    CUDA_TRY(cudaMemcpy(out_allowed, p->mask[PML_MASK_ANNOTATION].ptr, nc * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < nc; ++i) out_allowed[i] &= p->kmask;
+    std::memset(out_altered, 0, nc);
+    if (!p->n_rows) return PML_OK;
+    const size_t rc = (size_t) p->n_rows * p->C;
+    std::vector<uint64_t> alt(rc);
+    std::vector<uint8_t> flag(rc);
+    std::vector<int> rows(p->n_rows);
+    CUDA_TRY(cudaMemcpy(alt.data(), p->zc_alt.ptr, rc * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(flag.data(), p->zc_altflag.ptr, rc, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(rows.data(), p->row_node.ptr, sizeof(int) * p->n_rows, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < p->n_rows; ++r)
+        for (int c = 0; c < p->C; ++c)
+            if (flag[(size_t) r * p->C + c]) {
+                out_altered[(size_t) rows[r] * p->C + c] = 1;
+                out_allowed[(size_t) rows[r] * p->C + c] = alt[(size_t) r * p->C + c] & p->kmask;
+            }
+    return PML_OK;
+}
+
 int pml_zero_likelihood_info(pml_problem *p, int32_t *column, int32_t *param_set, int32_t *parent, int32_t *child) {
     if (!p) return fail(PML_ERR_INVALID, "null argument");
     if (column) *column = p->zero_info[0];

@@ -205,6 +205,16 @@ class Problem(object):
         self._check(self.lib.pml_get_initial(self._h, _p(has), _p(init)))
         return has, init
 
+    def bottom_up_state(self):
+        """(vec [NI][K][C], ex [NI][C], allowed [N][C], altered [N][C]) left by the last single-set sum-product pass;
+        the slot of internal node v is ``flat.slot[v]``."""
+        vec = np.empty((self.flat.n_internal, self.K, self.C), dtype=np.float64)
+        ex = np.empty((self.flat.n_internal, self.C), dtype=np.int32)
+        allowed = np.empty((self.N, self.C), dtype=np.uint64)
+        altered = np.empty((self.N, self.C), dtype=np.uint8)
+        self._check(self.lib.pml_get_bottom_up(self._h, _p(vec), _p(ex), _p(allowed), _p(altered)))
+        return vec, ex, allowed, altered
+
     # ------------------------------------------------------------------ subtree sharding hooks
     def root_partials(self, n_sets=1):
         """Bottom-up vectors of the roots after a loglik pass: (vec [T][K][J], ex [T][J])."""

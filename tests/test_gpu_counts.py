@@ -1,0 +1,46 @@
+"""``pastml_b200.ml.marginal_counts`` against the reference's ``marginal_counts`` (``ml.py:753-862``).  The function
+samples ancestral scenarios, so the comparison is statistical: the mean over several runs must agree with the mean of
+the reference's runs (``oracle/make_golden_counts.py`` -> ``tests/golden/counts/counts_*.npz``) within the Monte-Carlo error."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import Golden, annotated_forest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+CASES = ['albania_f81', 'synth_s4_n30_k3_f81_forest', 'sim152_hky_skew', 'synth_s2_n60_k7_f81']
+
+
+def _model(g, roots):
+    from pastml_b200.annotation import ForestStats
+    from pastml_b200.models import F81Model, HKYModel
+    fs = ForestStats(roots)
+    kw = dict(forest_stats=fs, sf=float(g['sf']), tau=float(g['tau']))
+    if g.kind == 0:
+        return F81Model(states=np.array(g.states), frequencies=np.array(g['pi'], dtype=float), **kw)
+    return HKYModel(states=np.array(g.states), frequencies=np.array(g['pi'], dtype=float), kappa=float(g['kappa']), **kw)
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_marginal_counts_match_reference_statistics(name):
+    from pastml_b200.ml import marginal_counts
+    g = Golden(name)
+    want = np.load(os.path.join(GOLDEN, 'counts', 'counts_{}.npz'.format(name)))
+    runs_ref, n_rep = int(want['runs']), int(want['n_repetitions'])
+    runs = []
+    for seed in range(runs_ref):
+        roots = annotated_forest(g)
+        np.random.seed(500 + seed)
+        runs.append(marginal_counts(roots, g.meta['column'], _model(g, roots), n_repetitions=n_rep))
+    runs = np.array(runs)
+    assert runs.shape[1:] == want['mean'].shape
+    mean, std = runs.mean(axis=0), runs.std(axis=0, ddof=1)
+    sigma = np.sqrt((std ** 2 + want['std'] ** 2) / runs_ref)
+    dev = np.abs(mean - want['mean'])
+    assert np.all(dev <= 5. * sigma + 0.02), (dev.max(), sigma.max())
+    # the number of changes per scenario (off-diagonal mass), a tighter aggregate
+    off = lambda m: m.sum() - np.trace(m)
+    assert off(mean) == pytest.approx(off(want['mean']), rel=0.01, abs=0.05)
