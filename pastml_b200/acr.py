@@ -17,7 +17,7 @@ from pastml_b200.ml import is_ml, MPPA, ml_acr_batch
 from pastml_b200.models import model2class, F81, HKY, JTT, HKY_STATES, JTT_STATES
 from pastml_b200.parsimony import is_parsimonious, parsimonious_acr_batch, MP_METHODS
 from pastml_b200.ml import ML_METHODS
-from pastml_b200.tree import Tree, flatten_forest
+from pastml_b200.tree import Tree, flatten_forest, resolve_trees, unresolve_trees, IS_POLYTOMY
 
 COPY = 'COPY'
 
@@ -52,9 +52,6 @@ def acr(forest, df=None, columns=None, column2states=None, prediction_method=MPP
     logger = logging.getLogger('pastml')
     if not isinstance(forest, (list, tuple)):
         forest = [forest]
-    if resolve_polytomies:
-        raise NotImplementedError('resolve_polytomies is outside the accelerated path (SURVEY.md section 8f-4)')
-
     if columns is None:
         if df is None:
             raise ValueError('Either the tree should be preannotated with character values and columns and '
@@ -67,6 +64,12 @@ def acr(forest, df=None, columns=None, column2states=None, prediction_method=MPP
 
     flat = flatten_forest(forest)
     forest_stats = ForestStats(flat=flat)
+    # the reconstruction overwrites the features with its predictions: polytomy resolution starts again from these
+    n2c2states = {}
+    for node in flat.nodes:
+        c2states = {c: getattr(node, c) for c in columns if getattr(node, c, None)}
+        if c2states:
+            n2c2states[node] = c2states
     logger.debug('\n=============ACR===============================')
     column2parameters = column2parameters if column2parameters else {}
     column2rates = column2rates if column2rates else {}
@@ -125,29 +128,63 @@ def acr(forest, df=None, columns=None, column2states=None, prediction_method=MPP
             key = ('MP', method, len(model_or_states))
         groups.setdefault(key, []).append(character)
 
-    per_character = {}
-    for key, members in groups.items():
-        if key[0] == COPY:
-            ch = members[0]
-            per_character[ch] = {CHARACTER: ch, STATES: settings[ch][1], METHOD: COPY}
-        elif key[0] == 'ML':
-            res = ml_acr_batch(forest, members, key[1], [settings[ch][1] for ch in members],
-                               [settings[ch][2] for ch in members], force_joint=force_joint, flat=flat, device=device)
-            per_character.update(zip(members, res))
-        else:
-            res = parsimonious_acr_batch(forest, members, key[1], [settings[ch][1] for ch in members],
-                                         forest_stats.num_nodes, forest_stats.num_tips, flat=flat, device=device)
-            per_character.update(zip(members, res))
+    def reconstruct(flat, forest_stats):
+        """One reconstruction of every character on the forest as it is now."""
+        per_character = {}
+        for key, members in groups.items():
+            if key[0] == COPY:
+                ch = members[0]
+                per_character[ch] = {CHARACTER: ch, STATES: settings[ch][1], METHOD: COPY}
+            elif key[0] == 'ML':
+                res = ml_acr_batch(forest, members, key[1], [settings[ch][1] for ch in members],
+                                   [settings[ch][2] for ch in members], force_joint=force_joint, flat=flat, device=device)
+                per_character.update(zip(members, res))
+            else:
+                res = parsimonious_acr_batch(forest, members, key[1], [settings[ch][1] for ch in members],
+                                             forest_stats.num_nodes, forest_stats.num_tips, flat=flat, device=device)
+                per_character.update(zip(members, res))
+        results = []
+        for character in settings:
+            r = per_character[character]
+            if isinstance(r, list):
+                results.extend(r)
+            else:
+                results.append(r)
+        return results
 
-    acr_results = []
-    for character in settings:
-        r = per_character[character]
-        if isinstance(r, list):
-            acr_results.extend(r)
-        else:
-            acr_results.append(r)
+    acr_results = reconstruct(flat, forest_stats)
+    if not resolve_polytomies:
+        return acr_results
+
+    # polytomy resolution (acr.py:234-278): children of a multifurcation predicted in one state that differs from their
+    # parent's get a parent of their own; the likelihoods are recalculated with the fitted parameters frozen, and
+    # resolutions that the recalculation does not support are undone until none is left to undo
+    column2states = {res[CHARACTER]: res[STATES] for res in acr_results}
+    column2copy = {res[CHARACTER]: res[METHOD] == COPY for res in acr_results}
+    if not resolve_trees(column2states, forest):
+        return acr_results
+    level = logger.level
+    logger.setLevel(logging.ERROR)
+    for root in forest:
+        for n in root.traverse():
+            c2states = n2c2states.get(n, {})
+            for c in columns:
+                if c in c2states:
+                    n.add_feature(c, c2states[c])
+                elif not getattr(n, IS_POLYTOMY, False) or not column2copy.get(c, False):
+                    n.del_feature(c)   # a COPY character keeps the state its new node was created with
+    flat = flatten_forest(forest)
+    forest_stats = ForestStats(flat=flat)
+    for method, model_or_states, _ in settings.values():
+        if is_ml(method):
+            model_or_states.freeze()
+            model_or_states.forest_stats = forest_stats
+    acr_results = reconstruct(flat, forest_stats)
+    while unresolve_trees(column2states, forest):
+        flat = flatten_forest(forest)
+        acr_results = reconstruct(flat, forest_stats)
+    logger.setLevel(level)
     return acr_results
-
 
 def pastml_pipeline(*args, **kwargs):
     """``pastml.acr.pastml_pipeline`` lives here in the reference; the implementation is in

@@ -18,6 +18,8 @@ from __future__ import annotations
 import os
 from collections import deque
 
+import logging
+
 import numpy as np
 
 DEFAULT_DIST = 1.0
@@ -90,11 +92,8 @@ class Tree(object):
             child.dist = float(dist)
         if support is not None:
             child.support = float(support)
-        if child.up is not None and child.up is not self:
-            try:
-                child.up.children.remove(child)
-            except ValueError:
-                pass
+        # like ete3: the child is NOT taken off its previous parent's list (callers detach it themselves; the
+        # reference's polytomy surgery iterates over that list while re-hanging the children)
         child.up = self
         self.children.append(child)
         return child
@@ -789,3 +788,99 @@ def forest_from_arrays(parent, dist, names=None):
             node.up = nodes[p]
             nodes[p].children.append(node)
     return roots
+
+
+# ---------------------------------------------------------------------------------------- polytomy resolution
+
+IS_POLYTOMY = 'polytomy'
+DATE, DATE_CI = 'date', 'date_CI'
+
+
+def _prediction_key(node, columns, col2state2i):
+    """The node's predicted states as one string (state indices joined per column), used to group siblings."""
+    return '.'.join('-'.join(str(i) for i in sorted(col2state2i[c][s] for s in getattr(node, c, set())))
+                    for c in columns)
+
+
+def states_are_different(n1, n2, columns):
+    """True when the two nodes share no state in at least one column (``tree.py:383-387`` of the reference)."""
+    return any(not (getattr(n1, c, set()) & getattr(n2, c, set())) for c in columns)
+
+
+def group_children_if_needed(n, children, columns, state):
+    """Hangs ``children`` (siblings predicted in the same state, different from their parent's) on a new node between
+    them and ``n``, at the distance of the closest of them (``tree.py:390-417``).  Returns True if a node was made."""
+    if len(children) <= 1:
+        return False
+    child = min(children, key=lambda _: _.dist)
+    if not states_are_different(n, child, columns):
+        return False
+    dist = child.dist
+    pol = n.add_child(dist=dist, name='{}.polytomy_{}'.format(n.name, state))
+    pol.add_feature(IS_POLYTOMY, 1)
+    c_date = getattr(child, DATE, None)
+    pol.add_feature(DATE, c_date)
+    n_ci = getattr(n, DATE_CI, None)
+    c_ci = getattr(child, DATE_CI, None)
+    pol.add_feature(DATE_CI, None if not n_ci or not isinstance(n_ci, list)
+                    else [n_ci[0], c_ci[1] if c_ci and isinstance(c_ci, list) and len(c_ci) > 1 else c_date])
+    for c in columns:
+        pol.add_feature(c, getattr(child, c))
+    for c in children:
+        n.remove_child(c)
+        pol.add_child(c, dist=c.dist - dist)
+    return True
+
+
+def resolve_trees(column2states, forest):
+    """Resolves polytomies from the state predictions (``tree.py:344-380``): when a node with more than two children
+    has at least two of them in one predicted state that differs from its own, those children get a parent of their
+    own.  Returns the number of nodes created."""
+    columns = sorted(column2states.keys())
+    col2state2i = {c: dict(zip(states, range(len(states)))) for c, states in column2states.items()}
+    num_new_nodes = 0
+    for tree in forest:
+        todo = [tree]
+        while todo:
+            n = todo.pop()
+            todo.extend(n.children)
+            if len(n.children) > 2:
+                state2children = {}
+                for c in n.children:
+                    state2children.setdefault(_prediction_key(c, columns, col2state2i), []).append(c)
+                if len(state2children) > 1:
+                    for state, children in state2children.items():
+                        if group_children_if_needed(n, children, columns, state):
+                            num_new_nodes += 1
+    logging.getLogger('pastml').debug('Created {} new internal nodes while resolving polytomies'.format(num_new_nodes)
+                                      if num_new_nodes else 'Could not resolve any polytomy')
+    return num_new_nodes
+
+
+def unresolve_trees(column2states, forest):
+    """Removes the polytomy resolutions whose state no longer matches their children after the likelihoods were
+    recalculated (``tree.py:420-489``).  Returns the number of nodes removed.  (The reference also means to regroup
+    the freed children under their grandparent, but collects the candidates in a dictionary it never fills, so no
+    node is ever created there; the behaviour, not the intent, is reproduced.)"""
+    columns = sorted(column2states.keys())
+    col2state2i = {c: dict(zip(states, range(len(states)))) for c, states in column2states.items()}
+    num_removed_nodes = 0
+    for tree in forest:
+        for n in list(tree.traverse('postorder')):
+            if not getattr(n, IS_POLYTOMY, False):
+                continue
+            children = list(n.children)
+            keys = {_prediction_key(c, columns, col2state2i) for c in children}
+            parent = n.up
+            if len(keys) == 1 and not states_are_different(n, children[0], columns):
+                # still a consistent resolution; useless only if the parent is in the same state
+                if states_are_different(n, parent, columns):
+                    continue
+            num_removed_nodes += 1
+            for c in children:
+                parent.add_child(c, dist=c.dist + n.dist)
+            parent.remove_child(n)
+    if num_removed_nodes:
+        logging.getLogger('pastml').debug('Removed {} polytomy resolution{} as inconsistent with model parameters.'
+                                          .format(num_removed_nodes, 's' if num_removed_nodes > 1 else ''))
+    return num_removed_nodes

@@ -266,3 +266,59 @@ def test_lockstep_fit_lane_lists_match_the_grid():
     assert lane_batch.lanes_evaluated < grid_batch.lanes_evaluated
     for c, m in enumerate(lane_models):   # the optimum of the stand-in objective
         assert m.sf == pytest.approx(0.5 + c, rel=1e-3)
+
+
+# ------------------------------------------------------------------ polytomy resolution (tree surgery)
+
+def _random_predicted_tree(rng, n_tips):
+    """A tree with polytomies, names, dates and a predicted state set on every node (two columns)."""
+    from pastml_b200 import tree as T
+    text = _random_newick(rng, n_tips, named_internal=1.)
+    root = T.read_tree(text)
+    T.name_tree(root)
+    for node in root.traverse('preorder'):
+        node.add_feature('date', 0. if node.is_root() else node.up.date + node.dist)
+        a = {str(rng.choice(['x', 'y', 'z']))}
+        if rng.random() < 0.15:
+            a.add(str(rng.choice(['x', 'y', 'z'])))
+        node.add_feature('colA', a)
+        node.add_feature('colB', {str(rng.choice(['p', 'q']))})
+    return root
+
+
+def _describe(root):
+    return [(n.name, round(n.dist, 9), n.up.name if n.up else None, sorted(n.colA), sorted(n.colB),
+             int(getattr(n, 'polytomy', 0))) for n in root.traverse()]
+
+
+def test_polytomy_surgery_matches_reference():
+    """resolve_trees / unresolve_trees against the reference's functions on the same predicted trees."""
+    from oracle import ref_env
+    if not ref_env.reference_available():
+        pytest.skip('reference sources not available')
+    ref_env.install()
+    from pastml import tree as R
+    from pastml_b200 import tree as T
+    column2states = {'colA': np.array(['x', 'y', 'z']), 'colB': np.array(['p', 'q'])}
+    rng = np.random.default_rng(5)
+    created = removed = 0
+    for trial in range(25):
+        seed = int(rng.integers(1 << 30))
+        mine = _random_predicted_tree(np.random.default_rng(seed), int(rng.integers(6, 60)))
+        theirs = _random_predicted_tree(np.random.default_rng(seed), 0) if False else mine.copy()
+        n_mine, n_theirs = T.resolve_trees(column2states, [mine]), R.resolve_trees(column2states, [theirs])
+        assert n_mine == n_theirs
+        assert _describe(mine) == _describe(theirs)
+        created += n_mine
+        # new predictions (as after a likelihood recalculation), the same on both copies
+        flip = np.random.default_rng(seed + 1)
+        for a, b in zip(mine.traverse(), theirs.traverse()):
+            if flip.random() < 0.3:
+                s = {str(flip.choice(['x', 'y', 'z']))}
+                a.add_feature('colA', s)
+                b.add_feature('colA', set(s))
+        r_mine, r_theirs = T.unresolve_trees(column2states, [mine]), R.unresolve_trees(column2states, [theirs])
+        assert r_mine == r_theirs
+        assert _describe(mine) == _describe(theirs)
+        removed += r_mine
+    assert created > 10 and removed > 5
