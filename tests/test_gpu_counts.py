@@ -44,3 +44,25 @@ def test_marginal_counts_match_reference_statistics(name):
     # the number of changes per scenario (off-diagonal mass), a tighter aggregate
     off = lambda m: m.sum() - np.trace(m)
     assert off(mean) == pytest.approx(off(want['mean']), rel=0.01, abs=0.05)
+
+
+def test_count_transitions_table(tmp_path):
+    """The table-writing wrapper on the Albania pipeline inputs with the reference-fitted parameter file: labels, and
+    a number of changes per scenario in line with the reference's marginal_counts runs on the same tree."""
+    import pandas as pd
+    from pastml_b200.utilities.transition_counter import count_transitions
+    src = os.path.join(GOLDEN, 'pipeline', 'albania_mppa_f81')
+    out = str(tmp_path / 'transitions.tab')
+    np.random.seed(3)
+    count_transitions(tree=os.path.join(src, 'input.nwk'), data=os.path.join(src, 'input.tab'), column='Country',
+                      parameters=os.path.join(src, 'expected', 'params.character_Country.method_MPPA.model_F81.tab'),
+                      out_transitions=out, model='F81', n_repetitions=4000)
+    df = pd.read_csv(out, sep='\t', index_col=0)
+    want = np.load(os.path.join(GOLDEN, 'counts', 'counts_albania_f81.npz'))
+    assert list(df.index) == list(df.columns) == sorted(df.columns) and df.index.name == 'from'
+    assert df.values.shape == want['mean'].shape
+    off = lambda m: m.sum() - np.trace(m)
+    assert off(df.values) == pytest.approx(off(want['mean']), rel=0.02)
+    with pytest.raises(NotImplementedError):
+        count_transitions(tree=os.path.join(src, 'input.nwk'), data=os.path.join(src, 'input.tab'), column='Country',
+                          parameters=None, out_transitions=out, html=str(tmp_path / 'x.html'))
