@@ -1,0 +1,139 @@
+"""Array-native ACR for large trees: newick file + annotation table in, arrays and result files out, without a Python
+object per node.
+
+``read_forest_flat`` (C++ newick parser) gives the level-ordered forest, :func:`table_masks` turns the columns of the
+annotation table into the engine's bit masks, :func:`acr_flat` runs the same fit and reconstruction as
+:func:`pastml_b200.acr.acr` (ML methods) and returns the usual result dictionaries with the predicted states as
+``state_masks`` arrays, :func:`write_results` writes the reference's result files from them
+(``combined_ancestral_states.tab``, ``params.*.tab``, ``marginal_probabilities.*.tab``; ``acr.py:45-73, 831-860``).
+"""
+import logging
+import os
+
+import numpy as np
+import pandas as pd
+
+from pastml_b200 import value2list, col_name2cat, CHARACTER, STATES
+from pastml_b200.annotation import ForestStats
+from pastml_b200.ml import (ColumnBatch, fit_batch, reconstruct_batch, is_ml, MPPA, STATE_MASKS, ML_METHODS)
+from pastml_b200.models import model2class, F81, HKY, JTT, HKY_STATES, JTT_STATES
+
+
+def table_masks(flat, df, column, states=None):
+    """(states, annot_mask [N] uint64, has_state [N] uint8) for one column of an annotation table indexed by node
+    names (a node listed several times gets the union of its states, as ``annotation.df2gdf`` does;
+    ``annotation.py:104-123``; ``has_state`` marks every node the table lists).  ``states`` defaults to the sorted values of the column (``acr.py:211-213``)."""
+    values = df[column]
+    listed = values.index
+    keep = values.notna() & (values.astype(str) != '')
+    values = values[keep].astype(str)
+    if states is None:
+        states = np.array(sorted(values.unique()))
+    state2bit = {s: np.uint64(1) << np.uint64(i) for i, s in enumerate(states)}
+    name2node = pd.Series(np.arange(flat.n_nodes), index=pd.Index(np.asarray(flat.names, dtype=object)))
+    name2node = name2node[~name2node.index.duplicated()]
+    known = values.index.isin(name2node.index) & values.isin(list(state2bit))
+    nodes = name2node.loc[values.index[known]].to_numpy()
+    bits = values[known].map(state2bit).to_numpy(dtype=np.uint64)
+    mask = np.zeros(flat.n_nodes, dtype=np.uint64)
+    np.bitwise_or.at(mask, nodes, bits)
+    # "has a state" in the reference's zero-branch clusters = the node carries the feature at all, and
+    # preannotate_forest gives it (as an empty set) to every node the table lists, missing values included (ml.py:329-331)
+    has = np.zeros(flat.n_nodes, dtype=np.uint8)
+    has[name2node.loc[listed[listed.isin(name2node.index)]].to_numpy()] = 1
+    return np.asarray(states), mask, has
+
+
+def observed_frequencies(flat, mask, K):
+    """Tip-state frequencies, a tip with n states counting 1/n for each (``acr.py:282-299``)."""
+    tips = mask[flat.is_tip]
+    bits = ((tips[:, None] >> np.arange(K, dtype=np.uint64)) & np.uint64(1)).astype(np.float64)
+    n = bits.sum(axis=1)
+    freqs = (bits[n > 0] / n[n > 0, None]).sum(axis=0)
+    return freqs / freqs.sum()
+
+
+def acr_flat(flat, df, columns=None, prediction_method=MPPA, model=F81, column2parameters=None, column2rates=None,
+             force_joint=True, reoptimise=False, tau=0, frequency_smoothing=False, device=0):
+    """:func:`pastml_b200.acr.acr` for an array-native forest (``tree.read_forest_flat``) and an annotation table
+    indexed by node names; ML methods only.  Returns the list of result dictionaries; the predicted states of a
+    character are ``result['state_masks']`` (uint64 per node, bit k = ``result['states'][k]``) and the marginal
+    probabilities keep their DataFrame (rows in the forest's level order)."""
+    columns = list(df.columns if columns is None else ([columns] if isinstance(columns, str) else columns))
+    methods = value2list(len(columns), prediction_method, MPPA)
+    models = value2list(len(columns), model, F81)
+    column2parameters = column2parameters or {}
+    column2rates = column2rates or {}
+    forest_stats = ForestStats(flat=flat)
+    settings = []
+    for column, method, model_name in zip(columns, methods, models):
+        if not is_ml(method):
+            raise ValueError('acr_flat reconstructs with the ML methods ({}), got {}'.format(', '.join(ML_METHODS), method))
+        fixed_states = HKY_STATES if model_name == HKY else JTT_STATES if model_name == JTT else None
+        states, mask, has = table_masks(flat, df, column, fixed_states)
+        optimise_tau = tau is None or reoptimise
+        instance = model2class[model_name](parameter_file=column2parameters.get(column),
+                                           rate_matrix_file=column2rates.get(column), reoptimise=reoptimise,
+                                           frequency_smoothing=frequency_smoothing, tau=0 if tau is None else tau,
+                                           optimise_tau=optimise_tau, states=states, forest_stats=forest_stats,
+                                           observed_frequencies=observed_frequencies(flat, mask, len(states)),
+                                           character=col_name2cat(column))
+        settings.append((col_name2cat(column), method, instance, mask, has))
+    groups = {}
+    for i, (character, method, instance, _, _) in enumerate(settings):
+        groups.setdefault((method, instance.engine_kind, len(instance.states)), []).append(i)
+    per_character = {}
+    for (method, _, _), members in groups.items():
+        batch = ColumnBatch(flat, [settings[i][0] for i in members], [settings[i][2] for i in members], device=device,
+                            annot_mask=np.stack([settings[i][3] for i in members]),
+                            has_state=np.stack([settings[i][4] for i in members]))
+        try:
+            obs = [observed_frequencies(flat, settings[i][3], len(settings[i][2].states)) for i in members]
+            likelihoods, _ = fit_batch(batch, obs)
+            res = reconstruct_batch(batch, method, likelihoods, force_joint, write_likelihood_features=False)
+        finally:
+            batch.close()
+        per_character.update(zip(members, res))
+    return [r for i in range(len(settings)) for r in per_character[i]]
+
+
+def write_results(results, flat, work_dir, out_data=None):
+    """The reference's result files from array-native results: ``combined_ancestral_states.tab`` (one row per node and
+    per rank of its predicted states, ``acr.py:831-860``) and, per character, the parameter and
+    marginal-probability files (``acr.py:45-73``)."""
+    from pastml_b200.pipeline import serialize_acr, get_combined_ancestral_state_file
+    os.makedirs(work_dir, exist_ok=True)
+    by_character = {r[CHARACTER]: r for r in results}
+    columns = sorted(by_character)
+    names = np.asarray(flat.names, dtype=object)
+    N = flat.n_nodes
+    # per column: the states of every node in increasing order of their names, row r of a node = its r-th state
+    ranked, depth = {}, np.zeros(N, dtype=np.int64)
+    for c in columns:
+        states = np.asarray(by_character[c][STATES], dtype=object)
+        order = np.argsort(states.astype(str), kind='stable')
+        mask = by_character[c][STATE_MASKS]
+        bits = ((mask[:, None] >> order.astype(np.uint64)[None, :]) & np.uint64(1)).astype(bool)   # [N][K] in name order
+        rank = np.cumsum(bits, axis=1) - 1
+        ranked[c] = (bits, rank, states[order])
+        depth = np.maximum(depth, bits.sum(axis=1))
+    with open(out_data or os.path.join(work_dir, get_combined_ancestral_state_file()), 'w+') as f:
+        f.write('node\t{}\n'.format('\t'.join(columns)))
+        rows_of = np.repeat(np.arange(N), depth)
+        row_rank = np.arange(len(rows_of)) - np.repeat(np.cumsum(depth) - depth, depth)
+        cells = []
+        for c in columns:
+            bits, rank, state_names = ranked[c]
+            col = np.full(len(rows_of), '', dtype=object)
+            node_idx, state_idx = np.nonzero(bits)
+            # row of (node, its r-th state) = first row of the node + r
+            first = np.cumsum(depth) - depth
+            col[first[node_idx] + rank[node_idx, state_idx]] = state_names[state_idx]
+            cells.append(col)
+        table = np.column_stack([names[rows_of]] + cells)
+        f.write('\n'.join('\t'.join(map(str, row)) for row in table))
+        if len(table):
+            f.write('\n')
+    for r in results:
+        serialize_acr(r, work_dir)
+    logging.getLogger('pastml').debug('Serialized the results to {}.'.format(work_dir))

@@ -482,6 +482,9 @@ def get_bottom_up_loglikelihood(tree, character, model, is_marginal=True, alter=
 
 # ---------------------------------------------------------------------------------------- reconstruction
 
+STATE_MASKS = 'state_masks'   # array-native result: uint64 [N], bit k = state k, in the forest's level order
+
+
 def _write_states(flat, mask_column, states, feature):
     for node, value in zip(flat.nodes, mask_to_sets(mask_column, states)):
         node.add_feature(feature, value)
@@ -508,8 +511,11 @@ def reconstruct_batch(batch, prediction_method, likelihoods, force_joint=True, w
         for c in range(C):
             character = batch.characters[c]
             feature = get_personalized_feature_name(character, method) if prediction_method != method else character
-            _write_states(flat, mask_nc[:, c], batch.models[c].states, feature)
             res = current[c].copy()
+            if flat.nodes is not None:
+                _write_states(flat, mask_nc[:, c], batch.models[c].states, feature)
+            else:   # array-native forest: the predicted states travel with the result instead of the node objects
+                res[STATE_MASKS] = np.ascontiguousarray(mask_nc[:, c]) & np.uint64((1 << batch.K) - 1)
             res[CHARACTER] = feature
             res[METHOD] = method
             results[c].append(res)
@@ -540,7 +546,7 @@ def reconstruct_batch(batch, prediction_method, likelihoods, force_joint=True, w
         for c in range(C):
             states = batch.models[c].states
             current[c][MARGINAL_PROBABILITIES] = pd.DataFrame(probs[order, c, :], index=index, columns=states)
-        if write_likelihood_features:
+        if write_likelihood_features and flat.nodes is not None:
             has_init, init = pb.get_initial()
             for c in range(C):
                 lh_f = get_personalized_feature_name(batch.characters[c], LH)

@@ -18,7 +18,7 @@ from pastml_b200 import col_name2cat, get_personalized_feature_name, METHOD, CHA
 from pastml_b200.acr import acr, COPY
 from pastml_b200.annotation import preannotate_forest
 from pastml_b200.ml import (MPPA, is_ml, is_marginal, is_meta_ml, get_default_ml_method, MODEL,
-                            MARGINAL_PROBABILITIES)
+                            MARGINAL_PROBABILITIES, STATE_MASKS)
 from pastml_b200.models import F81
 from pastml_b200.parsimony import is_meta_mp, get_default_mp_method
 from pastml_b200.tree import read_forest, name_tree
@@ -216,7 +216,7 @@ def serialize_acr(acr_result, work_dir):
         f.write('parameter\tvalue\n')
         f.write('pastml_version\t{}\n'.format(PASTML_VERSION))
         for name in sorted(acr_result.keys()):
-            if name not in [STATES, MARGINAL_PROBABILITIES, METHOD, MODEL]:
+            if name not in [STATES, MARGINAL_PROBABILITIES, METHOD, MODEL, STATE_MASKS]:
                 f.write('{}\t{}\n'.format(name, acr_result[name]))
         f.write('{}\t{}\n'.format(METHOD, acr_result[METHOD]))
         if is_ml(acr_result[METHOD]):

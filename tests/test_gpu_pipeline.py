@@ -87,3 +87,32 @@ def test_pipeline_input_errors(tmp_path):
     bad.write_text('id\tCountry\nnobody\tX\n')
     with pytest.raises(ValueError, match='do not correspond to annotation id'):
         pastml_pipeline(tree=os.path.join(src, 'input.nwk'), data=str(bad), columns=['Country'], work_dir=str(tmp_path / 'w2'))
+
+
+@pytest.mark.parametrize('case', ['albania_mppa_f81', 'albania_map_jc', 'albania_joint_eft'])
+def test_array_native_path_matches_reference_files(case, tmp_path):
+    """read_forest_flat + acr_flat + write_results (no node objects) against the reference pipeline's files."""
+    from pastml_b200.arrays import acr_flat, write_results
+    from pastml_b200.tree import read_forest_flat
+    column, method, model, _ = CASES[case]
+    src = os.path.join(BASE, case)
+    flat = read_forest_flat(os.path.join(src, 'input.nwk'))
+    assert flat.nodes is None
+    df = pd.read_csv(os.path.join(src, 'input.tab'), sep='\t', index_col=0, header=0, dtype=str)
+    np.random.seed(0)
+    results = acr_flat(flat, df, columns=[column], prediction_method=method, model=model, force_joint=False)
+    work = str(tmp_path / 'out')
+    write_results(results, flat, work)
+    want_dir = os.path.join(src, 'expected')
+    assert open(os.path.join(work, 'combined_ancestral_states.tab')).read() == \
+        open(os.path.join(want_dir, 'combined_ancestral_states.tab')).read()
+    for name in os.listdir(want_dir):
+        if name.startswith('params.'):
+            got, want = _params(os.path.join(work, name)), _params(os.path.join(want_dir, name))
+            assert list(got) == list(want)
+            assert float(got['log_likelihood']) == pytest.approx(float(want['log_likelihood']), rel=1e-7)
+        elif name.startswith('marginal_probabilities.'):
+            got = pd.read_csv(os.path.join(work, name), sep='\t', index_col=0)
+            want = pd.read_csv(os.path.join(want_dir, name), sep='\t', index_col=0)
+            assert list(got.index) == list(want.index)
+            np.testing.assert_allclose(got.values, want.values, rtol=0, atol=2e-3)

@@ -5,6 +5,7 @@ import os
 import re
 
 import numpy as np
+import pandas as pd
 import pytest
 
 from helpers import Golden, golden_names, annotated_forest
@@ -322,3 +323,46 @@ def test_polytomy_surgery_matches_reference():
         assert _describe(mine) == _describe(theirs)
         removed += r_mine
     assert created > 10 and removed > 5
+
+
+# ------------------------------------------------------------------ array-native tables (pastml_b200/arrays.py)
+
+def test_table_masks_and_frequencies_match_the_node_path():
+    from helpers import Golden, annotated_forest
+    from pastml_b200.acr import calculate_observed_freqs
+    from pastml_b200.arrays import table_masks, observed_frequencies
+    for name in ('albania_f81', 'denv2_location_f81', 'synth_s2_n60_k7_f81'):
+        g = Golden(name)
+        column = g.meta['column']
+        rows = [(str(g['names'][i]), g.states[k]) for i in range(len(g['names'])) if g['has_state'][i]
+                for k in range(g.K) if (int(g['annot_mask'][i]) >> k) & 1]
+        rows += [(str(g['names'][i]), None) for i in range(len(g['names'])) if g['has_state'][i] and not g['annot_mask'][i]]
+        df = pd.DataFrame({column: [s for _, s in rows]}, index=[n for n, _ in rows])
+        states, mask, has = table_masks(g.flat, df, column, np.array(g.states))
+        assert list(states) == list(g.states)
+        assert np.array_equal(mask, g['annot_mask']) and np.array_equal(has, g['has_state'])
+        roots = annotated_forest(g)
+        _, want, _ = calculate_observed_freqs(column, roots, list(g.states))
+        np.testing.assert_allclose(observed_frequencies(g.flat, mask, g.K), want, rtol=1e-14)
+
+
+def test_write_results_combined_states_match_the_node_writer(tmp_path):
+    """combined_ancestral_states.tab from state masks = the file the node-object writer produces."""
+    from pastml_b200.arrays import write_results
+    from pastml_b200.ml import STATE_MASKS
+    from pastml_b200.pipeline import serialize_predicted_states
+    from pastml_b200.tree import read_tree, name_tree, flatten_forest
+    rng = np.random.default_rng(9)
+    root = read_tree(_random_newick(rng, 40))
+    name_tree(root)
+    flat = flatten_forest(root)
+    states = {'colA': np.array(['b', 'a', 'c']), 'col B': np.array(['x', 'y'])}
+    results = []
+    for c, st in states.items():
+        masks = rng.integers(1, 1 << len(st), size=flat.n_nodes).astype(np.uint64)
+        for node, m in zip(flat.nodes, masks.tolist()):
+            node.add_feature(c, {st[k] for k in range(len(st)) if (m >> k) & 1})
+        results.append({'character': c, 'states': st, 'method': 'DOWNPASS', STATE_MASKS: masks})
+    serialize_predicted_states(sorted(states), str(tmp_path / 'nodes.tab'), [root])
+    write_results(results, flat, str(tmp_path / 'w'), out_data=str(tmp_path / 'arrays.tab'))
+    assert open(tmp_path / 'arrays.tab').read() == open(tmp_path / 'nodes.tab').read()
