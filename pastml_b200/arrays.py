@@ -24,23 +24,24 @@ def table_masks(flat, df, column, states=None):
     names (a node listed several times gets the union of its states, as ``annotation.df2gdf`` does;
     ``annotation.py:104-123``; ``has_state`` marks every node the table lists).  ``states`` defaults to the sorted values of the column (``acr.py:211-213``)."""
     values = df[column]
-    listed = values.index
-    keep = values.notna() & (values.astype(str) != '')
-    values = values[keep].astype(str)
+    # node index of every table row (-1: the id is not a node name); get_indexer is one vectorised hash join
+    node_names = pd.Index(np.asarray(flat.names, dtype=object))
+    if node_names.has_duplicates:
+        node_names = pd.Index(np.where(node_names.duplicated(), None, node_names))   # first occurrence wins
+    row_node = node_names.get_indexer(pd.Index(values.index.astype(str)))
+    text = values.astype(object).where(values.notna(), None)
+    filled = np.array([v is not None and str(v) != '' for v in text], dtype=bool)
     if states is None:
-        states = np.array(sorted(values.unique()))
-    state2bit = {s: np.uint64(1) << np.uint64(i) for i, s in enumerate(states)}
-    name2node = pd.Series(np.arange(flat.n_nodes), index=pd.Index(np.asarray(flat.names, dtype=object)))
-    name2node = name2node[~name2node.index.duplicated()]
-    known = values.index.isin(name2node.index) & values.isin(list(state2bit))
-    nodes = name2node.loc[values.index[known]].to_numpy()
-    bits = values[known].map(state2bit).to_numpy(dtype=np.uint64)
+        states = np.array(sorted({str(v) for v in text[filled]}))
+    codes = pd.Index(np.asarray(states, dtype=object)).get_indexer(pd.Index([str(v) for v in text[filled]]))
+    rows = row_node[filled]
+    ok = (rows >= 0) & (codes >= 0)
     mask = np.zeros(flat.n_nodes, dtype=np.uint64)
-    np.bitwise_or.at(mask, nodes, bits)
+    np.bitwise_or.at(mask, rows[ok], np.uint64(1) << codes[ok].astype(np.uint64))
     # "has a state" in the reference's zero-branch clusters = the node carries the feature at all, and
     # preannotate_forest gives it (as an empty set) to every node the table lists, missing values included (ml.py:329-331)
     has = np.zeros(flat.n_nodes, dtype=np.uint8)
-    has[name2node.loc[listed[listed.isin(name2node.index)]].to_numpy()] = 1
+    has[row_node[row_node >= 0]] = 1
     return np.asarray(states), mask, has
 
 
