@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <string_view>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -276,25 +277,32 @@ int pml_newick_name_nodes(pml_newick *nw, int use_tree_suffix) {
             order.push_back(v);
             for (size_t k = children[v].size(); k-- > 0;) stack.push_back(children[v][k]);
         }
-        std::unordered_map<std::string, int> seen;
+        // names of this tree and how often each occurs (views into the stored names: nothing is renamed before the
+        // counting is over, and the renaming pass below looks a name up before it overwrites it)
+        std::unordered_map<std::string_view, int> seen;
+        seen.reserve(order.size() * 2);
         for (int32_t v : order)
-            if (!nw->names[v].empty()) seen[nw->names[v]]++;
+            if (!nw->names[v].empty()) seen[std::string_view(nw->names[v])]++;
         if (seen.size() == order.size()) continue;   // every node has its own name
         long long counter = 0;
-        std::unordered_set<std::string> taken;
-        for (int32_t v : order) {
-            std::string prefix;
+        std::vector<std::string> renamed(order.size());
+        std::unordered_set<std::string_view> taken;
+        taken.reserve(order.size() * 2);
+        std::string candidate, prefix;
+        for (size_t k = 0; k < order.size(); ++k) {
+            const int32_t v = order[k];
             const std::string &nm = nw->names[v];
-            if (!nm.empty() && seen[nm] < 10) prefix = nm;
+            if (!nm.empty() && seen[std::string_view(nm)] < 10) prefix = nm;
             else prefix = (children[v].empty() ? "t" : "n") + std::to_string(counter) + suffix;
-            std::string candidate = (nw->parent[v] < 0) ? "root" + suffix : prefix;
-            while (taken.count(candidate)) {
+            candidate = (nw->parent[v] < 0) ? "root" + suffix : prefix;
+            while (taken.count(std::string_view(candidate))) {
                 candidate = prefix + std::to_string(counter) + suffix;
                 ++counter;
             }
-            nw->names[v] = candidate;
-            taken.insert(candidate);
+            renamed[k] = candidate;
+            taken.insert(std::string_view(renamed[k]));   // renamed[] is never resized: the views stay valid
         }
+        for (size_t k = 0; k < order.size(); ++k) nw->names[order[k]] = std::move(renamed[k]);
     }
     return PML_OK;
 }

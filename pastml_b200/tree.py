@@ -747,7 +747,7 @@ def read_forest_flat(tree_path_or_newick, name_nodes=True):
     from pastml_b200 import _lib
     lib = _lib.load()
     text = tree_path_or_newick
-    if isinstance(text, str) and os.path.exists(text):
+    if isinstance(text, str) and len(text) < 4096 and '(' not in text and os.path.exists(text):
         with open(text, 'rb') as f:
             data = f.read()
     else:
@@ -768,7 +768,12 @@ def read_forest_flat(tree_path_or_newick, name_nodes=True):
     finally:
         lib.pml_newick_free(handle)
     raw = buf.tobytes()
-    names = np.array([raw[offsets[i]:offsets[i + 1]].decode() for i in range(n)], dtype=object)
+    cuts = offsets.tolist()
+    if raw.isascii():   # byte offsets are character offsets
+        text = raw.decode('ascii')
+        names = np.array([text[a:b] for a, b in zip(cuts[:-1], cuts[1:])], dtype=object)
+    else:
+        names = np.array([raw[a:b].decode() for a, b in zip(cuts[:-1], cuts[1:])], dtype=object)
     return FlatForest(parent, dist, names=names)
 
 
