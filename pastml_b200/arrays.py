@@ -3,7 +3,7 @@ object per node.
 
 ``read_forest_flat`` (C++ newick parser) gives the level-ordered forest, :func:`table_masks` turns the columns of the
 annotation table into the engine's bit masks, :func:`acr_flat` runs the same fit and reconstruction as
-:func:`pastml_b200.acr.acr` (ML methods) and returns the usual result dictionaries with the predicted states as
+:func:`pastml_b200.acr.acr` and returns the usual result dictionaries with the predicted states as
 ``state_masks`` arrays, :func:`write_results` writes the reference's result files from them
 (``combined_ancestral_states.tab``, ``params.*.tab``, ``marginal_probabilities.*.tab``; ``acr.py:45-73, 831-860``).
 """
@@ -16,7 +16,9 @@ import pandas as pd
 from pastml_b200 import value2list, col_name2cat, CHARACTER, STATES
 from pastml_b200.annotation import ForestStats
 from pastml_b200.ml import (ColumnBatch, fit_batch, reconstruct_batch, is_ml, MPPA, STATE_MASKS, ML_METHODS)
+from pastml_b200.engine import Problem
 from pastml_b200.models import model2class, F81, HKY, JTT, HKY_STATES, JTT_STATES
+from pastml_b200.parsimony import is_parsimonious, parsimony_on_problem, MP_METHODS
 
 
 def table_masks(flat, df, column, states=None):
@@ -57,7 +59,7 @@ def observed_frequencies(flat, mask, K):
 def acr_flat(flat, df, columns=None, prediction_method=MPPA, model=F81, column2parameters=None, column2rates=None,
              force_joint=True, reoptimise=False, tau=0, frequency_smoothing=False, device=0):
     """:func:`pastml_b200.acr.acr` for an array-native forest (``tree.read_forest_flat``) and an annotation table
-    indexed by node names; ML methods only.  Returns the list of result dictionaries; the predicted states of a
+    indexed by node names, ML and parsimony methods.  Returns the list of result dictionaries; the predicted states of a
     character are ``result['state_masks']`` (uint64 per node, bit k = ``result['states'][k]``) and the marginal
     probabilities keep their DataFrame (rows in the forest's level order)."""
     columns = list(df.columns if columns is None else ([columns] if isinstance(columns, str) else columns))
@@ -68,8 +70,14 @@ def acr_flat(flat, df, columns=None, prediction_method=MPPA, model=F81, column2p
     forest_stats = ForestStats(flat=flat)
     settings = []
     for column, method, model_name in zip(columns, methods, models):
+        character = col_name2cat(column)
+        if is_parsimonious(method):
+            states, mask, has = table_masks(flat, df, column)
+            settings.append((character, method, states, mask, has))
+            continue
         if not is_ml(method):
-            raise ValueError('acr_flat reconstructs with the ML methods ({}), got {}'.format(', '.join(ML_METHODS), method))
+            raise ValueError('Method {} is unknown, should be one of ML ({}) or one of MP ({})'
+                             .format(method, ', '.join(ML_METHODS), ', '.join(MP_METHODS)))
         fixed_states = HKY_STATES if model_name == HKY else JTT_STATES if model_name == JTT else None
         states, mask, has = table_masks(flat, df, column, fixed_states)
         optimise_tau = tau is None or reoptimise
@@ -78,22 +86,34 @@ def acr_flat(flat, df, columns=None, prediction_method=MPPA, model=F81, column2p
                                            frequency_smoothing=frequency_smoothing, tau=0 if tau is None else tau,
                                            optimise_tau=optimise_tau, states=states, forest_stats=forest_stats,
                                            observed_frequencies=observed_frequencies(flat, mask, len(states)),
-                                           character=col_name2cat(column))
-        settings.append((col_name2cat(column), method, instance, mask, has))
+                                           character=character)
+        settings.append((character, method, instance, mask, has))
     groups = {}
-    for i, (character, method, instance, _, _) in enumerate(settings):
-        groups.setdefault((method, instance.engine_kind, len(instance.states)), []).append(i)
+    for i, (_, method, model_or_states, _, _) in enumerate(settings):
+        key = ('ML', method, model_or_states.engine_kind, len(model_or_states.states)) if is_ml(method) \
+            else ('MP', method, len(model_or_states))
+        groups.setdefault(key, []).append(i)
     per_character = {}
-    for (method, _, _), members in groups.items():
-        batch = ColumnBatch(flat, [settings[i][0] for i in members], [settings[i][2] for i in members], device=device,
-                            annot_mask=np.stack([settings[i][3] for i in members]),
-                            has_state=np.stack([settings[i][4] for i in members]))
-        try:
-            obs = [observed_frequencies(flat, settings[i][3], len(settings[i][2].states)) for i in members]
-            likelihoods, _ = fit_batch(batch, obs)
-            res = reconstruct_batch(batch, method, likelihoods, force_joint, write_likelihood_features=False)
-        finally:
-            batch.close()
+    for key, members in groups.items():
+        masks = np.stack([settings[i][3] for i in members])
+        has = np.stack([settings[i][4] for i in members])
+        characters = [settings[i][0] for i in members]
+        if key[0] == 'MP':
+            problem = Problem(flat, key[2], 0, masks, has, device=device)
+            try:
+                res = parsimony_on_problem(problem, flat, characters, [settings[i][2] for i in members], key[1],
+                                           forest_stats.num_nodes, forest_stats.num_tips)[0]
+            finally:
+                problem.close()
+        else:
+            batch = ColumnBatch(flat, characters, [settings[i][2] for i in members], device=device, annot_mask=masks,
+                                has_state=has)
+            try:
+                obs = [observed_frequencies(flat, settings[i][3], len(settings[i][2].states)) for i in members]
+                likelihoods, _ = fit_batch(batch, obs)
+                res = reconstruct_batch(batch, key[1], likelihoods, force_joint, write_likelihood_features=False)
+            finally:
+                batch.close()
         per_character.update(zip(members, res))
     return [r for i in range(len(settings)) for r in per_character[i]]
 

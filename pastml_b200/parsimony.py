@@ -67,7 +67,7 @@ def parsimony_on_problem(problem, flat, characters, states_per_column, predictio
         masks, steps = out[m]
         for c, character in enumerate(characters):
             feature = get_personalized_feature_name(character, m) if prediction_method != m else character
-            if write_features:
+            if write_features and flat.nodes is not None:
                 for node, value in zip(flat.nodes, mask_to_sets(masks[:, c], states_per_column[c])):
                     node.add_feature(feature, value)
             scenarios, unresolved, per_node, perc = _set_stats(masks[:, c], num_nodes)
@@ -77,6 +77,10 @@ def parsimony_on_problem(problem, flat, characters, states_per_column, predictio
             results[c].append({STATES: states_per_column[c], NUM_NODES: num_nodes, NUM_TIPS: num_tips,
                                STEPS: int(steps[c]), NUM_SCENARIOS: scenarios, NUM_UNRESOLVED_NODES: unresolved,
                                NUM_STATES_PER_NODE: per_node, PERC_UNRESOLVED: perc, CHARACTER: feature, METHOD: m})
+            if flat.nodes is None:   # array-native forest: the predicted states travel with the result
+                from pastml_b200.ml import STATE_MASKS
+                results[c][-1][STATE_MASKS] = np.ascontiguousarray(masks[:, c]) & \
+                    np.uint64((1 << len(states_per_column[c])) - 1)
     for c, character in enumerate(characters):
         if results[c]:
             logger.debug('Parsimonious reconstruction for {} requires {} state changes.'
