@@ -366,3 +366,38 @@ def test_write_results_combined_states_match_the_node_writer(tmp_path):
     serialize_predicted_states(sorted(states), str(tmp_path / 'nodes.tab'), [root])
     write_results(results, flat, str(tmp_path / 'w'), out_data=str(tmp_path / 'arrays.tab'))
     assert open(tmp_path / 'arrays.tab').read() == open(tmp_path / 'nodes.tab').read()
+
+
+def test_array_native_parsimony_plumbing(tmp_path, monkeypatch):
+    """acr_flat + write_results for a parsimony method with the engine problem replaced by the oracle (host plumbing
+    only: masks from the table, result dictionaries, result files) against the reference pipeline's files."""
+    from oracle import cpu_oracle
+    from pastml_b200 import arrays
+    from pastml_b200.tree import read_forest_flat
+
+    class OracleProblem(object):
+        def __init__(self, flat, K, kind, masks, has, device=0):
+            self.flat, self.K, self.masks = flat, K, masks
+
+        def parsimony(self, flags, want_masks=True):
+            out = {}
+            per_column = [cpu_oracle.parsimony_fixed(self.flat, self.K, m) for m in self.masks]
+            for name, flag in (('ACCTRAN', 1), ('DOWNPASS', 2), ('DELTRAN', 4)):
+                if flags & flag:
+                    out[name] = (np.stack([r[name + '_mask'] for r in per_column], axis=1),
+                                 np.array([r[name + '_steps'] for r in per_column], dtype=np.int64))
+            return out
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(arrays, 'Problem', OracleProblem)
+    src = os.path.join(REPO, 'tests', 'golden', 'pipeline', 'albania_downpass')
+    flat = read_forest_flat(os.path.join(src, 'input.nwk'))
+    df = pd.read_csv(os.path.join(src, 'input.tab'), sep='\t', index_col=0, header=0, dtype=str)
+    results = arrays.acr_flat(flat, df, columns=['Country'], prediction_method='DOWNPASS')
+    work = str(tmp_path / 'out')
+    arrays.write_results(results, flat, work)
+    want_dir = os.path.join(src, 'expected')
+    for name in ('combined_ancestral_states.tab', 'params.character_Country.method_DOWNPASS.tab'):
+        assert open(os.path.join(work, name)).read() == open(os.path.join(want_dir, name)).read(), name
