@@ -5,7 +5,8 @@ object per node.
 annotation table into the engine's bit masks, :func:`acr_flat` runs the same fit and reconstruction as
 :func:`pastml_b200.acr.acr` and returns the usual result dictionaries with the predicted states as
 ``state_masks`` arrays, :func:`write_results` writes the reference's result files from them
-(``combined_ancestral_states.tab``, ``params.*.tab``, ``marginal_probabilities.*.tab``; ``acr.py:45-73, 831-860``).
+(``combined_ancestral_states.tab``, ``params.*.tab``, ``marginal_probabilities.*.tab``; ``acr.py:45-73, 831-860``) and
+:func:`write_named_tree` the annotated newick.
 """
 import logging
 import os
@@ -158,3 +159,41 @@ def write_results(results, flat, work_dir, out_data=None):
     for r in results:
         serialize_acr(r, work_dir)
     logging.getLogger('pastml').debug('Serialized the results to {}.'.format(work_dir))
+
+
+def write_named_tree(results, flat, path):
+    """The named, annotated tree file of ``pastml_pipeline`` (``named.tree_<tree>.nwk``: extended newick with the
+    distance to the root as ``date`` and the predicted states of every character, ``acr.py:503-507``) written from the
+    arrays: same text as ``Tree.write(format=3, format_root_node=True, features=[date, ...])`` on node objects."""
+    N = flat.n_nodes
+    parent, dist = flat.parent, flat.dist
+    dates = [0] * N   # a root's date is the integer 0, a child's its parent's plus the branch (tree.py:51-63)
+    for v in range(N):
+        if parent[v] >= 0:
+            dates[v] = dates[parent[v]] + float(dist[v])
+    labels = ['{}:{:g}[&&NHX:date={}'.format(flat.names[v], float(dist[v]), dates[v]) for v in range(N)]
+    for r in results:
+        states = np.asarray(r[STATES], dtype=object)
+        order = np.argsort(states.astype(str), kind='stable')
+        names_sorted = [str(s) for s in states[order]]
+        mask = r[STATE_MASKS]
+        bits = ((mask[:, None] >> order.astype(np.uint64)[None, :]) & np.uint64(1)).astype(bool)
+        character = r[CHARACTER]
+        for v in range(N):
+            row = bits[v]
+            if row.any():
+                labels[v] += ':{}={}'.format(character, '|'.join(n for n, b in zip(names_sorted, row) if b))
+    # children are contiguous in level order: assemble bottom-up, one string per subtree
+    text = [None] * N
+    first, count = flat.first_child, flat.n_children
+    for v in range(N - 1, -1, -1):
+        label = labels[v] + ']'
+        if count[v]:
+            kids = range(first[v], first[v] + count[v])
+            text[v] = '(' + ','.join(text[k] for k in kids) + ')' + label
+            for k in kids:
+                text[k] = None
+        else:
+            text[v] = label
+    with open(path, 'w+') as f:
+        f.write('\n'.join(text[r] + ';' for r in flat.roots))

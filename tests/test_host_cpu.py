@@ -401,3 +401,28 @@ def test_array_native_parsimony_plumbing(tmp_path, monkeypatch):
     want_dir = os.path.join(src, 'expected')
     for name in ('combined_ancestral_states.tab', 'params.character_Country.method_DOWNPASS.tab'):
         assert open(os.path.join(work, name)).read() == open(os.path.join(want_dir, name)).read(), name
+
+
+def test_write_named_tree_matches_the_node_writer(tmp_path):
+    from pastml_b200.arrays import write_named_tree
+    from pastml_b200.ml import STATE_MASKS
+    from pastml_b200.pipeline import annotate_dist_to_root
+    from pastml_b200.tree import read_tree, name_tree, flatten_forest
+    rng = np.random.default_rng(21)
+    roots = []
+    for i in range(2):
+        root = read_tree(_random_newick(rng, 30 + 10 * i))
+        name_tree(root, suffix='_%d' % i)
+        roots.append(root)
+    annotate_dist_to_root(roots)
+    flat = flatten_forest(roots)
+    states = {'colA': np.array(['b', 'a', 'c']), 'colB': np.array(['x', 'y'])}
+    results = []
+    for c, st in states.items():
+        masks = rng.integers(1, 1 << len(st), size=flat.n_nodes).astype(np.uint64)
+        for node, m in zip(flat.nodes, masks.tolist()):
+            node.add_feature(c, {st[k] for k in range(len(st)) if (m >> k) & 1})
+        results.append({'character': c, 'states': st, 'method': 'MPPA', STATE_MASKS: masks})
+    want = '\n'.join(r.write(format_root_node=True, format=3, features=['date', 'date_CI', 'colA', 'colB']) for r in roots)
+    write_named_tree(results, flat, str(tmp_path / 'named.nwk'))
+    assert open(tmp_path / 'named.nwk').read() == want
