@@ -16,7 +16,7 @@ import pandas as pd
 
 from pastml_b200 import value2list, col_name2cat, CHARACTER, STATES
 from pastml_b200.annotation import ForestStats
-from pastml_b200.ml import (ColumnBatch, fit_batch, reconstruct_batch, is_ml, MPPA, STATE_MASKS, ML_METHODS)
+from pastml_b200.ml import (ColumnBatch, fit_batch, reconstruct_batch, is_ml, MPPA, ALL, STATE_MASKS, ML_METHODS)
 from pastml_b200.engine import Problem
 from pastml_b200.models import model2class, F81, HKY, JTT, HKY_STATES, JTT_STATES
 from pastml_b200.parsimony import is_parsimonious, parsimony_on_problem, MP_METHODS
@@ -112,7 +112,11 @@ def acr_flat(flat, df, columns=None, prediction_method=MPPA, model=F81, column2p
             try:
                 obs = [observed_frequencies(flat, settings[i][3], len(settings[i][2].states)) for i in members]
                 likelihoods, _ = fit_batch(batch, obs)
-                res = reconstruct_batch(batch, key[1], likelihoods, force_joint, write_likelihood_features=False)
+                hook = None
+                if key[1] == ALL:   # the parsimony part of the ALL meta-method, as in ml_acr_batch
+                    from pastml_b200.parsimony import all_methods_hook as hook
+                res = reconstruct_batch(batch, key[1], likelihoods, force_joint, write_likelihood_features=False,
+                                        parsimony_hook=hook)
             finally:
                 batch.close()
         per_character.update(zip(members, res))

@@ -426,3 +426,26 @@ def test_write_named_tree_matches_the_node_writer(tmp_path):
     want = '\n'.join(r.write(format_root_node=True, format=3, features=['date', 'date_CI', 'colA', 'colB']) for r in roots)
     write_named_tree(results, flat, str(tmp_path / 'named.nwk'))
     assert open(tmp_path / 'named.nwk').read() == want
+
+
+def test_lockstep_fit_reports_a_failing_lane_to_its_column():
+    """A zero-likelihood lane of a lane-list pass surfaces as the error of the column that asked for it, the other
+    columns finish their fit."""
+    from pastml_b200.ml import fit_batch, PastMLLikelihoodError
+    from pastml_b200.annotation import ForestStats
+    from pastml_b200.models import F81Model
+    from pastml_b200.tree import FlatForest
+
+    class Failing(_FakeBatch):
+        def loglik_lanes(self, params, lane_columns):
+            values, _ = _FakeBatch.loglik_lanes(self, params, lane_columns)
+            errs = {j: PastMLLikelihoodError('column {} is broken'.format(c)) for j, c in enumerate(lane_columns) if c == 2}
+            return values, errs
+
+    flat = FlatForest(np.array([-1, 0, 0, 1, 1], dtype=np.int32), np.array([0., 1., 2., 1., 1.]))
+    fs = ForestStats(flat=flat)
+    models = [F81Model(states=np.array(['a', 'b', 'c']), forest_stats=fs, character='c%d' % c) for c in range(4)]
+    batch = Failing(models, True)
+    with pytest.raises(PastMLLikelihoodError, match='column 2 is broken'):
+        fit_batch(batch, [np.full(3, 1. / 3)] * 4)
+    assert any(kind == 'lanes' for kind, _ in batch.calls)
