@@ -201,3 +201,40 @@ def write_named_tree(results, flat, path):
             text[v] = label
     with open(path, 'w+') as f:
         f.write('\n'.join(text[r] + ';' for r in flat.roots))
+
+
+def pastml_pipeline_flat(tree, data, data_sep='\t', id_index=0, columns=None, prediction_method=MPPA, model=F81,
+                         parameters=None, rate_matrix=None, out_data=None, work_dir=None, forced_joint=False,
+                         reoptimise=False, smoothing=False, frequency_smoothing=False, device=0):
+    """``pastml_pipeline`` for trees too large for a Python object per node: C++ newick ingest, annotation table to bit
+    masks, the same fit and reconstruction, and the same result files (combined states, named tree, parameters,
+    marginal probabilities) written from arrays.  Same argument meaning as :func:`pastml_b200.pipeline.pastml_pipeline`
+    (``acr.py:316``); returns ``(flat, results)``."""
+    from pastml_b200.pipeline import get_pastml_work_dir, get_named_tree_file, _keyed
+    from pastml_b200.tree import read_forest_flat
+    flat = read_forest_flat(tree)
+    df = pd.read_csv(data, sep=data_sep, index_col=id_index, header=0, dtype=str)
+    df.index = df.index.map(str)
+    if columns:
+        columns = [columns] if isinstance(columns, str) else list(columns)
+        unknown = set(columns) - set(df.columns)
+        if unknown:
+            raise ValueError('{} of the specified columns ({}) {} not found among the annotation columns: {}.'
+                             .format('One' if len(unknown) == 1 else 'Some', ', '.join('"{}"'.format(c) for c in unknown),
+                                     'is' if len(unknown) == 1 else 'are', ', '.join('"{}"'.format(c) for c in df.columns)))
+        df = df[columns]
+    columns = list(df.columns)
+    if not len(set(df.index) & set(flat.names)):
+        raise ValueError('Your tree tip names (e.g. {}) do not correspond to annotation id column values (e.g. {}). '
+                         'Check your annotation file.'.format(', '.join(map(str, flat.names[flat.is_tip][:3])),
+                                                            ', '.join(map(str, df.index[:3]))))
+    results = acr_flat(flat, df, columns=columns, prediction_method=prediction_method, model=model,
+                       column2parameters=_keyed(parameters, columns, 'Parameters'),
+                       column2rates=_keyed(rate_matrix, columns, 'Rate matrices'), force_joint=forced_joint,
+                       reoptimise=reoptimise, tau=None if smoothing else 0, frequency_smoothing=frequency_smoothing,
+                       device=device)
+    if not work_dir:
+        work_dir = get_pastml_work_dir(tree)
+    write_results(results, flat, work_dir, out_data=out_data)
+    write_named_tree(results, flat, os.path.join(work_dir, get_named_tree_file(tree)))
+    return flat, results

@@ -401,6 +401,16 @@ def test_array_native_parsimony_plumbing(tmp_path, monkeypatch):
     want_dir = os.path.join(src, 'expected')
     for name in ('combined_ancestral_states.tab', 'params.character_Country.method_DOWNPASS.tab'):
         assert open(os.path.join(work, name)).read() == open(os.path.join(want_dir, name)).read(), name
+    # the whole array-native pipeline: every file of the reference's work directory, with the same text
+    work2 = str(tmp_path / 'out2')
+    arrays.pastml_pipeline_flat(os.path.join(src, 'input.nwk'), os.path.join(src, 'input.tab'), columns=['Country'],
+                                prediction_method='DOWNPASS', work_dir=work2)
+    assert sorted(os.listdir(work2)) == sorted(os.listdir(want_dir))
+    for name in os.listdir(want_dir):
+        assert open(os.path.join(work2, name)).read() == open(os.path.join(want_dir, name)).read(), name
+    with pytest.raises(ValueError, match='not found among the annotation columns'):
+        arrays.pastml_pipeline_flat(os.path.join(src, 'input.nwk'), os.path.join(src, 'input.tab'), columns=['Nope'],
+                                    work_dir=work2)
 
 
 def test_write_named_tree_matches_the_node_writer(tmp_path):
