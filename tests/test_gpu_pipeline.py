@@ -119,3 +119,21 @@ def test_array_native_path_matches_reference_files(case, tmp_path):
             want = pd.read_csv(os.path.join(want_dir, name), sep='\t', index_col=0)
             assert list(got.index) == list(want.index)
             np.testing.assert_allclose(got.values, want.values, rtol=0, atol=2e-3)
+
+
+def test_array_native_pipeline_in_one_call(tmp_path):
+    """pastml_pipeline_flat with an ML method: the reference's work directory, states and named tree with the same text."""
+    from pastml_b200.arrays import pastml_pipeline_flat
+    src = os.path.join(BASE, 'albania_mppa_f81')
+    work = str(tmp_path / 'out')
+    np.random.seed(0)
+    pastml_pipeline_flat(os.path.join(src, 'input.nwk'), os.path.join(src, 'input.tab'), columns=['Country'],
+                         prediction_method='MPPA', model='F81', work_dir=work)
+    want_dir = os.path.join(src, 'expected')
+    assert sorted(os.listdir(work)) == sorted(os.listdir(want_dir))
+    for name in ('combined_ancestral_states.tab', 'named.tree_input.nwk'):
+        assert open(os.path.join(work, name)).read() == open(os.path.join(want_dir, name)).read(), name
+    got = _params(os.path.join(work, 'params.character_Country.method_MPPA.model_F81.tab'))
+    want = _params(os.path.join(want_dir, 'params.character_Country.method_MPPA.model_F81.tab'))
+    assert list(got) == list(want)
+    assert float(got['log_likelihood']) == pytest.approx(float(want['log_likelihood']), rel=1e-7)
