@@ -17,7 +17,7 @@ from pastml_b200.ml import is_ml, MPPA, ml_acr_batch
 from pastml_b200.models import model2class, F81, HKY, JTT, HKY_STATES, JTT_STATES
 from pastml_b200.parsimony import is_parsimonious, parsimonious_acr_batch, MP_METHODS
 from pastml_b200.ml import ML_METHODS
-from pastml_b200.tree import Tree, flatten_forest, resolve_trees, unresolve_trees, IS_POLYTOMY
+from pastml_b200.tree import flatten_forest, resolve_trees, unresolve_trees, IS_POLYTOMY
 
 COPY = 'COPY'
 

@@ -1,7 +1,6 @@
 """Forest statistics and table -> node annotation (``/root/reference/pastml/annotation.py``)."""
 import logging
 
-import numpy as np
 import pandas as pd
 
 
