@@ -6,12 +6,17 @@ zero-branch alteration, bottom-up (pruning) sweep, fused top-down / marginal / p
 node-states = nodes x states x columns.  ``value`` is timed on the device with CUDA events on resident inputs
 (L2 flushed between steps; the working set, 2.7 GB of partials, is far larger than L2 anyway); ``e2e`` goes through
 the C ABI with pinned host buffers: problem creation (H2D of topology and annotation masks), the pipeline, and D2H
-of the marginal probabilities, MAP/MPPA masks and the k histogram, every step.
+of the marginal probabilities, MAP/MPPA masks and the k histogram, every step (median step; PCIe- and host-bound).
+``roofline`` = algorithmic bytes of the dominant sweep / its CUDA-event time / MEASURED_PEAKS.json, with the ncu DRAM
+traffic of the same sweep beside it; ``ml_fit`` = metric ii, the whole ML ACR of the columns (two-stage L-BFGS-B fit on
+the host with the device objective, then JOINT + marginal + MAP + MPPA + restricted likelihoods); ``cpu_baseline`` and
+``--impl reference`` time the C port of the reference's algorithm (oracle/) on the host cores.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--tips T] [--states K] [--columns C]
 
 With --gpus N > 1 the driver launches one rank per GPU through torchrun; every rank owns an independent
-(tree x columns) batch of the same shape (weak scaling, no data-path collective).  ``--sharding subtree`` instead
+(tree x columns) batch of the same shape (weak scaling, no data-path collective), and ``ml_fit.one_tree_columns_sharded``
+is the ML ACR of ONE tree with its columns spread over the ranks (strong scaling, no exchange).  ``--sharding subtree`` instead
 cuts ONE tree into clades spread over the ranks, with one NCCL all-gather of clade-root vectors per step (strong
 scaling; pastml_b200/sharded.py).
 """
