@@ -180,13 +180,13 @@ def write_named_tree(results, flat, path):
         states = np.asarray(r[STATES], dtype=object)
         order = np.argsort(states.astype(str), kind='stable')
         names_sorted = [str(s) for s in states[order]]
-        mask = r[STATE_MASKS]
-        bits = ((mask[:, None] >> order.astype(np.uint64)[None, :]) & np.uint64(1)).astype(bool)
-        character = r[CHARACTER]
-        for v in range(N):
-            row = bits[v]
-            if row.any():
-                labels[v] += ':{}={}'.format(character, '|'.join(n for n, b in zip(names_sorted, row) if b))
+        # one piece of text per distinct state set (few of them, whatever the number of nodes)
+        uniq, inverse = np.unique(r[STATE_MASKS], return_inverse=True)
+        pieces = []
+        for m in uniq.tolist():
+            chosen = [n for n, k in zip(names_sorted, order.tolist()) if (m >> k) & 1]
+            pieces.append(':{}={}'.format(r[CHARACTER], '|'.join(chosen)) if chosen else '')
+        labels = [label + pieces[i] for label, i in zip(labels, inverse.tolist())]
     # children are contiguous in level order: assemble bottom-up, one string per subtree
     text = [None] * N
     first, count = flat.first_child, flat.n_children
