@@ -459,3 +459,38 @@ def test_lockstep_fit_reports_a_failing_lane_to_its_column():
     with pytest.raises(PastMLLikelihoodError, match='column 2 is broken'):
         fit_batch(batch, [np.full(3, 1. / 3)] * 4)
     assert any(kind == 'lanes' for kind, _ in batch.calls)
+
+
+def test_pipeline_input_validation_on_cpu(tmp_path):
+    """validate_input (acr.py:677-822): column checks, id matching, states and naming -- no engine involved."""
+    from pastml_b200.pipeline import validate_input, get_pastml_parameter_file, get_pastml_marginal_prob_file, \
+        get_named_tree_file, get_pastml_work_dir
+    src = os.path.join(REPO, 'tests', 'golden', 'pipeline', 'albania_mppa_f81')
+    tree, data = os.path.join(src, 'input.nwk'), os.path.join(src, 'input.tab')
+    roots, columns, column2states, parameters, rates = validate_input(tree, ['Country'], data)
+    assert columns == ['Country'] and len(roots) == 1 and parameters == {} and rates == {}
+    assert list(column2states['Country']) == sorted(column2states['Country'])
+    annotated = sum(1 for n in roots[0].traverse() if getattr(n, 'Country', None))
+    assert annotated > 100
+    with pytest.raises(ValueError, match='not found among the annotation columns'):
+        validate_input(tree, ['Nope'], data)
+    with pytest.raises(ValueError, match='need to provide an annotated tree'):
+        validate_input(tree, None, None)
+    bad = tmp_path / 'bad.tab'
+    bad.write_text('id\tCountry\nnobody\tX\n')
+    with pytest.raises(ValueError, match='do not correspond to annotation id'):
+        validate_input(tree, ['Country'], str(bad))
+    sparse = tmp_path / 'sparse.tab'
+    first_tip = next(iter(roots[0])).name
+    sparse.write_text('id\tCountry\n{}\tX\n'.format(first_tip))
+    with pytest.raises(ValueError, match='are unknown'):
+        validate_input(tree, ['Country'], str(sparse))
+    _, _, _, params, _ = validate_input(tree, ['Country'], data, parameters={'Country': {'scaling_factor': 1.}})
+    assert params == {'Country': {'scaling_factor': 1.}}
+    # file names of pastml/file.py
+    assert get_pastml_parameter_file('MPPA', 'F81', 'Country') == 'params.character_Country.method_MPPA.model_F81.tab'
+    assert get_pastml_parameter_file('DOWNPASS', None, 'Country') == 'params.character_Country.method_DOWNPASS.tab'
+    assert get_pastml_marginal_prob_file('MAP', 'JC', 'Country') == 'marginal_probabilities.character_Country.model_JC.tab'
+    assert get_pastml_marginal_prob_file('JOINT', 'JC', 'Country') is None
+    assert get_named_tree_file('/x/y/my.tree.nwk') == 'named.tree_my.tree.nwk'
+    assert get_pastml_work_dir('/x/y/my.tree.nwk') == '/x/y/my.tree_pastml'
