@@ -146,22 +146,55 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------ CPU arm (oracle port)
 
-def cpu_pipeline_rate(flat, masks, has, pis, sfs, K, columns, threads, repeats=1):
-    """node-states/s of the oracle's MPPA pipeline on `columns` columns of the workload with `threads` host threads."""
+def cpu_pipeline_rate(flat, masks, has, pis, sfs, K, columns, threads, repeats=1, check=None):
+    """node-states/s of the oracle's MPPA pipeline on `columns` columns of the workload with `threads` host threads.
+    ``check(c, loglh, probs, map_mask, mppa_mask)`` (optional) receives every column's oracle outputs: the parity
+    check of the GPU results at benchmark scale rides on the work this leg does anyway."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import cpu_oracle
     cpu_oracle.build()
     cpu_oracle.lib()
 
     def one(c):
-        cpu_oracle.marginal_pipeline(flat, cpu_oracle.OracleModel(0, pis[c], sfs[c]), masks[c], has[c])
+        return cpu_oracle.marginal_pipeline(flat, cpu_oracle.OracleModel(0, pis[c], sfs[c]), masks[c], has[c])
 
     t0 = time.perf_counter()
     for _ in range(repeats):
         with ThreadPoolExecutor(max_workers=threads) as pool:
-            list(pool.map(one, columns))
+            results = list(pool.map(one, columns))
     dt = (time.perf_counter() - t0) / repeats
+    if check is not None:
+        for c, r in zip(columns, results):
+            check(c, *r)
     return flat.n_nodes * K * len(columns) / dt, dt
+
+
+class ParityAtScale(object):
+    """GPU outputs of the benchmark workload against the oracle's on the same tree (tolerances of the north star:
+    log-likelihood 1e-10 relative, probabilities 1e-9 absolute, MAP / MPPA state sets and k histogram exact)."""
+
+    def __init__(self, lh, probs, map_mask, mppa_mask, k_hist):
+        self.lh, self.probs, self.map_mask, self.mppa_mask, self.k_hist = lh, probs, map_mask, mppa_mask, k_hist
+        self.cols, self.max_rel_lh, self.max_abs_prob = [], 0., 0.
+        self.map_mismatch = self.mppa_mismatch = self.khist_mismatch = 0
+
+    def __call__(self, c, loglh, probs, map_mask, mppa_mask):
+        self.cols.append(int(c))
+        self.max_rel_lh = max(self.max_rel_lh, abs(float(self.lh[c]) - loglh) / abs(loglh))
+        self.max_abs_prob = max(self.max_abs_prob, float(np.abs(self.probs[:, c, :] - probs).max()))
+        self.map_mismatch += int((self.map_mask[:, c].view(np.uint64) != map_mask).sum())
+        self.mppa_mismatch += int((self.mppa_mask[:, c].view(np.uint64) != mppa_mask).sum())
+        sizes = np.bincount(np.bitwise_count(mppa_mask).astype(np.int64), minlength=self.k_hist.shape[1])
+        self.khist_mismatch += int((sizes != self.k_hist[c]).sum())
+
+    def summary(self):
+        ok = (self.max_rel_lh <= 1e-10 and self.max_abs_prob <= 1e-9 and
+              self.map_mismatch == self.mppa_mismatch == self.khist_mismatch == 0 and len(self.cols) > 0)
+        return {'ok': bool(ok), 'columns_checked': self.cols, 'max_rel_dev_loglh': self.max_rel_lh,
+                'max_abs_dev_probability': self.max_abs_prob, 'map_state_mismatches': self.map_mismatch,
+                'mppa_state_mismatches': self.mppa_mismatch, 'k_hist_mismatches': self.khist_mismatch,
+                'against': 'oracle/pastml_oracle.c (CPU restatement pinned on the reference) on the same tree, '
+                           'outputs of the last end-to-end step (C ABI, host buffers)'}
 
 
 def run_reference(args):
@@ -193,7 +226,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------ B200 arm
 
-def full_ml_acr(flat, masks, has, cols, K, device, sync):
+def full_ml_acr(flat, masks, has, cols, K, device, sync, check_column=None):
     """(fit seconds, reconstruction seconds, device passes, log-likelihood of the first column) of the ML ACR of the
     given columns: the call sequence of ml_acr (ml.py:640-750) on array-native inputs, outputs left on the device."""
     from pastml_b200.annotation import ForestStats
@@ -215,15 +248,38 @@ def full_ml_acr(flat, masks, has, cols, K, device, sync):
     t1 = time.perf_counter()
     params = batch.params()
     pb = batch.problem
-    pb.joint(params, want_states=False)
+    lh_joint, _ = pb.joint(params, want_states=False)
     pb.marginal(params, force_joint=True, want_probs=False, want_masks=False, results_on_device=True)
-    pb.loglik(params, mask_kind=MASK_MAP)
-    pb.mppa_finalize(force_joint=True, want_masks=False)
-    pb.loglik(params, mask_kind=MASK_MPPA)
+    lh_map = pb.loglik(params, mask_kind=MASK_MAP)[0]
+    _, k_hist = pb.mppa_finalize(force_joint=True, want_masks=False)
+    lh_mppa = pb.loglik(params, mask_kind=MASK_MPPA)[0]
     sync()
     t2 = time.perf_counter()
+    parity = None
+    if check_column is not None:
+        # outside the timed region: the oracle replays ml_acr at the FITTED parameters of one column
+        from pastml_b200.engine import MASK_JOINT
+        from oracle import cpu_oracle
+        i = cols.index(check_column)
+        m = models[i]
+        want = cpu_oracle.ml_acr_fixed(flat, cpu_oracle.OracleModel(0, m.frequencies, float(m.sf)), masks[check_column],
+                                       has[check_column], method='MPPA', force_joint=True)
+        rel = lambda a, b: abs(float(a) - float(b)) / abs(float(b))
+        got_masks = {k: pb.get_masks(kind)[:, i] for k, kind in (('joint', MASK_JOINT), ('map', MASK_MAP), ('mppa', MASK_MPPA))}
+        parity = {'column': int(check_column),
+                  'rel_dev_loglh': rel(lhs[i], want['log_likelihood']),
+                  'rel_dev_loglh_joint': rel(lh_joint[i], want['log_likelihood_restricted_JOINT']),
+                  'rel_dev_loglh_map': rel(lh_map[i], want['log_likelihood_restricted_MAP']),
+                  'rel_dev_loglh_mppa': rel(lh_mppa[i], want['log_likelihood_restricted_MPPA']),
+                  'joint_state_mismatches': int((got_masks['joint'] != want['joint_mask']).sum()),
+                  'map_state_mismatches': int((got_masks['map'] != want['map_mask']).sum()),
+                  'mppa_state_mismatches': int((got_masks['mppa'] != want['mppa_mask']).sum()),
+                  'k_hist_mismatches': int((k_hist[i] != want['k_hist']).sum()),
+                  'against': 'oracle ml_acr_fixed at the fitted sf and frequencies of this column'}
+        parity['ok'] = bool(max(parity[k] for k in parity if k.startswith('rel_dev')) <= 1e-10 and
+                            sum(parity[k] for k in parity if k.endswith('mismatches')) == 0)
     batch.close()
-    return t1 - t0, t2 - t1, passes, float(lhs[0])
+    return t1 - t0, t2 - t1, passes, float(lhs[0]), parity
 
 
 def run_subtree_sharded(args):
@@ -416,11 +472,14 @@ def run_b200(args):
     ml_fit = None
     if not args.no_fit:
         barrier()
-        fit_s, rec_s, passes, lh0 = full_ml_acr(flat, masks, has, list(range(C)), K, local_rank, torch.cuda.synchronize)
+        fit_s, rec_s, passes, lh0, fit_parity = full_ml_acr(
+            flat, masks, has, list(range(C)), K, local_rank, torch.cuda.synchronize,
+            check_column=0 if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None)
         barrier()
         fit_s = max_over_ranks(fit_s, device='cuda')
         rec_s = max_over_ranks(rec_s, device='cuda')
         ml_fit = {'seconds': fit_s + rec_s, 'fit_seconds': fit_s, 'reconstruction_seconds': rec_s, 'device_passes': int(passes),
+                  'parity_at_fitted_parameters': fit_parity,
                   'what': 'two-stage L-BFGS-B fit of sf + {} frequencies for all {} columns of this rank in lock step '
                           '(finite-difference gradients batched as parameter sets), then JOINT + marginal + MAP + MPPA + '
                           'restricted-likelihood passes'.format(K - 1, C)}
@@ -433,7 +492,7 @@ def run_b200(args):
             mine = list(range(lo, hi))
             barrier()
             if mine:
-                f1, r1, p1, _ = full_ml_acr(flat0, masks0, has0, mine, K, local_rank, torch.cuda.synchronize)
+                f1, r1, p1, _, _ = full_ml_acr(flat0, masks0, has0, mine, K, local_rank, torch.cuda.synchronize)
             else:
                 f1 = r1 = 0.
                 p1 = 0
@@ -491,7 +550,9 @@ def run_b200(args):
         cores = os.cpu_count() or 1
         threads = max(1, min(cores, C))
         cols = list(range(threads))
-        rate, dt = cpu_pipeline_rate(flat, masks, has, pis, sfs, K, cols, threads)
+        parity = ParityAtScale(h_lh, h_probs, h_map, h_mppa, h_hist)
+        rate, dt = cpu_pipeline_rate(flat, masks, has, pis, sfs, K, cols, threads, check=parity)
+        line['parity_at_scale'] = parity.summary()
         line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                                 'sample': 'one step of {} of the {} columns of the same tree, one thread per column '
                                           '({:.1f} s)'.format(len(cols), C, dt), 'host_cores': cores}

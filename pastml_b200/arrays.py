@@ -20,6 +20,7 @@ from pastml_b200.ml import (ColumnBatch, fit_batch, reconstruct_batch, is_ml, MP
 from pastml_b200.engine import Problem
 from pastml_b200.models import model2class, F81, HKY, JTT, HKY_STATES, JTT_STATES
 from pastml_b200.parsimony import is_parsimonious, parsimony_on_problem, MP_METHODS
+from pastml_b200.tree import newick_safe
 
 
 def table_masks(flat, df, column, states=None):
@@ -175,7 +176,7 @@ def write_named_tree(results, flat, path):
     for v in range(N):
         if parent[v] >= 0:
             dates[v] = dates[parent[v]] + float(dist[v])
-    labels = ['{}:{:g}[&&NHX:date={}'.format(flat.names[v], float(dist[v]), dates[v]) for v in range(N)]
+    labels = ['{}:{:g}[&&NHX:date={}'.format(newick_safe(flat.names[v]), float(dist[v]), dates[v]) for v in range(N)]
     for r in results:
         states = np.asarray(r[STATES], dtype=object)
         order = np.argsort(states.astype(str), kind='stable')
@@ -185,7 +186,7 @@ def write_named_tree(results, flat, path):
         pieces = []
         for m in uniq.tolist():
             chosen = [n for n, k in zip(names_sorted, order.tolist()) if (m >> k) & 1]
-            pieces.append(':{}={}'.format(r[CHARACTER], '|'.join(chosen)) if chosen else '')
+            pieces.append(':{}={}'.format(r[CHARACTER], newick_safe('|'.join(chosen))) if chosen else '')
         labels = [label + pieces[i] for label, i in zip(labels, inverse.tolist())]
     # children are contiguous in level order: assemble bottom-up, one string per subtree
     text = [None] * N

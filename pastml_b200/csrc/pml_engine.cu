@@ -350,8 +350,10 @@ void run_graphed(pml_problem *p, const std::array<long long, 6> &key, F enqueue)
 
 void run_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marginal, int alter, bool keep_ptr,
                    int n_lanes = 0) {
+    // everything that selects kernels at capture time belongs to the key: eig_shared decides between the tensor-core
+    // sweep (one decomposition for all lanes) and the per-lane kernels, and it changes when the frequencies do
     run_graphed(p, {n_lanes > 0 ? 2 : 0, n_lanes > 0 ? n_lanes : n_sets, (long long) (uintptr_t) mask, is_marginal, alter,
-                    (keep_ptr ? 1 : 0) + 2 * p->n_ext},
+                    (keep_ptr ? 1 : 0) + 2 * (p->eig_shared ? 1 : 0) + 4 * (long long) p->n_ext},
                 [&]() { enqueue_bottom_up(p, n_sets, mask, is_marginal, alter, keep_ptr, n_lanes); });
 }
 

@@ -167,13 +167,21 @@ class LockstepEvaluator(object):
 
     def _flush(self):
         cols = sorted(self.pending)
-        n_lanes = lane_list_size(sum(len(self.pending[c]) for c in cols))
-        if self.batch.lane_lists and n_lanes <= self.batch.max_sets * self.batch.C:
-            self._flush_lanes(cols)
-        else:
-            self._flush_grid(cols)
-        self.pending.clear()
-        self.cond.notify_all()
+        try:
+            n_lanes = lane_list_size(sum(len(self.pending[c]) for c in cols))
+            if self.batch.lane_lists and n_lanes <= self.batch.max_sets * self.batch.C:
+                self._flush_lanes(cols)
+            else:
+                self._flush_grid(cols)
+        except BaseException as e:
+            # the device pass itself failed (engine error, out of memory, a zero likelihood the batch did not
+            # tolerate): every column that waits for this pass gets the error instead of waiting forever
+            for c in cols:
+                self.errors[c] = e
+                self.results[c] = None
+        finally:
+            self.pending.clear()
+            self.cond.notify_all()
 
     def _flush_grid(self, cols):
         """One pass over (parameter sets) x (all columns): columns without a request ride along on their last block."""
@@ -236,10 +244,12 @@ class LockstepEvaluator(object):
             return self.results[c]
 
     def retire(self, c):
+        """Column c takes no further part (fitted, or failed); never raises (it runs in a ``finally``)."""
         with self.cond:
             self.active.discard(c)
+            self.pending.pop(c, None)
             if self.pending and set(self.pending) >= self.active:
-                self._flush()
+                self._flush()   # delivers failures through self.errors
 
 
 class ColumnBatch(object):

@@ -133,3 +133,26 @@ def simulate_tip_masks(flat, K, n_columns, rng, pi=None, changes_per_avg_branch=
             h[drop] = 0
         masks[c], has[c], pis[c], sfs[c] = m, h, p, sf
     return masks, has, pis, sfs
+
+
+def forest(flats):
+    """Merges forests (usually single trees) into ONE level-ordered :class:`FlatForest`: depth level d of the result
+    is the concatenation of the level-d nodes of every input, input by input, so siblings stay contiguous and parents
+    stay sorted.  The stand-in for a set of bootstrap trees analysed together (``Sum_trees``, ml.py:206-207)."""
+    n_levels = max(f.n_levels for f in flats)
+    total = sum(f.n_nodes for f in flats)
+    parent = np.empty(total, dtype=np.int32)
+    dist = np.empty(total, dtype=np.float64)
+    new_id = [np.empty(f.n_nodes, dtype=np.int64) for f in flats]
+    pos = 0
+    for lvl in range(n_levels):
+        for f, ids in zip(flats, new_id):
+            if lvl >= f.n_levels:
+                continue
+            lo, hi = int(f.level_ptr[lvl]), int(f.level_ptr[lvl + 1])
+            ids[lo:hi] = np.arange(pos, pos + hi - lo)
+            par = f.parent[lo:hi]
+            parent[pos:pos + hi - lo] = np.where(par >= 0, ids[np.maximum(par, 0)], -1)
+            dist[pos:pos + hi - lo] = f.dist[lo:hi]
+            pos += hi - lo
+    return FlatForest(parent, dist)

@@ -20,6 +20,8 @@ from collections import deque
 
 import logging
 
+import re
+
 import numpy as np
 
 DEFAULT_DIST = 1.0
@@ -367,17 +369,26 @@ class Tree(object):
 TreeNode = Tree
 
 
+# characters that cannot appear in an unquoted newick label or an NHX value: ete3 (which the reference writes its
+# trees with) replaces each of them by an underscore, so that the files stay parseable
+_ILLEGAL_NEWICK = re.compile(r'[:;(),\[\]\t\n\r=]')
+
+
+def newick_safe(text):
+    return _ILLEGAL_NEWICK.sub('_', str(text))
+
+
 def _fmt_name(name, formatter, quoted):
     text = formatter % (name if name is not None else '')
     if quoted:
         return '"{}"'.format(text)
-    return text
+    return newick_safe(text)
 
 
 def _fmt_feature(value):
     if isinstance(value, (set, frozenset, list, tuple)):
-        return '|'.join(str(_) for _ in sorted(value, key=str))
-    return str(value)
+        return newick_safe('|'.join(str(_) for _ in sorted(value, key=str)))
+    return newick_safe(value)
 
 
 def _copy_value(value):

@@ -461,6 +461,67 @@ def test_lockstep_fit_reports_a_failing_lane_to_its_column():
     assert any(kind == 'lanes' for kind, _ in batch.calls)
 
 
+def test_lockstep_fit_propagates_a_failing_device_pass():
+    """When the device pass itself raises (engine error, out of memory), every column thread gets the exception and
+    fit_batch returns it to the caller instead of hanging on the rendezvous."""
+    import threading
+    from pastml_b200.ml import fit_batch
+    from pastml_b200.annotation import ForestStats
+    from pastml_b200.models import F81Model
+    from pastml_b200.tree import FlatForest
+
+    class Broken(_FakeBatch):
+        def loglik_lanes(self, params, lane_columns):
+            if len(self.calls) >= 3:
+                raise RuntimeError('device pass failed')
+            return _FakeBatch.loglik_lanes(self, params, lane_columns)
+
+    flat = FlatForest(np.array([-1, 0, 0, 1, 1], dtype=np.int32), np.array([0., 1., 2., 1., 1.]))
+    fs = ForestStats(flat=flat)
+    models = [F81Model(states=np.array(['a', 'b', 'c']), forest_stats=fs, character='c%d' % c) for c in range(4)]
+    batch = Broken(models, True)
+    outcome = []
+
+    def run():
+        try:
+            fit_batch(batch, [np.full(3, 1. / 3)] * 4)
+            outcome.append(None)
+        except BaseException as e:
+            outcome.append(e)
+
+    t = threading.Thread(target=run, daemon=True)
+    t.start()
+    t.join(timeout=60)
+    assert not t.is_alive(), 'fit_batch hangs when the device pass raises'
+    assert isinstance(outcome[0], RuntimeError) and 'device pass failed' in str(outcome[0])
+
+
+def test_newick_writers_sanitise_names_and_feature_values(tmp_path):
+    """ete3 (the reference's writer) replaces the characters that would break a newick / NHX file by underscores, in
+    names and in feature values: states such as 'Congo (DRC)' or 'Korea, South' must not corrupt named.tree_*.nwk."""
+    from pastml_b200.arrays import write_named_tree
+    from pastml_b200.ml import STATE_MASKS
+    from pastml_b200.pipeline import annotate_dist_to_root
+    from pastml_b200.tree import read_tree, name_tree, flatten_forest
+    root = read_tree('((a:1,b:2):1,(c:1,d:1):2);')
+    name_tree(root)
+    root.children[0].name = 'odd;name'
+    annotate_dist_to_root([root])
+    flat = flatten_forest([root])
+    states = np.array(['Congo (DRC)', 'Korea, South', 'x=y'])
+    masks = np.array([3, 1, 2, 4, 1, 2, 7], dtype=np.uint64)
+    for node, m in zip(flat.nodes, masks.tolist()):
+        node.add_feature('Country', {states[k] for k in range(3) if (m >> k) & 1})
+    text = root.write(format_root_node=True, format=3, features=['date', 'Country'])
+    assert 'Country=Congo _DRC_|Korea_ South' in text and 'x_y' in text and 'odd_name' in text
+    assert re.search(r'Country=[^:\]]*[(),;=]', text) is None
+    write_named_tree([{'character': 'Country', 'states': states, 'method': 'MPPA', STATE_MASKS: masks}], flat,
+                     str(tmp_path / 'named.nwk'))
+    assert open(tmp_path / 'named.nwk').read() == text
+    back = read_tree(text)   # and it parses again
+    assert len(list(back.traverse())) == 7
+
+
 def test_pipeline_input_validation_on_cpu(tmp_path):
     """validate_input (acr.py:677-822): column checks, id matching, states and naming -- no engine involved."""
     from pastml_b200.pipeline import validate_input, get_pastml_parameter_file, get_pastml_marginal_prob_file, \
