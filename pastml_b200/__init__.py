@@ -43,6 +43,21 @@ def value2list(n, value, default_value):
     return value + [default_value] * (n - len(value))
 
 
+def datetime2numeric(d):
+    """Calendar date -> decimal year (the day's start as a fraction of its year, leap years included)."""
+    from datetime import datetime
+    start, end = datetime(d.year, 1, 1), datetime(d.year + 1, 1, 1)
+    return d.year + (datetime(d.year, d.month, d.day) - start).days / (end - start).days
+
+
+def numeric2datetime(x):
+    """Decimal year -> calendar date (inverse of :func:`datetime2numeric`, rounding to the nearest day)."""
+    from datetime import datetime, timedelta
+    year = int(x)
+    start, end = datetime(year, 1, 1), datetime(year + 1, 1, 1)
+    return start + timedelta(days=round((x - year) * (end - start).days))
+
+
 def _set_up_pastml_logger(verbose):
     import logging
     logger = logging.getLogger('pastml')

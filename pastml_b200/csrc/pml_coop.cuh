@@ -126,6 +126,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 __host__ __device__ constexpr int round16(int x) { return (x + 15) & ~15; }
 
+// Programmatic dependent launch: the level kernels of a sweep are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the blocks of level N + 1 become resident while level N drains and
+// run their prologue (parameter staging, barrier set-up, first descriptors -- nothing level N produces) before
+// pdl_wait(), which returns once level N has completed and its stores are visible.  Without the launch attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // dynamic shared memory of the TMA variants (host side of the layout the kernels carve up)
 __host__ __device__ constexpr int td_tma_sub_bytes(int K, int C) { return 3 * (K * C * 8 + C * 4); }
 inline size_t td_tma_smem(int K, int C, int G) {
@@ -443,10 +451,12 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT, TMA)) td_coop_
             bulk_g2s(stage + 3 * VB + 2 * EB, a.td_ex + (size_t) ps * C, EB, bar);
         }
     };
+    if constexpr (TMA) pdl_launch_dependents();
     if (base < n_nodes) {
         if constexpr (TMA) {
             const int n0 = node_of(base);
             cu_desc = a.t.td_desc[n0];
+            pdl_wait();   // everything above is independent of the previous level
             issue(cu_desc);
             cu_raw = a.mask[(size_t) n0 * C + c];
             if (fj) cu_js = a.joint_state[(size_t) n0 * C + c];
@@ -559,28 +569,28 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT, TMA)) td_coop_
         {
             // the reciprocals: the range check of fast_rcp is hoisted out of the loop (one vote per warp instead of a
             // branch per element); tiny / huge contributions take the exact path for the whole batch
+            // contribution_k = e L_k + (1 - e) s >= (1 - e) s: when that floor is a normal number away from the ends of
+            // the exponent range (practically always: only zero-length branches and vanishing vectors fail it), every
+            // contribution is, and the reciprocals take the short path without a range check per element
             const double os = ome * s;
-            bool plain = true;
-#pragma unroll
-            for (int i = 0; i < KT; ++i) {
-                q[i] = fma(e, Lc[i], os);   // >= 0: e in [0, 1] and the inputs are non-negative
-                plain = plain && (!(q[i] > 0.) || (q[i] > 0x1p-900 && q[i] < 0x1p+900));
-            }
-            if (__all_sync(kFullMask, plain)) {
+            if (__all_sync(kFullMask, os > 0x1p-900 && s < 0x1p+800)) {
 #pragma unroll
                 for (int i = 0; i < KT; ++i) {
-                    const double cv = q[i];
+                    const double cv = fma(e, Lc[i], os);
                     double rr;
                     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rr) : "d"(cv));
                     double tt = fma(-cv, rr, 1.);
                     rr = fma(rr, tt, rr);
                     tt = fma(-cv, rr, 1.);
                     rr = fma(rr, tt, rr);
-                    q[i] = (cv > 0.) ? X[i] * rr : X[i];
+                    q[i] = X[i] * rr;
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < KT; ++i) q[i] = (q[i] > 0.) ? X[i] * fast_rcp(q[i]) : X[i];
+                for (int i = 0; i < KT; ++i) {
+                    const double cv = fma(e, Lc[i], os);   // >= 0: e in [0, 1] and the inputs are non-negative
+                    q[i] = (cv > 0.) ? X[i] * fast_rcp(cv) : X[i];
+                }
             }
         }
         double s2 = 0.;

@@ -72,7 +72,7 @@ void td_tma_launch(cudaStream_t st, const TdArgs &a, int n0, int nn) {
     const size_t sh = td_tma_smem(G * KT, JT, G);
     static bool done = false;
     prefer_smem(td_coop_kernel<KT, G, JT, KX, true>, sh, done);
-    td_coop_kernel<KT, G, JT, KX, true><<<coop_grid(nn, JT, kTmaBlocks), kCoopBlock, sh, st>>>(a, n0, nn);
+    launch_pdl(td_coop_kernel<KT, G, JT, KX, true>, dim3(coop_grid(nn, JT, kTmaBlocks)), dim3(kCoopBlock), sh, st, a, n0, nn);
 }
 #endif
 }  // namespace

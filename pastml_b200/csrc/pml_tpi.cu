@@ -29,7 +29,7 @@ void bu_launch_t(cudaStream_t st, const BuArgs &a, int s0, int ns) {
     long long cap = (148LL * resident + tiles - 1) / tiles;   // persistent grid: one resident wave over all tiles
     if (cap < 1) cap = 1;
     if (gx > cap) gx = cap;
-    bu_tpi_kernel<JT><<<dim3((unsigned) gx, (unsigned) tiles), block, sh, st>>>(a, s0, ns);
+    launch_pdl(bu_tpi_kernel<JT>, dim3((unsigned) gx, (unsigned) tiles), dim3(block), sh, st, a, s0, ns);
 }
 
 }  // namespace
