@@ -181,16 +181,6 @@ int pml_trim_memory(void);
  * with CUDA events on the handle's stream (ms), and the number of kernels launched. */
 int pml_last_call_stats(pml_problem *p, double *device_ms, int64_t *kernel_launches);
 
-/* Host-only view of the schedule of the single-launch sweeps (pastml_b200/csrc/pml_flow.cu): the order in which the
- * persistent kernels hand out the nodes of a forest, for tests and tools; no device is touched.  kind 0 = bottom-up
- * (entries are internal-node slots = ranks among the nodes that have children), 1 = top-down (entries are node ids).
- * parent[n_nodes] in level order as for pml_problem_create.  Returns the number of schedule entries (a multiple of
- * nodes_per_batch; padding entries are -1) and copies at most `capacity` of them into out_order; out_chunk_of_batch
- * (capacity / nodes_per_batch entries, may be null) receives the ticket that hands out every batch.  Negative on a
- * malformed forest. */
-int64_t pml_flow_schedule(int32_t kind, int32_t n_nodes, const int32_t *parent, int32_t nodes_per_batch,
-                          int32_t parents_per_batch, int32_t *out_order, int32_t *out_chunk_of_batch, int64_t capacity);
-
 /* Device-resident variant used by bench.py: runs a pass n_iter times back to back on resident inputs and returns
  * the average / minimum device time per pass (CUDA events on the handle's stream).  which: 0 = bottom-up
  * objective (annotation masks, marginal, alter) for n_sets parameter sets; 1 = the marginal sweep (bottom-up +

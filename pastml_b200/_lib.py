@@ -16,7 +16,6 @@ EXPORTS = ['pml_last_error', 'pml_version', 'pml_device_count', 'pml_param_strid
            'pml_zero_likelihood_all', 'pml_trim_memory', 'pml_get_root_partials', 'pml_set_tip_partials',
            'pml_get_tip_td', 'pml_set_root_td',
            'pml_last_call_stats', 'pml_bench_pass', 'pml_supports_lane_lists', 'pml_loglik_lanes', 'pml_get_bottom_up',
-           'pml_flow_schedule',
            'pml_newick_last_error', 'pml_newick_parse', 'pml_newick_num_nodes', 'pml_newick_num_trees',
            'pml_newick_names_bytes', 'pml_newick_name_nodes', 'pml_newick_fill', 'pml_newick_free']
 
@@ -52,8 +51,6 @@ def load():
     lib.pml_problem_create.argtypes = [i32, vp, vp, i32, i32, i32, vp, vp, i32, i32, C.POINTER(vp)]
     lib.pml_problem_destroy.restype = None
     lib.pml_problem_destroy.argtypes = [vp]
-    lib.pml_flow_schedule.restype = C.c_int64
-    lib.pml_flow_schedule.argtypes = [i32, i32, vp, i32, i32, vp, vp, C.c_int64]
     lib.pml_loglik.restype = C.c_int
     lib.pml_loglik.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.pml_supports_lane_lists.restype = C.c_int

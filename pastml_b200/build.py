@@ -23,23 +23,10 @@ INST_SRC = os.path.join(CSRC, 'pml_inst.cu')
 COOP_SRC = os.path.join(CSRC, 'pml_coop_inst.cu')
 TPI_SRC = os.path.join(CSRC, 'pml_tpi.cu')
 MMA_SRC = os.path.join(CSRC, 'pml_mma.cu')
-FLOW_SRC = os.path.join(CSRC, 'pml_flow.cu')
-FLOW_TD_SRC = os.path.join(CSRC, 'pml_flow_td_inst.cu')
-FLOW_TDI_SRC = os.path.join(CSRC, 'pml_flow_tdi_inst.cu')
 NEWICK_SRC = os.path.join(CSRC, 'pml_newick.cpp')
 HEADERS = [os.path.join(CSRC, 'pml_kernels.cuh'), os.path.join(CSRC, 'pml_coop.cuh'), os.path.join(CSRC, 'pml_tpi.cuh'),
            os.path.join(CSRC, 'pml_launch.h'),
            os.path.join(os.path.dirname(HERE), 'include', 'pastml_b200.h')]
-# the single-launch sweeps: their headers only enter the digests of the translation units that include them
-FLOW_HEADERS = [os.path.join(CSRC, 'pml_flow.cuh'), os.path.join(CSRC, 'pml_flow_host.h')]
-FLOW_TDI_HEADERS = [os.path.join(CSRC, 'pml_flow_tdi.cuh')]
-
-# states per thread of the single-launch top-down sweep (two threads per item); the second field asks for the
-# variants that know K == 2 KT at compile time; keep in sync with PML_FTD_ALL in pml_flow.cu
-FLOW_TD_KTS = [(1, 1), (2, 1), (3, 0), (4, 0), (5, 1), (6, 1), (8, 0), (10, 1), (12, 0), (16, 0)]
-# register-array lengths of the thread-per-item single-launch top-down sweep (second field: also the K == KP variants);
-# keep in sync with PML_FTDI_ALL in pml_flow.cu
-FLOW_TDI_KPS = [(2, 1), (4, 1), (8, 0), (10, 1), (12, 0), (16, 0), (20, 1), (24, 0), (32, 0)]
 
 # (family, KP): 0 = F81/JC/EFT, 1 = HKY, 2 = eigen-decomposition models (CUSTOM_RATES, JTT); keep in sync with
 # PML_ALL in pml_engine.cu
@@ -94,16 +81,7 @@ def build(force=False, verbose=False, jobs=None):
         for f in os.listdir(OBJ_DIR):
             os.remove(os.path.join(OBJ_DIR, f))
     flags = ' '.join(NVCC_FLAGS)
-    tasks = [(ENGINE_SRC, os.path.join(OBJ_DIR, 'pml_engine.o'), [], _digest([ENGINE_SRC] + HEADERS + FLOW_HEADERS, flags))]
-    tasks.append((FLOW_SRC, os.path.join(OBJ_DIR, 'pml_flow.o'), [], _digest([FLOW_SRC] + HEADERS + FLOW_HEADERS, flags)))
-    flow_td_digest = _digest([FLOW_TD_SRC] + HEADERS + FLOW_HEADERS, flags)
-    for kt, kx in FLOW_TD_KTS:
-        tasks.append((FLOW_TD_SRC, os.path.join(OBJ_DIR, 'pml_flow_td_{}.o'.format(kt)),
-                      ['-DPML_KT={}'.format(kt), '-DPML_KX={}'.format(kx)], flow_td_digest))
-    flow_tdi_digest = _digest([FLOW_TDI_SRC] + HEADERS + FLOW_HEADERS + FLOW_TDI_HEADERS, flags)
-    for kp, kx in FLOW_TDI_KPS:
-        tasks.append((FLOW_TDI_SRC, os.path.join(OBJ_DIR, 'pml_flow_tdi_{}.o'.format(kp)),
-                      ['-DPML_KP={}'.format(kp), '-DPML_KX={}'.format(kx)], flow_tdi_digest))
+    tasks = [(ENGINE_SRC, os.path.join(OBJ_DIR, 'pml_engine.o'), [], _digest([ENGINE_SRC] + HEADERS, flags))]
     tasks.append((TPI_SRC, os.path.join(OBJ_DIR, 'pml_tpi.o'), [], _digest([TPI_SRC] + HEADERS, flags)))
     tasks.append((MMA_SRC, os.path.join(OBJ_DIR, 'pml_mma.o'), [], _digest([MMA_SRC] + HEADERS, flags)))
     tasks.append((NEWICK_SRC, os.path.join(OBJ_DIR, 'pml_newick.o'), [], _digest([NEWICK_SRC, HEADERS[-1]], flags)))

@@ -126,13 +126,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 __host__ __device__ constexpr int round16(int x) { return (x + 15) & ~15; }
 
-// Programmatic dependent launch: the level kernels of a sweep are launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization, so the blocks of level N + 1 become resident while level N drains and
-// run their prologue (parameter staging, barrier set-up, first descriptors -- nothing level N produces) before
-// pdl_wait(), which returns once level N has completed and its stores are visible.  Without the launch attribute both
-// instructions are no-ops.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // dynamic shared memory of the TMA variants (host side of the layout the kernels carve up)
 __host__ __device__ constexpr int td_tma_sub_bytes(int K, int C) { return 3 * (K * C * 8 + C * 4); }
@@ -288,7 +281,9 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT)) bu_coop_kerne
         len = a.t.bu_desc[2 * slot + 1];
         node = a.t.int_nodes[slot];
     };
+    pdl_launch_dependents();
     if (base < n_slots) load_desc(base, nx_top, nx_len, nx_node);
+    pdl_wait();   // everything above is independent of the previous level
     for (; base < n_slots; base += stride) {
         const int sl = base + cl.sub;
         const bool on = cl.lane_on && sl < n_slots;
@@ -464,6 +459,10 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT, TMA)) td_coop_
         } else {
             nx_desc = a.t.td_desc[node_of(base)];
         }
+    }
+    if constexpr (!TMA) {
+        pdl_launch_dependents();
+        pdl_wait();
     }
     for (; base < n_nodes; base += stride) {
         const int nd = base + cl.sub;

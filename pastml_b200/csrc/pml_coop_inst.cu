@@ -49,20 +49,20 @@ void bu_launch(cudaStream_t st, const BuArgs &a, int s0, int ns) {
         unsigned gx = coop_grid(ns, JT);
         const unsigned per_row = (148u * PML_COOP_GRID + tiles - 1) / tiles;
         if (gx > per_row) gx = per_row;
-        bu_coop_kernel<KT, G, JT, KX, true><<<dim3(gx, tiles), kCoopBlock, sh, st>>>(a, s0, ns);
+        launch_pdl(bu_coop_kernel<KT, G, JT, KX, true>, dim3(gx, tiles), dim3(kCoopBlock), sh, st, a, s0, ns);
         return;
     }
     const size_t sh = sizeof(double) * (4 + a.ln.K) * a.ln.J;
     if (sh > 48 * 1024)
         cudaFuncSetAttribute(bu_coop_kernel<KT, G, JT, KX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
-    bu_coop_kernel<KT, G, JT, KX, false><<<coop_grid(ns, a.ln.J), kCoopBlock, sh, st>>>(a, s0, ns);
+    launch_pdl(bu_coop_kernel<KT, G, JT, KX, false>, dim3(coop_grid(ns, a.ln.J)), dim3(kCoopBlock), sh, st, a, s0, ns);
 }
 
 void td_launch(cudaStream_t st, const TdArgs &a, int n0, int nn) {
     const size_t sh = sizeof(double) * (4 + a.ln.K) * a.ln.C + sizeof(unsigned) * a.ln.C * (a.ln.K + 1);
     if (sh > 48 * 1024)
         cudaFuncSetAttribute(td_coop_kernel<KT, G, JT, KX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
-    td_coop_kernel<KT, G, JT, KX><<<coop_grid(nn, a.ln.C), kCoopBlock, sh, st>>>(a, n0, nn);
+    launch_pdl(td_coop_kernel<KT, G, JT, KX>, dim3(coop_grid(nn, a.ln.C)), dim3(kCoopBlock), sh, st, a, n0, nn);
 }
 
 #if PML_JT > 0

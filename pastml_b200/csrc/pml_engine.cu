@@ -12,7 +12,6 @@
 
 #include "../../include/pastml_b200.h"
 #include "pml_launch.h"
-#include "pml_flow.cuh"
 
 using namespace pml;
 
@@ -189,20 +188,6 @@ struct pml_problem {
         return TreeDev{N, NI, parent.ptr, first_child.ptr, n_children.ptr, slot.ptr, int_nodes.ptr, dist.ptr,
                        zc_index.ptr, fc_slot.ptr, nc_slot.ptr, pslot.ptr, n_root_slots, bu_desc.ptr, td_desc.ptr};
     }
-    // single-launch ("dataflow") sweeps of the F81 family: own vector buffers (exponent row inside the run), ready
-    // flags, control block, schedules per batch geometry
-    struct FlowSchedDev {
-        DevBuf<int4> desc, seg;
-        int n_seg = 0, n_batches = 0, n_chunks = 0;
-        FlowSched view() const { return FlowSched{desc.ptr, seg.ptr, n_seg, n_batches, n_chunks}; }
-    };
-    std::vector<int> h_parent;                 // host copy of the topology the top-down schedules are built from
-    std::map<int, FlowSchedDev> flow_bu_sched, flow_td_sched;   // key: nodes per batch (x 64 + parent regions)
-    DevBuf<double> fbu, ftd;                   // [NI][T][K + 1][JT]
-    DevBuf<unsigned> flow_ctl, flow_bu_flags, flow_td_flags;
-    int flow_cap_lanes = 0, flow_max_tiles = 0;   // padded lane capacity of fbu, most tiles any pass can have
-    int bu_state = 0, bu_state_jt = 0;         // where the current bottom-up state lives: 0 none, 1 level kernels' buffers,
-                                               // 2 flow buffer (one parameter set, bu_state_jt lanes per tile)
     // subtree sharding: external tip vectors / root top-down vectors
     DevBuf<int> lane_col;      // explicit column per lane (pml_loglik_lanes), B * C entries, allocated on first use
     bool eig_shared = false;   // EIG: every lane of the uploaded parameters carries the same d, A, A^-1
@@ -231,126 +216,6 @@ inline bool tpi_enabled() {   // PASTML_B200_NO_TPI=1: the cooperative kernels i
 inline bool tma_enabled() {   // PASTML_B200_NO_TMA=1: the register-path cooperative kernels (A/B measurements)
     static const bool off = getenv("PASTML_B200_NO_TMA") != nullptr;
     return !off;
-}
-
-inline bool flow_enabled() {   // PASTML_B200_NO_FLOW=1: the level-synchronous sweeps instead (A/B measurements)
-    static const bool off = getenv("PASTML_B200_NO_FLOW") != nullptr;
-    return !off;
-}
-// the single-launch sweeps serve the F81 family without external tables, 2 <= K <= 32
-bool flow_ok(const pml_problem *p) {
-    return flow_enabled() && p->kind == PML_MODEL_F81 && !p->ext_index.ptr && !p->have_root_td && p->K >= 2 && p->K <= 32;
-}
-// lanes per tile of the marginal pipeline (bottom-up + top-down on one parameter set), 0 = level kernels
-int flow_jt_marginal(const pml_problem *p) {
-    if (!flow_ok(p)) return 0;
-    const int jt = flow_tile_lanes(p->C, 16);
-    return flow_td_available(p->K, jt) ? jt : 0;
-}
-int flow_jt_for(const pml_problem *p, int n_sets, int n_lanes) {
-    if (!flow_ok(p)) return 0;
-    if (n_lanes == 0 && n_sets == 1) return flow_jt_marginal(p);
-    return flow_tile_lanes(n_lanes > 0 ? n_lanes : n_sets * p->C, 32);
-}
-
-int ensure_legacy_bu(pml_problem *p) {
-    const size_t J = (size_t) p->B * p->C;
-    if (!p->bu.ptr) CUDA_TRY(p->bu.alloc(std::max<size_t>((size_t) p->NI * p->K * J, 1)));
-    if (!p->bu_ex.ptr) CUDA_TRY(p->bu_ex.alloc(std::max<size_t>((size_t) p->NI * J, 1)));
-    return PML_OK;
-}
-
-// buffers and the schedule of a flow bottom-up pass with `jt` lanes per tile (outside any stream capture)
-int ensure_flow_bu(pml_problem *p, int jt) {
-    if (!p->flow_cap_lanes) {
-        int cap = 2, tiles = 1;
-        for (int J = 1; J <= p->B * p->C; ++J) {
-            for (int max_jt : {16, 32}) {
-                const int t = flow_tile_lanes(J, max_jt);
-                cap = std::max(cap, (J + t - 1) / t * t);
-                tiles = std::max(tiles, (J + t - 1) / t);
-            }
-        }
-        p->flow_cap_lanes = cap;
-        p->flow_max_tiles = tiles;
-    }
-    if (!p->fbu.ptr) CUDA_TRY(p->fbu.alloc(std::max<size_t>((size_t) p->NI * (p->K + 1) * p->flow_cap_lanes, 1)));
-    if (!p->flow_ctl.ptr) {
-        const size_t n = (size_t) flow_ctl_word_count(p->flow_max_tiles);
-        CUDA_TRY(p->flow_ctl.alloc(n));
-        CUDA_TRY(cudaMemsetAsync(p->flow_ctl.ptr, 0, n * sizeof(unsigned), p->stream));
-    }
-    if (!p->flow_bu_flags.ptr) {
-        const size_t n = std::max<size_t>((size_t) p->NI * p->flow_max_tiles, 1);
-        CUDA_TRY(p->flow_bu_flags.alloc(n));
-        CUDA_TRY(cudaMemsetAsync(p->flow_bu_flags.ptr, 0, n * sizeof(unsigned), p->stream));
-    }
-    const int npw = 32 / jt;
-    if (!p->flow_bu_sched.count(npw)) {
-        FlowHostSched hs;
-        flow_schedule_bu(p->level_ptr, p->h_parent.data(), npw, hs);
-        pml_problem::FlowSchedDev &d = p->flow_bu_sched[npw];
-        DevBuf<int> order;
-        CUDA_TRY(order.alloc(std::max<size_t>(hs.order.size(), 1)));
-        CUDA_TRY(d.desc.alloc(std::max<size_t>(3 * hs.order.size(), 1)));
-        CUDA_TRY(d.seg.alloc(std::max<size_t>(hs.seg.size() / 4, 1)));
-        if (!hs.order.empty()) {
-            CUDA_TRY(cudaMemcpyAsync(order.ptr, hs.order.data(), hs.order.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-            CUDA_TRY(cudaMemcpyAsync(d.seg.ptr, hs.seg.data(), hs.seg.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-            flow_gather_bu(p->stream, (long long) hs.order.size(), order.ptr, p->bu_desc.ptr, p->int_nodes.ptr, d.desc.ptr);
-        }
-        CUDA_TRY(cudaStreamSynchronize(p->stream));   // hs and order go out of scope
-        d.n_seg = hs.n_seg; d.n_batches = hs.n_batches; d.n_chunks = hs.n_chunks;
-    }
-    return PML_OK;
-}
-
-int ensure_flow_td(pml_problem *p, int jt) {
-    if (!p->ftd.ptr) {
-        const int lanes = (p->C + jt - 1) / jt * jt;
-        CUDA_TRY(p->ftd.alloc(std::max<size_t>((size_t) p->NI * (p->K + 1) * lanes, 1)));
-    }
-    if (!p->flow_td_flags.ptr) {
-        const size_t n = std::max<size_t>((size_t) p->NI * ((p->C + 1) / 2), 1);
-        CUDA_TRY(p->flow_td_flags.alloc(n));
-        CUDA_TRY(cudaMemsetAsync(p->flow_td_flags.ptr, 0, n * sizeof(unsigned), p->stream));
-    }
-    int npw = 0, npar = 0;
-    flow_td_geometry(jt, &npw, &npar);
-    const int key = npw * 64 + npar;
-    if (!p->flow_td_sched.count(key)) {
-        FlowHostSched hs;
-        flow_schedule_td(p->level_ptr, p->h_parent.data(), npw, npar, hs);
-        pml_problem::FlowSchedDev &d = p->flow_td_sched[key];
-        DevBuf<int> order, aux;
-        CUDA_TRY(order.alloc(std::max<size_t>(hs.order.size(), 1)));
-        CUDA_TRY(aux.alloc(std::max<size_t>(hs.aux.size(), 1)));
-        CUDA_TRY(d.desc.alloc(std::max<size_t>(2 * hs.order.size(), 1)));
-        CUDA_TRY(d.seg.alloc(std::max<size_t>(hs.seg.size() / 4, 1)));
-        CUDA_TRY(cudaMemcpyAsync(order.ptr, hs.order.data(), hs.order.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-        CUDA_TRY(cudaMemcpyAsync(aux.ptr, hs.aux.data(), hs.aux.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-        CUDA_TRY(cudaMemcpyAsync(d.seg.ptr, hs.seg.data(), hs.seg.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-        flow_gather_td(p->stream, (long long) hs.order.size(), order.ptr, aux.ptr, p->td_desc.ptr, d.desc.ptr);
-        CUDA_TRY(cudaStreamSynchronize(p->stream));
-        d.n_seg = hs.n_seg; d.n_batches = hs.n_batches; d.n_chunks = hs.n_chunks;
-    }
-    return PML_OK;
-}
-
-// root_partials_kernel on the single-launch sweeps' layout [slot][T][K + 1][JT]
-__global__ void root_partials_flow_kernel(TreeDev t, ZcDev zc, LaneDev ln, const uint64_t *mask, int alter,
-                                          const double *vec, int JT, int n_roots, double *out, int *out_ex) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_roots * ln.J) return;
-    const int node = g / ln.J, j = g % ln.J, c = j % ln.C;
-    const int T = (ln.J + JT - 1) / JT, tile = j / JT, jl = j - tile * JT;
-    const int s = t.slot[node];
-    const double *p = ln.params + (size_t) j * ln.stride;
-    const uint64_t m = (s >= 0) ? 0ULL : eff_mask(mask, t, zc, ln.C, node, c, alter && p[1] == 0., ln.kmask);
-    const double *v = vec + (((size_t) max(s, 0) * T + tile) * (ln.K + 1)) * JT + jl;
-    for (int k = 0; k < ln.K; ++k)
-        out[((size_t) node * ln.K + k) * ln.J + j] = (s >= 0) ? v[(size_t) k * JT] : bit_as_double(m, k);
-    out_ex[(size_t) node * ln.J + j] = (s >= 0) ? __double2loint(v[(size_t) ln.K * JT]) : 0;
 }
 
 void run_root_loglik(pml_problem *p, const LaneDev &ln, const uint64_t *mask, int alter, int is_marginal) {
@@ -408,21 +273,6 @@ void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_
         ln.J = n_lanes;
         ln.divJ = FastDiv::make((unsigned) n_lanes);
         ln.lane_col = p->lane_col.ptr;
-    }
-    const int flow_jt = is_marginal ? flow_jt_for(p, n_sets, n_lanes) : 0;
-    if (flow_jt) {
-        // one persistent launch for the whole sweep (pml_flow.cuh)
-        const int tiles = (ln.J + flow_jt - 1) / flow_jt;
-        if (alter) run_alter(p, mask);
-        fill_int_kernel<<<grid_for(2LL * tiles * flow_jt), kBlock, 0, p->stream>>>(2LL * tiles * flow_jt, -1, p->err.ptr);
-        flow_begin(p->stream, p->flow_ctl.ptr, tiles);
-        FlowBuArgs fa{p->tree(), p->zc(), ln, ln.J, mask, alter, p->fbu.ptr, p->err.ptr,
-                      p->flow_bu_sched[32 / flow_jt].view(), p->flow_ctl.ptr, p->flow_bu_flags.ptr};
-        flow_bu_launch(flow_jt, p->stream, fa, tiles);
-        flow_root_loglik(p->stream, p->tree(), p->zc(), ln, mask, alter, p->fbu.ptr, flow_jt, p->roots.ptr, p->n_roots,
-                         p->out_lh.ptr);
-        p->launches += 4;
-        return;
     }
     const int tpi_jt = n_lanes > 0 ? tpi_tile_lanes(p->K, n_lanes) : (is_marginal ? bu_tile_lanes(p, ln.J) : 0);
     ln.jt = tpi_jt;
@@ -498,38 +348,18 @@ void run_graphed(pml_problem *p, const std::array<long long, 6> &key, F enqueue)
     p->launches += it->second.launches;
 }
 
-int run_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marginal, int alter, bool keep_ptr,
-                  int n_lanes = 0) {
-    const int flow_jt = is_marginal ? flow_jt_for(p, n_sets, n_lanes) : 0;
-    if (flow_jt) {
-        const int rc = ensure_flow_bu(p, flow_jt);
-        if (rc) return rc;
-    } else {
-        const int rc = ensure_legacy_bu(p);
-        if (rc) return rc;
-    }
-    // where the bottom-up state of (one set, annotation masks, marginal, alter) lives after this pass
-    const bool is_state = n_sets == 1 && n_lanes == 0 && is_marginal && alter && mask == p->mask[PML_MASK_ANNOTATION].ptr;
-    if (flow_jt) { if (is_state) { p->bu_state = 2; p->bu_state_jt = flow_jt; } else if (p->bu_state == 2) p->bu_state = 0; }
-    else { p->bu_state = is_state ? 1 : (p->bu_state == 1 ? 0 : p->bu_state); }
+void run_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marginal, int alter, bool keep_ptr,
+                   int n_lanes = 0) {
     // everything that selects kernels at capture time belongs to the key: eig_shared decides between the tensor-core
     // sweep (one decomposition for all lanes) and the per-lane kernels, and it changes when the frequencies do
     run_graphed(p, {n_lanes > 0 ? 2 : 0, n_lanes > 0 ? n_lanes : n_sets, (long long) (uintptr_t) mask, is_marginal, alter,
-                    (keep_ptr ? 1 : 0) + 2 * (p->eig_shared ? 1 : 0) + 4 * (long long) p->n_ext + (flow_jt ? (1LL << 40) : 0)},
+                    (keep_ptr ? 1 : 0) + 2 * (p->eig_shared ? 1 : 0) + 4 * (long long) p->n_ext},
                 [&]() { enqueue_bottom_up(p, n_sets, mask, is_marginal, alter, keep_ptr, n_lanes); });
-    return PML_OK;
 }
 
-// the fused top-down sweep on the current bottom-up state (p->bu_state says which buffers hold it)
-int run_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh) {
-    const bool flow = p->bu_state == 2;
-    if (flow) {
-        const int rc = ensure_flow_td(p, p->bu_state_jt);
-        if (rc) return rc;
-    }
-    run_graphed(p, {1, force_joint, want_probs ? 1 : 0, want_node_lh ? 1 : 0, p->n_ext, (p->have_root_td ? 1 : 0) + (flow ? 2 : 0)},
+void run_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh) {
+    run_graphed(p, {1, force_joint, want_probs ? 1 : 0, want_node_lh ? 1 : 0, p->n_ext, p->have_root_td ? 1 : 0},
                 [&]() { enqueue_top_down(p, force_joint, want_probs, want_node_lh); });
-    return PML_OK;
 }
 
 int fetch_loglik(pml_problem *p, int n_sets, double *out, int n_lanes = 0) {
@@ -574,11 +404,9 @@ struct CallTimer {
 };
 
 int ensure_marginal_buffers(pml_problem *p, bool want_probs, bool want_node_lh) {
-    if (!flow_jt_marginal(p)) {   // the level kernels' top-down buffers
-        const size_t nik = (size_t) p->NI * p->K * p->C;
-        if (!p->td.ptr && nik) CUDA_TRY(p->td.alloc(nik));
-        if (!p->td_ex.ptr && p->NI) CUDA_TRY(p->td_ex.alloc((size_t) p->NI * p->C));
-    }
+    const size_t nik = (size_t) p->NI * p->K * p->C;
+    if (!p->td.ptr && nik) CUDA_TRY(p->td.alloc(nik));
+    if (!p->td_ex.ptr && p->NI) CUDA_TRY(p->td_ex.alloc((size_t) p->NI * p->C));
     if (want_probs && !p->probs.ptr) CUDA_TRY(p->probs.alloc((size_t) p->N * p->C * p->K));
     if (want_node_lh && !p->node_lh.ptr) CUDA_TRY(p->node_lh.alloc((size_t) p->N * p->C));
     if (want_node_lh && !p->node_ex.ptr) CUDA_TRY(p->node_ex.alloc((size_t) p->N * p->C));
@@ -592,25 +420,6 @@ int ensure_marginal_buffers(pml_problem *p, bool want_probs, bool want_node_lh) 
 void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh) {
     const LaneDev ln = p->lanes(1);
     cudaMemsetAsync(p->k_hist.ptr, 0, sizeof(unsigned long long) * p->C * (p->K + 1), p->stream);
-    if (p->bu_state == 2) {
-        // one persistent launch for the whole sweep (pml_flow.cuh), on the flow bottom-up state
-        const int jt = p->bu_state_jt, tiles = (p->C + jt - 1) / jt;
-        int npw = 0, npar = 0;
-        flow_td_geometry(jt, &npw, &npar);
-        flow_begin(p->stream, p->flow_ctl.ptr, tiles);
-        FlowTdArgs fa{p->tree(), p->zc(), ln, p->mask[PML_MASK_ANNOTATION].ptr, p->fbu.ptr, p->ftd.ptr, p->joint_state.ptr,
-                      force_joint, want_probs ? p->probs.ptr : nullptr, want_node_lh ? p->node_lh.ptr : nullptr,
-                      p->node_ex.ptr, p->mask[PML_MASK_MAP].ptr, p->mask[PML_MASK_MPPA].ptr, p->k_hist.ptr, p->zc_lh.ptr,
-                      p->zc_k.ptr, p->flow_td_sched[npw * 64 + npar].view(), p->flow_ctl.ptr, p->flow_td_flags.ptr};
-        flow_td_launch(p->K, jt, p->stream, fa, tiles);
-        p->launches += 2;
-        if (want_node_lh) {
-            const long long n = (long long) p->N * p->C;
-            log10_finish_kernel<<<grid_for(n), kBlock, 0, p->stream>>>(n, p->node_lh.ptr, p->node_ex.ptr);
-            p->launches++;
-        }
-        return;
-    }
     TdArgs a{p->tree(), p->zc(), p->ext(), ln, p->mask[PML_MASK_ANNOTATION].ptr, p->bu.ptr, p->bu_ex.ptr, p->td.ptr,
              p->td_ex.ptr, p->joint_state.ptr, force_joint, want_probs ? p->probs.ptr : nullptr,
              want_node_lh ? p->node_lh.ptr : nullptr, p->node_ex.ptr, p->mask[PML_MASK_MAP].ptr, p->mask[PML_MASK_MPPA].ptr,
@@ -1001,11 +810,10 @@ int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dis
     }
     const size_t J = (size_t) p->B * C;
     PML_TRY_FREE(p->params.alloc(J * p->stride));
-    // the vector buffers are allocated by the first pass that needs them (level kernels: ensure_legacy_bu; single-launch
-    // sweeps: ensure_flow_bu / ensure_flow_td)
-    PML_TRY_FREE(p->err.alloc(2 * (J + 32)));   // room for the padding lanes of a tiled pass
-    PML_TRY_FREE(p->out_lh.alloc(J + 32));
-    p->h_parent.assign(parent, parent + N);
+    PML_TRY_FREE(p->bu.alloc(std::max<size_t>((size_t) NI * K * J, 1)));
+    PML_TRY_FREE(p->bu_ex.alloc(std::max<size_t>((size_t) NI * J, 1)));
+    PML_TRY_FREE(p->err.alloc(2 * J));
+    PML_TRY_FREE(p->out_lh.alloc(J));
 #undef PML_UPLOAD
 #undef PML_TRY_FREE
     *out = p;
@@ -1034,8 +842,7 @@ int pml_loglik(pml_problem *p, const double *params, int32_t n_sets, int32_t mas
     int rc = upload_params(p, params, n_sets);
     if (rc) return rc;
     CallTimer timer(p);
-    rc = run_bottom_up(p, n_sets, p->mask[mask_kind].ptr, is_marginal, alter, false);
-    if (rc) return rc;
+    run_bottom_up(p, n_sets, p->mask[mask_kind].ptr, is_marginal, alter, false);
     timer.stop();
     CUDA_TRY(cudaGetLastError());
     return fetch_loglik(p, n_sets, out_loglh);
@@ -1065,7 +872,7 @@ int pml_loglik_lanes(pml_problem *p, const double *params, const int32_t *lane_c
     CUDA_TRY(cudaMemcpyAsync(p->record_col.ptr, rec.data(), p->C, cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));   // rec is a stack-local host buffer
     CallTimer timer(p);
-    { const int rc2 = run_bottom_up(p, 1, p->mask[PML_MASK_ANNOTATION].ptr, 1, 1, false, n_lanes); if (rc2) return rc2; }
+    run_bottom_up(p, 1, p->mask[PML_MASK_ANNOTATION].ptr, 1, 1, false, n_lanes);
     timer.stop();
     CUDA_TRY(cudaGetLastError());
     const int rc = fetch_loglik(p, 1, out_loglh, n_lanes);
@@ -1086,13 +893,12 @@ int pml_joint(pml_problem *p, const double *params, double *out_loglh, int32_t *
     if (rc) return rc;
     CallTimer timer(p);
     const uint64_t *base = p->mask[PML_MASK_ANNOTATION].ptr;
-    rc = run_bottom_up(p, 1, base, 0, 1, true);
-    if (rc) return rc;
+    run_bottom_up(p, 1, base, 0, 1, true);
     JointArgs a{p->tree(), p->zc(), p->lanes(1), base, p->bu.ptr, p->ptr.ptr, p->joint_state.ptr,
                 p->mask[PML_MASK_JOINT].ptr};
     for (int lvl = 0; lvl < p->n_levels; ++lvl) {
         const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
-        joint_trace_kernel<<<grid_for((long long) nn * p->C), kBlock, 0, p->stream>>>(a, n0, nn);
+        launch_pdl(joint_trace_kernel, dim3(grid_for((long long) nn * p->C)), dim3(kBlock), 0, p->stream, a, n0, nn);
         p->launches++;
     }
     timer.stop();
@@ -1128,15 +934,8 @@ int pml_marginal(pml_problem *p, const double *params, int32_t force_joint, doub
     if (rc) return rc;
     CallTimer timer(p);
     // ml.py:700-706: allowed states are re-initialised and altered, then BU(alter=False), TD, marginals
-    // (a reused state must sit where this handle's top-down sweep reads it: the flow buffer when the single-launch
-    // sweeps apply, the level kernels' buffers otherwise)
-    const int want_state = flow_jt_marginal(p) ? 2 : 1;
-    if (!reuse_bu || p->bu_state != want_state) {
-        rc = run_bottom_up(p, 1, p->mask[PML_MASK_ANNOTATION].ptr, 1, 1, false);
-        if (rc) return rc;
-    }
-    rc = run_top_down(p, force_joint, do_probs, do_node_lh);
-    if (rc) return rc;
+    if (!reuse_bu) run_bottom_up(p, 1, p->mask[PML_MASK_ANNOTATION].ptr, 1, 1, false);
+    run_top_down(p, force_joint, do_probs, do_node_lh);
     // remember the '.initial' state MAP saw: pml_mppa_finalize needs it
     if (p->n_rows) {
         cudaMemcpyAsync(p->zc_prev_initial.ptr, p->zc_initial.ptr, sizeof(uint64_t) * (size_t) p->n_rows * p->C,
@@ -1203,7 +1002,7 @@ int pml_parsimony(pml_problem *p, int32_t methods, uint64_t *out_mask, int64_t *
     for (int lvl = p->n_levels - 1; lvl >= 0; --lvl) {
         const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
         if (ns <= 0) continue;
-        pars_uppass_kernel<<<grid_for((long long) ns * C), kBlock, 0, p->stream>>>(t, C, p->kmask, down, s0, ns);
+        launch_pdl(pars_uppass_kernel, dim3(grid_for((long long) ns * C)), dim3(kBlock), 0, p->stream, t, C, p->kmask, down, s0, ns);
         p->launches++;
     }
     int slot_out = 0;
@@ -1211,8 +1010,7 @@ int pml_parsimony(pml_problem *p, int32_t methods, uint64_t *out_mask, int64_t *
         for (int lvl = p->n_levels - 1; lvl >= 0; --lvl) {
             const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
             if (ns <= 0) continue;
-            pars_steps_kernel<<<grid_for((long long) ns * C), kBlock, 0, p->stream>>>(t, C, K, states,
-                                                                                     p->steps_num.ptr, s0, ns);
+            launch_pdl(pars_steps_kernel, dim3(grid_for((long long) ns * C)), dim3(kBlock), 0, p->stream, t, C, K, states, p->steps_num.ptr, s0, ns);
             p->launches++;
         }
         pars_steps_root_kernel<<<grid_for(C), kBlock, 0, p->stream>>>(t, C, K, states, p->steps_num.ptr, p->roots.ptr,
@@ -1242,7 +1040,7 @@ int pml_parsimony(pml_problem *p, int32_t methods, uint64_t *out_mask, int64_t *
         for (int lvl = 0; lvl < p->n_levels; ++lvl) {
             const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
             if (ns <= 0) continue;
-            pars_acctran_kernel<<<grid_for((long long) ns * C), kBlock, 0, p->stream>>>(t, C, down, res, s0, ns);
+            launch_pdl(pars_acctran_kernel, dim3(grid_for((long long) ns * C)), dim3(kBlock), 0, p->stream, t, C, (const uint64_t *) down, res, s0, ns);
             p->launches++;
         }
         int rc = emit(res);
@@ -1255,8 +1053,7 @@ int pml_parsimony(pml_problem *p, int32_t methods, uint64_t *out_mask, int64_t *
         for (int lvl = 0; lvl < p->n_levels; ++lvl) {
             const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
             if (ns <= 0) continue;
-            pars_downpass_kernel<<<grid_for((long long) ns * C), kBlock, 0, p->stream>>>(t, C, p->kmask, down, up, res,
-                                                                                        s0, ns);
+            launch_pdl(pars_downpass_kernel, dim3(grid_for((long long) ns * C)), dim3(kBlock), 0, p->stream, t, C, p->kmask, (const uint64_t *) down, up, res, s0, ns);
             p->launches++;
         }
         if (methods & PML_PARS_DOWNPASS) {
@@ -1267,7 +1064,7 @@ int pml_parsimony(pml_problem *p, int32_t methods, uint64_t *out_mask, int64_t *
             for (int lvl = 0; lvl < p->n_levels; ++lvl) {
                 const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
                 if (ns <= 0) continue;
-                pars_deltran_kernel<<<grid_for((long long) ns * C), kBlock, 0, p->stream>>>(t, C, res, s0, ns);
+                launch_pdl(pars_deltran_kernel, dim3(grid_for((long long) ns * C)), dim3(kBlock), 0, p->stream, t, C, res, s0, ns);
                 p->launches++;
             }
             int rc = emit(res);
@@ -1335,17 +1132,7 @@ int pml_get_bottom_up(pml_problem *p, double *out_vec, int32_t *out_ex, uint64_t
     CUDA_TRY(cudaSetDevice(p->device));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     const size_t nc = (size_t) p->N * p->C;
-    if (!p->bu_state) return fail(PML_ERR_INVALID, "no bottom-up state: run a single-set marginal pass (pml_loglik) first");
-    if (p->NI && p->bu_state == 2) {   // the single-launch sweep's layout: unpack on the device
-        DevBuf<double> vec;
-        DevBuf<int> ex;
-        CUDA_TRY(vec.alloc((size_t) p->NI * p->K * p->C));
-        CUDA_TRY(ex.alloc((size_t) p->NI * p->C));
-        flow_unpack(p->stream, p->NI, p->K, p->C, p->bu_state_jt, p->fbu.ptr, vec.ptr, ex.ptr);
-        CUDA_TRY(cudaMemcpyAsync(out_vec, vec.ptr, sizeof(double) * (size_t) p->NI * p->K * p->C, cudaMemcpyDeviceToHost, p->stream));
-        CUDA_TRY(cudaMemcpyAsync(out_ex, ex.ptr, sizeof(int) * (size_t) p->NI * p->C, cudaMemcpyDeviceToHost, p->stream));
-        CUDA_TRY(cudaStreamSynchronize(p->stream));
-    } else if (p->NI) {
+    if (p->NI) {
         CUDA_TRY(cudaMemcpy(out_vec, p->bu.ptr, sizeof(double) * (size_t) p->NI * p->K * p->C, cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(out_ex, p->bu_ex.ptr, sizeof(int) * (size_t) p->NI * p->C, cudaMemcpyDeviceToHost));
     }
@@ -1399,16 +1186,8 @@ int pml_get_root_partials(pml_problem *p, int32_t n_sets, double *out_vec, int32
     DevBuf<int> ex;
     CUDA_TRY(vec.alloc(nv));
     CUDA_TRY(ex.alloc(ne));
-    const int flow_jt = flow_jt_for(p, n_sets, 0);   // the layout the last pass with this many sets left behind
-    if (flow_jt) {
-        if (!p->fbu.ptr) return fail(PML_ERR_INVALID, "no bottom-up pass has run yet");
-        root_partials_flow_kernel<<<grid_for((long long) ne), kBlock, 0, p->stream>>>(
-            p->tree(), p->zc(), ln, p->mask[PML_MASK_ANNOTATION].ptr, 1, p->fbu.ptr, flow_jt, p->n_roots, vec.ptr, ex.ptr);
-    } else {
-        if (!p->bu.ptr) return fail(PML_ERR_INVALID, "no bottom-up pass has run yet");
-        root_partials_kernel<<<grid_for((long long) ne), kBlock, 0, p->stream>>>(
-            p->tree(), p->zc(), ln, p->mask[PML_MASK_ANNOTATION].ptr, 1, p->bu.ptr, p->bu_ex.ptr, p->n_roots, vec.ptr, ex.ptr);
-    }
+    root_partials_kernel<<<grid_for((long long) ne), kBlock, 0, p->stream>>>(
+        p->tree(), p->zc(), ln, p->mask[PML_MASK_ANNOTATION].ptr, 1, p->bu.ptr, p->bu_ex.ptr, p->n_roots, vec.ptr, ex.ptr);
     p->launches++;
     CUDA_TRY(cudaMemcpyAsync(out_vec, vec.ptr, nv * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaMemcpyAsync(out_ex, ex.ptr, ne * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
@@ -1495,36 +1274,6 @@ int pml_last_call_stats(pml_problem *p, double *device_ms, int64_t *kernel_launc
     return PML_OK;
 }
 
-int64_t pml_flow_schedule(int32_t kind, int32_t n_nodes, const int32_t *parent, int32_t nodes_per_batch,
-                          int32_t parents_per_batch, int32_t *out_order, int32_t *out_chunk_of_batch, int64_t capacity) {
-    if (n_nodes < 1 || !parent || nodes_per_batch < 1 || kind < 0 || kind > 1) return -1;
-    int n_roots = 0;
-    for (int v = 0; v < n_nodes; ++v) {
-        if (parent[v] >= v || (v > 0 && parent[v] < parent[v - 1])) return -1;
-        if (parent[v] < 0) ++n_roots;
-    }
-    std::vector<int> level_ptr{0, n_roots};
-    while (level_ptr.back() < n_nodes) {
-        const int hi = level_ptr.back();
-        const int nxt = (int) (std::lower_bound(parent + hi, parent + n_nodes, hi) - parent);
-        if (nxt == hi) return -1;
-        level_ptr.push_back(nxt);
-    }
-    FlowHostSched hs;
-    if (kind == 0) flow_schedule_bu(level_ptr, parent, nodes_per_batch, hs);
-    else flow_schedule_td(level_ptr, parent, nodes_per_batch, std::max(parents_per_batch, 1), hs);
-    const int64_t n = (int64_t) hs.order.size();
-    for (int64_t i = 0; i < n && i < capacity; ++i) out_order[i] = hs.order[i];
-    if (out_chunk_of_batch) {
-        for (int sgi = 0; sgi < hs.n_seg; ++sgi) {
-            const int c0 = hs.seg[4 * sgi], b0 = hs.seg[4 * sgi + 1], nb = hs.seg[4 * sgi + 2], ch = hs.seg[4 * sgi + 3];
-            for (int b = 0; b < nb; ++b)
-                if ((int64_t) (b0 + b) * nodes_per_batch < capacity) out_chunk_of_batch[b0 + b] = c0 + b / ch;
-        }
-    }
-    return n;
-}
-
 int pml_bench_pass(pml_problem *p, const double *params, int32_t n_sets, int32_t which, int32_t n_iter,
                    int32_t flush_l2, double *avg_ms, double *min_ms, int64_t *kernel_launches) {
     if (!p || !params || n_iter < 1) return fail(PML_ERR_INVALID, "bad argument");
@@ -1564,7 +1313,7 @@ int pml_bench_pass(pml_problem *p, const double *params, int32_t n_sets, int32_t
                         p->mask[PML_MASK_JOINT].ptr};
             for (int lvl = 0; lvl < p->n_levels; ++lvl) {
                 const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
-                joint_trace_kernel<<<grid_for((long long) nn * p->C), kBlock, 0, p->stream>>>(a, n0, nn);
+                launch_pdl(joint_trace_kernel, dim3(grid_for((long long) nn * p->C)), dim3(kBlock), 0, p->stream, a, n0, nn);
                 p->launches++;
             }
         }

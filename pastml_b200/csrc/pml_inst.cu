@@ -38,10 +38,10 @@ void bu_launch(cudaStream_t st, const BuArgs &a, bool maxp, int s0, int ns) {
     const size_t sh = sizeof(double) * staged_doubles(kFamily, a.ln.K, a.ln.J);
     if (maxp) {
         allow_big_smem(bu_level_kernel<KP, TheLane, true>, sh);
-        bu_level_kernel<KP, TheLane, true><<<grid_for(items), kBlock, sh, st>>>(a, s0, ns);
+        launch_pdl(bu_level_kernel<KP, TheLane, true>, dim3(grid_for(items)), dim3(kBlock), sh, st, a, s0, ns);
     } else {
         allow_big_smem(bu_level_kernel<KP, TheLane, false>, sh);
-        bu_level_kernel<KP, TheLane, false><<<grid_for(items), kBlock, sh, st>>>(a, s0, ns);
+        launch_pdl(bu_level_kernel<KP, TheLane, false>, dim3(grid_for(items)), dim3(kBlock), sh, st, a, s0, ns);
     }
 }
 
@@ -59,7 +59,7 @@ size_t td_smem(const TdArgs &a) {
 void td_launch(cudaStream_t st, const TdArgs &a, int s0, int ns) {
     const size_t sh = td_smem(a);
     allow_big_smem(td_level_kernel<KP, TheLane>, sh);
-    td_level_kernel<KP, TheLane><<<grid_for((long long) ns * a.ln.C), kBlock, sh, st>>>(a, s0, ns);
+    launch_pdl(td_level_kernel<KP, TheLane>, dim3(grid_for((long long) ns * a.ln.C)), dim3(kBlock), sh, st, a, s0, ns);
 }
 
 void mppa_fix_launch(cudaStream_t st, int n_rows, const int *row_node, int C, int K, uint64_t kmask, const ZcDev &zc,

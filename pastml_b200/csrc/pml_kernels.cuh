@@ -101,6 +101,14 @@ constexpr long long kMaxItemsPerLaunch = 1LL << 30;
 
 // ------------------------------------------------------------------------------------------ helpers
 
+// Programmatic dependent launch: the level kernels of a sweep are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the blocks of level N + 1 become resident while level N drains and
+// run their prologue (parameter staging, barrier set-up, first descriptors -- nothing level N produces) before
+// pdl_wait(), which returns once level N has completed and its stores are visible.  Without the launch attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ int exponent_of(double x) {  // floor(log2 x) for positive normal x
     return ((__double2hiint(x) >> 20) & 0x7ff) - 1023;
 }
@@ -527,7 +535,9 @@ __global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_BU_MINB : 1)) bu_level
     const int J = a.ln.J, K = a.ln.K, C = a.ln.C;
     const int nf = staged_fields(Lane<KP>::family, K);
     const bool with_eig = eig_staged(Lane<KP>::family, K, J);
+    pdl_launch_dependents();
     stage_params(s_par, a.ln, nf, with_eig);
+    pdl_wait();   // the staging above is independent of the previous level
     const unsigned n_items = (unsigned) n_slots * (unsigned) J;
     for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n_items; g += gridDim.x * blockDim.x) {
         const unsigned sl = a.ln.divJ.div(g);
@@ -643,6 +653,8 @@ struct JointArgs {
 // choose_ancestral_states_joint (ml.py:598-622) + unalter_zero_node_joint_states (ml.py:408-428) for the nodes
 // [node_begin, node_begin + n_nodes) of one level.
 static __global__ void joint_trace_kernel(JointArgs a, int node_begin, int n_nodes) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int C = a.ln.C, K = a.ln.K;
     const long long n_items = (long long) n_nodes * C;
     for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
@@ -816,7 +828,9 @@ __global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_TD_MINB : 1)) td_level
     const bool with_eig = eig_staged(Lane<KP>::family, K, C);
     unsigned int *sh_hist = reinterpret_cast<unsigned int *>(s_par + staged_doubles(Lane<KP>::family, K, C));   // [C][K+1]
     for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x) sh_hist[i] = 0u;
+    pdl_launch_dependents();
     stage_params(s_par, a.ln, nf, with_eig);
+    pdl_wait();   // the staging above is independent of the previous level
     const unsigned n_items = (unsigned) n_nodes * (unsigned) C;
     for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n_items; g += gridDim.x * blockDim.x) {
         const unsigned nd = a.ln.divC.div(g);
@@ -973,6 +987,8 @@ __device__ __forceinline__ uint64_t most_common(uint64_t first, bool has_first, 
 
 // uppass (parsimony.py:92-122) for the internal nodes of one level; down[] was initialised to the annotation sets.
 static __global__ void pars_uppass_kernel(TreeDev t, int C, uint64_t kmask, uint64_t *down, int slot_begin, int n_slots) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long n_items = (long long) n_slots * C;
     for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
          g += (long long) gridDim.x * blockDim.x) {
@@ -988,6 +1004,8 @@ static __global__ void pars_uppass_kernel(TreeDev t, int C, uint64_t kmask, uint
 // acctran (parsimony.py:125-158): the children of the internal nodes of one level.
 static __global__ void pars_acctran_kernel(TreeDev t, int C, const uint64_t *down, uint64_t *out, int slot_begin,
                                     int n_slots) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long n_items = (long long) n_slots * C;
     for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
          g += (long long) gridDim.x * blockDim.x) {
@@ -1006,6 +1024,8 @@ static __global__ void pars_acctran_kernel(TreeDev t, int C, const uint64_t *dow
 // up() of its children; tip children are finished on the spot.  res[] starts as the pre-uppass sets.
 static __global__ void pars_downpass_kernel(TreeDev t, int C, uint64_t kmask, const uint64_t *down, uint64_t *up,
                                      uint64_t *res, int slot_begin, int n_slots) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long n_items = (long long) n_slots * C;
     for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
          g += (long long) gridDim.x * blockDim.x) {
@@ -1032,6 +1052,8 @@ static __global__ void pars_downpass_kernel(TreeDev t, int C, uint64_t kmask, co
 
 // deltran (parsimony.py:213-242): children of the internal nodes of one level, on top of the DOWNPASS result.
 static __global__ void pars_deltran_kernel(TreeDev t, int C, uint64_t *res, int slot_begin, int n_slots) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long n_items = (long long) n_slots * C;
     for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;
          g += (long long) gridDim.x * blockDim.x) {
@@ -1049,6 +1071,8 @@ static __global__ void pars_deltran_kernel(TreeDev t, int C, uint64_t *res, int 
 // num[slot][k][C] int32 (INF for states outside the node's set).
 static __global__ void pars_steps_kernel(TreeDev t, int C, int K, const uint64_t *states, int *num, int slot_begin,
                                   int n_slots) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int INF = 1 << 29;
     const long long n_items = (long long) n_slots * C;
     for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items;

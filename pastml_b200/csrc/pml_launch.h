@@ -3,7 +3,6 @@
 // so that the build parallelises; the engine picks the table once per problem.
 #pragma once
 #include <cstdlib>
-#include <vector>
 #include "pml_kernels.cuh"
 
 namespace pml {
@@ -65,31 +64,5 @@ void tpi_bu_launch(int jt, cudaStream_t, const BuArgs &, int slot_begin, int n_s
 // Bottom-up sweep of the eigen-decomposition models on the FP64 tensor cores (pml_mma.cu): lanes share one decomposition
 bool mma_bu_applicable(int K, int J);
 void mma_bu_launch(cudaStream_t, const BuArgs &, int slot_begin, int n_slots);
-
-
-// Single-launch ("dataflow") sweeps of the F81 family (pml_flow.cuh / pml_flow.cu / pml_flow_td_inst.cu)
-struct FlowBuArgs;
-struct FlowTdArgs;
-struct FlowHostSched {          // a schedule as the host builds it
-    std::vector<int> order;     // scheduled nodes (bottom-up: slots; top-down: node ids), -1 = padding
-    std::vector<int> aux;       // top-down: (parent region, issues-the-parent-copies) per scheduled node
-    std::vector<int> seg;       // 4 ints per segment: first chunk, first batch, batches, chunk size
-    int n_seg = 0, n_batches = 0, n_chunks = 0;
-};
-void flow_schedule_bu(const std::vector<int> &level_ptr, const int *parent, int npw, FlowHostSched &out);
-void flow_schedule_td(const std::vector<int> &level_ptr, const int *parent, int npw, int npar, FlowHostSched &out);
-void flow_gather_bu(cudaStream_t, long long n, const int *order, const int4 *bu_desc, const int *int_nodes, int4 *out);
-void flow_gather_td(cudaStream_t, long long n, const int *order, const int *aux, const int4 *td_desc, int4 *out);
-void flow_begin(cudaStream_t, unsigned *ctl, int tiles);
-int flow_ctl_word_count(int tiles);
-int flow_tile_lanes(int J, int max_jt);            // lanes per tile for a pass with J lanes
-void flow_bu_launch(int jt, cudaStream_t, const FlowBuArgs &, int tiles);
-void flow_root_loglik(cudaStream_t, const TreeDev &, const ZcDev &, const LaneDev &, const uint64_t *mask, int alter,
-                      const double *vec, int jt, const int *roots, int n_roots, double *out);
-void flow_unpack(cudaStream_t, long long n_slots, int K, int C, int jt, const double *vec, double *out_vec, int *out_ex);
-// top-down: G = 2 threads per item; available for 2 <= K <= 32 and JT in {2, 4, 8, 16}
-bool flow_td_available(int K, int jt);
-void flow_td_geometry(int jt, int *npw, int *npar);
-void flow_td_launch(int K, int jt, cudaStream_t, const FlowTdArgs &, int tiles);
 
 }  // namespace pml

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) bu_mma_kernel(BuArgs
             f_a[mt][s] = in ? Am[row * K + col] : 0.;
         }
     }
+    pdl_launch_dependents();   // the fragments above are loaded while the previous level drains
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const long long n_items = (long long) n_slots * tiles;
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) bu_mma_kernel(BuArgs
         nx_len = a.t.bu_desc[2 * s0 + 1];
         nx_node = a.t.int_nodes[s0];
     }
+    pdl_wait();   // from here on the previous level's vectors are read
     for (long long w = warp_global; w < n_items; w += n_warps) {
         const int sl = (int) (w / tiles), tile = (int) (w - (long long) sl * tiles);
         const int slot = slot_begin + sl;
@@ -249,10 +251,10 @@ void mma_bu_launch(cudaStream_t st, const BuArgs &a, int s0, int ns) {
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     const int K = a.ln.K;
-    if (K <= 8) bu_mma_kernel<1, 2><<<(unsigned) g, kMmaBlock, 0, st>>>(a, s0, ns);
-    else if (K <= 16) bu_mma_kernel<2, 4><<<(unsigned) g, kMmaBlock, 0, st>>>(a, s0, ns);
-    else if (K <= 20) bu_mma_kernel<3, 5><<<(unsigned) g, kMmaBlock, 0, st>>>(a, s0, ns);
-    else bu_mma_kernel<3, 6><<<(unsigned) g, kMmaBlock, 0, st>>>(a, s0, ns);
+    if (K <= 8) launch_pdl(bu_mma_kernel<1, 2>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
+    else if (K <= 16) launch_pdl(bu_mma_kernel<2, 4>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
+    else if (K <= 20) launch_pdl(bu_mma_kernel<3, 5>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
+    else launch_pdl(bu_mma_kernel<3, 6>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
 }
 
 }  // namespace pml

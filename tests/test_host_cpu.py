@@ -25,87 +25,6 @@ def test_library_exports_every_declared_symbol():
     assert lib.pml_param_stride(0, 5) == 9 and lib.pml_param_stride(1, 4) == 8 and lib.pml_param_stride(2, 20) == 844
 
 
-def _flow_schedule(kind, flat, npw, npar=1):
-    import ctypes as C
-    from pastml_b200 import _lib
-    lib = _lib.load()
-    cap = 2 * flat.n_nodes * 9 + 64 * npw
-    order = np.empty(cap, dtype=np.int32)
-    chunk = np.full(cap // npw, -1, dtype=np.int32)
-    n = lib.pml_flow_schedule(kind, flat.n_nodes, flat.parent.ctypes.data_as(C.c_void_p), npw, npar,
-                              order.ctypes.data_as(C.c_void_p), chunk.ctypes.data_as(C.c_void_p), cap)
-    assert 0 <= n <= cap and n % npw == 0
-    return order[:n].reshape(-1, npw), chunk[:n // npw]
-
-
-@pytest.mark.parametrize('kind_of_tree,n_tips', [('yule', 300), ('yule', 120_000), ('coalescent', 90_000), ('comb', 4_000),
-                                                 ('polytomies', 50_000)])
-def test_flow_schedules_respect_the_dependencies(kind_of_tree, n_tips, monkeypatch):
-    """The order in which the single-launch sweeps hand out the nodes (level order with the thin deep levels interleaved
-    with filler batches): every node exactly once, producers strictly before consumers in BATCH order (a batch never
-    holds a node together with the node that produces one of its operands), tickets non-decreasing along the order,
-    top-down batches within their parent-region budget."""
-    from pastml_b200 import synth
-    from pastml_b200.tree import FlatForest
-    monkeypatch.setenv('PASTML_B200_FLOW_THIN', '300')   # so that trees of this size have fat levels and a thin tail
-    rng = np.random.default_rng(5)
-    if kind_of_tree == 'yule':
-        flat = synth.yule_tree(n_tips, rng)
-    elif kind_of_tree == 'coalescent':
-        flat = synth.coalescent_tree(n_tips, rng)
-    elif kind_of_tree == 'comb':       # a caterpillar: as many levels as tips
-        parent = np.empty(2 * n_tips - 1, dtype=np.int32)
-        parent[0] = -1
-        parent[1::2] = np.arange(0, 2 * n_tips - 2, 2)[:n_tips - 1] if False else 0
-        # level l holds (internal, tip) = ids (2l - 1, 2l); the internal one is the parent of the next level
-        ids = np.arange(1, 2 * n_tips - 1)
-        parent[ids] = np.where((ids - 1) // 2 == 0, 0, 2 * ((ids - 1) // 2) - 1)
-        flat = FlatForest(parent, np.ones(len(parent)))
-    else:                               # random multifurcations
-        sizes = rng.integers(2, 6, size=n_tips)
-        parent = [-1]
-        frontier = [0]
-        while len(parent) < n_tips:
-            nxt = []
-            for v in frontier:
-                if rng.random() < 0.25 and len(frontier) > 1:
-                    continue
-                for _ in range(int(sizes[v % len(sizes)])):
-                    parent.append(v)
-                    nxt.append(len(parent) - 1)
-            frontier = nxt or frontier
-            if not nxt:
-                break
-        flat = FlatForest(np.array(parent, dtype=np.int32), np.ones(len(parent)))
-    N, NI = flat.n_nodes, flat.n_internal
-    for npw in (2, 4, 16):
-        order, chunk = _flow_schedule(0, flat, npw)
-        slots = order[order >= 0]
-        assert len(slots) == NI and len(np.unique(slots)) == NI
-        assert np.all(np.diff(chunk) >= 0) and chunk[0] == 0
-        batch_of = np.empty(NI, dtype=np.int64)
-        rows = np.repeat(np.arange(order.shape[0]), npw).reshape(order.shape)
-        batch_of[order[order >= 0]] = rows[order >= 0]
-        # every internal child is handed out in an EARLIER batch than its parent
-        child = np.flatnonzero((flat.slot >= 0) & (flat.parent >= 0))
-        assert np.all(batch_of[flat.slot[child]] < batch_of[flat.slot[flat.parent[child]]])
-    for npw, npar in ((2, 1), (4, 2), (8, 4), (1, 1)):
-        order, chunk = _flow_schedule(1, flat, npw, npar)
-        nodes = order[order >= 0]
-        assert len(nodes) == N and len(np.unique(nodes)) == N
-        assert np.all(np.diff(chunk) >= 0) and chunk[0] == 0
-        batch_of = np.empty(N, dtype=np.int64)
-        rows = np.repeat(np.arange(order.shape[0]), npw).reshape(order.shape)
-        batch_of[order[order >= 0]] = rows[order >= 0]
-        kids = np.flatnonzero(flat.parent >= 0)
-        assert np.all(batch_of[flat.parent[kids]] < batch_of[kids])
-        # distinct parents per batch
-        par = np.where(order >= 0, flat.parent[np.maximum(order, 0)], -1)
-        changes = (par[:, 1:] != par[:, :-1]) & (par[:, 1:] >= 0)
-        distinct = (par[:, 0] >= 0).astype(int) + changes.sum(axis=1)
-        assert distinct.max() <= npar
-
-
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

@@ -41,17 +41,16 @@ def build_variant(spec):
             if 'Compiling entry function' in line and 'coop_kernel' in line:
                 info.append(('bu_coop' if 'bu_coop' in line else 'td_coop') + ' G={} KT={} JT={}: '.format(g, kt, jt) + ' | '.join(
                     x.replace('ptxas info    : ', '').strip() for x in lines[i + 2:i + 4]))
-    for src, extra, tag, pat in (('pml_tpi.cu', [], 'tpi', 'tpi_kernel'), ('pml_flow.cu', [], 'flow', 'bu_flow_kernelILi20ELi8'),
-                                 ('pml_flow_td_inst.cu', ['-DPML_KT=10', '-DPML_KX=1'], 'flowtd', 'td_flow_kernelILi10ELi2ELi8ELb1'),
-                                 ('pml_mma.cu', [], 'mma', None), ('pml_newick.cpp', [], 'newick', None)):
+    for src, extra, tag in (('pml_tpi.cu', [], 'tpi'),):
         o4 = os.path.join(OUT, name + '_' + tag + '.o')
         objs.append(o4)
-        res = subprocess.run(['nvcc'] + FLAGS + defs + extra + ['-DPML_ONLY_F81_20', '-Xptxas', '-v', '-c', os.path.join(CSRC, src), '-o', o4],
+        res = subprocess.run(['nvcc'] + FLAGS + defs + extra + ['-Xptxas', '-v', '-c', os.path.join(CSRC, src), '-o', o4],
                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, check=True)
         lines = res.stdout.splitlines()
         for i, line in enumerate(lines):
-            if pat and 'Compiling entry function' in line and pat in line:
-                info.append(tag + ': ' + ' | '.join(x.replace('ptxas info    : ', '').strip() for x in lines[i + 2:i + 4]))
+            if 'Compiling entry function' in line and 'tpi_kernel' in line and 'Li8EEE' in line:
+                info.append(('bu_tpi' if 'bu_tpi' in line else 'td_tpi') + ' JT=8: ' + ' | '.join(
+                    x.replace('ptxas info    : ', '').strip() for x in lines[i + 2:i + 4]))
     lib = os.path.join(OUT, 'lib_' + name + '.so')
     subprocess.check_call(['nvcc', '--shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', lib] + objs)
     for o in objs:
