@@ -451,11 +451,11 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT, TMA)) td_coop_
         if constexpr (TMA) {
             const int n0 = node_of(base);
             cu_desc = a.t.td_desc[n0];
-            pdl_wait();   // everything above is independent of the previous level
-            issue(cu_desc);
             cu_raw = a.mask[(size_t) n0 * C + c];
             if (fj) cu_js = a.joint_state[(size_t) n0 * C + c];
             if (base + stride < n_nodes) nx_desc = a.t.td_desc[node_of(base + stride)];
+            pdl_wait();   // everything above (topology, masks, joint states) is independent of the previous level
+            issue(cu_desc);
         } else {
             nx_desc = a.t.td_desc[node_of(base)];
         }

@@ -213,6 +213,12 @@ inline bool tpi_enabled() {   // PASTML_B200_NO_TPI=1: the cooperative kernels i
     static const bool off = getenv("PASTML_B200_NO_TPI") != nullptr;
     return !off;
 }
+// levels narrower than this (about half a wave of the staged kernel) take the low-latency cooperative bottom-up kernel;
+// PASTML_B200_THIN=<nodes> overrides (measured on the 1M-tip workload: 0 -> 0.740 ms, 5000 -> 0.716 ms per sweep)
+inline int thin_level_threshold() {
+    static const int n = getenv("PASTML_B200_THIN") ? atoi(getenv("PASTML_B200_THIN")) : 5000;
+    return n;
+}
 inline bool tma_enabled() {   // PASTML_B200_NO_TMA=1: the register-path cooperative kernels (A/B measurements)
     static const bool off = getenv("PASTML_B200_NO_TMA") != nullptr;
     return !off;
@@ -296,7 +302,11 @@ void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_
             continue;
         }
         if (tpi_jt) {
-            tpi_bu_launch(tpi_jt, p->stream, a, s0, ns);
+            // thin levels are latency-bound: the cooperative kernel (a node's states split over a thread group, plain
+            // loads) finishes a single wave sooner than the staged thread-per-item kernel
+            // (not for lane lists: the cooperative kernels take lane j's column to be j % C)
+            if (coop && !ln.lane_col && tpi_jt == ln.J && ns < thin_level_threshold()) coop->bu(p->stream, a, s0, ns);
+            else tpi_bu_launch(tpi_jt, p->stream, a, s0, ns);
             p->launches++;
             continue;
         }
@@ -442,7 +452,8 @@ void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool wan
     }
     if (coop && want_node_lh) {
         const long long n = (long long) p->N * p->C;
-        log10_finish_kernel<<<grid_for(n), kBlock, 0, p->stream>>>(n, p->node_lh.ptr, p->node_ex.ptr);
+        launch_pdl(log10_finish_kernel, dim3((unsigned) std::min<long long>(148 * 8, (n / 2 + 255) / 256 + 1)), dim3(256), 0, p->stream, n,
+                   p->node_lh.ptr, (const int *) p->node_ex.ptr);
         p->launches++;
     }
 }

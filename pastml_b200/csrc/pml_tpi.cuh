@@ -147,10 +147,10 @@ __global__ void __launch_bounds__(PML_TPI_BLOCK, PML_TPI_BU_MINB) bu_tpi_kernel(
     pdl_launch_dependents();
     if (base < n_slots) {
         load_desc(base, cu_top, cu_len, cu_node);
-        pdl_wait();   // everything above is independent of the previous level
-        issue(cu_top);
         load_masks(base, cu_top, cu_node, cu_mo, cu_m0, cu_m1);
         if (base + stride < n_slots) load_desc(base + stride, nx_top, nx_len, nx_node);
+        pdl_wait();   // everything above (topology, annotation masks) is independent of the previous level
+        issue(cu_top);
     }
     for (; base < n_slots; base += stride) {
         const bool on = base + sub < n_slots;
