@@ -282,59 +282,36 @@ def full_ml_acr(flat, masks, has, cols, K, device, sync, check_column=None):
     return t1 - t0, t2 - t1, passes, float(lhs[0]), parity
 
 
-def run_subtree_sharded(args):
-    """One tree for all the GPUs: every rank prunes its clades, the clade-root vectors are all-gathered (NCCL), every
-    rank finishes the replicated top of the tree and sweeps back down into its own clades."""
-    import torch
+def subtree_sharded_step(args, flat, masks, has, params, rank, world, local_rank, steps, warmup, with_fit):
+    """ONE tree cut by subtree over the GPUs (pastml_b200/sharded.py): every rank prunes its clades, the clade-root
+    vectors are all-gathered by NCCL on the engine's stream, every rank finishes the replicated top tree and sweeps
+    back down into its own clades -- nothing goes through the host inside a step.  Device-timed (CUDA events around
+    every step on each rank), max over ranks."""
     import torch.distributed as dist
     from pastml_b200.parallel import max_over_ranks
-    from pastml_b200.sharded import SubtreePlan, ShardedProblem, all_gather_partials
-
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    flat, masks, has, pis, sfs, params = make_workload(args, 0)     # the SAME tree on every rank
+    from pastml_b200.sharded import SubtreePlan, DeviceShard
     K, C = args.states, args.columns
     plan = SubtreePlan(flat, world)
-    sp = ShardedProblem(plan, rank, K, 0, masks, has, device=local_rank)
-
-    def step():
-        vec, ex = sp.local_root_partials(params)
-        gathered = all_gather_partials(vec, ex, plan, rank)
-        vec, ex = sp.assemble(gathered)
-        return sp.marginal(params, vec, ex, want_probs=False, want_masks=False, reuse_bottom_up=True,
-                           results_on_device=True)   # same device work as the N = 1 step: probabilities are written
-
-    for _ in range(max(args.warmup, 3)):
-        top, mine = step()
-    torch.cuda.synchronize()
+    sh = DeviceShard(plan, rank, K, 0, masks, has, device=local_rank)
+    if world > 1:
+        sh.connect()
+    sh.bench_step(params, max(warmup, 3))
     dist.barrier()
-    with ClockSampler(local_rank) as clocks:
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            top, mine = step()
-        torch.cuda.synchronize()
-        dist.barrier()
-        dt = (time.perf_counter() - t0) / args.steps
-    dt = max_over_ranks(dt, device='cuda')
-    node_states = flat.n_nodes * K * C
-    line = {'metric': METRIC, 'value': node_states / dt, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': max(args.warmup, 3), 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'strong',
-            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, flat),
-            'clocks': clocks.summary(), 'loglh_column0': float(top['loglh'][0]),
-            'sharding': {'kind': 'subtree', 'top_levels': int(plan.top_forest().n_levels), 'clades': int(len(plan.boundary)),
-                         'top_nodes': int(plan.n_top), 'nodes_per_rank': [int(len(n)) for n in plan.nodes],
-                         'exchange': 'one all_gather_into_tensor of {} x (K+1) x C doubles per step'.format(
-                             max(len(p) for p in plan.roots_pos))},
-            'timing': 'host wall clock around K steps (the exchange goes through the host), max over ranks',
-            'gpu_launches': None}
-    line['config']['sharding'] = 'one tree cut into clades over the GPUs (subtree sharding)'
-    sp.close()
-    if not args.no_fit:
-        # the full ML fit of the 8 columns on the sharded tree: every rank runs the same host optimiser on values that
-        # are identical on all ranks, one all-gather per objective batch
+    ms_local, phases = sh.bench_step(params, steps, phases=True)
+    ms = max_over_ranks(ms_local, device='cuda')
+    loglh = sh.loglik(params)[0]
+    out = {'ms_per_step': ms, 'node_states_per_s': flat.n_nodes * K * C / (ms * 1e-3),
+           'clades': int(len(plan.boundary)), 'top_nodes': int(plan.n_top), 'top_levels': int(plan.top_forest().n_levels),
+           'nodes_per_rank': [int(len(n)) for n in plan.nodes], 'loglh_column0': float(loglh[0]),
+           'phases_ms_last_step_this_rank': phases,
+           'exchange': 'one ncclAllGather of {} x (K+1) x C doubles per step on the engine stream, no host hop'.format(
+               max(len(p) for p in plan.roots_pos)),
+           'timing': 'CUDA events around each step on every rank (L2 flushed between steps), mean over {} steps, max over '
+                     'ranks'.format(steps)}
+    sh.close()
+    if with_fit:
+        # the two-stage fit of all the columns on the sharded tree: every rank runs the same host optimiser on values
+        # that are identical on all ranks, one all-gather per objective batch
         from pastml_b200.annotation import ForestStats
         from pastml_b200.ml import fit_batch
         from pastml_b200.models import F81Model
@@ -351,17 +328,39 @@ def run_subtree_sharded(args):
         t0 = time.perf_counter()
         lhs, passes = fit_batch(batch, obs)
         dist.barrier()
-        fit_s = max_over_ranks(time.perf_counter() - t0, device='cuda')
-        phases = dict(batch.phase_seconds)
+        out['fit'] = {'seconds': max_over_ranks(time.perf_counter() - t0, device='cuda'), 'device_passes': int(passes),
+                      'loglh_column0': float(lhs[0]),
+                      'what': 'two-stage L-BFGS-B fit of all {} columns of the ONE tree, clades spread over {} GPUs'.format(C, world)}
         batch.close()
-        line['ml_fit'] = {'seconds': fit_s, 'device_passes': int(passes), 'loglh_column0': float(lhs[0]), 'phases_rank0': phases,
-                          'what': 'two-stage L-BFGS-B fit of all {} columns of the ONE sharded tree'.format(C)}
+    return out
+
+
+def run_subtree_sharded(args):
+    """--sharding subtree: the subtree-sharded step of ONE tree as the headline line (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    flat, masks, has, pis, sfs, params = make_workload(args, 0)     # the SAME tree on every rank
+    K, C = args.states, args.columns
+    with ClockSampler(local_rank) as clocks:
+        sub = subtree_sharded_step(args, flat, masks, has, params, rank, world, local_rank, args.steps, args.warmup,
+                                   not args.no_fit)
+    line = {'metric': METRIC, 'value': sub['node_states_per_s'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': sub['ms_per_step'], 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, flat),
+            'clocks': clocks.summary(), 'sharding': sub, 'gpu_launches': None}
+    line['config']['sharding'] = 'one tree cut into clades over the GPUs (subtree sharding)'
     if rank == 0:   # outside the timed region: the same tree, unsharded, on this GPU
         from pastml_b200.engine import Problem
         whole = Problem(flat, K, 0, masks, has, device=local_rank)
         ref = whole.loglik(params)[0]
         whole.close()
-        line['check_max_rel_dev_loglh_vs_unsharded'] = float(np.max(np.abs(top['loglh'] - ref) / np.abs(ref)))
+        line['check_rel_dev_loglh_column0_vs_unsharded'] = abs(sub['loglh_column0'] - float(ref[0])) / abs(float(ref[0]))
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
@@ -504,6 +503,23 @@ def run_b200(args):
                 'what': 'the {} columns of rank 0\'s tree fitted and reconstructed on {} GPUs, columns partitioned over the '
                         'ranks (independent, no exchange), max over ranks'.format(C, world)}
 
+    # ---- strong scaling of ONE tree cut by subtree over the GPUs (north star config 4's split), in the same run
+    one_tree_subtree = None
+    if world > 1:
+        flat0, masks0, has0, _, _, params0 = (flat, masks, has, pis, sfs, params) if rank == 0 else make_workload(args, 0)
+        barrier()
+        one_tree_subtree = subtree_sharded_step(args, flat0, masks0, has0, params0, rank, world, local_rank,
+                                                args.steps, args.warmup, with_fit=not args.no_fit)
+        one_tree_subtree['speedup_vs_this_runs_single_gpu_step'] = None   # filled below from rank 0's own step time
+        if rank == 0:
+            whole = Problem(flat0, K, 0, masks0, has0, device=local_rank)
+            ref = whole.loglik(params0)[0]
+            whole.close()
+            one_tree_subtree['check_rel_dev_loglh_column0_vs_unsharded'] = \
+                abs(one_tree_subtree['loglh_column0'] - float(ref[0])) / abs(float(ref[0]))
+        one_tree_subtree['speedup_vs_this_runs_single_gpu_step'] = step_ms / one_tree_subtree['ms_per_step']
+        barrier()
+
     # ---- roofline of the dominant kernel family (per-level launches of one templated kernel)
     peaks_path = os.path.join(REPO, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
@@ -544,7 +560,8 @@ def run_b200(args):
             'gpu_launches': int(launches * args.steps),
             'roofline': roof(dom), 'roofline_other': roof([k for k in sweeps if k != dom][0]),
             'min_ms_per_step': min_ms, 'wall_s_timed_region': wall,
-            'bu_objective_ms': bu_ms, 'bu_node_states_per_s': node_states / (bu_ms * 1e-3), 'ml_fit': ml_fit}
+            'bu_objective_ms': bu_ms, 'bu_node_states_per_s': node_states / (bu_ms * 1e-3), 'ml_fit': ml_fit,
+            'one_tree_subtree': one_tree_subtree}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

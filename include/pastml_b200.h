@@ -181,6 +181,37 @@ int pml_trim_memory(void);
  * with CUDA events on the handle's stream (ms), and the number of kernels launched. */
 int pml_last_call_stats(pml_problem *p, double *device_ms, int64_t *kernel_launches);
 
+/* ---- The same split with the exchange kept on the device (pastml_b200/sharded.py, bench.py --gpus N).  A pml_shard ties
+ * one rank's clade forest and its copy of the top tree (same device).  boundary_top[n_clades]: the clade roots as tip ids
+ * of the top tree, in boundary order; clade_owner[n_clades]: the rank that owns each clade (the clade forest's roots are
+ * this rank's clades in boundary order).  Per sweep:
+ *   pml_shard_bottom_up   clades bottom-up (masks of the given kind), clade-root runs packed and all-gathered over NCCL
+ *                         on the clade problem's stream -- no host synchronisation;
+ *   pml_shard_finish      gathered runs -> external tips of the top tree, top tree bottom-up, log-likelihood of the whole
+ *                         tree (the same on every rank; ml.py:82-121); out_loglh null = nothing fetched, no host sync;
+ *   pml_shard_top_down    fused top-down / marginal / MAP / MPPA sweep (ml.py:240-290, 431-465, 505-595): top tree on
+ *                         every rank, the rank's clade roots receive their top-down vectors on the device, clades;
+ *   pml_shard_results     outputs of either problem (which: 0 = top tree, 1 = clade forest), shapes as pml_marginal.
+ * NCCL is resolved from the running process (libnccl.so.2): pml_shard_unique_id on rank 0, the 128 bytes broadcast by the
+ * caller, pml_shard_connect on every rank.  pml_shard_exchange_local replaces the all-gather when the ranks are
+ * simulated in one process on one device (tests). */
+typedef struct pml_shard pml_shard;
+int pml_shard_create(pml_problem *clades, pml_problem *top, int32_t rank, int32_t world, int32_t n_clades,
+                     const int32_t *boundary_top, const int32_t *clade_owner, pml_shard **out);
+void pml_shard_destroy(pml_shard *sh);
+int pml_shard_unique_id(uint8_t *out_id128);
+int pml_shard_connect(pml_shard *sh, const uint8_t *id128);
+int pml_shard_bottom_up(pml_shard *sh, const double *params, int32_t n_sets, int32_t mask_kind);
+int pml_shard_exchange_local(pml_shard **shards, int32_t world);
+int pml_shard_finish(pml_shard *sh, const double *params, int32_t n_sets, double *out_loglh);
+int pml_shard_top_down(pml_shard *sh, int32_t want_probs, int32_t want_node_lh);
+int pml_shard_results(pml_shard *sh, int32_t which, double *out_probs, double *out_node_log10lh, uint64_t *out_map_mask,
+                      uint64_t *out_mppa_mask, int64_t *out_k_hist);
+/* device-timed sharded MPPA step, n_iter times (CUDA events on the clade stream around each step); phase_ms: clades
+ * bottom-up + pack, exchange, top tree bottom-up, top tree top-down, clades top-down */
+int pml_shard_bench_step(pml_shard *sh, const double *params, int32_t n_iter, int32_t flush_l2, double *avg_ms,
+                         double *phase_ms /* [5] of the last step, or null */);
+
 /* Device-resident variant used by bench.py: runs a pass n_iter times back to back on resident inputs and returns
  * the average / minimum device time per pass (CUDA events on the handle's stream).  which: 0 = bottom-up
  * objective (annotation masks, marginal, alter) for n_sets parameter sets; 1 = the marginal sweep (bottom-up +

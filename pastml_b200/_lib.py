@@ -16,6 +16,9 @@ EXPORTS = ['pml_last_error', 'pml_version', 'pml_device_count', 'pml_param_strid
            'pml_zero_likelihood_all', 'pml_trim_memory', 'pml_get_root_partials', 'pml_set_tip_partials',
            'pml_get_tip_td', 'pml_set_root_td',
            'pml_last_call_stats', 'pml_bench_pass', 'pml_supports_lane_lists', 'pml_loglik_lanes', 'pml_get_bottom_up',
+           'pml_shard_create', 'pml_shard_destroy', 'pml_shard_unique_id', 'pml_shard_connect', 'pml_shard_bottom_up',
+           'pml_shard_exchange_local', 'pml_shard_finish', 'pml_shard_top_down', 'pml_shard_results',
+           'pml_shard_bench_step',
            'pml_newick_last_error', 'pml_newick_parse', 'pml_newick_num_nodes', 'pml_newick_num_trees',
            'pml_newick_names_bytes', 'pml_newick_name_nodes', 'pml_newick_fill', 'pml_newick_free']
 
@@ -51,6 +54,26 @@ def load():
     lib.pml_problem_create.argtypes = [i32, vp, vp, i32, i32, i32, vp, vp, i32, i32, C.POINTER(vp)]
     lib.pml_problem_destroy.restype = None
     lib.pml_problem_destroy.argtypes = [vp]
+    lib.pml_shard_create.restype = C.c_int
+    lib.pml_shard_create.argtypes = [vp, vp, i32, i32, i32, vp, vp, C.POINTER(vp)]
+    lib.pml_shard_destroy.restype = None
+    lib.pml_shard_destroy.argtypes = [vp]
+    lib.pml_shard_unique_id.restype = C.c_int
+    lib.pml_shard_unique_id.argtypes = [vp]
+    lib.pml_shard_connect.restype = C.c_int
+    lib.pml_shard_connect.argtypes = [vp, vp]
+    lib.pml_shard_bottom_up.restype = C.c_int
+    lib.pml_shard_bottom_up.argtypes = [vp, vp, i32, i32]
+    lib.pml_shard_exchange_local.restype = C.c_int
+    lib.pml_shard_exchange_local.argtypes = [vp, i32]
+    lib.pml_shard_finish.restype = C.c_int
+    lib.pml_shard_finish.argtypes = [vp, vp, i32, vp]
+    lib.pml_shard_top_down.restype = C.c_int
+    lib.pml_shard_top_down.argtypes = [vp, i32, i32]
+    lib.pml_shard_results.restype = C.c_int
+    lib.pml_shard_results.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.pml_shard_bench_step.restype = C.c_int
+    lib.pml_shard_bench_step.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.pml_loglik.restype = C.c_int
     lib.pml_loglik.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.pml_supports_lane_lists.restype = C.c_int

@@ -504,7 +504,18 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT, TMA)) td_coop_
 #pragma unroll
                     for (int i = 0; i < KT; ++i) X[i] *= st_vec[2 * (VB / 8) + (r + G * i) * C + c];
                     pex += st_ex[2 * C + c];
+                } else if (a.ext.root_td) {   // child of a clade root: the root's top-down vector came from above the cut
+                    const int rn = a.t.int_nodes[ps];
+                    const double *src2 = a.ext.root_td + ((size_t) (rn * K + r) * C + c);
+#pragma unroll
+                    for (int i = 0; i < KT; ++i) X[i] *= src2[(G * i) * C];
+                    pex += a.ext.root_td_ex[(size_t) rn * C + c];
                 }
+            } else if (a.ext.root_td) {   // a clade root (subtree sharding): its top-down vector arrives from above the cut
+                const double *src = a.ext.root_td + ((size_t) (node * K + r) * C + c);
+#pragma unroll
+                for (int i = 0; i < KT; ++i) X[i] = src[(G * i) * C];
+                ex_total += a.ext.root_td_ex[(size_t) node * C + c];
             } else {
 #pragma unroll
                 for (int i = 0; i < KT; ++i) X[i] = 1.;
@@ -736,8 +747,10 @@ __global__ void __launch_bounds__(kCoopBlock, coop_min_blocks(KT, TMA)) td_coop_
             if (sum > 0. && !(bv * inv >= 0.76 && ji == best)) { sel = mine; best_k = bk; }
         }
         if (on && r == 0) {
-            a.map_mask[nc] = (1ULL << best) | flag;
-            a.mppa_mask[nc] = sel | flag;
+            // (the marker of an external tip travels with the state sets: restricted passes on these masks must still
+            // take the tip's vector from the tables of the clade below the cut)
+            a.map_mask[nc] = (1ULL << best) | flag | (base_mask & kExtFlag);
+            a.mppa_mask[nc] = sel | flag | (base_mask & kExtFlag);
             if (flag) a.zc_k[zr] = (uint8_t) best_k;
             atomicAdd(sh_hist + c * (K + 1) + best_k, 1u);
         }

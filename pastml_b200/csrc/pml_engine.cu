@@ -1,5 +1,7 @@
 // Host side of the pastml_b200 engine: problem handles, level-synchronous launch sequences, the C ABI declared
 // in include/pastml_b200.h.  Built by nvcc for sm_100a only (see pastml_b200/build.py).
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -175,7 +177,7 @@ struct pml_problem {
     DevBuf<float> flush;
     bool joint_done = false, marginal_done = false;
     // host staging
-    std::vector<double> h_out;
+    std::vector<double> h_out, h_params;   // h_params: the parameter block that is on the device (upload_params)
     std::vector<int> h_err;
     int zero_info[4] = {-1, -1, -1, -1};
     double last_ms = 0.;
@@ -242,6 +244,9 @@ void run_alter(pml_problem *p, const uint64_t *src) {
 // uploads params [n_sets][C][stride] and the per-column "tau == 0 somewhere" flags
 int upload_params(pml_problem *p, const double *params, int n_sets) {
     const size_t n = (size_t) n_sets * p->C * p->stride;
+    // the same block as last time (restricted-likelihood passes, repeated sweeps): nothing to copy, nothing to wait for
+    if (p->h_params.size() == n && std::memcmp(p->h_params.data(), params, n * sizeof(double)) == 0) return PML_OK;
+    p->h_params.assign(params, params + n);
     CUDA_TRY(cudaMemcpyAsync(p->params.ptr, params, n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     std::vector<uint8_t> rec(p->C, 0);
     for (int b = 0; b < n_sets; ++b)
@@ -434,9 +439,9 @@ void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool wan
              p->td_ex.ptr, p->joint_state.ptr, force_joint, want_probs ? p->probs.ptr : nullptr,
              want_node_lh ? p->node_lh.ptr : nullptr, p->node_ex.ptr, p->mask[PML_MASK_MAP].ptr, p->mask[PML_MASK_MPPA].ptr,
              p->k_hist.ptr, p->zc_lh.ptr, p->zc_k.ptr};
-    const bool tma_ok = !p->ext_index.ptr && !p->have_root_td && tma_enabled();
+    const bool tma_ok = !p->ext_index.ptr && tma_enabled();   // (top-down vectors arriving at the roots are fine)
     const CoopSet *coop = pick_coop(p, ln.C, tma_ok && !getenv("PASTML_B200_COOP_G"), false);
-    const bool td_tma = coop && coop->td_tma && !p->ext_index.ptr && !p->have_root_td && tma_enabled();
+    const bool td_tma = coop && coop->td_tma && !p->ext_index.ptr && tma_enabled();
     for (int lvl = 0; lvl < p->n_levels; ++lvl) {
         const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
         if (coop) {
@@ -877,6 +882,7 @@ int pml_loglik_lanes(pml_problem *p, const double *params, const int32_t *lane_c
         if (c < 0 || c >= p->C) return fail(PML_ERR_INVALID, "lane column out of range");
         if (params[(size_t) j * p->stride + 1] == 0.) rec[c] = 1;
     }
+    p->h_params.clear();   // the lane-list layout replaces whatever upload_params left on the device
     CUDA_TRY(cudaMemcpyAsync(p->params.ptr, params, (size_t) n_lanes * p->stride * sizeof(double), cudaMemcpyHostToDevice,
                              p->stream));
     CUDA_TRY(cudaMemcpyAsync(p->lane_col.ptr, lane_columns, (size_t) n_lanes * sizeof(int), cudaMemcpyHostToDevice, p->stream));
@@ -1272,6 +1278,402 @@ int pml_set_root_td(pml_problem *p, const double *vec, const int32_t *ex) {
     p->have_root_td = true;
     return PML_OK;
 }
+
+}  // extern "C" (the sharding block below opens its own)
+
+// ---------------------------------------------------------------------------------- device-resident subtree sharding
+//
+// One rank's share of a tree cut by subtree: its clade forest and the replicated top tree on one
+// device, with the exchange kept on the device.  Per sweep: clades bottom-up -> pack the clade-root runs -> ALL-GATHER
+// (NCCL on the clade problem's stream; the library is taken from the process at run time, so a single-GPU user never
+// needs it) -> unpack into the top tree's external-tip tables -> top tree (bottom-up, log-likelihood on every rank,
+// top-down) -> the rank's own clade roots receive their top-down vectors -> clades top-down.  Nothing goes through
+// the host inside a step; the two problems' streams are ordered with events.
+
+namespace {
+
+// the handful of NCCL entry points, resolved with dlopen (signatures of nccl.h; ncclFloat64 = 8)
+struct NcclApi {
+    struct UniqueId { char internal[128]; };
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+NcclApi &nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void *h = nullptr;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) { api.why = "libnccl.so.2 cannot be loaded (import torch first, or put NCCL on the library path)"; return; }
+        api.GetUniqueId = (int (*)(NcclApi::UniqueId *)) dlsym(h, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(void **, int, NcclApi::UniqueId, int)) dlsym(h, "ncclCommInitRank");
+        api.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t)) dlsym(h, "ncclAllGather");
+        api.CommDestroy = (int (*)(void *)) dlsym(h, "ncclCommDestroy");
+        api.GetErrorString = (const char *(*)(int)) dlsym(h, "ncclGetErrorString");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString;
+        if (!api.ok) api.why = "NCCL symbols missing";
+    });
+    return api;
+}
+
+// clade-root runs of this rank, [root][K + 1][J]: K mantissa rows and the exponents (as doubles, exact)
+__global__ void shard_pack_kernel(TreeDev t, LaneDev ln, const double *bu, const int *bu_ex, int n_roots, double *out) {
+    const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const int K = ln.K, J = ln.J;
+    if (g >= (long long) n_roots * (K + 1) * J) return;
+    const int j = (int) (g % J), k = (int) ((g / J) % (K + 1)), root = (int) (g / ((long long) J * (K + 1)));
+    const int s = t.slot[root];   // clade roots are internal nodes
+    out[g] = (k < K) ? bu[bu_at(ln, s, k, j)] : (double) bu_ex[(size_t) s * J + j];
+}
+
+// gathered runs -> the top tree's external-tip tables (rows in boundary order)
+__global__ void shard_unpack_kernel(const double *gathered, const int *row_src, int n_rows, int K, int J, double *ext_bu,
+                                    int *ext_bu_ex) {
+    const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long) n_rows * (K + 1) * J) return;
+    const int j = (int) (g % J), k = (int) ((g / J) % (K + 1)), row = (int) (g / ((long long) J * (K + 1)));
+    const double v = gathered[((size_t) row_src[row] * (K + 1) + k) * J + j];
+    if (k < K) ext_bu[((size_t) row * K + k) * J + j] = v;
+    else ext_bu_ex[(size_t) row * J + j] = (int) v;
+}
+
+// top-down vectors the top tree computed for this rank's clade roots -> the clade forest's roots
+__global__ void shard_root_td_kernel(const double *ext_td, const int *ext_td_ex, const int *my_rows, int n_mine, int K, int C,
+                                     double *root_td, int *root_td_ex) {
+    const long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long) n_mine * (K + 1) * C) return;
+    const int c = (int) (g % C), k = (int) ((g / C) % (K + 1)), i = (int) (g / ((long long) C * (K + 1)));
+    const int row = my_rows[i];
+    if (k < K) root_td[((size_t) i * K + k) * C + c] = ext_td[((size_t) row * K + k) * C + c];
+    else root_td_ex[(size_t) i * C + c] = ext_td_ex[(size_t) row * C + c];
+}
+
+}  // namespace
+
+struct pml_shard {
+    pml_problem *clades = nullptr, *top = nullptr;
+    int rank = 0, world = 1, n_clades = 0, n_mine = 0, n_max = 0;
+    DevBuf<int> row_src, my_rows;
+    DevBuf<double> xsend, xbuf;
+    size_t slot_doubles = 0;   // capacity of one rank's part of the exchange: n_max * (K + 1) * B * C
+    cudaEvent_t ev_gather = nullptr, ev_top = nullptr;
+    void *comm = nullptr;
+    int last_sets = 0, last_mask_kind = 0;
+    cudaEvent_t phase_event = nullptr;   // benchmark instrumentation: recorded between the pack and the collective
+};
+
+extern "C" {
+
+int pml_shard_create(pml_problem *clades, pml_problem *top, int32_t rank, int32_t world, int32_t n_clades,
+                     const int32_t *boundary_top, const int32_t *clade_owner, pml_shard **out) {
+    if (!out) return fail(PML_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!clades || !top || !boundary_top || !clade_owner || world < 1 || rank < 0 || rank >= world || n_clades < world)
+        return fail(PML_ERR_INVALID, "bad shard description");
+    if (clades->device != top->device || clades->K != top->K || clades->C != top->C || clades->B != top->B ||
+        clades->kind != top->kind)
+        return fail(PML_ERR_INVALID, "the clade forest and the top tree must share device, states, columns and capacity");
+    CUDA_TRY(cudaSetDevice(top->device));
+    std::vector<int> count(world, 0), local(n_clades), mine;
+    for (int i = 0; i < n_clades; ++i) {
+        const int r = clade_owner[i];
+        if (r < 0 || r >= world) return fail(PML_ERR_INVALID, "clade owner out of range");
+        local[i] = count[r]++;
+        if (r == rank) mine.push_back(i);
+    }
+    const int n_max = *std::max_element(count.begin(), count.end());
+    if ((int) mine.size() != clades->n_roots)
+        return fail(PML_ERR_INVALID, "the clade forest must have one root per clade of this rank, in boundary order");
+    std::vector<int> row_src(n_clades);
+    for (int i = 0; i < n_clades; ++i) row_src[i] = clade_owner[i] * n_max + local[i];
+    // the top tree's external tips: allocate and mark (zero vectors for now)
+    {
+        const size_t J = (size_t) top->B * top->C;
+        std::vector<double> zv((size_t) n_clades * top->K * J, 0.);
+        std::vector<int32_t> ze((size_t) n_clades * J, 0);
+        const int rc = pml_set_tip_partials(top, n_clades, boundary_top, zv.data(), ze.data(), top->B);
+        if (rc) return rc;
+    }
+    pml_shard *sh = new pml_shard();
+    sh->clades = clades; sh->top = top; sh->rank = rank; sh->world = world;
+    sh->n_clades = n_clades; sh->n_mine = (int) mine.size(); sh->n_max = n_max;
+    sh->slot_doubles = (size_t) n_max * (top->K + 1) * top->B * top->C;
+#define PML_SH_TRY(expr)                                                                                 \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e);                          \
+            pml_shard_destroy(sh);                                                                       \
+            return fail(PML_ERR_CUDA, m);                                                                \
+        }                                                                                                \
+    } while (0)
+    PML_SH_TRY(sh->row_src.alloc(n_clades));
+    PML_SH_TRY(sh->my_rows.alloc(std::max<size_t>(mine.size(), 1)));
+    PML_SH_TRY(sh->xsend.alloc(sh->slot_doubles));
+    PML_SH_TRY(sh->xbuf.alloc(sh->slot_doubles * world));
+    PML_SH_TRY(cudaMemset(sh->xsend.ptr, 0, sh->slot_doubles * sizeof(double)));
+    PML_SH_TRY(cudaMemcpy(sh->row_src.ptr, row_src.data(), sizeof(int) * n_clades, cudaMemcpyHostToDevice));
+    PML_SH_TRY(cudaMemcpy(sh->my_rows.ptr, mine.data(), sizeof(int) * mine.size(), cudaMemcpyHostToDevice));
+    PML_SH_TRY(cudaEventCreateWithFlags(&sh->ev_gather, cudaEventDisableTiming));
+    PML_SH_TRY(cudaEventCreateWithFlags(&sh->ev_top, cudaEventDisableTiming));
+    // the clade forest's roots take their top-down vectors from the top tree from now on
+    const size_t nv = (size_t) clades->n_roots * clades->K * clades->C, ne = (size_t) clades->n_roots * clades->C;
+    if (!clades->root_td.ptr) {
+        PML_SH_TRY(clades->root_td.alloc(nv));
+        PML_SH_TRY(clades->root_td_ex.alloc(ne));
+        PML_SH_TRY(cudaMemset(clades->root_td.ptr, 0, nv * sizeof(double)));
+        PML_SH_TRY(cudaMemset(clades->root_td_ex.ptr, 0, ne * sizeof(int)));
+    }
+    clades->have_root_td = true;
+#undef PML_SH_TRY
+    *out = sh;
+    return PML_OK;
+}
+
+void pml_shard_destroy(pml_shard *sh) {
+    if (!sh) return;
+    cudaSetDevice(sh->top->device);
+    cudaStreamSynchronize(sh->clades->stream);
+    cudaStreamSynchronize(sh->top->stream);
+    if (sh->comm && nccl().ok) nccl().CommDestroy(sh->comm);
+    if (sh->ev_gather) cudaEventDestroy(sh->ev_gather);
+    if (sh->ev_top) cudaEventDestroy(sh->ev_top);
+    delete sh;
+}
+
+int pml_shard_unique_id(uint8_t *out_id128) {
+    if (!out_id128) return fail(PML_ERR_INVALID, "null argument");
+    NcclApi &api = nccl();
+    if (!api.ok) return fail(PML_ERR_INVALID, api.why);
+    NcclApi::UniqueId id;
+    const int rc = api.GetUniqueId(&id);
+    if (rc) return fail(PML_ERR_CUDA, std::string("ncclGetUniqueId: ") + api.GetErrorString(rc));
+    std::memcpy(out_id128, id.internal, 128);
+    return PML_OK;
+}
+
+int pml_shard_connect(pml_shard *sh, const uint8_t *id128) {
+    if (!sh || !id128) return fail(PML_ERR_INVALID, "null argument");
+    NcclApi &api = nccl();
+    if (!api.ok) return fail(PML_ERR_INVALID, api.why);
+    CUDA_TRY(cudaSetDevice(sh->top->device));
+    NcclApi::UniqueId id;
+    std::memcpy(id.internal, id128, 128);
+    const int rc = api.CommInitRank(&sh->comm, sh->world, id, sh->rank);
+    if (rc) return fail(PML_ERR_CUDA, std::string("ncclCommInitRank: ") + api.GetErrorString(rc));
+    return PML_OK;
+}
+
+// phase A: this rank's clades bottom-up, the clade-root runs packed and (when connected) all-gathered; no host sync
+int pml_shard_bottom_up(pml_shard *sh, const double *params, int32_t n_sets, int32_t mask_kind) {
+    if (!sh || !params) return fail(PML_ERR_INVALID, "null argument");
+    pml_problem *p = sh->clades;
+    if (n_sets < 1 || n_sets > p->B) return fail(PML_ERR_INVALID, "n_sets exceeds the capacity given at creation");
+    if (mask_kind < 0 || mask_kind > PML_MASK_CUSTOM || !p->mask_valid[mask_kind])
+        return fail(PML_ERR_INVALID, "the requested mask set has not been produced yet");
+    CUDA_TRY(cudaSetDevice(p->device));
+    int rc = upload_params(p, params, n_sets);
+    if (rc) return rc;
+    run_bottom_up(p, n_sets, p->mask[mask_kind].ptr, 1, 1, false);
+    LaneDev ln = p->lanes(n_sets);
+    ln.jt = bu_tile_lanes(p, ln.J);
+    const long long n = (long long) p->n_roots * (p->K + 1) * ln.J;
+    shard_pack_kernel<<<grid_for(n), kBlock, 0, p->stream>>>(p->tree(), ln, p->bu.ptr, p->bu_ex.ptr, p->n_roots, sh->xsend.ptr);
+    p->launches++;
+    sh->last_sets = n_sets;
+    sh->last_mask_kind = mask_kind;
+    const size_t count = (size_t) sh->n_max * (p->K + 1) * ln.J;   // doubles per rank for this pass
+    if (sh->phase_event) cudaEventRecord(sh->phase_event, p->stream);
+    if (sh->comm) {
+        const int nrc = nccl().AllGather(sh->xsend.ptr, sh->xbuf.ptr, count, 8 /* ncclFloat64 */, sh->comm, p->stream);
+        if (nrc) return fail(PML_ERR_CUDA, std::string("ncclAllGather: ") + nccl().GetErrorString(nrc));
+    }
+    CUDA_TRY(cudaEventRecord(sh->ev_gather, p->stream));
+    CUDA_TRY(cudaGetLastError());
+    return PML_OK;
+}
+
+// single-process stand-in for the all-gather (tests; ranks simulated on one device): every shard's packed runs are
+// copied into every shard's gather buffer.  Call between pml_shard_bottom_up and pml_shard_finish.
+int pml_shard_exchange_local(pml_shard **shards, int32_t world) {
+    if (!shards || world < 1) return fail(PML_ERR_INVALID, "bad argument");
+    for (int r = 0; r < world; ++r)
+        if (!shards[r] || shards[r]->world != world || shards[r]->comm) return fail(PML_ERR_INVALID, "shards do not form a local group");
+    const pml_problem *p0 = shards[0]->clades;
+    const size_t count = (size_t) shards[0]->n_max * (p0->K + 1) * shards[0]->last_sets * p0->C;
+    for (int r = 0; r < world; ++r) CUDA_TRY(cudaStreamSynchronize(shards[r]->clades->stream));
+    for (int dst = 0; dst < world; ++dst)
+        for (int src = 0; src < world; ++src)
+            CUDA_TRY(cudaMemcpy(shards[dst]->xbuf.ptr + (size_t) src * count, shards[src]->xsend.ptr, count * sizeof(double),
+                                cudaMemcpyDeviceToDevice));
+    for (int r = 0; r < world; ++r) CUDA_TRY(cudaEventRecord(shards[r]->ev_gather, shards[r]->clades->stream));
+    return PML_OK;
+}
+
+// phase B: the gathered runs become the top tree's external tips; top tree bottom-up; log-likelihoods [n_sets][C] of the
+// whole tree (identical on every rank).  out_loglh null: nothing is fetched and the host is not synchronised.
+int pml_shard_finish(pml_shard *sh, const double *params, int32_t n_sets, double *out_loglh) {
+    if (!sh || !params) return fail(PML_ERR_INVALID, "null argument");
+    pml_problem *p = sh->top;
+    if (n_sets != sh->last_sets) return fail(PML_ERR_INVALID, "n_sets differs from the bottom-up phase");
+    CUDA_TRY(cudaSetDevice(p->device));
+    int rc = upload_params(p, params, n_sets);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamWaitEvent(p->stream, sh->ev_gather, 0));
+    const int J = n_sets * p->C;
+    const long long n = (long long) sh->n_clades * (p->K + 1) * J;
+    shard_unpack_kernel<<<grid_for(n), kBlock, 0, p->stream>>>(sh->xbuf.ptr, sh->row_src.ptr, sh->n_clades, p->K, J,
+                                                             p->ext_bu.ptr, p->ext_bu_ex.ptr);
+    p->launches++;
+    p->ext_sets = n_sets;
+    // the top tree's own nodes take the same kind of masks (the clade roots, its external tips, were restricted by
+    // their own problem already)
+    if (!p->mask_valid[sh->last_mask_kind]) return fail(PML_ERR_INVALID, "the top tree has not produced this mask set yet");
+    run_bottom_up(p, n_sets, p->mask[sh->last_mask_kind].ptr, 1, 1, false);
+    CUDA_TRY(cudaGetLastError());
+    if (!out_loglh) return PML_OK;
+    return fetch_loglik(p, n_sets, out_loglh);
+}
+
+// the fused top-down sweep of the sharded tree after pml_shard_bottom_up + pml_shard_finish with one parameter set:
+// top tree on every rank, then this rank's clades from the top-down vectors of their roots.  Outputs stay in the two
+// problems' device buffers (fetch them with pml_shard_results); the host is synchronised once, at the end.
+int pml_shard_top_down(pml_shard *sh, int32_t want_probs, int32_t want_node_lh) {
+    if (!sh) return fail(PML_ERR_INVALID, "null argument");
+    if (sh->last_sets != 1) return fail(PML_ERR_INVALID, "the top-down sweep takes one parameter set");
+    pml_problem *t = sh->top, *c = sh->clades;
+    CUDA_TRY(cudaSetDevice(t->device));
+    int rc = ensure_marginal_buffers(t, want_probs != 0, want_node_lh != 0);
+    if (rc) return rc;
+    rc = ensure_marginal_buffers(c, want_probs != 0, want_node_lh != 0);
+    if (rc) return rc;
+    run_top_down(t, 0, want_probs != 0, want_node_lh != 0);
+    const long long n = (long long) sh->n_mine * (t->K + 1) * t->C;
+    shard_root_td_kernel<<<grid_for(n), kBlock, 0, t->stream>>>(t->ext_td.ptr, t->ext_td_ex.ptr, sh->my_rows.ptr, sh->n_mine, t->K,
+                                                              t->C, c->root_td.ptr, c->root_td_ex.ptr);
+    t->launches++;
+    CUDA_TRY(cudaEventRecord(sh->ev_top, t->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, sh->ev_top, 0));
+    run_top_down(c, 0, want_probs != 0, want_node_lh != 0);
+    CUDA_TRY(cudaGetLastError());
+    for (pml_problem *p : {t, c}) {
+        p->mask_valid[PML_MASK_MAP] = p->mask_valid[PML_MASK_MPPA] = true;
+        p->marginal_done = true;
+        if (p->n_rows) {
+            cudaMemcpyAsync(p->zc_prev_initial.ptr, p->zc_initial.ptr, sizeof(uint64_t) * (size_t) p->n_rows * p->C,
+                            cudaMemcpyDeviceToDevice, p->stream);
+            cudaMemcpyAsync(p->zc_prev_hasinit.ptr, p->zc_hasinit.ptr, (size_t) p->n_rows * p->C, cudaMemcpyDeviceToDevice, p->stream);
+            cudaMemsetAsync(p->zc_touched.ptr, 0, (size_t) p->n_rows * p->C, p->stream);
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PML_OK;
+}
+
+// results of the last pml_shard_top_down for one of the two problems (which: 0 = top tree, 1 = clade forest); any
+// pointer may be null.  Shapes as in pml_marginal.
+int pml_shard_results(pml_shard *sh, int32_t which, double *out_probs, double *out_node_log10lh, uint64_t *out_map_mask,
+                      uint64_t *out_mppa_mask, int64_t *out_k_hist) {
+    if (!sh || which < 0 || which > 1) return fail(PML_ERR_INVALID, "bad argument");
+    pml_problem *p = which ? sh->clades : sh->top;
+    if (!p->marginal_done) return fail(PML_ERR_INVALID, "call pml_shard_top_down first");
+    CUDA_TRY(cudaSetDevice(p->device));
+    const size_t nc = (size_t) p->N * p->C;
+    if (out_probs) {
+        if (!p->probs.ptr) return fail(PML_ERR_INVALID, "probabilities were not requested");
+        CUDA_TRY(cudaMemcpyAsync(out_probs, p->probs.ptr, nc * p->K * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    }
+    if (out_node_log10lh) {
+        if (!p->node_lh.ptr) return fail(PML_ERR_INVALID, "node likelihoods were not requested");
+        CUDA_TRY(cudaMemcpyAsync(out_node_log10lh, p->node_lh.ptr, nc * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (out_map_mask) { int r2 = copy_masks_out(p, p->mask[PML_MASK_MAP].ptr, out_map_mask); if (r2) return r2; }
+    if (out_mppa_mask) { int r2 = copy_masks_out(p, p->mask[PML_MASK_MPPA].ptr, out_mppa_mask); if (r2) return r2; }
+    if (out_k_hist) { int r2 = copy_khist_out(p, out_k_hist); if (r2) return r2; }
+    return PML_OK;
+}
+
+// device-timed benchmark of the sharded MPPA step (bottom-up, exchange, top tree, top-down): n_iter steps back to back,
+// CUDA events on the clade stream around the whole run; the communicator must be connected unless world == 1
+int pml_shard_bench_step(pml_shard *sh, const double *params, int32_t n_iter, int32_t flush_l2, double *avg_ms,
+                         double *phase_ms) {
+    if (!sh || !params || n_iter < 1) return fail(PML_ERR_INVALID, "bad argument");
+    // (development: PASTML_B200_SHARD_BENCH_LOCAL=1 times one rank's share alone, on the gather buffer a previous
+    // pml_shard_exchange_local left behind)
+    const bool local_only = !sh->comm && sh->world > 1 && getenv("PASTML_B200_SHARD_BENCH_LOCAL") != nullptr;
+    if (!sh->comm && sh->world > 1 && !local_only) return fail(PML_ERR_INVALID, "connect the shard first");
+    pml_problem *t = sh->top, *c = sh->clades;
+    CUDA_TRY(cudaSetDevice(t->device));
+    int rc = ensure_marginal_buffers(t, true, true);
+    if (rc) return rc;
+    rc = ensure_marginal_buffers(c, true, true);
+    if (rc) return rc;
+    const long long flush_n = 64LL << 20;
+    if (flush_l2 && !c->flush.ptr) CUDA_TRY(c->flush.alloc(flush_n));
+    double total = 0.;
+    // phase boundaries of the last step (phase_ms[5]: clades bottom-up + pack, exchange, top tree bottom-up, top tree
+    // top-down, clades top-down)
+    cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (phase_ms) for (auto &e : pe) CUDA_TRY(cudaEventCreate(&e));
+    for (int it = 0; it < n_iter; ++it) {
+        if (flush_l2) flush_kernel<<<148 * 8, 256, 0, c->stream>>>(flush_n, c->flush.ptr, (float) it);
+        cudaEventRecord(c->ev0, c->stream);
+        sh->phase_event = phase_ms ? pe[0] : nullptr;
+        rc = pml_shard_bottom_up(sh, params, 1, PML_MASK_ANNOTATION);
+        if (rc) return rc;
+        if (phase_ms) cudaEventRecord(pe[1], c->stream);
+        if (!sh->comm && !local_only) {   // world == 1: the gather is this rank's own runs
+            CUDA_TRY(cudaMemcpyAsync(sh->xbuf.ptr, sh->xsend.ptr, (size_t) sh->n_max * (c->K + 1) * c->C * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_TRY(cudaEventRecord(sh->ev_gather, c->stream));
+        }
+        rc = pml_shard_finish(sh, params, 1, nullptr);
+        if (rc) return rc;
+        if (phase_ms) cudaEventRecord(pe[2], t->stream);
+        run_top_down(t, 0, true, true);
+        const long long n = (long long) sh->n_mine * (t->K + 1) * t->C;
+        shard_root_td_kernel<<<grid_for(n), kBlock, 0, t->stream>>>(t->ext_td.ptr, t->ext_td_ex.ptr, sh->my_rows.ptr, sh->n_mine,
+                                                                  t->K, t->C, c->root_td.ptr, c->root_td_ex.ptr);
+        CUDA_TRY(cudaEventRecord(sh->ev_top, t->stream));
+        if (phase_ms) cudaEventRecord(pe[3], t->stream);
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, sh->ev_top, 0));
+        run_top_down(c, 0, true, true);
+        cudaEventRecord(c->ev1, c->stream);
+        CUDA_TRY(cudaEventSynchronize(c->ev1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        total += ms;
+        if (phase_ms && it == n_iter - 1) {
+            float x = 0.f;
+            cudaEventElapsedTime(&x, c->ev0, pe[0]); phase_ms[0] = x;
+            cudaEventElapsedTime(&x, pe[0], pe[1]); phase_ms[1] = x;
+            cudaEventElapsedTime(&x, pe[1], pe[2]); phase_ms[2] = x;
+            cudaEventElapsedTime(&x, pe[2], pe[3]); phase_ms[3] = x;
+            cudaEventElapsedTime(&x, pe[3], c->ev1); phase_ms[4] = x;
+        }
+    }
+    sh->phase_event = nullptr;
+    if (phase_ms) for (auto &e : pe) cudaEventDestroy(e);
+    CUDA_TRY(cudaStreamSynchronize(t->stream));
+    CUDA_TRY(cudaGetLastError());
+    for (pml_problem *p : {t, c}) { p->mask_valid[PML_MASK_MAP] = p->mask_valid[PML_MASK_MPPA] = true; p->marginal_done = true; }
+    if (avg_ms) *avg_ms = total / n_iter;
+    return PML_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 int pml_trim_memory(void) {
     g_pool.trim();

@@ -803,14 +803,14 @@ __device__ __forceinline__ void emit_node(const TdArgs &a, const LaneT &lane, in
 #pragma unroll
     for (int k = 1; k < KP; ++k)
         if (m[k] > bv) { bv = m[k]; best = k; }
-    a.map_mask[nc] = (1ULL << best) | flag;
+    a.map_mask[nc] = (1ULL << best) | flag | (base & kExtFlag);   // external tips keep their marker
     int best_k;
     uint64_t sel;
     const int ji = a.force_joint ? a.joint_state[nc] : best;
     if (!(sum > 0.)) { sel = a.ln.kmask; best_k = K; }   // NaN probabilities: no k beats +inf, all states kept
     else if (bv * inv >= 0.76 && ji == best) { sel = 1ULL << best; best_k = 1; }   // k = 1 is optimal when p1 > 3/4
     else sel = mppa_select<KP>(m, inv, K, ji, a.force_joint != 0, best_k);
-    a.mppa_mask[nc] = sel | flag;
+    a.mppa_mask[nc] = sel | flag | (base & kExtFlag);
     if (flag) a.zc_k[(size_t) a.t.zc_index[node] * C + c] = (uint8_t) best_k;
     atomicAdd(sh_hist + c * (K + 1) + best_k, 1u);
 }

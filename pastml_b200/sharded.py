@@ -184,6 +184,124 @@ class ShardedProblem(object):
         return top, mine
 
 
+class DeviceShard(object):
+    """One rank's share of a sharded tree with the exchange kept on the device (C ABI ``pml_shard_*``): the clade-root
+    runs are packed by a kernel, all-gathered by NCCL on the engine's stream and unpacked into the top tree's tables
+    without touching the host; the top-down vectors of the rank's clade roots travel the same way in the other
+    direction.  ``connect()`` builds the NCCL communicator (the unique id is broadcast through ``torch.distributed``);
+    ranks simulated in one process exchange with :func:`exchange_local` instead."""
+
+    def __init__(self, plan, rank, n_states, model_kind, annot_mask, has_state, max_param_sets=1, device=0):
+        import ctypes as C
+        from pastml_b200 import _lib
+        self.plan, self.rank = plan, rank
+        annot_mask = np.atleast_2d(annot_mask)
+        has_state = np.atleast_2d(has_state)
+        ids = plan.nodes[rank]
+        self.clades = Problem(plan.clade_forest(rank), n_states, model_kind, annot_mask[:, ids], has_state[:, ids],
+                              max_param_sets=max_param_sets, device=device)
+        self.top = Problem(plan.top_forest(), n_states, model_kind, annot_mask[:, plan.top_ids],
+                           has_state[:, plan.top_ids], max_param_sets=max_param_sets, device=device)
+        self.K, self.C = int(n_states), annot_mask.shape[0]
+        self.lib = _lib.load()
+        boundary_top = np.ascontiguousarray(plan.boundary_top, dtype=np.int32)
+        owner = np.ascontiguousarray(plan.owner_of_clade, dtype=np.int32)
+        handle = C.c_void_p()
+        rc = self.lib.pml_shard_create(self.clades._h, self.top._h, rank, plan.world, len(boundary_top),
+                                       boundary_top.ctypes.data_as(C.c_void_p), owner.ctypes.data_as(C.c_void_p),
+                                       C.byref(handle))
+        self._h = handle if rc == 0 else None
+        self.top._check(rc)
+        self.connected = False
+
+    def close(self):
+        if getattr(self, '_h', None) is not None:
+            self.lib.pml_shard_destroy(self._h)
+            self._h = None
+        self.clades.close()
+        self.top.close()
+
+    def connect(self):
+        """Builds the NCCL communicator of the sharded step; needs an initialised ``torch.distributed`` group."""
+        import torch
+        import torch.distributed as dist
+        uid = np.zeros(128, dtype=np.uint8)
+        if dist.get_rank() == 0:
+            self.top._check(self.lib.pml_shard_unique_id(_ptr(uid)))
+        t = torch.from_numpy(uid)
+        if dist.get_backend() == 'nccl':
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        uid = np.ascontiguousarray(t.cpu().numpy())
+        self.top._check(self.lib.pml_shard_connect(self._h, _ptr(uid)))
+        self.connected = True
+
+    # ---- phases
+    def bottom_up(self, params, n_sets=1, mask_kind=0):
+        params = self.clades._params(params, n_sets)
+        self.clades._check(self.lib.pml_shard_bottom_up(self._h, _ptr(params), n_sets, mask_kind))
+
+    def finish(self, params, n_sets=1, fetch=True):
+        params = self.top._params(params, n_sets)
+        out = np.empty((n_sets, self.C), dtype=np.float64) if fetch else None
+        self.top._check(self.lib.pml_shard_finish(self._h, _ptr(params), n_sets, _ptr(out)))
+        return out
+
+    def loglik(self, params, n_sets=1, mask_kind=0):
+        """Log-likelihoods [n_sets][C] of the whole tree (identical on every rank); needs ``connect()`` (or one rank)."""
+        self.bottom_up(params, n_sets, mask_kind)
+        if not self.connected:
+            exchange_local([self])
+        return self.finish(params, n_sets)
+
+    def top_down(self, want_probs=True, want_node_lh=False):
+        self.top._check(self.lib.pml_shard_top_down(self._h, 1 if want_probs else 0, 1 if want_node_lh else 0))
+
+    def results(self, which, want_probs=True, want_node_lh=False, want_masks=True):
+        pb = self.clades if which else self.top
+        probs = np.empty((pb.N, pb.C, pb.K), dtype=np.float64) if want_probs else None
+        node_lh = np.empty((pb.N, pb.C), dtype=np.float64) if want_node_lh else None
+        map_mask = np.empty((pb.N, pb.C), dtype=np.uint64) if want_masks else None
+        mppa_mask = np.empty((pb.N, pb.C), dtype=np.uint64) if want_masks else None
+        k_hist = np.empty((pb.C, pb.K + 1), dtype=np.int64)
+        pb._check(self.lib.pml_shard_results(self._h, which, _ptr(probs), _ptr(node_lh), _ptr(map_mask), _ptr(mppa_mask),
+                                             _ptr(k_hist)))
+        return dict(probs=probs, node_log10lh=node_lh, map_mask=map_mask, mppa_mask=mppa_mask, k_hist=k_hist)
+
+    def marginal(self, params, want_probs=True, want_masks=True):
+        """The whole fixed-parameter pipeline on the sharded tree; returns (log-likelihoods [C], top-tree outputs with
+        global node ids ``plan.top_ids``, this rank's clade outputs with global node ids ``plan.nodes[rank]``)."""
+        loglh = self.loglik(params)[0]
+        self.top_down(want_probs=want_probs)
+        return loglh, self.results(0, want_probs, False, want_masks), self.results(1, want_probs, False, want_masks)
+
+    def bench_step(self, params, n_iter, flush_l2=True, phases=False):
+        """Mean device time (ms) of n_iter sharded MPPA steps; with ``phases`` also the last step's split."""
+        import ctypes as C
+        params = self.clades._params(params, 1)
+        ms = C.c_double()
+        ph = np.zeros(5, dtype=np.float64) if phases else None
+        self.clades._check(self.lib.pml_shard_bench_step(self._h, _ptr(params), n_iter, 1 if flush_l2 else 0, C.byref(ms),
+                                                         _ptr(ph)))
+        if phases:
+            names = ('clades_bottom_up', 'exchange', 'top_bottom_up', 'top_top_down', 'clades_top_down')
+            return ms.value, {k: float(v) for k, v in zip(names, ph)}
+        return ms.value
+
+
+def exchange_local(shards):
+    """Stand-in for the all-gather when the ranks of a sharded tree are simulated in ONE process on one device: call
+    between ``bottom_up`` and ``finish`` with every rank's :class:`DeviceShard`."""
+    import ctypes as C
+    arr = (C.c_void_p * len(shards))(*[sh._h for sh in shards])
+    shards[0].top._check(shards[0].lib.pml_shard_exchange_local(arr, len(shards)))
+
+
+def _ptr(a):
+    import ctypes as C
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
 def all_gather_partials(vec, ex, plan, rank):
     """All ranks' (vec, ex), exchanged with one all_gather of a padded tensor (torch.distributed must be
     initialised; the backend decides the transport: NCCL over NVLink on the GPU box, gloo on CPU)."""
@@ -237,10 +355,17 @@ class ShardedColumnBatch(object):
         self.max_sets = (1 + max(m.get_num_params() for m in self.models)) if batched_gradients() else 1
         self.lane_lists = False   # the sharded objective always runs the (sets x columns) grid
         self.batched_fd = self.max_sets > 1
-        self.sp = ShardedProblem(plan, rank, self.K, self.kind, annot_mask, has_state, max_param_sets=self.max_sets,
-                                 device=device)
+        self.gather = gather
+        if gather is None:
+            # device-resident exchange (NCCL on the engine's stream); a single rank needs no communicator
+            self.sp = DeviceShard(plan, rank, self.K, self.kind, annot_mask, has_state, max_param_sets=self.max_sets,
+                                  device=device)
+            if plan.world > 1:
+                self.sp.connect()
+        else:   # host-staged exchange through a caller-supplied gather (tests)
+            self.sp = ShardedProblem(plan, rank, self.K, self.kind, annot_mask, has_state, max_param_sets=self.max_sets,
+                                     device=device)
         self.problem = self.sp.top          # LockstepEvaluator reads .stride from here
-        self.gather = gather or (lambda vec, ex: all_gather_partials(vec, ex, plan, rank))
         self.phase_seconds = {}
 
     def close(self):
@@ -251,6 +376,11 @@ class ShardedColumnBatch(object):
 
     def loglik_sets(self, params, n_sets):
         import time
+        if self.gather is None:
+            t0 = time.perf_counter()
+            out = self.sp.loglik(params, n_sets)
+            self.phase_seconds['device_step_s'] = self.phase_seconds.get('device_step_s', 0.) + time.perf_counter() - t0
+            return out, {}
         t0 = time.perf_counter()
         vec, ex = self.sp.local_root_partials(params, n_sets)
         t1 = time.perf_counter()

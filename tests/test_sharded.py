@@ -83,6 +83,62 @@ def test_sharded_equals_unsharded(n_tips, K, C, world, kind):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('n_tips,K,C,world,kind', [(4000, 20, 8, 2, 'yule'), (3000, 7, 3, 3, 'coalescent'),
+                                                  (60_000, 20, 8, 8, 'yule'), (2500, 12, 20, 4, 'yule')])
+def test_device_shards_equal_unsharded(n_tips, K, C, world, kind):
+    """The device-resident split (pml_shard_*: pack kernel -> gather buffer -> external tips of the top tree; top-down
+    vectors handed to the clade roots on the device; TMA-staged clade sweeps) with the ranks simulated in one process:
+    objective with two parameter sets, restricted likelihood on the MAP masks, and the whole marginal pipeline."""
+    from pastml_b200 import synth
+    from pastml_b200.engine import Problem, pack_params, MASK_MAP
+    from pastml_b200.sharded import SubtreePlan, DeviceShard, exchange_local, merge_outputs
+    flat, rng = _tree(n_tips, 300 + n_tips + K, kind)
+    masks, has, pis, sfs = synth.simulate_tip_masks(flat, K, C, rng, missing=0.05)
+    params = np.stack([pack_params(0, K, sfs[c], 0., 1., pis[c]) for c in range(C)])
+    sets = np.stack([params, params])
+    sets[1, :, 0] *= 1.3
+    whole = Problem(flat, K, 0, masks, has, max_param_sets=2)
+    want_lh = whole.loglik(sets, n_sets=2)
+    want = whole.marginal(params, force_joint=False)
+    want_map = whole.loglik(params, mask_kind=MASK_MAP)
+    whole.close()
+
+    plan = SubtreePlan(flat, world, clades_per_rank=4)
+    ranks = [DeviceShard(plan, r, K, 0, masks, has, max_param_sets=2) for r in range(world)]
+    for sh in ranks:
+        sh.bottom_up(sets, n_sets=2)
+    exchange_local(ranks)
+    for sh in ranks:
+        np.testing.assert_allclose(sh.finish(sets, n_sets=2), want_lh, rtol=1e-12, atol=0)
+    for sh in ranks:
+        sh.bottom_up(params)
+    exchange_local(ranks)
+    pieces = []
+    for sh in ranks:
+        lh = sh.finish(params)
+        np.testing.assert_allclose(lh[0], want['loglh'], rtol=1e-12)
+        sh.top_down()
+        pieces.append((sh.results(0), sh.results(1)))
+    for key in ('probs', 'map_mask', 'mppa_mask'):
+        got = merge_outputs(plan, pieces, key, flat.n_nodes)
+        if key == 'probs':
+            np.testing.assert_allclose(got, want[key], rtol=0, atol=1e-12)
+        else:
+            assert np.array_equal(got, want[key]), key
+    hist = sum(piece[1]['k_hist'] for piece in pieces) + pieces[0][0]['k_hist']
+    # (the clade roots are counted twice: once as tips of the top tree, once as roots of their clade)
+    assert int(hist.sum()) == (flat.n_nodes + len(plan.boundary)) * 1 * C
+    # restricted likelihood: every problem applies its own MAP masks
+    for sh in ranks:
+        sh.bottom_up(params, mask_kind=MASK_MAP)
+    exchange_local(ranks)
+    for sh in ranks:
+        np.testing.assert_allclose(sh.finish(params), want_map, rtol=1e-12)
+    for sh in ranks:
+        sh.close()
+
+
+@pytest.mark.gpu
 def test_fit_on_a_sharded_tree_matches_the_plain_fit():
     """The lock-step fit driven by the sharded objective (one rank owning all clades: the exchange is the identity)
     gives what the plain ColumnBatch gives."""
