@@ -193,6 +193,11 @@ struct pml_problem {
     // subtree sharding: external tip vectors / root top-down vectors
     DevBuf<int> lane_col;      // explicit column per lane (pml_loglik_lanes), B * C entries, allocated on first use
     bool eig_shared = false;   // EIG: every lane of the uploaded parameters carries the same d, A, A^-1
+    // tensor-core top-down sweep (shared decomposition): the products P L_child kept by the bottom-up sweep and the
+    // top-down vectors of every node, all indexed by node
+    DevBuf<double> v_all, td_all;
+    DevBuf<int> td_ex_all;
+    bool v_valid = false;      // v_all belongs to the bottom-up state that is in bu / bu_ex
     int n_ext = 0, ext_sets = 0;
     bool have_root_td = false;
     DevBuf<int> ext_index, ext_bu_ex, ext_td_ex, root_td_ex, ext_nodes;
@@ -224,6 +229,14 @@ inline int thin_level_threshold() {
 inline bool tma_enabled() {   // PASTML_B200_NO_TMA=1: the register-path cooperative kernels (A/B measurements)
     static const bool off = getenv("PASTML_B200_NO_TMA") != nullptr;
     return !off;
+}
+
+// the top-down sweep can run on the tensor cores: eigen-decomposition model with one decomposition for all the columns
+// (JTT), columns a multiple of 8, no external tables (PASTML_B200_NO_MMA / PASTML_B200_NO_MMA_TD: A/B measurements)
+bool mma_td_wanted(const pml_problem *p) {
+    static const bool off = getenv("PASTML_B200_NO_MMA") != nullptr || getenv("PASTML_B200_NO_MMA_TD") != nullptr;
+    return !off && p->kind == PML_MODEL_EIG && p->eig_shared && !p->ext_index.ptr && !p->have_root_td &&
+           mma_bu_applicable(p->K, p->C);
 }
 
 void run_root_loglik(pml_problem *p, const LaneDev &ln, const uint64_t *mask, int alter, int is_marginal) {
@@ -291,12 +304,14 @@ void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_
     fill_int_kernel<<<grid_for(2LL * ln.J), kBlock, 0, p->stream>>>(2LL * ln.J, -1, p->err.ptr);
     p->launches++;
     BuArgs a{p->tree(), p->zc(), p->ext(), ln, mask, alter, p->bu.ptr, p->bu_ex.ptr, keep_ptr ? p->ptr.ptr : nullptr,
-             p->err.ptr};
+             p->err.ptr, nullptr};
     const bool maxp = !is_marginal;
     const CoopSet *coop = maxp ? nullptr : pick_coop(p, ln.J);
     static const bool no_mma = getenv("PASTML_B200_NO_MMA") != nullptr;
     const bool mma = !maxp && p->kind == PML_MODEL_EIG && p->eig_shared && !p->ext_index.ptr && !no_mma &&
                      mma_bu_applicable(p->K, ln.J);
+    // the state pass of the marginal pipeline (one set, annotation masks, alter) also keeps P L_child for the top-down sweep
+    if (mma && n_sets == 1 && n_lanes == 0 && alter && mask == p->mask[PML_MASK_ANNOTATION].ptr) a.v_all = p->v_all.ptr;
     // thread-per-item sweep with TMA-staged child vectors (F81 family, sum-product mode, no external tips)
     for (int lvl = p->n_levels - 1; lvl >= 0; --lvl) {
         const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
@@ -368,12 +383,16 @@ void run_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marg
     // everything that selects kernels at capture time belongs to the key: eig_shared decides between the tensor-core
     // sweep (one decomposition for all lanes) and the per-lane kernels, and it changes when the frequencies do
     run_graphed(p, {n_lanes > 0 ? 2 : 0, n_lanes > 0 ? n_lanes : n_sets, (long long) (uintptr_t) mask, is_marginal, alter,
-                    (keep_ptr ? 1 : 0) + 2 * (p->eig_shared ? 1 : 0) + 4 * (long long) p->n_ext},
+                    (keep_ptr ? 1 : 0) + 2 * (p->eig_shared ? 1 : 0) + 4 * (p->v_all.ptr ? 1 : 0) + 8 * (long long) p->n_ext},
                 [&]() { enqueue_bottom_up(p, n_sets, mask, is_marginal, alter, keep_ptr, n_lanes); });
+    // does v_all (the products P L_child kept by the tensor-core sweep) still go with the vectors in bu?
+    const bool state_pass = is_marginal && n_sets == 1 && n_lanes == 0 && alter && mask == p->mask[PML_MASK_ANNOTATION].ptr;
+    p->v_valid = state_pass && p->v_all.ptr && mma_td_wanted(p);
 }
 
 void run_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh) {
-    run_graphed(p, {1, force_joint, want_probs ? 1 : 0, want_node_lh ? 1 : 0, p->n_ext, p->have_root_td ? 1 : 0},
+    const bool mma = mma_td_wanted(p) && p->v_valid;
+    run_graphed(p, {1, force_joint, want_probs ? 1 : 0, want_node_lh ? 1 : 0, p->n_ext, (p->have_root_td ? 1 : 0) + (mma ? 2 : 0)},
                 [&]() { enqueue_top_down(p, force_joint, want_probs, want_node_lh); });
 }
 
@@ -439,6 +458,17 @@ void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool wan
              p->td_ex.ptr, p->joint_state.ptr, force_joint, want_probs ? p->probs.ptr : nullptr,
              want_node_lh ? p->node_lh.ptr : nullptr, p->node_ex.ptr, p->mask[PML_MASK_MAP].ptr, p->mask[PML_MASK_MPPA].ptr,
              p->k_hist.ptr, p->zc_lh.ptr, p->zc_k.ptr};
+    if (mma_td_wanted(p) && p->v_valid) {
+        // vectors level by level on the tensor cores, then marginals / MAP / MPPA of the whole forest in one launch
+        for (int lvl = 1; lvl < p->n_levels; ++lvl) {
+            const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
+            mma_td_launch(p->stream, a, p->v_all.ptr, p->td_all.ptr, p->td_ex_all.ptr, n0, nn);
+            p->launches++;
+        }
+        p->ks->td_select(p->stream, a, p->td_all.ptr, p->td_ex_all.ptr, p->N);
+        p->launches++;
+        return;
+    }
     const bool tma_ok = !p->ext_index.ptr && tma_enabled();   // (top-down vectors arriving at the roots are fine)
     const CoopSet *coop = pick_coop(p, ln.C, tma_ok && !getenv("PASTML_B200_COOP_G"), false);
     const bool td_tma = coop && coop->td_tma && !p->ext_index.ptr && tma_enabled();
@@ -461,6 +491,15 @@ void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool wan
                    p->node_lh.ptr, (const int *) p->node_ex.ptr);
         p->launches++;
     }
+}
+
+int ensure_mma_td_buffers(pml_problem *p) {
+    if (!mma_td_wanted(p) || p->v_all.ptr) return PML_OK;
+    const size_t n = (size_t) p->N * p->K * p->C;
+    CUDA_TRY(p->v_all.alloc(n));
+    CUDA_TRY(p->td_all.alloc(n));
+    CUDA_TRY(p->td_ex_all.alloc((size_t) p->N * p->C));
+    return PML_OK;
 }
 
 int ensure_joint_buffers(pml_problem *p) {
@@ -949,9 +988,12 @@ int pml_marginal(pml_problem *p, const double *params, int32_t force_joint, doub
     if (rc) return rc;
     rc = upload_params(p, params, 1);
     if (rc) return rc;
+    rc = ensure_mma_td_buffers(p);
+    if (rc) return rc;
     CallTimer timer(p);
     // ml.py:700-706: allowed states are re-initialised and altered, then BU(alter=False), TD, marginals
-    if (!reuse_bu) run_bottom_up(p, 1, p->mask[PML_MASK_ANNOTATION].ptr, 1, 1, false);
+    // (a reused bottom-up state must come with the products the tensor-core top-down sweep reads)
+    if (!reuse_bu || (mma_td_wanted(p) && !p->v_valid)) run_bottom_up(p, 1, p->mask[PML_MASK_ANNOTATION].ptr, 1, 1, false);
     run_top_down(p, force_joint, do_probs, do_node_lh);
     // remember the '.initial' state MAP saw: pml_mppa_finalize needs it
     if (p->n_rows) {
@@ -1703,6 +1745,7 @@ int pml_bench_pass(pml_problem *p, const double *params, int32_t n_sets, int32_t
     if (which == 2) { int r2 = ensure_joint_buffers(p); if (r2) return r2; }
     int rc = upload_params(p, params, n_sets);
     if (rc) return rc;
+    if (which == 1 || which == 3 || which == 4) { rc = ensure_mma_td_buffers(p); if (rc) return rc; }
     const long long flush_n = 64LL << 20;   // 256 MiB of floats > 126 MB L2
     if (flush_l2 && !p->flush.ptr) CUDA_TRY(p->flush.alloc(flush_n));
     double total = 0., best = 1e300;

@@ -62,6 +62,14 @@ void td_launch(cudaStream_t st, const TdArgs &a, int s0, int ns) {
     launch_pdl(td_level_kernel<KP, TheLane>, dim3(grid_for((long long) ns * a.ln.C)), dim3(kBlock), sh, st, a, s0, ns);
 }
 
+void td_select_launch(cudaStream_t st, const TdArgs &a, const double *td_all, const int *td_ex_all, int n_nodes) {
+    const size_t sh = sizeof(double) * staged_fields(TheLane<KP>::family, a.ln.K) * a.ln.C + sizeof(unsigned) * a.ln.C * (a.ln.K + 1);
+    allow_big_smem(td_select_kernel<KP, TheLane>, sh);
+    long long g = ((long long) n_nodes * a.ln.C + kBlock - 1) / kBlock;
+    if (g > 148LL * 16) g = 148LL * 16;   // grid-stride: the per-block histogram is flushed once
+    launch_pdl(td_select_kernel<KP, TheLane>, dim3((unsigned) (g < 1 ? 1 : g)), dim3(kBlock), sh, st, a, td_all, td_ex_all, n_nodes);
+}
+
 void mppa_fix_launch(cudaStream_t st, int n_rows, const int *row_node, int C, int K, uint64_t kmask, const ZcDev &zc,
                      const uint64_t *base_mask, const uint64_t *prev_initial, const uint8_t *prev_hasinit,
                      const double *zc_lh, uint8_t *zc_k, const int *joint_state, int force_joint, uint64_t *mppa_mask,
@@ -77,7 +85,7 @@ void mppa_fix_launch(cudaStream_t st, int n_rows, const int *row_node, int C, in
 #define PML_KS_NAME PML_KS_NAME2(PML_FAMILY, PML_KP)
 
 const KernelSet *PML_KS_NAME() {
-    static const KernelSet ks = {bu_launch, root_launch, td_launch, mppa_fix_launch};
+    static const KernelSet ks = {bu_launch, root_launch, td_launch, td_select_launch, mppa_fix_launch};
     return &ks;
 }
 

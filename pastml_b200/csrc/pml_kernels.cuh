@@ -498,6 +498,8 @@ struct BuArgs {
     int *bu_ex;             // [NI][J]
     uint8_t *ptr;           // joint mode: [N][C][K] argmax pointers stored on the child (may be null)
     int *err;               // [J][2] first failing (parent, child), initialised to -1
+    double *v_all;          // tensor-core sweep, one parameter set: [N][K][C] the products P(t) L_child it forms anyway,
+                            // kept for the top-down sweep (they are its node_contribution, ml.py:280); may be null
 };
 
 // loads the K-vector of a child: a stored mantissa vector for internal nodes, the allowed-state mask for tips
@@ -904,6 +906,53 @@ __global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_TD_MINB : 1)) td_level
 #pragma unroll
             for (int k = 0; k < KP; ++k) X[k] *= Lc[k];
             ex_total = qex + exc;
+        }
+        emit_node<KP>(a, lane, node, c, X, mc, ex_total, sh_hist);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x)
+        if (sh_hist[i]) atomicAdd(a.k_hist + i, (unsigned long long) sh_hist[i]);
+}
+
+// Second half of the top-down step on its own: marginal likelihoods, probabilities, MAP and MPPA states of every node
+// from the bottom-up vectors and top-down vectors that a vector-only sweep (the tensor-core one, pml_mma.cu) left in
+// td_all [N][K][C] / td_ex_all [N][C] (indexed by node, tips included).  No dependency between nodes: one launch for
+// the whole forest.
+template <int KP, template <int> class Lane>
+__global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_TD_MINB : 1)) td_select_kernel(TdArgs a, const double *td_all,
+                                                                                      const int *td_ex_all, int n_nodes) {
+    extern __shared__ double s_par[];
+    const int C = a.ln.C, K = a.ln.K;
+    const int nf = staged_fields(Lane<KP>::family, K);
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(s_par + (size_t) nf * C);   // [C][K+1]
+    for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x) sh_hist[i] = 0u;
+    pdl_launch_dependents();
+    stage_params(s_par, a.ln, nf, false);
+    pdl_wait();
+    const long long n_items = (long long) n_nodes * C;
+    for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items; g += (long long) gridDim.x * blockDim.x) {
+        const int node = (int) (g / C), c = (int) (g - (long long) node * C);
+        Lane<KP> lane;
+        lane.init(LaneSmem{s_par + c, C}, a.ln.params + (size_t) c * a.ln.stride, K, nullptr);
+        const bool use_alt = lane.tau == 0.;   // ml.py:702-703
+        const int cs = a.t.slot[node];
+        const uint64_t mc = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
+        double X[KP];
+        int ex_total = 0;
+        if (cs >= 0) {
+            const double *src = a.bu + ((size_t) cs * K) * C + c;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) X[k] = (k < K) ? src[(size_t) k * C] : 0.;
+            ex_total = a.bu_ex[(size_t) cs * C + c];
+        } else {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) X[k] = bit_as_double(mc, k);
+        }
+        if (a.t.parent[node] >= 0) {   // (a root's top-down vector is all ones, ml.py:274-277)
+            const double *src = td_all + ((size_t) node * K) * C + c;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) X[k] *= (k < K) ? src[(size_t) k * C] : 0.;
+            ex_total += td_ex_all[(size_t) node * C + c];
         }
         emit_node<KP>(a, lane, node, c, X, mc, ex_total, sh_hist);
     }

@@ -13,6 +13,8 @@ struct KernelSet {
                         int alter, const double *bu, const int *bu_ex, const int *roots, int n_roots,
                         int is_marginal, double *out);
     void (*td)(cudaStream_t, const TdArgs &, int node_begin, int n_nodes);
+    // marginal / MAP / MPPA of every node from stored top-down vectors (after a vector-only top-down sweep)
+    void (*td_select)(cudaStream_t, const TdArgs &, const double *td_all, const int *td_ex_all, int n_nodes);
     void (*mppa_fix)(cudaStream_t, int n_rows, const int *row_node, int C, int K, uint64_t kmask, const ZcDev &,
                      const uint64_t *base_mask, const uint64_t *prev_initial, const uint8_t *prev_hasinit,
                      const double *zc_lh, uint8_t *zc_k, const int *joint_state, int force_joint,
@@ -64,5 +66,9 @@ void tpi_bu_launch(int jt, cudaStream_t, const BuArgs &, int slot_begin, int n_s
 // Bottom-up sweep of the eigen-decomposition models on the FP64 tensor cores (pml_mma.cu): lanes share one decomposition
 bool mma_bu_applicable(int K, int J);
 void mma_bu_launch(cudaStream_t, const BuArgs &, int slot_begin, int n_slots);
+// top-down vectors of one level on the tensor cores (needs BuArgs::v_all of the preceding bottom-up sweep): writes
+// td_all [N][K][C] / td_ex_all [N][C]
+void mma_td_launch(cudaStream_t, const TdArgs &, const double *v_all, double *td_all, int *td_ex_all, int node_begin,
+                   int n_nodes);
 
 }  // namespace pml

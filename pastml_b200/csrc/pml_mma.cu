@@ -185,6 +185,8 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) bu_mma_kernel(BuArgs
                 double v0 = 0., v1 = 0.;
 #pragma unroll
                 for (int s = 0; s < KS; ++s) dmma(v0, v1, f_a[mt][s], bf[s]);
+                if (a.v_all && 8 * mt + g < K)   // kept for the top-down sweep: its node_contribution (ml.py:280)
+                    *reinterpret_cast<double2 *>(a.v_all + ((size_t) ch * K + 8 * mt + g) * J + jd) = make_double2(v0, v1);
                 acc[mt][0] *= fmax(v0, 0.);
                 acc[mt][1] *= fmax(v1, 0.);
                 m0 = fmax(m0, acc[mt][0]);
@@ -240,6 +242,176 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) bu_mma_kernel(BuArgs
     }
 }
 
+// Top-down vectors of one level (calc_node_td_likelihood, ml.py:273-290) on the tensor cores, one warp per (node, tile
+// of 8 lanes).  The node's contribution P L_node was formed -- and kept, BuArgs::v_all -- by the bottom-up sweep, so the
+// step is ONE application of P: q = TD_p L_p / contribution in the D-tile layout (rows = states, two adjacent lanes
+// per thread, read straight from memory as double2), turned into B fragments through the warp's shared-memory slot,
+// W = A^-1 q, W o exp(d t'), TD = A (.).  Vectors only: the marginal / MAP / MPPA half of the step has no dependency
+// between nodes and runs once for the whole forest afterwards (td_select_kernel).  Top-down vectors are stored for
+// every node that has a parent, tips included, indexed by node.
+template <int MT, int KS>
+__global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) td_mma_kernel(TdArgs a, const double *v_all, double *td_all,
+                                                                        int *td_ex_all, int node_begin, int n_nodes) {
+    __shared__ __align__(16) double s_w[kMmaBlock / 32][kMmaKP * 8];
+    const int K = a.ln.K, C = a.ln.C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int tiles = C >> 3;
+    double *sw = s_w[warp];
+    const double *dv = a.ln.params + 4 + K, *Am = dv + K, *Ai = Am + (size_t) K * K;
+    double f_inv[MT][KS], f_a[MT][KS], dm[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const int row = 8 * mt + g;
+        dm[mt] = (row < K) ? dv[row] : 0.;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const int col = 4 * s + t4;
+            const bool in = row < K && col < K;
+            f_inv[mt][s] = in ? Ai[row * K + col] : 0.;
+            f_a[mt][s] = in ? Am[row * K + col] : 0.;
+        }
+    }
+    pdl_launch_dependents();
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const long long n_items = (long long) n_nodes * tiles;
+    const int n_root_slots = a.t.n_root_slots;
+    int4 nx_desc = make_int4(-1, -1, 0, 0);
+    int nx_par = -1;
+    if (warp_global < n_items) {
+        const int n0 = node_begin + (int) (warp_global / tiles);
+        nx_desc = a.t.td_desc[n0];
+        nx_par = a.t.parent[n0];
+    }
+    pdl_wait();   // from here on the previous level's vectors are read
+    for (long long w = warp_global; w < n_items; w += n_warps) {
+        const int nd = (int) (w / tiles), tile = (int) (w - (long long) nd * tiles);
+        const int node = node_begin + nd;
+        const int4 desc = nx_desc;
+        const int par = nx_par;
+        if (w + n_warps < n_items) {
+            const int n1 = node_begin + (int) ((w + n_warps) / tiles);
+            nx_desc = a.t.td_desc[n1];
+            nx_par = a.t.parent[n1];
+        }
+        const int ps = desc.x, cs = desc.y;
+        if (ps < 0) continue;   // a root: all ones, never stored (ml.py:274-277)
+        const int jd = tile * 8 + 2 * t4;   // the two lanes of this thread's D elements
+        const double *p0 = a.ln.params + (size_t) jd * a.ln.stride, *p1 = p0 + a.ln.stride;
+        const double dist = __hiloint2double(desc.w, desc.z);
+        const double t0 = (dist + p0[1]) * p0[2] * p0[0], t1 = (dist + p1[1]) * p1[2] * p1[0];
+        // q = TD_p L_p / contribution, contribution <= 0 -> 1 (ml.py:281-283), in the D layout
+        double q[MT][2];
+        int pex0 = a.bu_ex[(size_t) ps * C + jd], pex1 = a.bu_ex[(size_t) ps * C + jd + 1];
+        const bool ptd = ps >= n_root_slots;
+        if (ptd) {
+            pex0 += td_ex_all[(size_t) par * C + jd];
+            pex1 += td_ex_all[(size_t) par * C + jd + 1];
+        }
+        double m0 = 0., m1 = 0.;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int row = 8 * mt + g;
+            q[mt][0] = q[mt][1] = 0.;
+            if (row < K) {
+                double2 x = *reinterpret_cast<const double2 *>(a.bu + ((size_t) ps * K + row) * C + jd);
+                if (ptd) {
+                    const double2 t = *reinterpret_cast<const double2 *>(td_all + ((size_t) par * K + row) * C + jd);
+                    x.x *= t.x;
+                    x.y *= t.y;
+                }
+                const double2 cv = *reinterpret_cast<const double2 *>(v_all + ((size_t) node * K + row) * C + jd);
+                q[mt][0] = (cv.x > 0.) ? x.x * __drcp_rn(cv.x) : x.x;
+                q[mt][1] = (cv.y > 0.) ? x.y * __drcp_rn(cv.y) : x.y;
+                m0 = fmax(m0, q[mt][0]);
+                m1 = fmax(m1, q[mt][1]);
+            }
+        }
+        int ex0 = pex0, ex1 = pex1;
+        if (cs >= 0) {
+            ex0 -= a.bu_ex[(size_t) cs * C + jd];
+            ex1 -= a.bu_ex[(size_t) cs * C + jd + 1];
+        }
+        // keep q in range (ml.py:284-286), lane by lane, before it goes through the products
+        m0 = colmax(m0);
+        m1 = colmax(m1);
+        auto rescale_lane = [&](double mx, int which, int &ex, bool always, double (&v)[MT][2]) {
+            if (!(mx > 0.) || isinf(mx)) return;
+            int e = exponent_of(mx);
+            if (!always && e >= -kKeep && e <= kKeep) return;
+            int extra = 0;
+            double lift = 1.;
+            if (e == -1023) { lift = 0x1p+200; e = exponent_of(mx * 0x1p+200); extra = -200; }
+            const double s1 = pow2(-(e / 2)), s2 = pow2(-(e - e / 2));
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) v[mt][which] = ((v[mt][which] * lift) * s1) * s2;
+            ex += e + extra;
+        };
+        rescale_lane(m0, 0, ex0, false, q);
+        rescale_lane(m1, 1, ex1, false, q);
+        // q as B fragments: through the warp's slot (D layout in, [state][lane] out)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+            *reinterpret_cast<double2 *>(sw + (8 * mt + g) * 8 + 2 * t4) = make_double2(q[mt][0], q[mt][1]);
+        __syncwarp();
+        double bf[KS];
+#pragma unroll
+        for (int s = 0; s < KS; ++s) bf[s] = sw[(4 * s + t4) * 8 + g];
+        __syncwarp();
+        // W = A^-1 q;  W o exp(d t')
+        double wv[MT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            wv[mt][0] = wv[mt][1] = 0.;
+#pragma unroll
+            for (int s = 0; s < KS; ++s) dmma(wv[mt][0], wv[mt][1], f_inv[mt][s], bf[s]);
+        }
+        {
+            double xs[2 * MT], es[2 * MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                xs[2 * mt] = dm[mt] * t0;
+                xs[2 * mt + 1] = dm[mt] * t1;
+            }
+            exp_nonpos_n<2 * MT>(xs, es);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+                *reinterpret_cast<double2 *>(sw + (8 * mt + g) * 8 + 2 * t4) = make_double2(wv[mt][0] * es[2 * mt], wv[mt][1] * es[2 * mt + 1]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < KS; ++s) bf[s] = sw[(4 * s + t4) * 8 + g];
+        __syncwarp();
+        // TD = max(A (W o exp(d t')), 0) (ml.py:288-289), normalised so that the stored maximum sits in [1, 2)
+        double td[MT][2];
+        m0 = m1 = 0.;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            double v0 = 0., v1 = 0.;
+#pragma unroll
+            for (int s = 0; s < KS; ++s) dmma(v0, v1, f_a[mt][s], bf[s]);
+            td[mt][0] = fmax(v0, 0.);
+            td[mt][1] = fmax(v1, 0.);
+            m0 = fmax(m0, td[mt][0]);
+            m1 = fmax(m1, td[mt][1]);
+        }
+        m0 = colmax(m0);
+        m1 = colmax(m1);
+        rescale_lane(m0, 0, ex0, true, td);
+        rescale_lane(m1, 1, ex1, true, td);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int row = 8 * mt + g;
+            if (row < K) *reinterpret_cast<double2 *>(td_all + ((size_t) node * K + row) * C + jd) = make_double2(td[mt][0], td[mt][1]);
+        }
+        if (g == 0) {
+            td_ex_all[(size_t) node * C + jd] = ex0;
+            td_ex_all[(size_t) node * C + jd + 1] = ex1;
+        }
+    }
+}
+
 }  // namespace
 
 bool mma_bu_applicable(int K, int J) { return K >= 2 && K <= kMmaKP && J >= 8 && J % 8 == 0; }
@@ -257,4 +429,19 @@ void mma_bu_launch(cudaStream_t st, const BuArgs &a, int s0, int ns) {
     else launch_pdl(bu_mma_kernel<3, 6>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
 }
 
+}  // namespace pml
+
+namespace pml {
+void mma_td_launch(cudaStream_t st, const TdArgs &a, const double *v_all, double *td_all, int *td_ex_all, int n0, int nn) {
+    const long long items = (long long) nn * (a.ln.C / 8);
+    long long g = (items + kMmaBlock / 32 - 1) / (kMmaBlock / 32);
+    const long long cap = 148LL * kMmaMinBlocks;   // persistent grid
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    const int K = a.ln.K;
+    if (K <= 8) launch_pdl(td_mma_kernel<1, 2>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, v_all, td_all, td_ex_all, n0, nn);
+    else if (K <= 16) launch_pdl(td_mma_kernel<2, 4>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, v_all, td_all, td_ex_all, n0, nn);
+    else if (K <= 20) launch_pdl(td_mma_kernel<3, 5>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, v_all, td_all, td_ex_all, n0, nn);
+    else launch_pdl(td_mma_kernel<3, 6>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, v_all, td_all, td_ex_all, n0, nn);
+}
 }  // namespace pml
