@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-fit', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip the sub-lines of the other named workloads')
     ap.add_argument('--sharding', default='batch', choices=['batch', 'subtree'],
                     help='batch: every GPU owns an independent (tree x columns) batch (weak scaling, default); '
                          'subtree: ONE tree is cut into clades spread over the GPUs, one all-gather per sweep (strong)')
@@ -280,6 +281,129 @@ def full_ml_acr(flat, masks, has, cols, K, device, sync, check_column=None):
                             sum(parity[k] for k in parity if k.endswith('mismatches')) == 0)
     batch.close()
     return t1 - t0, t2 - t1, passes, float(lhs[0]), parity
+
+
+# ------------------------------------------------------------------ the other named workloads (BASELINE.json configs)
+
+def _sweeps(pb, params, steps):
+    """(step ms, bottom-up ms, top-down ms) of the MPPA pipeline on a problem, device-timed, L2 flushed between steps."""
+    pb.bench_pass(params, which=1, n_iter=3, flush_l2=True)
+    step, _, launches = pb.bench_pass(params, which=1, n_iter=steps, flush_l2=True)
+    bu, _, _ = pb.bench_pass(params, which=0, n_iter=steps, flush_l2=True)
+    td, _, _ = pb.bench_pass(params, which=3, n_iter=steps, flush_l2=True)
+    return step, bu, td, launches
+
+
+def config3_line(device, sync, steps, check):
+    """BASELINE config 3: synthetic 100k-tip Yule tree, K = 10, 16 columns, MPPA + F81 with the full scaling-factor /
+    frequency fit on one B200."""
+    from pastml_b200 import synth
+    from pastml_b200.engine import Problem, pack_params
+    tips, K, C = 100_000, 10, 16
+    rng = np.random.default_rng(3000)
+    flat = synth.yule_tree(tips, rng)
+    masks, has, pis, sfs = synth.simulate_tip_masks(flat, K, C, rng)
+    params = np.stack([pack_params(0, K, sfs[c], 0., 1., pis[c]) for c in range(C)])
+    pb = Problem(flat, K, 0, masks, has, device=device)
+    step, bu, td, _ = _sweeps(pb, params, steps)
+    pb.close()
+    fit_s, rec_s, passes, lh0, parity = full_ml_acr(flat, masks, has, list(range(C)), K, device, sync,
+                                                    check_column=0 if check else None)
+    bu_bytes, td_bytes = algorithmic_bytes(flat, K, C)
+    return {'workload': 'synthetic Yule tree, 100k tips ({} nodes, {} levels), K=10, 16 columns, F81, MPPA'.format(
+                flat.n_nodes, flat.n_levels),
+            'ml_acr_seconds': fit_s + rec_s, 'fit_seconds': fit_s, 'reconstruction_seconds': rec_s, 'device_passes': int(passes),
+            'step_ms': step, 'node_states_per_s': flat.n_nodes * K * C / (step * 1e-3), 'bu_ms': bu, 'td_ms': td,
+            'algorithmic_GBps': {'bu': bu_bytes / bu / 1e6, 'td': td_bytes / td / 1e6},
+            'parity_at_fitted_parameters': parity}
+
+
+def config4_line(device, steps, check, tips=1_000_000):
+    """BASELINE config 4: synthetic 1M-tip coalescent tree, K = 20 amino-acid JTT, 8 columns, MPPA (tensor-core sweeps)."""
+    from pastml_b200 import synth
+    from pastml_b200.annotation import ForestStats
+    from pastml_b200.engine import Problem
+    from pastml_b200.models import JTTModel
+    K, C = 20, 8
+    rng = np.random.default_rng(4004)
+    flat = synth.coalescent_tree(tips, rng)
+    masks, has, pis, sfs = synth.simulate_tip_masks(flat, K, C, rng)
+    fs = ForestStats(flat=flat)
+    models = [JTTModel(forest_stats=fs, sf=float(sfs[c])) for c in range(C)]
+    params = np.stack([m.engine_block() for m in models])
+    pb = Problem(flat, K, models[0].engine_kind, masks, has, device=device)
+    step, bu, td, launches = _sweeps(pb, params, steps)
+    lh = pb.loglik(params)[0]
+    pb.close()
+    n_edges = flat.n_nodes - 1
+    out = {'workload': 'synthetic coalescent tree, {} tips ({} nodes, {} levels), K=20 JTT, 8 columns, MPPA'.format(
+               tips, flat.n_nodes, flat.n_levels),
+           'step_ms': step, 'node_states_per_s': flat.n_nodes * K * C / (step * 1e-3), 'bu_ms': bu, 'td_ms': td,
+           'launches_per_step': int(launches),
+           'fp64_tensor_TFLOPs': {'bu': 2 * 4 * K * K * n_edges * C / (bu * 1e-3) / 1e12, 'td': 2 * 2 * K * K * n_edges * C / (td * 1e-3) / 1e12,
+                                  'note': 'useful flops of the products A^-1 v and A w (2 K^2 multiply-adds each; two applications of P '
+                                          'per edge and lane bottom-up incl. the kept P L_child, one top-down)'},
+           'kernels': 'bu_mma_kernel / td_mma_kernel (mma.sync.m8n8k4.f64) + td_select_kernel'}
+    if check:   # log-likelihood of one column against the oracle's bottom-up pass on the same tree
+        from oracle import cpu_oracle
+        m = models[0]
+        om = cpu_oracle.OracleModel(2, m.frequencies, float(m.sf), d=np.real(m.D_DIAGONAL), A=np.real(m.A), Ainv=np.real(m.A_INV))
+        full = np.uint64((1 << K) - 1)
+        t0 = time.perf_counter()
+        want = cpu_oracle.loglikelihood(cpu_oracle.OracleTree(flat), om, np.where(masks[0] == 0, full, masks[0]), has[0])
+        out['parity_loglh_column0'] = {'rel_dev': abs(float(lh[0]) - want) / abs(want), 'oracle_seconds': time.perf_counter() - t0,
+                                       'ok': bool(abs(float(lh[0]) - want) / abs(want) <= 1e-10)}
+    return out
+
+
+def config5_line(device, rank, world, steps, check, n_trees=1000, tips=10_000):
+    """BASELINE config 5: 1,000 bootstrap-like 10k-tip trees x 8 columns, HKY and F81, MPPA + JOINT, sharded by tree:
+    every rank takes n_trees / world trees as ONE forest problem (no exchange); times are per rank, the caller takes
+    the maximum."""
+    from pastml_b200 import synth
+    from pastml_b200.engine import Problem, pack_params
+    from pastml_b200.parallel import partition
+    C = 8
+    lo, hi = partition(n_trees, world, rank)
+    rng = np.random.default_rng(5000 + rank)
+    flat = synth.forest([synth.yule_tree(tips, rng) for _ in range(hi - lo)])
+    out = {'trees_this_rank': hi - lo, 'nodes_this_rank': int(flat.n_nodes), 'levels': int(flat.n_levels)}
+    for name, kind, K in (('HKY', 1, 4), ('F81', 0, 10)):
+        masks, has, pis, sfs = synth.simulate_tip_masks(flat, K, C, rng)
+        if kind == 1:
+            params = np.stack([pack_params(1, K, sfs[c], 0., 1., pis[c], kappa=4.) for c in range(C)])
+        else:
+            params = np.stack([pack_params(0, K, sfs[c], 0., 1., pis[c]) for c in range(C)])
+        pb = Problem(flat, K, kind, masks, has, device=device)
+        pb.joint(params, want_states=False)
+        pb.bench_pass(params, which=4, n_iter=3, flush_l2=True)
+        mppa_ms, _, _ = pb.bench_pass(params, which=4, n_iter=steps, flush_l2=True)     # BU + TD with the joint state forced
+        joint_ms, _, _ = pb.bench_pass(params, which=2, n_iter=steps, flush_l2=True)    # max-product BU + traceback
+        entry = {'K': K, 'mppa_step_ms': mppa_ms, 'joint_ms': joint_ms, 'ms': mppa_ms + joint_ms}
+        if check and rank == 0:   # the first tree of the forest against the oracle (MPPA + JOINT, one column)
+            from oracle import cpu_oracle
+            res = pb.marginal(params, force_joint=True, want_probs=False)
+            _, joint_state = pb.joint(params)
+            first = np.flatnonzero(flat.tree_id == 0)
+            sub = _subforest(flat, first)
+            om = cpu_oracle.OracleModel(kind, pis[0], sfs[0], kappa=4.)
+            want = cpu_oracle.ml_acr_fixed(sub, om, masks[0][first], has[0][first], method='MPPA', force_joint=True)
+            entry['parity_first_tree_column0'] = {
+                'joint_state_mismatches': int((joint_state[first, 0] != want['joint_state']).sum()),
+                'mppa_state_mismatches': int((res['mppa_mask'][first, 0] != want['mppa_mask']).sum()),
+                'map_state_mismatches': int((res['map_mask'][first, 0] != want['map_mask']).sum())}
+        pb.close()
+        out[name] = entry
+    return out
+
+
+def _subforest(flat, ids):
+    """The nodes `ids` (one whole tree of a level-ordered forest, increasing) as a FlatForest of their own."""
+    from pastml_b200.tree import FlatForest
+    new_id = np.full(flat.n_nodes, -1, dtype=np.int64)
+    new_id[ids] = np.arange(len(ids))
+    par = flat.parent[ids].astype(np.int64)
+    return FlatForest(np.where(par < 0, -1, new_id[np.maximum(par, 0)]).astype(np.int32), flat.dist[ids])
 
 
 def subtree_sharded_step(args, flat, masks, has, params, rank, world, local_rank, steps, warmup, with_fit):
@@ -520,6 +644,27 @@ def run_b200(args):
         one_tree_subtree['speedup_vs_this_runs_single_gpu_step'] = step_ms / one_tree_subtree['ms_per_step']
         barrier()
 
+    # ---- the other named workloads (BASELINE.json configs 3-5), as sub-lines; the headline stays the 1M-tip F81 step
+    configs = None
+    if not args.no_configs:
+        check = not args.no_cpu_baseline
+        configs = {}
+        if world == 1:
+            configs['config3_100k_yule_K10_C16_F81_full_fit'] = config3_line(local_rank, torch.cuda.synchronize, args.steps, check)
+            configs['config4_1M_coalescent_JTT_C8'] = config4_line(local_rank, max(3, args.steps // 2), check)
+        barrier()
+        c5 = config5_line(local_rank, rank, world, max(3, args.steps // 2), check)
+        barrier()
+        for name in ('HKY', 'F81'):
+            for key in ('mppa_step_ms', 'joint_ms', 'ms'):
+                c5[name][key] = max_over_ranks(c5[name][key], device='cuda')
+            nodes_total = 1000 * (2 * 10_000 - 1)
+            c5[name]['node_states_per_s_mppa_plus_joint'] = nodes_total * c5[name]['K'] * 8 / (c5[name]['ms'] * 1e-3)
+        c5['what'] = ('1000 Yule trees of 10k tips x 8 columns as forest problems, trees partitioned over {} GPU(s) (no '
+                      'exchange); per model: fused MPPA step with the joint state forced + JOINT (max-product sweep and '
+                      'traceback), device-timed, max over ranks'.format(world))
+        configs['config5_1000x10k_forest_C8_HKY_F81_MPPA_JOINT'] = c5
+
     # ---- roofline of the dominant kernel family (per-level launches of one templated kernel)
     peaks_path = os.path.join(REPO, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
@@ -561,7 +706,7 @@ def run_b200(args):
             'roofline': roof(dom), 'roofline_other': roof([k for k in sweeps if k != dom][0]),
             'min_ms_per_step': min_ms, 'wall_s_timed_region': wall,
             'bu_objective_ms': bu_ms, 'bu_node_states_per_s': node_states / (bu_ms * 1e-3), 'ml_fit': ml_fit,
-            'one_tree_subtree': one_tree_subtree}
+            'one_tree_subtree': one_tree_subtree, 'configs': configs}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
