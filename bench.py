@@ -70,13 +70,16 @@ def parse_args():
     return ap.parse_args()
 
 
-def make_workload(args, rank):
+def make_workload(args, rank, want_params=True, tips=None):
     from pastml_b200 import synth
-    from pastml_b200.engine import pack_params
     rng = np.random.default_rng(4000 + rank)
-    flat = synth.yule_tree(args.tips, rng) if args.tree == 'yule' else synth.coalescent_tree(args.tips, rng)
+    tips = tips or args.tips
+    flat = synth.yule_tree(tips, rng) if args.tree == 'yule' else synth.coalescent_tree(tips, rng)
     masks, has, pis, sfs = synth.simulate_tip_masks(flat, args.states, args.columns, rng)
-    params = np.stack([pack_params(0, args.states, sfs[c], 0., 1., pis[c]) for c in range(args.columns)])
+    params = None
+    if want_params:   # (the reference arm never touches the engine)
+        from pastml_b200.engine import pack_params
+        params = np.stack([pack_params(0, args.states, sfs[c], 0., 1., pis[c]) for c in range(args.columns)])
     return flat, masks, has, pis, sfs, params
 
 
@@ -198,29 +201,70 @@ class ParityAtScale(object):
                            'outputs of the last end-to-end step (C ABI, host buffers)'}
 
 
+REFERENCE_SAMPLE_TIPS = 3_000   # down-scale of the workload the unmodified Python reference is timed on
+
+
+def _reference_column(job):
+    """Worker of the reference arm (one process per column): the UNMODIFIED reference's marginal pipeline on one column."""
+    parent, dist, mask, K, pi, sf = job
+    import warnings
+    warnings.filterwarnings('ignore')
+    from oracle import ref_pipeline
+    return ref_pipeline.run_column(parent, dist, mask, K, pi, sf)[0]
+
+
+def reference_python_rate(args, procs, steps, warmup):
+    """node-states/s of the unmodified Python reference (oracle/_ref or /root/reference) on a down-scaled tree of the
+    workload's recipe: every step runs all the columns, one process per column (the reference's own thread pool over
+    characters is bound by the interpreter lock; separate processes are the most it can use).  None if no copy of the
+    reference is around."""
+    from oracle import ref_pipeline
+    if ref_pipeline.reference_root() is None:
+        return None
+    import multiprocessing as mp
+    flat, masks, has, pis, sfs, _ = make_workload(args, 0, want_params=False, tips=REFERENCE_SAMPLE_TIPS)
+    jobs = [(flat.parent, flat.dist, masks[c], args.states, pis[c], sfs[c]) for c in range(args.columns)]
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(processes=procs) as pool:
+        for _ in range(warmup):
+            pool.map(_reference_column, jobs[:procs])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pool.map(_reference_column, jobs)
+        dt = (time.perf_counter() - t0) / steps
+    return {'value': flat.n_nodes * args.states * args.columns / dt, 'unit': UNIT, 'seconds_per_step': dt, 'cores': procs,
+            'kind': 'reference',
+            'sample': 'unmodified pastml {} functions (ml.py:697-742) on a {}-tip {} tree of the same recipe ({} nodes), all {} '
+                      'columns per step, one process per column ({} processes)'.format(
+                          'from ' + os.path.relpath(ref_pipeline.reference_root(), REPO) if ref_pipeline.reference_root().startswith(REPO)
+                          else 'from /root/reference', REFERENCE_SAMPLE_TIPS, args.tree, flat.n_nodes, args.columns, procs)}
+
+
 def run_reference(args):
-    """--impl reference: the CPU port of the reference's algorithm (oracle/pastml_oracle.c; the reference itself is
-    pure Python and does not travel to the GPU box) on all the host threads it can use -- one per column."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores.  The value is the
+    UNMODIFIED Python reference (staged under oracle/_ref by oracle/stage_reference.py) on a bounded down-scaled sample
+    -- its cost per node does not depend on the tree size (interpreter-bound, ~40 us per node and pass); the C port of
+    the same algorithm (oracle/pastml_oracle.c) on the full workload is reported beside it.  Without a copy of the
+    reference the port is the value."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    flat, masks, has, pis, sfs, _ = make_workload(args, 0)
     cores = os.cpu_count() or 1
-    threads = max(1, min(cores, args.columns))
-    # bounded sample: a 100k-tip subsample would change the level structure, so keep the tree and bound the work
-    # by the number of steps instead; each step = all columns of the workload
-    columns = list(range(args.columns))
-    steps = max(1, min(args.steps, 2))
-    warm = 1 if args.warmup else 0
-    for _ in range(warm):
-        cpu_pipeline_rate(flat, masks, has, pis, sfs, args.states, columns[:threads], threads)
-    rate, dt = cpu_pipeline_rate(flat, masks, has, pis, sfs, args.states, columns, threads, repeats=steps)
-    sample = '{} step(s) of all {} columns of the workload, {} threads (one per column)'.format(steps, args.columns, threads)
-    line = {'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
-            'warmup': warm, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, flat),
-            'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
-            'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    procs = max(1, min(cores, args.columns))
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    ref = reference_python_rate(args, procs, steps, min(warm, 2))
+    flat, masks, has, pis, sfs, _ = make_workload(args, 0, want_params=False)
+    threads = procs
+    port_rate, port_dt = cpu_pipeline_rate(flat, masks, has, pis, sfs, args.states, list(range(args.columns)), threads, repeats=1)
+    port = {'value': port_rate, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'seconds_per_step': port_dt,
+            'sample': 'one step of all {} columns of the full workload, C port of the reference algorithm, {} threads'.format(
+                args.columns, threads)}
+    main = ref or port
+    line = {'impl': 'reference', 'metric': METRIC, 'value': main['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+            'warmup': warm, 'ms_per_step': main['seconds_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, flat),
+            'cpu_baseline': main, 'cpu_baseline_port': port,
+            'e2e': {'value': main['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0, 'host_cores': cores}
     emit(line)
 
@@ -233,7 +277,7 @@ def full_ml_acr(flat, masks, has, cols, K, device, sync, check_column=None):
     from pastml_b200.annotation import ForestStats
     from pastml_b200.engine import MASK_MAP, MASK_MPPA
     from pastml_b200.ml import ColumnBatch, fit_batch
-    from pastml_b200.models import F81Model
+    from pastml_b200.models.F81Model import F81Model
     fs = ForestStats(flat=flat)
     names = np.array(['s{:02d}'.format(i) for i in range(K)])
     obs = []
@@ -323,7 +367,7 @@ def config4_line(device, steps, check, tips=1_000_000):
     from pastml_b200 import synth
     from pastml_b200.annotation import ForestStats
     from pastml_b200.engine import Problem
-    from pastml_b200.models import JTTModel
+    from pastml_b200.models.JTTModel import JTTModel
     K, C = 20, 8
     rng = np.random.default_rng(4004)
     flat = synth.coalescent_tree(tips, rng)
@@ -438,7 +482,7 @@ def subtree_sharded_step(args, flat, masks, has, params, rank, world, local_rank
         # that are identical on all ranks, one all-gather per objective batch
         from pastml_b200.annotation import ForestStats
         from pastml_b200.ml import fit_batch
-        from pastml_b200.models import F81Model
+        from pastml_b200.models.F81Model import F81Model
         from pastml_b200.sharded import ShardedColumnBatch
         fs = ForestStats(flat=flat)
         names = np.array(['s{:02d}'.format(i) for i in range(K)])
@@ -715,6 +759,7 @@ def run_b200(args):
         parity = ParityAtScale(h_lh, h_probs, h_map, h_mppa, h_hist)
         rate, dt = cpu_pipeline_rate(flat, masks, has, pis, sfs, K, cols, threads, check=parity)
         line['parity_at_scale'] = parity.summary()
+        line['reference_python'] = reference_python_rate(args, threads, 1, 0)   # the unmodified reference, down-scaled sample
         line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                                 'sample': 'one step of {} of the {} columns of the same tree, one thread per column '
                                           '({:.1f} s)'.format(len(cols), C, dt), 'host_cores': cores}

@@ -21,6 +21,15 @@ from pastml_b200.tree import flatten_forest, resolve_trees, unresolve_trees, IS_
 
 COPY = 'COPY'
 
+from pastml_b200 import _set_up_pastml_logger  # noqa: E402,F401  (pastml.acr exposes it)
+
+
+def _serialize_acr(args):
+    """``pastml.acr._serialize_acr((acr_result, work_dir))``: the parameter file and the marginal-probability table of one
+    reconstruction (``acr.py:45-73``)."""
+    from pastml_b200.pipeline import serialize_acr
+    serialize_acr(*args)
+
 
 def calculate_observed_freqs(character, forest, states):
     """Tip-state frequencies (a tip with n states counts 1/n for each) and the fraction of unannotated tips

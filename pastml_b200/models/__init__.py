@@ -350,311 +350,23 @@ class ModelWithFrequencies(Model):
         return '{}\tfrequencies\t{}\n{}\n'.format(Model._print_parameters(self), tag, rows)
 
 
-class F81Model(ModelWithFrequencies):
-    """P_ij(t) = pi_j (1 - e^{-mu t}) + [i == j] e^{-mu t},  mu = 1 / (1 - sum pi^2)."""
-
-    engine_kind = ENGINE_F81
-
-    def __init__(self, states, forest_stats, sf=None, frequencies=None, tau=0, frequency_smoothing=False,
-                 optimise_tau=False, parameter_file=None, reoptimise=False, **kwargs):
-        ModelWithFrequencies.__init__(self, states=states, forest_stats=forest_stats, sf=sf, tau=tau,
-                                      frequencies=frequencies, optimise_tau=optimise_tau,
-                                      frequency_smoothing=frequency_smoothing, reoptimise=reoptimise,
-                                      parameter_file=parameter_file, **kwargs)
-        self.name = F81
-
-    def get_mu(self):
-        return 1. / (1. - self.frequencies.dot(self.frequencies))
-
-    def get_Pij_t(self, t, *args, **kwargs):
-        t = self.transform_t(t)
-        with np.errstate(divide='ignore'):
-            mu = self.get_mu()
-        decay = 0. if mu == np.inf else np.exp(-mu * t)
-        return (1 - decay) * self.frequencies + np.eye(len(self.frequencies)) * decay
-
-    def _engine_fields(self):
-        with np.errstate(divide='ignore'):
-            return dict(pi=self.frequencies, mu=self.get_mu())
-
-
-class JCModel(F81Model):
-    """F81 with all-equal, fixed frequencies."""
-
-    def __init__(self, states, forest_stats, sf=None, tau=0, optimise_tau=False, parameter_file=None,
-                 reoptimise=False, **kwargs):
-        kwargs['frequency_smoothing'] = False
-        F81Model.__init__(self, states=states, forest_stats=forest_stats, sf=sf, tau=tau, optimise_tau=optimise_tau,
-                          frequencies=np.ones(len(states), dtype=np.float64) / len(states), reoptimise=reoptimise,
-                          parameter_file=parameter_file, **kwargs)
-        self._optimise_frequencies = False
-        self.name = JC
-
-    def parse_parameters(self, params, reoptimise=False):
-        return Model.parse_parameters(self, params, reoptimise)
-
-    def _print_parameters(self):
-        return '{}\tfrequencies\tall equal to {:g}\t(fixed)\n'.format(Model._print_parameters(self),
-                                                                      1 / len(self.states))
-
-
-class EFTModel(F81Model):
-    """F81 with frequencies fixed to the ones observed at the tips."""
-
-    def __init__(self, states, forest_stats, observed_frequencies, sf=None, tau=0, optimise_tau=False,
-                 parameter_file=None, reoptimise=False, **kwargs):
-        F81Model.__init__(self, states=states, forest_stats=forest_stats, sf=sf, tau=tau, optimise_tau=optimise_tau,
-                          frequencies=observed_frequencies, reoptimise=reoptimise, parameter_file=parameter_file,
-                          **kwargs)
-        self._optimise_frequencies = False
-        self._frequency_smoothing = False
-        self.name = EFT
-
-    def parse_parameters(self, params, reoptimise=False):
-        return Model.parse_parameters(self, params, reoptimise)
-
-    def _print_parameters(self):
-        return '{}\tfrequencies:\tobserved in the tree\t(fixed)\n'.format(Model._print_parameters(self))
-
-
-HKY_STATES = np.array(['A', 'C', 'G', 'T'])
-
-
-class HKYModel(ModelWithFrequencies):
-    """HKY85 on the fixed alphabet A, C, G, T with a transition/transversion ratio kappa."""
-
-    engine_kind = ENGINE_HKY
-
-    def __init__(self, forest_stats, sf=None, frequencies=None, kappa=4, tau=0, frequency_smoothing=False,
-                 optimise_tau=False, parameter_file=None, reoptimise=False, **kwargs):
-        self._kappa = None
-        self._optimise_kappa = True
-        kwargs['states'] = HKY_STATES
-        ModelWithFrequencies.__init__(self, forest_stats=forest_stats, sf=sf, tau=tau, optimise_tau=optimise_tau,
-                                      frequencies=frequencies, frequency_smoothing=frequency_smoothing,
-                                      reoptimise=reoptimise, parameter_file=parameter_file, **kwargs)
-        if self._kappa is None:
-            self._kappa = kappa
-        self.name = HKY
-
-    @property
-    def kappa(self):
-        return self._kappa
-
-    @kappa.setter
-    def kappa(self, kappa):
-        if not self._optimise_kappa:
-            raise NotImplementedError('The kappa value is preset and cannot be changed.')
-        self._kappa = kappa
-
-    @property
-    def states(self):
-        return self._states
-
-    @states.setter
-    def states(self, states):
-        raise NotImplementedError('The HKY model is only implemented for nucleotides: '
-                                  'the states are A, C, G, T and cannot be reset')
-
-    def get_Pij_t(self, t, *args, **kwargs):
-        """Closed-form HKY85 transition matrix (rows/columns in A, C, G, T order)."""
-        t = self.transform_t(t)
-        a, c, g, tt = self.frequencies
-        pur, pyr = a + g, c + tt
-        k = self.kappa
-        beta = .5 / (pur * pyr + k * (a * g + c * tt))
-        e_all = np.exp(-beta * t)
-        e_pyr = np.exp(-beta * t * (1. + pyr * (k - 1.))) / pyr
-        e_pur = np.exp(-beta * t * (1. + pur * (k - 1.))) / pur
-        s_pyr = (pyr + pur * e_all) / pyr
-        s_pur = (pur + pyr * e_all) / pur
-        p = np.ones((4, 4), dtype=np.float64) * (1 - e_all)
-        p *= self.frequencies
-        A_, C_, G_, T_ = 0, 1, 2, 3
-        p[T_, T_], p[T_, C_] = tt * s_pyr + c * e_pyr, c * s_pyr - c * e_pyr
-        p[C_, T_], p[C_, C_] = tt * s_pyr - tt * e_pyr, c * s_pyr + tt * e_pyr
-        p[A_, A_], p[A_, G_] = a * s_pur + g * e_pur, g * s_pur - g * e_pur
-        p[G_, A_], p[G_, G_] = a * s_pur - a * e_pur, g * s_pur + a * e_pur
-        return p
-
-    def get_num_params(self):
-        return ModelWithFrequencies.get_num_params(self) + (1 if self._optimise_kappa else 0)
-
-    def set_params_from_optimised(self, ps, **kwargs):
-        if self.extra_params_fixed():
-            Model.set_params_from_optimised(self, ps, **kwargs)
-            return
-        ModelWithFrequencies.set_params_from_optimised(self, ps, **kwargs)
-        if self._optimise_kappa:
-            self.kappa = ps[ModelWithFrequencies.get_num_params(self)]
-
-    def get_optimised_parameters(self):
-        if self.extra_params_fixed():
-            return Model.get_optimised_parameters(self)
-        return np.hstack((ModelWithFrequencies.get_optimised_parameters(self),
-                          [self.kappa] if self._optimise_kappa else []))
-
-    def get_bounds(self):
-        if self.extra_params_fixed():
-            return Model.get_bounds(self)
-        return np.array((*ModelWithFrequencies.get_bounds(self),
-                         *([np.array([1e-6, 20.])] if self._optimise_kappa else [])))
-
-    def parse_parameters(self, params, reoptimise=False):
-        params = ModelWithFrequencies.parse_parameters(self, params, reoptimise)
-        if KAPPA in params:
-            self._kappa = _positive_float(params[KAPPA], 'Kappa')
-            if self._kappa is not None:
-                self._optimise_kappa = reoptimise
-        return params
-
-    def freeze(self):
-        ModelWithFrequencies.freeze(self)
-        self._optimise_kappa = False
-
-    def save_parameters(self, filehandle):
-        ModelWithFrequencies.save_parameters(self, filehandle)
-        filehandle.write('{}\t{:g}\n'.format(KAPPA, self.kappa))
-
-    def _print_parameters(self):
-        return '{}\tkappa\t{:.6f}\t{}\n'.format(ModelWithFrequencies._print_parameters(self), self.kappa,
-                                               '(optimised)' if self._optimise_kappa else '(fixed)')
-
-    def _engine_fields(self):
-        return dict(pi=self.frequencies, kappa=float(self.kappa))
-
-
-# ---------------------------------------------------------------------- general reversible models
-
-def save_matrix(states, matrix, outfile):
-    """Writes a rate matrix with a '# state names' header line."""
-    np.savetxt(outfile, matrix, delimiter=' ', fmt='%.18e', header=' '.join(states))
-
-
-def get_normalised_generator(frequencies, rate_matrix=None):
-    """Q_ij = r_ij pi_j off the diagonal, rows summing to zero, scaled to one expected change per time unit."""
-    if rate_matrix is None:
-        n = len(frequencies)
-        rate_matrix = np.ones(shape=(n, n), dtype=np.float64) - np.eye(n)
-    generator = rate_matrix * frequencies
-    generator -= np.diag(generator.sum(axis=1))
-    generator /= -generator.diagonal().dot(frequencies)
-    return generator
-
-
-def get_diagonalisation(frequencies, rate_matrix=None):
-    """(d, A, A^-1) with A diag(d) A^-1 = the normalised generator (``numpy.linalg.eig`` like the reference,
-    ``generator.py:16-30``)."""
-    d, A = np.linalg.eig(get_normalised_generator(frequencies, rate_matrix))
-    return d, A, np.linalg.inv(A)
-
-
-def get_pij_matrix(t, diag, A, A_inv):
-    return A.dot(np.diag(np.exp(diag * t))).dot(A_inv)
-
-
-def load_custom_rates(infile):
-    """Reads a symmetric rate matrix (first line: '# ' + state names) and returns (sorted states, matrix)."""
-    rate_matrix = np.loadtxt(infile, dtype=np.float64, comments='#', delimiter=' ')
-    if rate_matrix.ndim != 2 or rate_matrix.shape[0] != rate_matrix.shape[1]:
-        raise ValueError('The input rate matrix must be squared, but yours is {}.'
-                         .format('x'.join(str(_) for _ in rate_matrix.shape)))
-    if not np.all(rate_matrix == rate_matrix.transpose()):
-        raise ValueError('The input rate matrix must be symmetric, but yours is not.')
-    np.fill_diagonal(rate_matrix, 0)
-    n = len(rate_matrix)
-    if np.count_nonzero(rate_matrix) != n * (n - 1):
-        _log.warning('The rate matrix contains zero rates (apart from the diagonal).')
-    with open(infile, 'r') as f:
-        header = f.readline()
-    if not header.startswith('#'):
-        raise ValueError('The rate matrix file should start with state names, separated by whitespaces and '
-                         'preceded by # .')
-    states = np.array(header.strip('#').strip('\n').strip().split(' '), dtype=str)
-    if len(states) != n:
-        raise ValueError('The number of specified state names ({}) does not correspond to the rate matrix '
-                         'dimensions ({}x{}).'.format(len(states), *rate_matrix.shape))
-    order = np.argsort(states)
-    return states[order], np.array(rate_matrix)[:, order][order, :]
-
-
-class CustomRatesModel(ModelWithFrequencies):
-    """General time-reversible model from a user rate matrix; P(t) through the eigen-decomposition."""
-
-    engine_kind = ENGINE_EIG
-
-    def __init__(self, forest_stats, sf=None, frequencies=None, rate_matrix_file=None, states=None, rate_matrix=None,
-                 tau=0, optimise_tau=False, frequency_smoothing=False, parameter_file=None, reoptimise=False,
-                 **kwargs):
-        ModelWithFrequencies.__init__(self, states=states, forest_stats=forest_stats, sf=sf, tau=tau,
-                                      frequencies=frequencies, optimise_tau=optimise_tau,
-                                      frequency_smoothing=frequency_smoothing, reoptimise=reoptimise,
-                                      parameter_file=parameter_file, **kwargs)
-        self.name = CUSTOM_RATES
-        if rate_matrix_file is None and (rate_matrix is None or states is None):
-            raise ValueError('Either the rate matrix file or the rate matrix plus the states must be specified for '
-                             '{} model'.format(CUSTOM_RATES))
-        if rate_matrix_file is None:
-            self._rate_matrix = rate_matrix
-        else:
-            self._states, self._rate_matrix = load_custom_rates(rate_matrix_file)
-        self.D_DIAGONAL, self.A, self.A_INV = get_diagonalisation(self.frequencies, self._rate_matrix)
-
-    @property
-    def rate_matrix(self):
-        return self._rate_matrix
-
-    @rate_matrix.setter
-    def rate_matrix(self, rate_matrix):
-        raise NotImplementedError('The rate matrix is preset and cannot be changed.')
-
-    @property
-    def frequencies(self):
-        return self._frequencies
-
-    @frequencies.setter
-    def frequencies(self, frequencies):
-        self._set_frequencies(frequencies)
-        self.D_DIAGONAL, self.A, self.A_INV = get_diagonalisation(frequencies, self.rate_matrix)
-
-    def get_Pij_t(self, t, *args, **kwargs):
-        return get_pij_matrix(self.transform_t(t), self.D_DIAGONAL, self.A, self.A_INV)
-
-    def _engine_fields(self):
-        return dict(pi=self.frequencies, d=np.real(self.D_DIAGONAL), A=np.real(self.A), Ainv=np.real(self.A_INV))
-
-
-def _load_jtt():
-    data = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'jtt.npz'))
-    return np.array([str(_) for _ in data['states']]), data['frequencies'], data['rate_matrix']
-
-
-JTT_STATES, JTT_FREQUENCIES, JTT_RATE_MATRIX = _load_jtt()
-
-
-class JTTModel(CustomRatesModel):
-    """Jones-Taylor-Thornton amino-acid model: fixed alphabet, rates and frequencies."""
-
-    def __init__(self, forest_stats, sf=None, tau=0, optimise_tau=False, parameter_file=None, reoptimise=False,
-                 **kwargs):
-        kwargs['states'] = JTT_STATES
-        kwargs.pop('frequency_smoothing', None)
-        CustomRatesModel.__init__(self, forest_stats=forest_stats, sf=sf, frequencies=JTT_FREQUENCIES,
-                                  rate_matrix=JTT_RATE_MATRIX, parameter_file=parameter_file, reoptimise=reoptimise,
-                                  frequency_smoothing=False, tau=tau, optimise_tau=optimise_tau, **kwargs)
-        self._optimise_frequencies = False
-        self.name = JTT
-
-    @property
-    def states(self):
-        return self._states
-
-    @states.setter
-    def states(self, states):
-        raise NotImplementedError('The JTT states are preset and cannot be changed.')
-
-    def parse_parameters(self, params, reoptimise=False):
-        return Model.parse_parameters(self, params, reoptimise)
-
-
-model2class = {F81: F81Model, JC: JCModel, CUSTOM_RATES: CustomRatesModel, HKY: HKYModel, JTT: JTTModel, EFT: EFTModel}
+def __getattr__(name):
+    """The model classes live in their own modules, as in pastml (``from pastml.models.F81Model import F81Model``);
+    ``pastml_b200.models.model2class`` and the class names are resolved on first use to keep the imports acyclic."""
+    if name == 'model2class':
+        from pastml_b200.models.F81Model import F81Model
+        from pastml_b200.models.JCModel import JCModel
+        from pastml_b200.models.EFTModel import EFTModel
+        from pastml_b200.models.HKYModel import HKYModel
+        from pastml_b200.models.CustomRatesModel import CustomRatesModel
+        from pastml_b200.models.JTTModel import JTTModel
+        table = {F81: F81Model, JC: JCModel, CUSTOM_RATES: CustomRatesModel, HKY: HKYModel, JTT: JTTModel, EFT: EFTModel}
+        globals()['model2class'] = table
+        return table
+    for module, names in (('HKYModel', ('HKY_STATES',)), ('JTTModel', ('JTT_STATES', 'JTT_FREQUENCIES', 'JTT_RATE_MATRIX')),
+                          ('generator', ('save_matrix', 'get_diagonalisation', 'get_normalised_generator', 'get_pij_matrix')),
+                          ('CustomRatesModel', ('load_custom_rates',))):
+        if name in names:
+            import importlib
+            return getattr(importlib.import_module('pastml_b200.models.' + module), name)
+    raise AttributeError('module {!r} has no attribute {!r}'.format(__name__, name))

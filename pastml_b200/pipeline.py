@@ -9,70 +9,28 @@ outside the accelerated path: asking for them raises ``NotImplementedError``.
 """
 import logging
 import os
-from collections import Counter, defaultdict
 
 import numpy as np
 import pandas as pd
 
-from pastml_b200 import col_name2cat, get_personalized_feature_name, METHOD, CHARACTER, STATES
+from pastml_b200 import col_name2cat, METHOD, CHARACTER, STATES
 from pastml_b200.acr import acr, COPY
 from pastml_b200.annotation import preannotate_forest
-from pastml_b200.ml import (MPPA, is_ml, is_marginal, is_meta_ml, get_default_ml_method, MODEL,
+from pastml_b200.ml import (MPPA, is_ml, is_marginal, MODEL,
                             MARGINAL_PROBABILITIES, STATE_MASKS)
 from pastml_b200.models import F81
-from pastml_b200.parsimony import is_meta_mp, get_default_mp_method
 from pastml_b200.tree import read_forest, name_tree
 
-PASTML_VERSION = '1.9.50'   # the reference version whose file formats are reproduced
-
-PASTML_WORK_DIR = '{tree}_pastml'
-COMBINED_ANCESTRAL_STATE_TAB = 'combined_ancestral_states.tab'
-NAMED_TREE_NWK = 'named.tree_{tree}.nwk'
-PASTML_ML_PARAMS_TAB = 'params.character_{state}.method_{method}.model_{model}.tab'
-PASTML_MP_PARAMS_TAB = 'params.character_{state}.method_{method}.tab'
-PASTML_MARGINAL_PROBS_TAB = 'marginal_probabilities.character_{state}.model_{model}.tab'
+from pastml_b200 import PASTML_VERSION   # the reference version whose file formats are reproduced
+from pastml_b200.file import (get_pastml_parameter_file, get_pastml_marginal_prob_file, get_combined_ancestral_state_file,  # noqa: F401
+                              get_named_tree_file, get_pastml_work_dir)
 
 
-# ---------------------------------------------------------------------------------------- file names (pastml/file.py)
-
-def get_column_method(column, method):
-    column = col_name2cat(column)
-    if is_meta_ml(method):
-        method = get_default_ml_method()
-    elif is_meta_mp(method):
-        method = get_default_mp_method()
-    else:
-        return column, method
-    return get_personalized_feature_name(column, method), method
-
-
-def get_pastml_parameter_file(method, model, column):
-    template = PASTML_ML_PARAMS_TAB if is_ml(method) else PASTML_MP_PARAMS_TAB
-    column, method = get_column_method(column, method)
-    return template.format(state=column, method=method, model=model)
-
-
-def get_pastml_marginal_prob_file(method, model, column):
-    if not is_marginal(method):
-        return None
-    column, method = get_column_method(column, method)
-    return PASTML_MARGINAL_PROBS_TAB.format(state=column, model=model)
-
-
-def get_combined_ancestral_state_file():
-    return COMBINED_ANCESTRAL_STATE_TAB
-
-
-def get_named_tree_file(tree):
-    tree_name = os.path.splitext(os.path.basename(tree))[0]
-    return NAMED_TREE_NWK.format(tree=tree_name)
-
-
-def get_pastml_work_dir(tree):
-    return PASTML_WORK_DIR.format(tree=os.path.splitext(tree)[0])
-
-
-# ---------------------------------------------------------------------------------------- input validation
+# ---------------------------------------------------------------------------------------- input checks
+#
+# What the reference checks before a reconstruction (``acr.py:677-822``, dates left out): the messages are part of its
+# observable behaviour and are kept; the checks themselves are independent steps over the annotation table and the
+# per-column tallies of the annotated forest.
 
 def _quote(names):
     return ', '.join('"{}"'.format(n) for n in names)
@@ -91,91 +49,95 @@ def _keyed(value, columns, what):
     raise ValueError('{} should be either a list or a dict, got {}.'.format(what, type(value)))
 
 
+def _read_table(data, data_sep, id_index, columns):
+    """The annotation table restricted to the requested columns, column names normalised."""
+    df = pd.read_csv(data, sep=data_sep, index_col=id_index, header=0, dtype=str)
+    df.index = df.index.map(str)
+    if columns:
+        unknown = [c for c in dict.fromkeys(columns) if c not in df.columns]
+        if unknown:
+            one = len(unknown) == 1
+            raise ValueError('{} of the specified columns ({}) {} not found among the annotation columns: {}.'
+                             .format('One' if one else 'Some', _quote(unknown), 'is' if one else 'are', _quote(df.columns)))
+        df = df[columns]
+    df.columns = [col_name2cat(c) for c in df.columns]
+    return df
+
+
+def _match_ids(roots, ids):
+    """Node names and table ids must overlap; names that only match without their quotes are unquoted in the tree."""
+    nodes = [n for root in roots for n in root.traverse()]
+    names = {n.name for n in nodes if n.name}
+    if names & ids:
+        return
+    strip = lambda name: name.strip("'").strip('"')   # noqa: E731
+    if {strip(name) for name in names} & ids:
+        for n in nodes:
+            n.name = strip(n.name)
+        return
+    some_tips = [tip.name for tip, _ in zip(roots[0].iter_leaves(), range(3))]
+    raise ValueError('Your tree tip names (e.g. {}) do not correspond to annotation id column values (e.g. {}). '
+                     'Check your annotation file.'.format(', '.join(some_tips), ', '.join(list(ids)[:3])))
+
+
+def _tally(roots, columns):
+    """Per column: the states seen on the nodes and the number of annotated nodes; plus the number of tips."""
+    seen = {c: set() for c in columns}
+    annotated = dict.fromkeys(columns, 0)
+    num_tips = 0
+    for root in roots:
+        for n in root.traverse():
+            num_tips += n.is_leaf()
+            for c in columns:
+                values = getattr(n, c, None)
+                if values:
+                    seen[c] |= values
+                    annotated[c] += 1
+    return seen, annotated, num_tips
+
+
 def validate_input(tree_nwk, columns=None, data=None, data_sep='\t', id_index=0, copy_only=False, parameters=None,
                    rates=None):
     """Reads the forest and the annotation table, annotates the nodes, collects the states of every character and
-    applies the reference's sanity checks (``acr.py:677-822`` without the date handling).  Returns
-    ``(roots, columns, column2states, parameters, rates)``."""
-    logger = logging.getLogger('pastml')
+    applies the reference's sanity checks.  Returns ``(roots, columns, column2states, parameters, rates)``."""
     if not columns and data is None:
         raise ValueError("If you don't provide the metadata file, "
                          "you need to provide an annotated tree and specify the columns argument, "
                          "which will be used to look for character annotations in your input tree.")
-    if columns and isinstance(columns, str):
+    if isinstance(columns, str):
         columns = [columns]
     roots = read_forest(tree_nwk, columns=columns if data is None else None)
-    column2states = defaultdict(set)
-
+    table_states = {}
     if data:
-        df = pd.read_csv(data, sep=data_sep, index_col=id_index, header=0, dtype=str)
-        df.index = df.index.map(str)
-        if columns:
-            unknown = set(columns) - set(df.columns)
-            if unknown:
-                raise ValueError('{} of the specified columns ({}) {} not found among the annotation columns: {}.'
-                                 .format('One' if len(unknown) == 1 else 'Some', _quote(unknown),
-                                         'is' if len(unknown) == 1 else 'are', _quote(df.columns)))
-            df = df[columns]
-        df.columns = [col_name2cat(column) for column in df.columns]
-        columns = df.columns
-        node_names = set.union(*[{n.name for n in root.traverse() if n.name} for root in roots])
-        ids = set(df.index)
-        common = node_names & ids
-        if not common:   # names quoted in the tree only
-            node_names = {_.strip("'").strip('"') for _ in node_names}
-            common = node_names & ids
-            if common:
-                for root in roots:
-                    for n in root.traverse():
-                        n.name = n.name.strip("'").strip('"')
-        if not common:
-            tips = [tip.name for tip, _ in zip(roots[0].iter_leaves(), range(3))]
-            raise ValueError('Your tree tip names (e.g. {}) do not correspond to annotation id column values (e.g. {}). '
-                             'Check your annotation file.'.format(', '.join(tips), ', '.join(list(ids)[:3])))
+        df = _read_table(data, data_sep, id_index, columns)
+        columns = list(df.columns)
+        _match_ids(roots, set(df.index))
         preannotate_forest(roots, df=df)
-        for c in df.columns:
-            column2states[c] |= {_ for _ in df[c].unique() if pd.notnull(_) and _ != ''}
+        table_states = {c: {v for v in df[c].unique() if pd.notnull(v) and v != ''} for c in columns}
     else:
         columns = [col_name2cat(c) for c in columns]
 
-    num_tips = 0
-    column2annotated = Counter()
-    column2annotated_states = defaultdict(set)
-    for root in roots:
-        for n in root.traverse():
-            for c in columns:
-                vs = getattr(n, c, set())
-                column2states[c] |= vs
-                column2annotated_states[c] |= vs
-                if vs:
-                    column2annotated[c] += 1
-            if n.is_leaf():
-                num_tips += 1
-    if column2annotated:
-        c, num_annotated = min(column2annotated.items(), key=lambda _: _[1])
-    else:
-        c, num_annotated = columns[0], 0
-    percentage_unknown = (num_tips - num_annotated) / num_tips
-    if percentage_unknown >= (.9 if not copy_only else 1):
+    seen, annotated, num_tips = _tally(roots, columns)
+    # the sparsest column decides whether there is enough data at all
+    sparsest = min(columns, key=lambda c: annotated[c])
+    unknown = (num_tips - annotated[sparsest]) / num_tips
+    if unknown >= (1 if copy_only else .9):
+        hint = 'Check your annotation file and if its ids correspond to the tree tip/node names.' if data else \
+            'You tree file should contain character state annotations, otherwise consider specifying a metadata file.'
         raise ValueError('{:.1f}% of tip annotations for character "{}" are unknown, '
-                         'not enough data to infer ancestral states. {}'
-                         .format(percentage_unknown * 100, c,
-                                 'Check your annotation file and if its ids correspond to the tree tip/node names.'
-                                 if data else 'You tree file should contain character state annotations, '
-                                              'otherwise consider specifying a metadata file.'))
-    c, states = min(column2annotated_states.items(), key=lambda _: len(_[1]))
-    if len(states) > num_tips * .75 and not copy_only:
+                         'not enough data to infer ancestral states. {}'.format(unknown * 100, sparsest, hint))
+    # a character with (almost) as many states as tips is not a discrete character
+    poorest = min(columns, key=lambda c: len(seen[c]))
+    if len(seen[poorest]) > num_tips * .75 and not copy_only:
         raise ValueError('Character "{}" has {} unique states annotated in this tree: {}, '
                          'which is too much to infer on a {} with only {} tips. '
                          'Make sure the character you are analysing is discrete, and if yes use a larger tree.'
-                         .format(c, len(states), states, 'tree' if len(roots) == 1 else 'forest', num_tips))
-    logger.debug('Finished input validation.')
-    column2states = {c: np.array(sorted(states)) for c, states in column2states.items()}
-    parameters = _keyed(parameters, columns, 'Parameters')
-    rates = _keyed(rates, columns, 'Rate matrices')
+                         .format(poorest, len(seen[poorest]), seen[poorest], 'tree' if len(roots) == 1 else 'forest', num_tips))
+    logging.getLogger('pastml').debug('Finished input validation.')
+    column2states = {c: np.array(sorted(seen[c] | table_states.get(c, set()))) for c in columns}
     for i, tree in enumerate(roots):
         name_tree(tree, suffix='' if len(roots) == 1 else '_{}'.format(i))
-    return roots, list(columns), column2states, parameters, rates
+    return roots, columns, column2states, _keyed(parameters, columns, 'Parameters'), _keyed(rates, columns, 'Rate matrices')
 
 
 # ---------------------------------------------------------------------------------------- output files

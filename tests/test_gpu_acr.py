@@ -21,7 +21,7 @@ def _fixed_params(g):
 def _rates_file(g, tmp_path):
     if g.model_name != 'CUSTOM_RATES':
         return None
-    from pastml_b200.models import save_matrix
+    from pastml_b200.models.generator import save_matrix
     path = str(tmp_path / 'rates.txt')
     save_matrix(g.states, g['rate_matrix'], path)
     return path

@@ -16,7 +16,8 @@ CASES = ['albania_f81', 'synth_s4_n30_k3_f81_forest', 'sim152_hky_skew', 'synth_
 
 def _model(g, roots):
     from pastml_b200.annotation import ForestStats
-    from pastml_b200.models import F81Model, HKYModel
+    from pastml_b200.models.F81Model import F81Model
+    from pastml_b200.models.HKYModel import HKYModel
     fs = ForestStats(roots)
     kw = dict(forest_stats=fs, sf=float(g['sf']), tau=float(g['tau']))
     if g.kind == 0:

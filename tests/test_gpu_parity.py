@@ -202,7 +202,7 @@ def test_jtt_columns_on_tensor_cores(n_tips, C, kind):
     parameter sets in one pass."""
     from pastml_b200.annotation import ForestStats
     from pastml_b200.engine import Problem
-    from pastml_b200.models import JTTModel
+    from pastml_b200.models.JTTModel import JTTModel
     from pastml_b200 import synth
     from oracle import cpu_oracle
     rng = np.random.default_rng(77 + n_tips)

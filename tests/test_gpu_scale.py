@@ -159,7 +159,7 @@ def test_jtt_at_scale():
     coalescent tree x 8 columns: objective, JOINT, marginal probabilities, MAP and MPPA states."""
     from pastml_b200.annotation import ForestStats
     from pastml_b200.engine import Problem
-    from pastml_b200.models import JTTModel
+    from pastml_b200.models.JTTModel import JTTModel
     from pastml_b200 import synth
     from oracle import cpu_oracle
     rng = np.random.default_rng(404)

@@ -242,7 +242,7 @@ class _FakeBatch(object):
 def _fake_fit(lane_lists, C=8):
     from pastml_b200.annotation import ForestStats
     from pastml_b200.ml import fit_batch
-    from pastml_b200.models import F81Model
+    from pastml_b200.models.F81Model import F81Model
     from pastml_b200.tree import FlatForest
     flat = FlatForest(np.array([-1, 0, 0, 1, 1], dtype=np.int32), np.array([0., 1., 2., 1., 1.]))
     fs = ForestStats(flat=flat)
@@ -443,7 +443,7 @@ def test_lockstep_fit_reports_a_failing_lane_to_its_column():
     columns finish their fit."""
     from pastml_b200.ml import fit_batch, PastMLLikelihoodError
     from pastml_b200.annotation import ForestStats
-    from pastml_b200.models import F81Model
+    from pastml_b200.models.F81Model import F81Model
     from pastml_b200.tree import FlatForest
 
     class Failing(_FakeBatch):
@@ -467,7 +467,7 @@ def test_lockstep_fit_propagates_a_failing_device_pass():
     import threading
     from pastml_b200.ml import fit_batch
     from pastml_b200.annotation import ForestStats
-    from pastml_b200.models import F81Model
+    from pastml_b200.models.F81Model import F81Model
     from pastml_b200.tree import FlatForest
 
     class Broken(_FakeBatch):

@@ -145,7 +145,7 @@ def test_fit_on_a_sharded_tree_matches_the_plain_fit():
     from pastml_b200 import synth
     from pastml_b200.annotation import ForestStats
     from pastml_b200.ml import ColumnBatch, fit_batch
-    from pastml_b200.models import F81Model
+    from pastml_b200.models.F81Model import F81Model
     from pastml_b200.sharded import SubtreePlan, ShardedColumnBatch
     flat, rng = _tree(3000, 77)
     K, C = 6, 3

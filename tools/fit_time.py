@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pastml_b200 import synth  # noqa: E402
 from pastml_b200.annotation import ForestStats  # noqa: E402
 from pastml_b200.ml import ColumnBatch, fit_batch  # noqa: E402
-from pastml_b200.models import F81Model  # noqa: E402
+from pastml_b200.models.F81Model import F81Model  # noqa: E402
 from pastml_b200.engine import MASK_MAP, MASK_MPPA  # noqa: E402
 
 tips = int(sys.argv[1]) if len(sys.argv) > 1 else 100000

@@ -19,7 +19,7 @@ flat = synth.yule_tree(tips, rng) if kind_of_tree == 'yule' else synth.coalescen
 K = {'JTT': 20, 'HKY': 4}.get(model, 20)
 masks, has, pis, sfs = synth.simulate_tip_masks(flat, K, C, rng)
 if model == 'JTT':
-    from pastml_b200.models import JTTModel
+    from pastml_b200.models.JTTModel import JTTModel
     fs = ForestStats(flat=flat)
     ms = [JTTModel(forest_stats=fs, sf=float(sfs[c])) for c in range(C)]
     params, kind = np.stack([m.engine_block() for m in ms]), ms[0].engine_kind
