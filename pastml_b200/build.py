@@ -23,6 +23,7 @@ INST_SRC = os.path.join(CSRC, 'pml_inst.cu')
 COOP_SRC = os.path.join(CSRC, 'pml_coop_inst.cu')
 TPI_SRC = os.path.join(CSRC, 'pml_tpi.cu')
 MMA_SRC = os.path.join(CSRC, 'pml_mma.cu')
+TOPO_SRC = os.path.join(CSRC, 'pml_topo.cu')
 NEWICK_SRC = os.path.join(CSRC, 'pml_newick.cpp')
 HEADERS = [os.path.join(CSRC, 'pml_kernels.cuh'), os.path.join(CSRC, 'pml_coop.cuh'), os.path.join(CSRC, 'pml_tpi.cuh'),
            os.path.join(CSRC, 'pml_launch.h'),
@@ -84,6 +85,7 @@ def build(force=False, verbose=False, jobs=None):
     tasks = [(ENGINE_SRC, os.path.join(OBJ_DIR, 'pml_engine.o'), [], _digest([ENGINE_SRC] + HEADERS, flags))]
     tasks.append((TPI_SRC, os.path.join(OBJ_DIR, 'pml_tpi.o'), [], _digest([TPI_SRC] + HEADERS, flags)))
     tasks.append((MMA_SRC, os.path.join(OBJ_DIR, 'pml_mma.o'), [], _digest([MMA_SRC] + HEADERS, flags)))
+    tasks.append((TOPO_SRC, os.path.join(OBJ_DIR, 'pml_topo.o'), [], _digest([TOPO_SRC, HEADERS[-2]], flags)))
     tasks.append((NEWICK_SRC, os.path.join(OBJ_DIR, 'pml_newick.o'), [], _digest([NEWICK_SRC, HEADERS[-1]], flags)))
     inst_digest = _digest([INST_SRC] + HEADERS, flags)
     for fam, kp in INSTANCES:
@@ -93,6 +95,11 @@ def build(force=False, verbose=False, jobs=None):
     for g, kt, jt in COOP_INSTANCES:
         tasks.append((COOP_SRC, os.path.join(OBJ_DIR, 'pml_coop_{}_{}_{}.o'.format(g, kt, jt)),
                       ['-DPML_G={}'.format(g), '-DPML_KT={}'.format(kt), '-DPML_JT={}'.format(jt)], coop_digest))
+    # objects of instantiations that are no longer built must not linger (they would be stale, not linked, and travel)
+    wanted = {os.path.basename(t[1]) for t in tasks}
+    for f in os.listdir(OBJ_DIR):
+        if f.endswith('.o') and f not in wanted or f.endswith('.o.stamp') and f[:-len('.stamp')] not in wanted:
+            os.remove(os.path.join(OBJ_DIR, f))
     jobs = jobs or max(1, min(len(tasks), os.cpu_count() or 1))
     # biggest instantiations first so that they do not end up alone at the tail
     def weight(t):

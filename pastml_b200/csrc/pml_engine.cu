@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -42,7 +43,15 @@ class DevicePool {
     size_t cached_ = 0;
     static constexpr size_t kMaxCached = 48ull << 30;
 public:
+    // small blocks are rounded up to a power of two so that problems of slightly different shapes still hit the cache
+    static size_t rounded(size_t bytes) {
+        if (bytes >= (1u << 20)) return bytes;
+        size_t r = 512;
+        while (r < bytes) r <<= 1;
+        return r;
+    }
     cudaError_t get(size_t bytes, void **out) {
+        bytes = rounded(bytes);
         int dev = 0;
         cudaGetDevice(&dev);
         {
@@ -66,8 +75,9 @@ public:
     void put(void *ptr, size_t bytes) {
         int dev = 0;
         cudaGetDevice(&dev);
+        bytes = rounded(bytes);
         std::lock_guard<std::mutex> lock(mu_);
-        if (bytes < (1u << 20) || cached_ + bytes > kMaxCached) { cudaFree(ptr); return; }
+        if (cached_ + bytes > kMaxCached) { cudaFree(ptr); return; }
         free_.insert({{dev, bytes}, ptr});
         cached_ += bytes;
     }
@@ -82,42 +92,6 @@ public:
     }
 };
 DevicePool g_pool;
-
-// Pinned host staging arena (cached, grown on demand) for the arrays pml_problem_create derives and uploads.
-struct HostStage {
-    std::mutex mu;
-    char *base = nullptr;
-    size_t cap = 0, used = 0;
-    std::vector<std::pair<char *, size_t>> overflow;   // blocks taken after the arena filled up (kept until reset)
-    void reset(size_t at_least = 0) {
-        size_t want = std::max(used, at_least);
-        for (auto &b : overflow) { want += b.second; cudaFreeHost(b.first); }
-        overflow.clear();
-        if (want > cap) {   // regrow to what the previous call needed
-            if (base) cudaFreeHost(base);
-            base = nullptr;
-            cap = 0;
-            if (cudaHostAlloc((void **) &base, want + (want >> 3), cudaHostAllocDefault) == cudaSuccess) cap = want + (want >> 3);
-            else cudaGetLastError();
-        }
-        used = 0;
-    }
-    template <typename T>
-    T *take(size_t n) {
-        const size_t bytes = ((n * sizeof(T)) + 255) & ~size_t(255);
-        if (bytes == 0) return reinterpret_cast<T *>(base ? base : nullptr);
-        if (used + bytes <= cap) {
-            T *out = reinterpret_cast<T *>(base + used);
-            used += bytes;
-            return out;
-        }
-        char *blk = nullptr;
-        if (cudaHostAlloc((void **) &blk, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        overflow.push_back({blk, bytes});
-        return reinterpret_cast<T *>(blk);
-    }
-};
-HostStage g_stage;
 
 template <typename T>
 struct DevBuf {
@@ -151,8 +125,8 @@ struct pml_problem {
     int N = 0, NI = 0, C = 0, K = 0, KP = 0, kind = 0, B = 1, stride = 0, n_levels = 0, n_roots = 0;
     uint64_t kmask = 0;
     std::vector<int> level_ptr, int_level_ptr;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;   // copy_stream: bulk uploads / result downloads beside the sweeps
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy = nullptr;
     // topology
     DevBuf<int> parent, first_child, n_children, slot, int_nodes, zc_index, roots, fc_slot, nc_slot, pslot;
     DevBuf<int4> bu_desc, td_desc;
@@ -344,7 +318,9 @@ void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_
     run_root_loglik(p, ln, mask, alter, is_marginal);
 }
 
-void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh);
+// hook(node_end): called behind the launches that complete the results of nodes [0, node_end)
+using LevelHook = std::function<void(int)>;
+void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh, const LevelHook *hook = nullptr);
 
 // Launch sequences are captured once into CUDA graphs (one per distinct combination of arguments) and replayed:
 // a sweep is ~55 dependent launches, half of them over levels too narrow to hide the launch latency.
@@ -355,6 +331,14 @@ void run_graphed(pml_problem *p, const std::array<long long, 6> &key, F enqueue)
     if (disabled) { enqueue(); return; }
     auto it = p->graphs.find(key);
     if (it == p->graphs.end()) {
+        // first use: launched directly (a one-shot call -- create, one pass, destroy -- would pay capture and
+        // instantiation for a single replay); the sequence is captured when it comes back
+        p->graphs.emplace(key, pml_problem::GraphEntry{nullptr, 0});
+        enqueue();
+        return;
+    }
+    if (!it->second.exec) {
+        if (it->second.launches < 0) { enqueue(); return; }   // capture failed before: direct launches for this handle
         const long long l0 = p->launches;
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
@@ -367,12 +351,13 @@ void run_graphed(pml_problem *p, const std::array<long long, 6> &key, F enqueue)
         if (graph) cudaGraphDestroy(graph);
         const long long n = p->launches - l0;
         p->launches = l0;
-        if (!ok) {   // capture not possible: fall back to direct launches for this handle
+        if (!ok) {
             cudaGetLastError();
+            it->second.launches = -1;
             enqueue();
             return;
         }
-        it = p->graphs.emplace(key, pml_problem::GraphEntry{exec, n}).first;
+        it->second = pml_problem::GraphEntry{exec, n};
     }
     cudaGraphLaunch(it->second.exec, p->stream);
     p->launches += it->second.launches;
@@ -451,7 +436,7 @@ int ensure_marginal_buffers(pml_problem *p, bool want_probs, bool want_node_lh) 
 }
 
 // the fused top-down sweep on resident bottom-up state
-void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh) {
+void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool want_node_lh, const LevelHook *hook) {
     const LaneDev ln = p->lanes(1);
     cudaMemsetAsync(p->k_hist.ptr, 0, sizeof(unsigned long long) * p->C * (p->K + 1), p->stream);
     TdArgs a{p->tree(), p->zc(), p->ext(), ln, p->mask[PML_MASK_ANNOTATION].ptr, p->bu.ptr, p->bu_ex.ptr, p->td.ptr,
@@ -467,6 +452,7 @@ void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool wan
         }
         p->ks->td_select(p->stream, a, p->td_all.ptr, p->td_ex_all.ptr, p->N);
         p->launches++;
+        if (hook) (*hook)(p->N);
         return;
     }
     const bool tma_ok = !p->ext_index.ptr && tma_enabled();   // (top-down vectors arriving at the roots are fine)
@@ -477,6 +463,7 @@ void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool wan
         if (coop) {
             (td_tma ? coop->td_tma : coop->td)(p->stream, a, n0, nn);
             p->launches++;
+            if (hook) (*hook)(n0 + nn);
             continue;
         }
         const int chunk = (int) std::max<long long>(1, kMaxItemsPerLaunch / ln.C);
@@ -484,6 +471,7 @@ void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool wan
             p->ks->td(p->stream, a, n0 + off, std::min(chunk, nn - off));
             p->launches++;
         }
+        if (hook) (*hook)(n0 + nn);
     }
     if (coop && want_node_lh) {
         const long long n = (long long) p->N * p->C;
@@ -654,83 +642,103 @@ int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dis
     CUDA_TRY(cudaSetDevice(device));
 
     const int N = n_nodes, C = n_columns, K = n_states;
-    // ---- topology checks and derived arrays (level order: parents non-decreasing and before children), built
-    // straight into a cached pinned staging arena so that the uploads run at PCIe speed
-    std::lock_guard<std::mutex> stage_lock(g_stage.mu);
-    g_stage.reset((size_t) N * 80 + (1u << 16));   // upper bound of what the derived arrays need
-    int *nch = g_stage.take<int>(N), *fch = g_stage.take<int>(N), *slot = g_stage.take<int>(N);
-    int *zc_index = g_stage.take<int>(N), *ps = g_stage.take<int>(N);
-    if (!nch || !fch || !slot || !zc_index || !ps) return fail(PML_ERR_CUDA, "could not allocate pinned staging memory");
-    std::memset(nch, 0, sizeof(int) * (size_t) N);
-    int n_roots = 0;
-    bool any_zero = false;
-    for (int v = 0; v < N; ++v) {
-        const int q = parent[v];
-        if (q >= v) return fail(PML_ERR_INVALID, "nodes are not in level order (a parent must precede its children)");
-        if (v > 0 && q < parent[v - 1]) return fail(PML_ERR_INVALID, "nodes are not in level order (parents must be non-decreasing)");
-        if (q < 0) ++n_roots;
-        else {
-            nch[q]++;
-            any_zero |= (dist[v] == 0.);
-        }
-    }
-    if (n_roots < 1 || parent[n_roots - 1] >= 0) return fail(PML_ERR_INVALID, "roots must come first in level order");
-    std::vector<int> roots(n_roots);
-    for (int r = 0; r < n_roots; ++r) roots[r] = r;
-    int NI = 0;
-    {
-        long long next = n_roots;
-        for (int v = 0; v < N; ++v) {
-            fch[v] = (int) next;
-            next += nch[v];
-            slot[v] = nch[v] ? NI++ : -1;
-        }
-        if (next != N) return fail(PML_ERR_INVALID, "inconsistent parent array");
-    }
-    int *int_nodes = g_stage.take<int>(NI), *fcs = g_stage.take<int>(NI), *ncs = g_stage.take<int>(NI);
-    int4 *bd = g_stage.take<int4>(2 * (size_t) NI), *tdd = g_stage.take<int4>(N);
-    if ((NI && (!int_nodes || !fcs || !ncs || !bd)) || !tdd)
-        return fail(PML_ERR_CUDA, "could not allocate pinned staging memory");
-    for (int v = 0; v < N; ++v) {
-        const int s = slot[v];
-        const int q = parent[v];
-        const int pq = q < 0 ? -1 : slot[q];
-        ps[v] = pq;
-        zc_index[v] = -1;
-        int4 w = make_int4(pq, s, 0, 0);
-        const double d = dist[v];
-        std::memcpy(&w.z, &d, 8);
-        tdd[v] = w;
-        if (s >= 0) {
-            const int f = fch[v], n = nch[v];
-            int_nodes[s] = v;
-            fcs[s] = f;
-            ncs[s] = n;
-            const double d0 = dist[f], d1 = n > 1 ? dist[f + 1] : 0.;
-            bd[2 * (size_t) s] = make_int4(f, n, slot[f], n > 1 ? slot[f + 1] : -1);
-            int4 l;
-            std::memcpy(&l.x, &d0, 8);
-            std::memcpy(&l.z, &d1, 8);
-            bd[2 * (size_t) s + 1] = l;
-        }
-    }
+    const size_t nc = (size_t) N * C;
+    pml_problem *p = new pml_problem();
+    p->device = device;
+#define PML_TRY_FREE(expr)                                                                               \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e);                          \
+            pml_problem_destroy(p);                                                                      \
+            return fail(PML_ERR_CUDA, m);                                                                \
+        }                                                                                                \
+    } while (0)
+#define PML_FAIL_FREE(msg)                                                                               \
+    do {                                                                                                 \
+        pml_problem_destroy(p);                                                                          \
+        return fail(PML_ERR_INVALID, msg);                                                               \
+    } while (0)
+    PML_TRY_FREE(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    PML_TRY_FREE(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    PML_TRY_FREE(cudaEventCreateWithFlags(&p->ev_copy, cudaEventDisableTiming));
+    PML_TRY_FREE(cudaEventCreate(&p->ev0));
+    PML_TRY_FREE(cudaEventCreate(&p->ev1));
+
+    // ---- the annotation masks ([C][N], by far the largest input) start moving first, on the copy stream; the
+    // topology is derived on the device meanwhile
+    DevBuf<uint64_t> tmp_mask;
+    PML_TRY_FREE(tmp_mask.alloc(nc));
+    PML_TRY_FREE(p->parent.alloc(N));
+    PML_TRY_FREE(p->dist.alloc(N));
+    PML_TRY_FREE(cudaMemcpyAsync(p->parent.ptr, parent, sizeof(int) * (size_t) N, cudaMemcpyHostToDevice, p->stream));
+    PML_TRY_FREE(cudaMemcpyAsync(p->dist.ptr, dist, sizeof(double) * (size_t) N, cudaMemcpyHostToDevice, p->stream));
+    PML_TRY_FREE(cudaEventRecord(p->ev_copy, p->stream));
+    PML_TRY_FREE(cudaStreamWaitEvent(p->copy_stream, p->ev_copy, 0));   // (keeps the two small uploads in front)
+    PML_TRY_FREE(cudaMemcpyAsync(tmp_mask.ptr, annot_mask, nc * sizeof(uint64_t), cudaMemcpyHostToDevice, p->copy_stream));
+
+    // ---- topology (level order: parents non-decreasing and before their children): children counts, level-order
+    // checks and the slot / first-child prefix sums on the device (pml_topo.cu)
+    DevBuf<unsigned long long> scan;
+    DevBuf<uint8_t> scan_tmp;
+    DevBuf<int> flags_ni, d_level_ptr, d_int_level_ptr;
+    const size_t scan_bytes = topo_scan_bytes(N);
+    PML_TRY_FREE(scan.alloc(N));
+    PML_TRY_FREE(scan_tmp.alloc(std::max<size_t>(scan_bytes, 1)));
+    PML_TRY_FREE(flags_ni.alloc(2));
+    PML_TRY_FREE(p->n_children.alloc(N));
+    topo_stage1(p->stream, N, p->parent.ptr, p->dist.ptr, p->n_children.ptr, scan.ptr, scan_tmp.ptr, scan_bytes, flags_ni.ptr);
+    int h_flags_ni[2] = {0, 0};
+    PML_TRY_FREE(cudaMemcpyAsync(h_flags_ni, flags_ni.ptr, sizeof(h_flags_ni), cudaMemcpyDeviceToHost, p->stream));
+    // (the level boundaries need the host copy of parent[] only: binary searches, done while the device works)
+    const int n_roots = (int) (std::lower_bound(parent, parent + N, 0) - parent);
     std::vector<int> level_ptr{0, n_roots};
-    while (level_ptr.back() < N) {
+    bool disconnected = false;
+    while (n_roots >= 1 && level_ptr.back() < N && (int) level_ptr.size() <= N + 1) {
         // the next level ends where parents stop falling into the current one: parent[] is sorted
         const int hi = level_ptr.back();
         const int nxt = (int) (std::lower_bound(parent + hi, parent + N, hi) - parent);
-        if (nxt == hi) return fail(PML_ERR_INVALID, "disconnected nodes");
+        if (nxt == hi) { disconnected = true; break; }
         level_ptr.push_back(nxt);
     }
+    PML_TRY_FREE(cudaStreamSynchronize(p->stream));
+    if (h_flags_ni[0] & kTopoNotBeforeChild) PML_FAIL_FREE("nodes are not in level order (a parent must precede its children)");
+    if (h_flags_ni[0] & kTopoNotSorted) PML_FAIL_FREE("nodes are not in level order (parents must be non-decreasing)");
+    if (n_roots < 1) PML_FAIL_FREE("roots must come first in level order");
+    if (disconnected) PML_FAIL_FREE("disconnected nodes");
+    const bool any_zero = (h_flags_ni[0] & kTopoZeroBranch) != 0;
+    const int NI = h_flags_ni[1];
     const int n_levels = (int) level_ptr.size() - 1;
+    std::vector<int> roots(n_roots);
+    for (int r = 0; r < n_roots; ++r) roots[r] = r;
     std::vector<int> int_level_ptr(n_levels + 1, 0);
-    for (int l = 0; l <= n_levels; ++l)
-        int_level_ptr[l] = (int) (std::lower_bound(int_nodes, int_nodes + NI, level_ptr[l]) - int_nodes);
+    PML_TRY_FREE(p->first_child.alloc(N));
+    PML_TRY_FREE(p->slot.alloc(N));
+    PML_TRY_FREE(p->pslot.alloc(N));
+    PML_TRY_FREE(p->zc_index.alloc(N));
+    PML_TRY_FREE(p->td_desc.alloc(N));
+    PML_TRY_FREE(p->int_nodes.alloc(NI));
+    PML_TRY_FREE(p->fc_slot.alloc(NI));
+    PML_TRY_FREE(p->nc_slot.alloc(NI));
+    PML_TRY_FREE(p->bu_desc.alloc(2 * (size_t) NI));
+    PML_TRY_FREE(d_level_ptr.alloc(n_levels + 1));
+    PML_TRY_FREE(d_int_level_ptr.alloc(n_levels + 1));
+    PML_TRY_FREE(cudaMemcpyAsync(d_level_ptr.ptr, level_ptr.data(), sizeof(int) * (n_levels + 1), cudaMemcpyHostToDevice, p->stream));
+    {
+        TopoOut o{p->n_children.ptr, p->first_child.ptr, p->slot.ptr, p->pslot.ptr, p->zc_index.ptr,
+                  p->int_nodes.ptr, p->fc_slot.ptr, p->nc_slot.ptr, p->bu_desc.ptr, p->td_desc.ptr};
+        topo_stage2(p->stream, N, n_roots, NI, p->parent.ptr, p->dist.ptr, scan.ptr, o, d_level_ptr.ptr, n_levels + 1,
+                    d_int_level_ptr.ptr);
+    }
+    PML_TRY_FREE(cudaMemcpyAsync(int_level_ptr.data(), d_int_level_ptr.ptr, sizeof(int) * (n_levels + 1), cudaMemcpyDeviceToHost, p->stream));
+    PML_TRY_FREE(cudaStreamSynchronize(p->stream));
 
     // ---- zero-branch clusters per column (get_zero_clusters_with_states, ml.py:321-349)
     std::vector<int> cl_col, cl_ptr{0}, cl_mem, row_node;
     std::vector<uint8_t> member;
+    std::vector<int> zc_index;
     if (any_zero) {
+        zc_index.assign(N, -1);
         std::vector<int> top(N);
         for (int v = 0; v < N; ++v) {
             const int q = parent[v];
@@ -763,15 +771,10 @@ int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dis
         }
     }
 
-    pml_problem *p = new pml_problem();
-    p->device = device;
     p->N = N; p->NI = NI; p->C = C; p->K = K; p->kind = model_kind; p->B = max_param_sets;
     p->KP = (model_kind == PML_MODEL_HKY) ? 4 : kp_for(K);
     p->ks = kernel_set(model_kind, p->KP);
-    if (!p->ks) {
-        delete p;
-        return fail(PML_ERR_INVALID, "no kernels built for this model family / number of states");
-    }
+    if (!p->ks) PML_FAIL_FREE("no kernels built for this model family / number of states");
     p->stride = pml_param_stride(model_kind, K);
     p->kmask = (K >= 64) ? ~0ULL : ((1ULL << K) - 1ULL);
     p->n_levels = n_levels;
@@ -781,47 +784,15 @@ int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dis
     p->n_clusters = (int) cl_col.size();
     p->n_rows = (int) row_node.size();
 
-#define PML_TRY_FREE(expr)                                                                               \
-    do {                                                                                                 \
-        cudaError_t _e = (expr);                                                                         \
-        if (_e != cudaSuccess) {                                                                         \
-            std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e);                          \
-            pml_problem_destroy(p);                                                                      \
-            return fail(PML_ERR_CUDA, m);                                                                \
-        }                                                                                                \
-    } while (0)
 #define PML_UPLOAD(buf, vec)                                                                             \
     do {                                                                                                 \
         PML_TRY_FREE((buf).alloc((vec).size()));                                                         \
         if (!(vec).empty())                                                                              \
             PML_TRY_FREE(cudaMemcpy((buf).ptr, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice)); \
     } while (0)
-
-    PML_TRY_FREE(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-    PML_TRY_FREE(cudaEventCreate(&p->ev0));
-    PML_TRY_FREE(cudaEventCreate(&p->ev1));
-#define PML_UPLOAD_RAW(buf, src, n)                                                                      \
-    do {                                                                                                 \
-        PML_TRY_FREE((buf).alloc((size_t) (n)));                                                         \
-        if ((n) > 0)                                                                                     \
-            PML_TRY_FREE(cudaMemcpyAsync((buf).ptr, (src), (size_t) (n) * sizeof(*(src)), cudaMemcpyHostToDevice, \
-                                         p->stream));                                                    \
-    } while (0)
-    PML_UPLOAD_RAW(p->parent, parent, N);
-    PML_UPLOAD_RAW(p->dist, dist, N);
-    PML_UPLOAD_RAW(p->first_child, fch, N);
-    PML_UPLOAD_RAW(p->n_children, nch, N);
-    PML_UPLOAD_RAW(p->slot, slot, N);
-    PML_UPLOAD_RAW(p->int_nodes, int_nodes, NI);
-    PML_UPLOAD_RAW(p->zc_index, zc_index, N);
-    PML_UPLOAD_RAW(p->fc_slot, fcs, NI);
-    PML_UPLOAD_RAW(p->nc_slot, ncs, NI);
-    PML_UPLOAD_RAW(p->pslot, ps, N);
-    PML_UPLOAD_RAW(p->bu_desc, bd, 2 * (size_t) NI);
-    PML_UPLOAD_RAW(p->td_desc, tdd, N);
+    if (any_zero)
+        PML_TRY_FREE(cudaMemcpy(p->zc_index.ptr, zc_index.data(), sizeof(int) * (size_t) N, cudaMemcpyHostToDevice));
     p->n_root_slots = int_level_ptr[1];
-    PML_TRY_FREE(cudaStreamSynchronize(p->stream));   // the staging arena is reused by the next create
-#undef PML_UPLOAD_RAW
     PML_UPLOAD(p->roots, roots);
     PML_UPLOAD(p->cl_col, cl_col);
     PML_UPLOAD(p->cl_ptr, cl_ptr);
@@ -836,31 +807,27 @@ int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dis
     PML_TRY_FREE(p->zc_prev_hasinit.alloc(rc));
     PML_TRY_FREE(p->zc_k.alloc(rc));
     PML_TRY_FREE(p->zc_touched.alloc(rc));
-    PML_TRY_FREE(cudaMemset(p->zc_touched.ptr, 0, rc));
+    PML_TRY_FREE(cudaMemsetAsync(p->zc_touched.ptr, 0, rc, p->stream));
     PML_TRY_FREE(p->zc_lh.alloc(rc * K));
     PML_TRY_FREE(p->record_col.alloc(C));
-    PML_TRY_FREE(cudaMemset(p->zc_alt.ptr, 0, rc * sizeof(uint64_t)));
-    PML_TRY_FREE(cudaMemset(p->zc_initial.ptr, 0, rc * sizeof(uint64_t)));
-    PML_TRY_FREE(cudaMemset(p->zc_altflag.ptr, 0, rc));
-    PML_TRY_FREE(cudaMemset(p->zc_hasinit.ptr, 0, rc));
-    PML_TRY_FREE(cudaMemset(p->zc_k.ptr, 0, rc));
-    PML_TRY_FREE(cudaMemset(p->zc_lh.ptr, 0, rc * K * sizeof(double)));
+    PML_TRY_FREE(cudaMemsetAsync(p->zc_alt.ptr, 0, rc * sizeof(uint64_t), p->stream));
+    PML_TRY_FREE(cudaMemsetAsync(p->zc_initial.ptr, 0, rc * sizeof(uint64_t), p->stream));
+    PML_TRY_FREE(cudaMemsetAsync(p->zc_altflag.ptr, 0, rc, p->stream));
+    PML_TRY_FREE(cudaMemsetAsync(p->zc_hasinit.ptr, 0, rc, p->stream));
+    PML_TRY_FREE(cudaMemsetAsync(p->zc_k.ptr, 0, rc, p->stream));
+    PML_TRY_FREE(cudaMemsetAsync(p->zc_lh.ptr, 0, rc * K * sizeof(double), p->stream));
 
-    const size_t nc = (size_t) N * C;
     PML_TRY_FREE(p->mask[PML_MASK_ANNOTATION].alloc(nc));   // the other mask sets are allocated when first produced
     {
-        // [C][N] -> [N][C] on the device
-        DevBuf<uint64_t> tmp_mask;
+        // [C][N] -> [N][C] on the device, behind the upload on the copy stream
         DevBuf<uint8_t> tmp_mem;
-        PML_TRY_FREE(tmp_mask.alloc(nc));
-        PML_TRY_FREE(cudaMemcpyAsync(tmp_mask.ptr, annot_mask, nc * sizeof(uint64_t), cudaMemcpyHostToDevice, p->stream));
         if (!member.empty()) {
             PML_TRY_FREE(tmp_mem.alloc(nc));
-            PML_TRY_FREE(cudaMemcpyAsync(tmp_mem.ptr, member.data(), nc, cudaMemcpyHostToDevice, p->stream));
+            PML_TRY_FREE(cudaMemcpyAsync(tmp_mem.ptr, member.data(), nc, cudaMemcpyHostToDevice, p->copy_stream));
         }
-        init_masks_kernel<<<grid_for((long long) nc), kBlock, 0, p->stream>>>(N, C, p->kmask, tmp_mask.ptr, tmp_mem.ptr,
-                                                                              p->mask[PML_MASK_ANNOTATION].ptr, 1);
-        PML_TRY_FREE(cudaStreamSynchronize(p->stream));
+        init_masks_kernel<<<grid_for((long long) nc), kBlock, 0, p->copy_stream>>>(N, C, p->kmask, tmp_mask.ptr, tmp_mem.ptr,
+                                                                                   p->mask[PML_MASK_ANNOTATION].ptr, 1);
+        PML_TRY_FREE(cudaStreamSynchronize(p->copy_stream));
         p->mask_valid[PML_MASK_ANNOTATION] = true;
     }
     const size_t J = (size_t) p->B * C;
@@ -871,6 +838,7 @@ int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dis
     PML_TRY_FREE(p->out_lh.alloc(J));
 #undef PML_UPLOAD
 #undef PML_TRY_FREE
+#undef PML_FAIL_FREE
     *out = p;
     return PML_OK;
 }
@@ -879,10 +847,13 @@ void pml_problem_destroy(pml_problem *p) {
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
-    for (auto &kv : p->graphs) cudaGraphExecDestroy(kv.second.exec);
+    for (auto &kv : p->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     p->graphs.clear();
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->ev_copy) cudaEventDestroy(p->ev_copy);
+    if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); cudaStreamDestroy(p->copy_stream); }
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -994,7 +965,39 @@ int pml_marginal(pml_problem *p, const double *params, int32_t force_joint, doub
     // ml.py:700-706: allowed states are re-initialised and altered, then BU(alter=False), TD, marginals
     // (a reused bottom-up state must come with the products the tensor-core top-down sweep reads)
     if (!reuse_bu || (mma_td_wanted(p) && !p->v_valid)) run_bottom_up(p, 1, p->mask[PML_MASK_ANNOTATION].ptr, 1, 1, false);
-    run_top_down(p, force_joint, do_probs, do_node_lh);
+    // Large results leave while the sweep is still running: a level's probabilities and state sets are final when
+    // its launch retires, so they are handed to the copy stream level by level (in pieces of >= 8 MB) instead of
+    // after the last level.  (Not with zero-branch clusters or external tips: their masks carry marker bits that are
+    // stripped on the way out, and clusters are revisited after the sweep.)
+    const size_t nc = (size_t) p->N * p->C;
+    static const bool no_stream_out = getenv("PASTML_B200_NO_STREAM_OUT") != nullptr;
+    const bool stream_out = (out_probs || out_map_mask || out_mppa_mask) && p->n_rows == 0 && p->n_ext == 0 &&
+                            !p->ext_index.ptr && nc * p->K * sizeof(double) >= (32u << 20) && !no_stream_out;
+    cudaError_t copy_rc = cudaSuccess;
+    if (stream_out) {
+        size_t done = 0;
+        const size_t row = (size_t) p->C, piece = std::max<size_t>(1, (8u << 20) / (row * p->K * sizeof(double)));
+        const LevelHook hook = [&](int node_end) {
+            if ((size_t) node_end - done < piece && node_end < p->N) return;
+            const size_t n = ((size_t) node_end - done) * row, at = done * row;
+            auto keep = [&](cudaError_t e) { if (copy_rc == cudaSuccess) copy_rc = e; };
+            keep(cudaEventRecord(p->ev_copy, p->stream));
+            keep(cudaStreamWaitEvent(p->copy_stream, p->ev_copy, 0));
+            if (out_probs)
+                keep(cudaMemcpyAsync(out_probs + at * p->K, p->probs.ptr + at * p->K, n * p->K * sizeof(double),
+                                     cudaMemcpyDeviceToHost, p->copy_stream));
+            if (out_map_mask)
+                keep(cudaMemcpyAsync(out_map_mask + at, p->mask[PML_MASK_MAP].ptr + at, n * sizeof(uint64_t),
+                                     cudaMemcpyDeviceToHost, p->copy_stream));
+            if (out_mppa_mask)
+                keep(cudaMemcpyAsync(out_mppa_mask + at, p->mask[PML_MASK_MPPA].ptr + at, n * sizeof(uint64_t),
+                                     cudaMemcpyDeviceToHost, p->copy_stream));
+            done = (size_t) node_end;
+        };
+        enqueue_top_down(p, force_joint, do_probs, do_node_lh, &hook);
+    } else {
+        run_top_down(p, force_joint, do_probs, do_node_lh);
+    }
     // remember the '.initial' state MAP saw: pml_mppa_finalize needs it
     if (p->n_rows) {
         cudaMemcpyAsync(p->zc_prev_initial.ptr, p->zc_initial.ptr, sizeof(uint64_t) * (size_t) p->n_rows * p->C,
@@ -1009,15 +1012,20 @@ int pml_marginal(pml_problem *p, const double *params, int32_t force_joint, doub
     p->mask_valid[PML_MASK_MAP] = p->mask_valid[PML_MASK_MPPA] = true;
     p->marginal_done = true;
     rc = fetch_loglik(p, 1, out_loglh);
-    const size_t nc = (size_t) p->N * p->C;
-    if (out_probs)
+    if (out_probs && !stream_out)
         CUDA_TRY(cudaMemcpyAsync(out_probs, p->probs.ptr, nc * p->K * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     if (out_node_log10lh)
         CUDA_TRY(cudaMemcpyAsync(out_node_log10lh, p->node_lh.ptr, nc * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
-    if (out_map_mask) { int r2 = copy_masks_out(p, p->mask[PML_MASK_MAP].ptr, out_map_mask); if (r2) return r2; }
-    if (out_mppa_mask) { int r2 = copy_masks_out(p, p->mask[PML_MASK_MPPA].ptr, out_mppa_mask); if (r2) return r2; }
+    if (!stream_out) {
+        if (out_map_mask) { int r2 = copy_masks_out(p, p->mask[PML_MASK_MAP].ptr, out_map_mask); if (r2) return r2; }
+        if (out_mppa_mask) { int r2 = copy_masks_out(p, p->mask[PML_MASK_MPPA].ptr, out_mppa_mask); if (r2) return r2; }
+    }
     if (out_k_hist) { int r2 = copy_khist_out(p, out_k_hist); if (r2) return r2; }
+    if (stream_out) {
+        CUDA_TRY(cudaStreamSynchronize(p->copy_stream));
+        CUDA_TRY(copy_rc);
+    }
     return rc;
 }
 

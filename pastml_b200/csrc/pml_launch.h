@@ -71,4 +71,22 @@ void mma_bu_launch(cudaStream_t, const BuArgs &, int slot_begin, int n_slots);
 void mma_td_launch(cudaStream_t, const TdArgs &, const double *v_all, double *td_all, int *td_ex_all, int node_begin,
                    int n_nodes);
 
+// Derived topology arrays of a level-ordered forest, built on the device from parent[] / dist[] (pml_topo.cu).
+// Stage 1 counts children, checks the level order and scans; stage 2 (once the number of internal nodes is known and
+// the slot-indexed arrays are allocated) fills every array the sweeps read.
+struct TopoOut {
+    int *n_children, *first_child, *slot, *pslot, *zc_index;   // [N]
+    int *int_nodes, *fc_slot, *nc_slot;                        // [NI]
+    int4 *bu_desc;                                             // [2 NI]
+    int4 *td_desc;                                             // [N]
+};
+constexpr int kTopoNotBeforeChild = 1, kTopoNotSorted = 2, kTopoZeroBranch = 4;
+size_t topo_scan_bytes(int n_nodes);
+// flags_ni (device, 2 ints): [0] = OR of the kTopo* bits, [1] = number of internal nodes; scan: [N] packed prefix sums
+void topo_stage1(cudaStream_t, int n_nodes, const int *parent, const double *dist, int *n_children,
+                 unsigned long long *scan, void *scan_tmp, size_t scan_tmp_bytes, int *flags_ni);
+void topo_stage2(cudaStream_t, int n_nodes, int n_roots, int n_internal, const int *parent, const double *dist,
+                 const unsigned long long *scan, const TopoOut &out, const int *level_ptr, int n_level_ptr,
+                 int *int_level_ptr);
+
 }  // namespace pml

@@ -95,20 +95,31 @@ def test_through_the_optimiser(name, tmp_path):
     mdl = r['model']
     ref_lh = float(g['log_likelihood'])
     ens = np.concatenate((g['ens_lh'], [ref_lh]))
+    ens_sf = np.concatenate((g['ens_sf'], [float(g['sf'])]))
     spread = float(np.abs(ens - ref_lh).max() / abs(ref_lh))
     if spread < 1e-8:
-        assert r['log_likelihood'] == pytest.approx(ref_lh, rel=1e-8)
-        assert float(mdl.sf) == pytest.approx(float(g['sf']), rel=2e-4)
+        # tolerances from the recorded outcome (profiles/r2_optimiser_parity.json, tools/optimiser_parity.py): the
+        # engine's fit lies INSIDE the spread the reference shows against itself under one ulp of objective noise
+        # (achieved: |dlh|/|lh| <= 3.5e-12, |dsf|/sf <= 2.6e-6, |dpi|/pi <= 3.1e-5, |d marginal| <= 3.5e-6)
+        self_lh = spread
+        self_sf = float(np.abs(ens_sf - float(g['sf'])).max() / float(g['sf']))
+        assert abs(r['log_likelihood'] - ref_lh) <= max(1e-11, 2 * self_lh) * abs(ref_lh)
+        assert abs(float(mdl.sf) - float(g['sf'])) <= max(1e-6, 2 * self_sf) * float(g['sf'])
         if hasattr(mdl, 'frequencies'):
-            np.testing.assert_allclose(mdl.frequencies, g['pi'], rtol=1e-3, atol=1e-7)
+            np.testing.assert_allclose(mdl.frequencies, g['pi'], rtol=1e-4, atol=1e-9)
+        if g.model_name == 'HKY':
+            assert float(mdl.kappa) == pytest.approx(float(g['kappa']), rel=5e-5)
         np.testing.assert_allclose(r['marginal_probabilities'].values, g['marginal_probabilities'][g.flat.ref_order],
-                                   rtol=0, atol=5e-5)
+                                   rtol=0, atol=1e-5)
         ours = masks_from_feature(flat.nodes, g.states, col)
         mismatch = int((ours != g['mppa_mask']).sum())
         assert mismatch == 0, '{} nodes differ after optimisation'.format(mismatch)
     else:
         margin = 0.5 * (ens.max() - ens.min())
         assert ens.min() - margin <= r['log_likelihood'] <= ens.max() + margin, (r['log_likelihood'], ens)
+        # (the likelihood AT the reference's reported parameters is compared strictly in
+        # test_fixed_parameters_all_methods; re-optimising from them is no yardstick -- the reference itself moves away
+        # from its own optimum on these columns: -35.986 -> -36.391 for denv2_genotype_f81)
     # whatever the optimum, the reported likelihood is the likelihood at the reported parameters
     from pastml_b200.ml import ColumnBatch
     from pastml_b200.tree import flatten_forest
