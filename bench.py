@@ -34,7 +34,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
-TRAFFIC_FILE = 'r1_l_dram_traffic.json'   # ncu capture of one step of the default workload with the current kernels
+TRAFFIC_FILE = 'r2_t_dram_traffic.json'   # ncu capture of one step of the default workload with the current kernels
 METRIC = 'mppa_node_states_per_s'
 UNIT = 'node-states/s'
 
@@ -572,6 +572,7 @@ def run_b200(args):
         # per-sweep split for the roofline, same settings
         bu_ms, _, bu_launches = pb.bench_pass(params, which=0, n_iter=args.steps, flush_l2=True)
         td_ms, _, td_launches = pb.bench_pass(params, which=3, n_iter=args.steps, flush_l2=True)
+        kernels_used = pb.last_kernels()   # what the engine launched for those sweeps (name -> launches, items)
     if args.sweeps_only:
         print('sweeps step_ms={:.3f} min={:.3f} bu_ms={:.3f} td_ms={:.3f} launches={} lib={}'.format(
             avg_ms, min_ms, bu_ms, td_ms, launches, os.environ.get('PASTML_B200_LIB', 'default')))
@@ -716,11 +717,11 @@ def run_b200(args):
     else:
         peak, peak_src = 6650., 'fallback (B200_PROFILING.md)'
     bu_bytes, td_bytes = algorithmic_bytes(flat, K, C)
-    # names of the kernels the engine picks for this shape (enqueue_bottom_up / enqueue_top_down in pml_engine.cu)
-    coop = C <= 16 and K >= 3 and not os.environ.get('PASTML_B200_NO_COOP')
-    td_name = 'td_coop_kernel' if coop else 'td_level_kernel'
-    bu_name = 'bu_tpi_kernel' if (C in (4, 8, 16, 32) and not os.environ.get('PASTML_B200_NO_TPI')) else \
-        ('bu_coop_kernel' if coop else 'bu_level_kernel')
+    # the kernel of a sweep = the one the engine reports to have covered most of its nodes (pml_last_kernels): thin
+    # levels may run on another kernel of the same sweep, listed under 'kernels_of_sweep'
+    bu_name = max(kernels_used['bottom_up'], key=lambda k: kernels_used['bottom_up'][k][1])
+    td_name = max(kernels_used['top_down'], key=lambda k: kernels_used['top_down'][k][1])
+    sweep_of = {bu_name: 'bottom_up', td_name: 'top_down'}
     sweeps = {td_name: (td_bytes, td_ms, td_launches), bu_name: (bu_bytes, bu_ms, bu_launches)}
     dom = max(sweeps, key=lambda k: sweeps[k][1])
 
@@ -735,7 +736,9 @@ def run_b200(args):
         b, ms, n = sweeps[name]
         ach = b / (ms * 1e-3) / 1e9
         return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                'traffic': traffic.get(name), 'traffic_source': 'profiles/{} (per sweep)'.format(TRAFFIC_FILE) if name in traffic else None,
+                'traffic': sum(traffic[k] for k in kernels_used[sweep_of[name]]) if all(k in traffic for k in kernels_used[sweep_of[name]]) else None,
+                'traffic_source': 'profiles/{} (all launches of the sweep)'.format(TRAFFIC_FILE) if name in traffic else None,
+                'kernels_of_sweep': {k: {'launches': v[0], 'items': v[1]} for k, v in kernels_used[sweep_of[name]].items()},
                 'algorithmic_bytes_per_sweep': int(b), 'launches_per_sweep': int(n),
                 'avg_launch_us': ms * 1e3 / max(n, 1), 'sweep_ms': ms, 'peak_source': peak_src}
 

@@ -181,6 +181,13 @@ int pml_trim_memory(void);
  * with CUDA events on the handle's stream (ms), and the number of kernels launched. */
 int pml_last_call_stats(pml_problem *p, double *device_ms, int64_t *kernel_launches);
 
+/* Which kernels the last bottom-up and the last top-down launch sequence of this handle consisted of, as text:
+ * "bottom_up:bu_coop_kernel=29/6011,bu_tpi_kernel=24/993988;top_down:td_coop_kernel=54/1999999"
+ * (kernel = launches per sequence / items -- internal nodes or nodes -- those launches cover).
+ * Measurement only (bench.py names the kernels of its roofline from this instead of guessing); no reference
+ * counterpart. */
+int pml_last_kernels(pml_problem *p, char *buf, int32_t buf_len);
+
 /* ---- The same split with the exchange kept on the device (pastml_b200/sharded.py, bench.py --gpus N).  A pml_shard ties
  * one rank's clade forest and its copy of the top tree (same device).  boundary_top[n_clades]: the clade roots as tip ids
  * of the top tree, in boundary order; clade_owner[n_clades]: the rank that owns each clade (the clade forest's roots are

@@ -157,7 +157,17 @@ struct pml_problem {
     double last_ms = 0.;
     long long last_launches = 0, launches = 0;
     const KernelSet *ks = nullptr;
-    struct GraphEntry { cudaGraphExec_t exec; long long launches; };
+    // which kernels a launch sequence consists of (name -> launches), reported by pml_last_kernels
+    typedef std::map<std::string, std::pair<int, long long>> KernelLog;   // launches, items (slots or nodes)
+    struct GraphEntry { cudaGraphExec_t exec; long long launches; KernelLog log; };
+    KernelLog *cur_log = nullptr;        // where the enqueue functions count their launches
+    KernelLog last_log[2];               // [0] the last bottom-up sequence, [1] the last top-down sequence
+    void note(const char *kernel, long long items) {
+        if (!cur_log) return;
+        auto &e = (*cur_log)[kernel];
+        e.first++;
+        e.second += items;
+    }
     std::map<std::array<long long, 6>, GraphEntry> graphs;
 
     TreeDev tree() const {
@@ -293,26 +303,31 @@ void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_
         if (mma) {
             mma_bu_launch(p->stream, a, s0, ns);
             p->launches++;
+            p->note("bu_mma_kernel", ns);
             continue;
         }
         if (tpi_jt) {
             // thin levels are latency-bound: the cooperative kernel (a node's states split over a thread group, plain
             // loads) finishes a single wave sooner than the staged thread-per-item kernel
             // (not for lane lists: the cooperative kernels take lane j's column to be j % C)
-            if (coop && !ln.lane_col && tpi_jt == ln.J && ns < thin_level_threshold()) coop->bu(p->stream, a, s0, ns);
+            const bool thin = coop && !ln.lane_col && tpi_jt == ln.J && ns < thin_level_threshold();
+            if (thin) coop->bu(p->stream, a, s0, ns);
             else tpi_bu_launch(tpi_jt, p->stream, a, s0, ns);
             p->launches++;
+            p->note(thin ? "bu_coop_kernel" : "bu_tpi_kernel", ns);
             continue;
         }
         if (coop) {
             coop->bu(p->stream, a, s0, ns);
             p->launches++;
+            p->note("bu_coop_kernel", ns);
             continue;
         }
         const int chunk = (int) std::max<long long>(1, kMaxItemsPerLaunch / ln.J);
         for (int off = 0; off < ns; off += chunk) {
             p->ks->bu(p->stream, a, maxp, s0 + off, std::min(chunk, ns - off));
             p->launches++;
+            p->note("bu_level_kernel", std::min(chunk, ns - off));
         }
     }
     run_root_loglik(p, ln, mask, alter, is_marginal);
@@ -328,23 +343,35 @@ void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool wan
 template <class F>
 void run_graphed(pml_problem *p, const std::array<long long, 6> &key, F enqueue) {
     static const bool disabled = getenv("PASTML_B200_NO_GRAPH") != nullptr;
-    if (disabled) { enqueue(); return; }
+    const int kind = key[0] == 1 ? 1 : 0;
+    auto logged = [&](pml_problem::KernelLog &log) {
+        log.clear();
+        p->cur_log = &log;
+        enqueue();
+        p->cur_log = nullptr;
+    };
+    if (disabled) { logged(p->last_log[kind]); return; }
     auto it = p->graphs.find(key);
     if (it == p->graphs.end()) {
         // first use: launched directly (a one-shot call -- create, one pass, destroy -- would pay capture and
         // instantiation for a single replay); the sequence is captured when it comes back
-        p->graphs.emplace(key, pml_problem::GraphEntry{nullptr, 0});
-        enqueue();
+        it = p->graphs.emplace(key, pml_problem::GraphEntry{nullptr, 0, {}}).first;
+        logged(it->second.log);
+        p->last_log[kind] = it->second.log;
         return;
     }
     if (!it->second.exec) {
-        if (it->second.launches < 0) { enqueue(); return; }   // capture failed before: direct launches for this handle
+        if (it->second.launches < 0) {   // capture failed before: direct launches for this handle
+            logged(it->second.log);
+            p->last_log[kind] = it->second.log;
+            return;
+        }
         const long long l0 = p->launches;
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
         bool ok = cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
         if (ok) {
-            enqueue();
+            logged(it->second.log);
             ok = cudaStreamEndCapture(p->stream, &graph) == cudaSuccess && graph != nullptr;
         }
         if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
@@ -354,13 +381,16 @@ void run_graphed(pml_problem *p, const std::array<long long, 6> &key, F enqueue)
         if (!ok) {
             cudaGetLastError();
             it->second.launches = -1;
-            enqueue();
+            logged(it->second.log);
+            p->last_log[kind] = it->second.log;
             return;
         }
-        it->second = pml_problem::GraphEntry{exec, n};
+        it->second.exec = exec;
+        it->second.launches = n;
     }
     cudaGraphLaunch(it->second.exec, p->stream);
     p->launches += it->second.launches;
+    p->last_log[kind] = it->second.log;
 }
 
 void run_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_marginal, int alter, bool keep_ptr,
@@ -449,9 +479,11 @@ void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool wan
             const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
             mma_td_launch(p->stream, a, p->v_all.ptr, p->td_all.ptr, p->td_ex_all.ptr, n0, nn);
             p->launches++;
+            p->note("td_mma_kernel", nn);
         }
         p->ks->td_select(p->stream, a, p->td_all.ptr, p->td_ex_all.ptr, p->N);
         p->launches++;
+        p->note("td_select_kernel", p->N);
         if (hook) (*hook)(p->N);
         return;
     }
@@ -463,6 +495,7 @@ void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool wan
         if (coop) {
             (td_tma ? coop->td_tma : coop->td)(p->stream, a, n0, nn);
             p->launches++;
+            p->note("td_coop_kernel", nn);
             if (hook) (*hook)(n0 + nn);
             continue;
         }
@@ -470,6 +503,7 @@ void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool wan
         for (int off = 0; off < nn; off += chunk) {
             p->ks->td(p->stream, a, n0 + off, std::min(chunk, nn - off));
             p->launches++;
+            p->note("td_level_kernel", std::min(chunk, nn - off));
         }
         if (hook) (*hook)(n0 + nn);
     }
@@ -994,7 +1028,10 @@ int pml_marginal(pml_problem *p, const double *params, int32_t force_joint, doub
                                      cudaMemcpyDeviceToHost, p->copy_stream));
             done = (size_t) node_end;
         };
+        p->last_log[1].clear();
+        p->cur_log = &p->last_log[1];
         enqueue_top_down(p, force_joint, do_probs, do_node_lh, &hook);
+        p->cur_log = nullptr;
     } else {
         run_top_down(p, force_joint, do_probs, do_node_lh);
     }
@@ -1734,6 +1771,25 @@ int pml_last_call_stats(pml_problem *p, double *device_ms, int64_t *kernel_launc
     if (!p) return fail(PML_ERR_INVALID, "null argument");
     if (device_ms) *device_ms = p->last_ms;
     if (kernel_launches) *kernel_launches = p->last_launches;
+    return PML_OK;
+}
+
+int pml_last_kernels(pml_problem *p, char *buf, int32_t buf_len) {
+    if (!p || !buf || buf_len < 1) return fail(PML_ERR_INVALID, "null argument");
+    std::string out;
+    const char *label[2] = {"bottom_up", "top_down"};
+    for (int k = 0; k < 2; ++k) {
+        if (k) out += ";";
+        out += label[k];
+        out += ":";
+        bool first = true;
+        for (const auto &kv : p->last_log[k]) {
+            if (!first) out += ",";
+            first = false;
+            out += kv.first + "=" + std::to_string(kv.second.first) + "/" + std::to_string(kv.second.second);
+        }
+    }
+    std::snprintf(buf, (size_t) buf_len, "%s", out.c_str());
     return PML_OK;
 }
 

@@ -253,6 +253,17 @@ class Problem(object):
         self._check(self.lib.pml_last_call_stats(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def last_kernels(self):
+        """{'bottom_up': {kernel: (launches, items)}, 'top_down': {...}} of the last launch sequences, as the engine
+        recorded them when it enqueued the sequence (items: the internal nodes / nodes those launches cover)."""
+        buf = C.create_string_buffer(1024)
+        self._check(self.lib.pml_last_kernels(self._h, buf, len(buf)))
+        out = {}
+        for part in buf.value.decode().split(';'):
+            label, _, items = part.partition(':')
+            out[label] = {k: tuple(int(x) for x in v.split('/')) for k, v in (item.split('=') for item in items.split(',') if item)}
+        return out
+
     def bench_pass(self, params, which, n_iter, n_sets=1, flush_l2=True):
         params = self._params(params, n_sets)
         avg, best, n = C.c_double(), C.c_double(), C.c_int64()
