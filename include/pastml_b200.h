@@ -181,6 +181,14 @@ int pml_trim_memory(void);
  * with CUDA events on the handle's stream (ms), and the number of kernels launched. */
 int pml_last_call_stats(pml_problem *p, double *device_ms, int64_t *kernel_launches);
 
+/* Expected numbers of state transitions over the forest from n_repetitions ancestral scenarios sampled from the
+ * marginal posterior -- pastml.ml.marginal_counts (pastml/ml.py:753-862): the alteration of zero-branch clusters and
+ * the bottom-up sweep run first, then the roots' states are drawn from their marginal probabilities and every branch
+ * draws the child's state given the parent's, level by level (Philox4x32-10 keyed by `seed`, counted by repetition,
+ * node and column: same seed, same result).  out_counts: [n_columns][K][K], row = from, column = to, per repetition;
+ * the diagonal holds the lineages that stay (ml.py:856-858). */
+int pml_marginal_counts(pml_problem *p, const double *params, int32_t n_repetitions, uint64_t seed, double *out_counts);
+
 /* Which kernels the last bottom-up and the last top-down launch sequence of this handle consisted of, as text:
  * "bottom_up:bu_coop_kernel=29/6011,bu_tpi_kernel=24/993988;top_down:td_coop_kernel=54/1999999"
  * (kernel = launches per sequence / items -- internal nodes or nodes -- those launches cover).

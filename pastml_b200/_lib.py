@@ -15,7 +15,7 @@ EXPORTS = ['pml_last_error', 'pml_version', 'pml_device_count', 'pml_param_strid
            'pml_set_custom_masks', 'pml_get_masks', 'pml_get_initial', 'pml_zero_likelihood_info',
            'pml_zero_likelihood_all', 'pml_trim_memory', 'pml_get_root_partials', 'pml_set_tip_partials',
            'pml_get_tip_td', 'pml_set_root_td',
-           'pml_last_call_stats', 'pml_last_kernels', 'pml_bench_pass', 'pml_supports_lane_lists', 'pml_loglik_lanes', 'pml_get_bottom_up',
+           'pml_last_call_stats', 'pml_last_kernels', 'pml_marginal_counts', 'pml_bench_pass', 'pml_supports_lane_lists', 'pml_loglik_lanes', 'pml_get_bottom_up',
            'pml_shard_create', 'pml_shard_destroy', 'pml_shard_unique_id', 'pml_shard_connect', 'pml_shard_bottom_up',
            'pml_shard_exchange_local', 'pml_shard_finish', 'pml_shard_top_down', 'pml_shard_results',
            'pml_shard_bench_step',
@@ -127,6 +127,8 @@ def load():
     lib.pml_set_root_td.argtypes = [vp, vp, vp]
     lib.pml_trim_memory.restype = C.c_int
     lib.pml_trim_memory.argtypes = []
+    lib.pml_marginal_counts.restype = C.c_int
+    lib.pml_marginal_counts.argtypes = [vp, vp, C.c_int32, C.c_uint64, vp]
     lib.pml_last_kernels.restype = C.c_int
     lib.pml_last_kernels.argtypes = [vp, C.c_char_p, C.c_int32]
     lib.pml_last_call_stats.restype = C.c_int

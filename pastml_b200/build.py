@@ -25,7 +25,7 @@ TPI_SRC = os.path.join(CSRC, 'pml_tpi.cu')
 MMA_SRC = os.path.join(CSRC, 'pml_mma.cu')
 TOPO_SRC = os.path.join(CSRC, 'pml_topo.cu')
 NEWICK_SRC = os.path.join(CSRC, 'pml_newick.cpp')
-HEADERS = [os.path.join(CSRC, 'pml_kernels.cuh'), os.path.join(CSRC, 'pml_coop.cuh'), os.path.join(CSRC, 'pml_tpi.cuh'),
+HEADERS = [os.path.join(CSRC, 'pml_kernels.cuh'), os.path.join(CSRC, 'pml_counts.cuh'), os.path.join(CSRC, 'pml_coop.cuh'), os.path.join(CSRC, 'pml_tpi.cuh'),
            os.path.join(CSRC, 'pml_launch.h'),
            os.path.join(os.path.dirname(HERE), 'include', 'pastml_b200.h')]
 

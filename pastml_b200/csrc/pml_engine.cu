@@ -1066,6 +1066,54 @@ int pml_marginal(pml_problem *p, const double *params, int32_t force_joint, doub
     return rc;
 }
 
+int pml_marginal_counts(pml_problem *p, const double *params, int32_t n_repetitions, uint64_t seed, double *out_counts) {
+    if (!p || !params || !out_counts) return fail(PML_ERR_INVALID, "null argument");
+    if (n_repetitions < 1) return fail(PML_ERR_INVALID, "need at least one repetition");
+    if (p->ext_index.ptr) return fail(PML_ERR_INVALID, "scenario sampling is not available on a problem with external tips");
+    CUDA_TRY(cudaSetDevice(p->device));
+    int rc = upload_params(p, params, 1);
+    if (rc) return rc;
+    // ml.py:786-791: allowed states re-initialised and altered, bottom-up likelihoods (the top-down vector of a root
+    // is all ones, and the conditional draws below need no other top-down vector)
+    run_bottom_up(p, 1, p->mask[PML_MASK_ANNOTATION].ptr, 1, 1, false);
+    rc = fetch_loglik(p, 1, nullptr);
+    if (rc) return rc;
+    const int K = p->K, C = p->C;
+    size_t width = 1;
+    for (int l = 0; l < p->n_levels; ++l) width = std::max<size_t>(width, (size_t) (p->int_level_ptr[l + 1] - p->int_level_ptr[l]));
+    DevBuf<uint8_t> st[2];
+    DevBuf<double> result;
+    CUDA_TRY(st[0].alloc(width * C * (size_t) n_repetitions));
+    CUDA_TRY(st[1].alloc(width * C * (size_t) n_repetitions));
+    CUDA_TRY(result.alloc((size_t) C * K * K));
+    CUDA_TRY(cudaMemsetAsync(result.ptr, 0, sizeof(double) * (size_t) C * K * K, p->stream));
+    const LaneDev ln = p->lanes(1);
+    CountsArgs a{p->tree(), p->zc(), p->ext(), ln, p->mask[PML_MASK_ANNOTATION].ptr, p->bu.ptr, p->bu_ex.ptr,
+                 n_repetitions, (unsigned long long) seed, nullptr, st[0].ptr, 0, p->int_level_ptr[1], 0, result.ptr};
+    if (a.n_slots > 0) {
+        p->ks->counts(p->stream, a, true);
+        p->launches++;
+    }
+    int cur = 0;
+    for (int l = 0; l < p->n_levels; ++l) {
+        const int s0 = p->int_level_ptr[l], ns = p->int_level_ptr[l + 1] - s0;
+        if (ns <= 0) continue;
+        a.st_cur = st[cur].ptr;
+        a.st_next = st[cur ^ 1].ptr;
+        a.slot_begin = s0;
+        a.n_slots = ns;
+        a.next_slot_begin = p->int_level_ptr[l + 1];
+        p->ks->counts(p->stream, a, false);
+        p->launches++;
+        cur ^= 1;
+    }
+    CUDA_TRY(cudaMemcpyAsync(out_counts, result.ptr, sizeof(double) * (size_t) C * K * K, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    CUDA_TRY(cudaGetLastError());
+    for (size_t i = 0; i < (size_t) C * K * K; ++i) out_counts[i] /= (double) n_repetitions;
+    return PML_OK;
+}
+
 int pml_mppa_finalize(pml_problem *p, int32_t force_joint, uint64_t *out_mppa_mask, int64_t *out_k_hist) {
     if (!p) return fail(PML_ERR_INVALID, "null argument");
     if (!p->marginal_done) return fail(PML_ERR_INVALID, "call pml_marginal first");

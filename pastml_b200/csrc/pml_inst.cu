@@ -1,4 +1,5 @@
 // One (model family, KP) instantiation of the level kernels.  Compile with -DPML_FAMILY={0,1,2} -DPML_KP=<n>.
+#include <algorithm>
 #include "pml_launch.h"
 
 #ifndef PML_FAMILY
@@ -78,6 +79,17 @@ void mppa_fix_launch(cudaStream_t st, int n_rows, const int *row_node, int C, in
         n_rows, row_node, C, K, kmask, zc, base_mask, prev_initial, prev_hasinit, zc_lh, zc_k, joint_state,
         force_joint, mppa_mask, k_hist);
 }
+void counts_launch(cudaStream_t st, const CountsArgs &a, bool roots) {
+    const size_t sh = counts_smem_bytes(kFamily, a.ln.K, a.ln.C);
+    const dim3 grid((unsigned) std::max(1, std::min(a.n_slots, 148 * 8)), (unsigned) a.ln.C);
+    if (roots) {
+        allow_big_smem(counts_root_kernel<KP, TheLane>, sh);
+        counts_root_kernel<KP, TheLane><<<grid, 128, sh, st>>>(a);
+    } else {
+        allow_big_smem(counts_level_kernel<KP, TheLane>, sh);
+        counts_level_kernel<KP, TheLane><<<grid, 128, sh, st>>>(a);
+    }
+}
 }  // namespace
 
 #define PML_KS_NAME3(f, k) pml_ks_##f##_##k
@@ -85,7 +97,7 @@ void mppa_fix_launch(cudaStream_t st, int n_rows, const int *row_node, int C, in
 #define PML_KS_NAME PML_KS_NAME2(PML_FAMILY, PML_KP)
 
 const KernelSet *PML_KS_NAME() {
-    static const KernelSet ks = {bu_launch, root_launch, td_launch, td_select_launch, mppa_fix_launch};
+    static const KernelSet ks = {bu_launch, root_launch, td_launch, td_select_launch, mppa_fix_launch, counts_launch};
     return &ks;
 }
 

@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdlib>
 #include "pml_kernels.cuh"
+#include "pml_counts.cuh"
 
 namespace pml {
 
@@ -19,6 +20,8 @@ struct KernelSet {
                      const uint64_t *base_mask, const uint64_t *prev_initial, const uint8_t *prev_hasinit,
                      const double *zc_lh, uint8_t *zc_k, const int *joint_state, int force_joint,
                      uint64_t *mppa_mask, unsigned long long *k_hist);
+    // scenario sampling for marginal_counts (pml_counts.cuh): the roots' states, then one level of branches
+    void (*counts)(cudaStream_t, const CountsArgs &, bool roots);
 };
 
 // Launch of a level kernel with programmatic stream serialization (see pdl_wait in pml_coop.cuh); PASTML_B200_NO_PDL=1

@@ -253,6 +253,13 @@ class Problem(object):
         self._check(self.lib.pml_last_call_stats(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def marginal_counts(self, params, n_repetitions, seed):
+        """[C][K][K] expected transition counts per sampled scenario (pml_marginal_counts)."""
+        params = self._params(params, 1)
+        out = np.empty((self.C, self.K, self.K), dtype=np.float64)
+        self._check(self.lib.pml_marginal_counts(self._h, _p(params), int(n_repetitions), int(seed) & (2 ** 64 - 1), _p(out)))
+        return out
+
     def last_kernels(self):
         """{'bottom_up': {kernel: (launches, items)}, 'top_down': {...}} of the last launch sequences, as the engine
         recorded them when it enqueued the sequence (items: the internal nodes / nodes those launches cover)."""

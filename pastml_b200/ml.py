@@ -630,78 +630,22 @@ def marginal_counts(forest, character, model, n_repetitions=1_000):
     posterior (drop-in for ``pastml.ml.marginal_counts``, ``/root/reference/pastml/ml.py:753-862``): the root state is
     drawn ``n_repetitions`` times from its marginal probabilities, then every branch is walked in level order and the
     child's state is drawn given the parent's state and the subtree below the child
-    (``P(i | j) ~ L_child[i] P_ji(t) allowed_child[i]``).  Returns the K x K matrix of counts per repetition, the diagonal
-    holding the number of lineages that stay in a state.
+    (``P(i | j) ~ L_child[i] P_ij(t) pi_i allowed_child[i]``).  Returns the K x K matrix of counts per repetition, the
+    diagonal holding the number of lineages that stay in a state.
 
-    The bottom-up vectors come from the engine (one ``pml_loglik`` pass + ``pml_get_bottom_up``); the draws use numpy's
-    global random state like the reference (``np.random.seed`` controls them), as multinomial counts -- the reference
-    draws the states one by one and counts them, which is the same distribution on a different random stream."""
+    Everything runs on the device (``pml_marginal_counts``): the alteration of zero-branch clusters, the bottom-up
+    sweep, and one sampling kernel per level in which every repetition carries its own state down the tree --  the same
+    distribution of counts as the reference's per-state multinomial draws, on a different random stream (Philox,
+    counter-based).  The stream's seed is taken from numpy's global random state, so ``np.random.seed`` controls the
+    result like it does for the reference."""
     if not isinstance(forest, (list, tuple)):
         forest = [forest]
     states = list(model.states)
-    K = len(states)
     flat = flatten_forest(forest)
     mask, has = state_masks(flat, character, states)
-    pb = Problem(flat, K, model.engine_kind, mask[None, :], has[None, :])
+    seed = int(np.random.randint(0, 2 ** 62))
+    pb = Problem(flat, len(states), model.engine_kind, mask[None, :], has[None, :])
     try:
-        pb.loglik(model.engine_block(), alter=True)   # the engine alters zero-branch clusters only where tau == 0
-        vec, ex, allowed_mask, altered = pb.bottom_up_state()
-        _, initial_mask = pb.get_initial()
+        return pb.marginal_counts(model.engine_block(), n_repetitions, seed)[0]
     finally:
         pb.close()
-    bits = np.arange(K, dtype=np.uint64)
-
-    def unpack(m):
-        return ((np.uint64(m) >> bits) & np.uint64(1)).astype(np.float64)
-
-    freqs = np.asarray(model.frequencies, dtype=np.float64)
-    N = flat.n_nodes
-    slot = flat.slot
-    counts = np.zeros((N, K), dtype=np.int64)
-    result = np.zeros((K, K), dtype=np.float64)
-
-    def bottom_up(v):
-        return vec[slot[v], :, 0] if slot[v] >= 0 else unpack(allowed_mask[v, 0])
-
-    def redistribute(state_counts, v):
-        """Counts of an altered node, restricted to its own ('.initial') states (ml.py:808-812, 846-852)."""
-        initial = unpack(initial_mask[v, 0])
-        restricted = state_counts * initial
-        if np.count_nonzero(restricted):
-            return n_repetitions * restricted / restricted.sum()
-        return n_repetitions * initial / initial.sum()
-
-    for parent in range(N):   # level order: a parent always precedes its children
-        if flat.parent[parent] < 0:
-            lh = bottom_up(parent) * freqs * unpack(allowed_mask[parent, 0])   # the root's top-down vector is all ones
-            counts[parent] = np.random.multinomial(n_repetitions, lh / lh.sum())
-        n_children = flat.n_children[parent]
-        if not n_children:
-            continue
-        parent_counts = counts[parent]
-        parent_altered = bool(altered[parent, 0])
-        ps_counts_initial = redistribute(parent_counts, parent) if parent_altered else parent_counts
-        same_state_counts = np.zeros(K)
-        first = flat.first_child[parent]
-        for node in range(first, first + n_children):
-            pji = np.transpose(model.get_Pij_t(flat.dist[node]))
-            lh = bottom_up(node)[np.newaxis, :] * pji * (freqs * unpack(allowed_mask[node, 0]))[np.newaxis, :]
-            node_altered = bool(altered[node, 0])
-            update_results = not parent_altered and not node_altered
-            state_counts = np.zeros(K, dtype=np.int64)
-            for j in np.flatnonzero(parent_counts):
-                drawn = np.random.multinomial(parent_counts[j], lh[j] / lh[j].sum())
-                state_counts += drawn
-                if update_results:
-                    result[j, :] += drawn
-                    same_state_counts[j] += drawn[j]
-            counts_initial = redistribute(state_counts, node) if node_altered else state_counts
-            if not update_results:
-                norm_counts = counts_initial / counts_initial.sum()
-                for i in np.flatnonzero(ps_counts_initial > 0):
-                    adjusted = norm_counts * ps_counts_initial[i]
-                    result[i, :] += adjusted
-                    same_state_counts[i] += adjusted[i]
-            counts[node] = state_counts
-        result[np.arange(K), np.arange(K)] -= np.minimum(ps_counts_initial, same_state_counts)
-    return result / n_repetitions

@@ -67,3 +67,25 @@ def test_count_transitions_table(tmp_path):
     with pytest.raises(NotImplementedError):
         count_transitions(tree=os.path.join(src, 'input.nwk'), data=os.path.join(src, 'input.tab'), column='Country',
                           parameters=None, out_transitions=out, html=str(tmp_path / 'x.html'))
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_marginal_counts_many_repetitions(name):
+    """The sampler runs on the device, so 200k scenarios cost nothing: its own Monte-Carlo error becomes negligible
+    and the comparison is against the reference's mean within the REFERENCE's standard error alone.  Same seed, same
+    counts (the random stream is counter-based)."""
+    from pastml_b200.ml import marginal_counts
+    g = Golden(name)
+    want = np.load(os.path.join(GOLDEN, 'counts', 'counts_{}.npz'.format(name)))
+    runs_ref = int(want['runs'])
+    out = []
+    for _ in range(2):
+        roots = annotated_forest(g)
+        np.random.seed(77)
+        out.append(marginal_counts(roots, g.meta['column'], _model(g, roots), n_repetitions=200_000))
+    assert np.array_equal(out[0], out[1])
+    sigma = want['std'] / np.sqrt(runs_ref)
+    dev = np.abs(out[0] - want['mean'])
+    assert np.all(dev <= 5. * sigma + 0.02), (dev.max(), sigma.max())
+    off = lambda m: m.sum() - np.trace(m)
+    assert off(out[0]) == pytest.approx(off(want['mean']), rel=0.01, abs=0.05)
