@@ -350,6 +350,12 @@ def config3_line(device, sync, steps, check):
     params = np.stack([pack_params(0, K, sfs[c], 0., 1., pis[c]) for c in range(C)])
     pb = Problem(flat, K, 0, masks, has, device=device)
     step, bu, td, _ = _sweeps(pb, params, steps)
+    # scenario sampling (marginal_counts, ml.py:753-862) of all 16 columns: alteration + bottom-up sweep + one sampling
+    # kernel per level, 1000 repetitions, result on the host
+    pb.marginal_counts(params, 1000, 1)
+    t0 = time.perf_counter()
+    counts = pb.marginal_counts(params, 1000, 2)
+    counts_ms = (time.perf_counter() - t0) * 1e3
     pb.close()
     fit_s, rec_s, passes, lh0, parity = full_ml_acr(flat, masks, has, list(range(C)), K, device, sync,
                                                     check_column=0 if check else None)
@@ -359,6 +365,8 @@ def config3_line(device, sync, steps, check):
             'ml_acr_seconds': fit_s + rec_s, 'fit_seconds': fit_s, 'reconstruction_seconds': rec_s, 'device_passes': int(passes),
             'step_ms': step, 'node_states_per_s': flat.n_nodes * K * C / (step * 1e-3), 'bu_ms': bu, 'td_ms': td,
             'algorithmic_GBps': {'bu': bu_bytes / bu / 1e6, 'td': td_bytes / td / 1e6},
+            'marginal_counts_1000_repetitions_ms': counts_ms,
+            'marginal_counts_changes_per_scenario_column0': float(counts[0].sum() - np.trace(counts[0])),
             'parity_at_fitted_parameters': parity}
 
 

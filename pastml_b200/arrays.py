@@ -23,13 +23,14 @@ from pastml_b200.parsimony import is_parsimonious, parsimony_on_problem, MP_METH
 from pastml_b200.tree import newick_safe
 
 
-def table_masks(flat, df, column, states=None):
+def table_masks(flat, df, column, states=None, names=None):
     """(states, annot_mask [N] uint64, has_state [N] uint8) for one column of an annotation table indexed by node
     names (a node listed several times gets the union of its states, as ``annotation.df2gdf`` does;
     ``annotation.py:104-123``; ``has_state`` marks every node the table lists).  ``states`` defaults to the sorted values of the column (``acr.py:211-213``)."""
     values = df[column]
     # node index of every table row (-1: the id is not a node name); get_indexer is one vectorised hash join
-    node_names = pd.Index(np.asarray(flat.names, dtype=object))
+    # (``names``: join on these instead of flat.names -- the names as written in the tree file, before name_tree)
+    node_names = pd.Index(np.asarray(flat.names if names is None else names, dtype=object))
     if node_names.has_duplicates:
         node_names = pd.Index(np.where(node_names.duplicated(), None, node_names))   # first occurrence wins
     row_node = node_names.get_indexer(pd.Index(values.index.astype(str)))
@@ -59,33 +60,47 @@ def observed_frequencies(flat, mask, K):
 
 
 def acr_flat(flat, df, columns=None, prediction_method=MPPA, model=F81, column2parameters=None, column2rates=None,
-             force_joint=True, reoptimise=False, tau=0, frequency_smoothing=False, device=0):
+             force_joint=True, reoptimise=False, tau=0, frequency_smoothing=False, device=0, join_names=None):
     """:func:`pastml_b200.acr.acr` for an array-native forest (``tree.read_forest_flat``) and an annotation table
     indexed by node names, ML and parsimony methods.  Returns the list of result dictionaries; the predicted states of a
     character are ``result['state_masks']`` (uint64 per node, bit k = ``result['states'][k]``) and the marginal
-    probabilities keep their DataFrame (rows in the forest's level order)."""
+    probabilities keep their DataFrame (rows in the forest's level order).  ``join_names``: the node names the table
+    is joined on when they differ from ``flat.names`` (the pipeline joins on the names as written in the file and names
+    the nodes afterwards, like the reference: ``acr.py:487-531``).  Per-column parameters / rate matrices may be keyed by
+    the column name as given or normalised (``col_name2cat``)."""
     columns = list(df.columns if columns is None else ([columns] if isinstance(columns, str) else columns))
     methods = value2list(len(columns), prediction_method, MPPA)
     models = value2list(len(columns), model, F81)
     column2parameters = column2parameters or {}
     column2rates = column2rates or {}
+
+    def option(table, column):
+        return table.get(column, table.get(col_name2cat(column)))
+
     forest_stats = ForestStats(flat=flat)
     settings = []
     for column, method, model_name in zip(columns, methods, models):
         character = col_name2cat(column)
         if is_parsimonious(method):
-            states, mask, has = table_masks(flat, df, column)
+            states, mask, has = table_masks(flat, df, column, names=join_names)
             settings.append((character, method, states, mask, has))
             continue
         if not is_ml(method):
             raise ValueError('Method {} is unknown, should be one of ML ({}) or one of MP ({})'
                              .format(method, ', '.join(ML_METHODS), ', '.join(MP_METHODS)))
         fixed_states = HKY_STATES if model_name == HKY else JTT_STATES if model_name == JTT else None
-        states, mask, has = table_masks(flat, df, column, fixed_states)
+        states, mask, has = table_masks(flat, df, column, fixed_states, names=join_names)
+        if fixed_states is not None and not mask.any():
+            raise ValueError('The {} model is only available for characters with states in {}, but none of the values '
+                             'of "{}" is one of them.'.format(model_name, ', '.join(fixed_states), column))
+        # acr.py:185-187: tau is reassigned inside the loop over the characters, so only the first ML character has
+        # its smoothing factor optimised when smoothing is on (and every character when reoptimise is)
         optimise_tau = tau is None or reoptimise
-        instance = model2class[model_name](parameter_file=column2parameters.get(column),
-                                           rate_matrix_file=column2rates.get(column), reoptimise=reoptimise,
-                                           frequency_smoothing=frequency_smoothing, tau=0 if tau is None else tau,
+        if tau is None:
+            tau = 0
+        instance = model2class[model_name](parameter_file=option(column2parameters, column),
+                                           rate_matrix_file=option(column2rates, column), reoptimise=reoptimise,
+                                           frequency_smoothing=frequency_smoothing, tau=tau,
                                            optimise_tau=optimise_tau, states=states, forest_stats=forest_stats,
                                            observed_frequencies=observed_frequencies(flat, mask, len(states)),
                                            character=character)
@@ -204,6 +219,30 @@ def write_named_tree(results, flat, path):
         f.write('\n'.join(text[r] + ';' for r in flat.roots))
 
 
+def _check_table(flat, names, df, columns):
+    """validate_input's sanity checks (``acr.py:487-531``) on the table: enough annotated tips, a discrete character."""
+    num_tips = int(flat.is_tip.sum())
+    listed = df[df.index.isin(set(names))]
+    annotated, seen = {}, {}
+    for c in columns:
+        values = listed[c].dropna()
+        values = values[values != '']
+        annotated[c] = values.index.nunique()
+        seen[c] = set(values)
+    sparsest = min(columns, key=lambda c: annotated[c])
+    unknown = (num_tips - annotated[sparsest]) / num_tips
+    if unknown >= .9:
+        raise ValueError('{:.1f}% of tip annotations for character "{}" are unknown, not enough data to infer ancestral '
+                         'states. Check your annotation file and if its ids correspond to the tree tip/node names.'
+                         .format(unknown * 100, sparsest))
+    poorest = min(columns, key=lambda c: len(seen[c]))
+    if len(seen[poorest]) > num_tips * .75:
+        raise ValueError('Character "{}" has {} unique states annotated in this tree: {}, which is too much to infer on a '
+                         '{} with only {} tips. Make sure the character you are analysing is discrete, and if yes use a '
+                         'larger tree.'.format(poorest, len(seen[poorest]), seen[poorest],
+                                               'tree' if len(flat.roots) == 1 else 'forest', num_tips))
+
+
 def pastml_pipeline_flat(tree, data, data_sep='\t', id_index=0, columns=None, prediction_method=MPPA, model=F81,
                          parameters=None, rate_matrix=None, out_data=None, work_dir=None, forced_joint=False,
                          reoptimise=False, smoothing=False, frequency_smoothing=False, device=0):
@@ -214,6 +253,7 @@ def pastml_pipeline_flat(tree, data, data_sep='\t', id_index=0, columns=None, pr
     from pastml_b200.pipeline import get_pastml_work_dir, get_named_tree_file, _keyed
     from pastml_b200.tree import read_forest_flat
     flat = read_forest_flat(tree)
+    original_names = read_forest_flat(tree, name_nodes=False).names   # what the table ids are matched against
     df = pd.read_csv(data, sep=data_sep, index_col=id_index, header=0, dtype=str)
     df.index = df.index.map(str)
     if columns:
@@ -225,11 +265,12 @@ def pastml_pipeline_flat(tree, data, data_sep='\t', id_index=0, columns=None, pr
                                      'is' if len(unknown) == 1 else 'are', ', '.join('"{}"'.format(c) for c in df.columns)))
         df = df[columns]
     columns = list(df.columns)
-    if not len(set(df.index) & set(flat.names)):
+    if not len(set(df.index) & set(original_names)):
         raise ValueError('Your tree tip names (e.g. {}) do not correspond to annotation id column values (e.g. {}). '
                          'Check your annotation file.'.format(', '.join(map(str, flat.names[flat.is_tip][:3])),
                                                             ', '.join(map(str, df.index[:3]))))
-    results = acr_flat(flat, df, columns=columns, prediction_method=prediction_method, model=model,
+    _check_table(flat, original_names, df, columns)
+    results = acr_flat(flat, df, columns=columns, prediction_method=prediction_method, model=model, join_names=original_names,
                        column2parameters=_keyed(parameters, columns, 'Parameters'),
                        column2rates=_keyed(rate_matrix, columns, 'Rate matrices'), force_joint=forced_joint,
                        reoptimise=reoptimise, tau=None if smoothing else 0, frequency_smoothing=frequency_smoothing,

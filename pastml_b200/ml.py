@@ -320,11 +320,15 @@ class ColumnBatch(object):
 
 # ---------------------------------------------------------------------------------------- parameter fit
 
-def optimize_likelihood_params(evaluate, observed_frequencies, model, evaluate_many=None):
+def optimize_likelihood_params(evaluate, observed_frequencies, model, evaluate_many=None, rng=None):
     """One stage of the fit for one column (``ml.py:174-237``): L-BFGS-B from the current parameters, then from the
     observed frequencies, then from uniform random points, returning at the first successful run that is not worse
     than the better starting point.  ``evaluate()`` returns the log-likelihood at the model's current parameters;
-    ``evaluate_many(blocks)`` (optional) the log-likelihoods for several parameter blocks in one device pass."""
+    ``evaluate_many(blocks)`` (optional) the log-likelihoods for several parameter blocks in one device pass.
+    ``rng``: source of the random restart points (default: numpy's global state, like the reference).  With
+    ``evaluate_many`` scipy's finite differences go through ``workers`` and are not counted in ``nfev``: the
+    ``maxfun`` limit (15000) then counts base-point evaluations only -- it is never reached on either path for the
+    models here (a fit takes a few hundred evaluations)."""
     bounds = model.get_bounds()
 
     def get_v(ps):
@@ -377,7 +381,7 @@ def optimize_likelihood_params(evaluate, observed_frequencies, model, evaluate_m
         elif optimise_frequencies and i == 1:
             vs = x0_EFT
         else:
-            vs = np.random.uniform(bounds[:, 0], bounds[:, 1])
+            vs = (rng or np.random).uniform(bounds[:, 0], bounds[:, 1])
         fres = minimize(get_v, x0=vs, method='L-BFGS-B', bounds=bounds, options=options)
         if fres.success and not np.any(np.isnan(fres.x)):
             if -fres.fun >= best_log_lh:
@@ -387,7 +391,7 @@ def optimize_likelihood_params(evaluate, observed_frequencies, model, evaluate_m
     return best_log_lh
 
 
-def _fit_one(evaluate, character, model, observed_frequencies, evaluate_many=None):
+def _fit_one(evaluate, character, model, observed_frequencies, evaluate_many=None, rng=None):
     """optimise_likelihood for one column (``ml.py:865-920``) given its objective."""
     logger = logging.getLogger('pastml')
     likelihood = evaluate()
@@ -406,7 +410,7 @@ def _fit_one(evaluate, character, model, observed_frequencies, evaluate_many=Non
               'https://github.com/evolbioinfo/pastml/issues'.format(character)
     if not model.basic_params_fixed():
         model.fix_extra_params()
-        likelihood = optimize_likelihood_params(evaluate, observed_frequencies, model, evaluate_many)
+        likelihood = optimize_likelihood_params(evaluate, observed_frequencies, model, evaluate_many, rng)
         if np.isnan(likelihood) or likelihood == -np.inf:
             raise PastMLLikelihoodError(failure)
         model.unfix_extra_params()
@@ -414,7 +418,7 @@ def _fit_one(evaluate, character, model, observed_frequencies, evaluate_many=Non
             logger.debug('Pre-optimised basic parameters for {}:\n{}\tlog likelihood:\t{:.6f}.'
                          .format(character, model._print_basic_parameters(), likelihood))
     if not model.extra_params_fixed():
-        likelihood = optimize_likelihood_params(evaluate, observed_frequencies, model, evaluate_many)
+        likelihood = optimize_likelihood_params(evaluate, observed_frequencies, model, evaluate_many, rng)
         if np.isnan(likelihood) or likelihood == -np.inf:
             raise PastMLLikelihoodError(failure)
     logger.debug('Optimised parameters for {}:\n{}\tlog likelihood:\t{:.6f}'
@@ -427,13 +431,17 @@ def fit_batch(batch, observed_frequencies):
     ev = LockstepEvaluator(batch)
     out = [None] * batch.C
     failures = [None] * batch.C
+    # restart points: one generator per column, seeded from numpy's global state before the threads start, so that a
+    # run is reproducible under np.random.seed whatever the thread interleaving (a single column draws from the
+    # global state itself, like the reference)
+    rngs = [None] if batch.C == 1 else [np.random.default_rng(int(seed)) for seed in np.random.randint(0, 2 ** 31 - 1, size=batch.C)]
 
     def work(c):
         try:
             model = batch.models[c]
             many = (lambda blocks: ev.evaluate(c, blocks)) if batch.batched_fd else None
             out[c] = _fit_one(lambda: ev.evaluate(c, [model.engine_block()])[0], batch.characters[c], model,
-                              observed_frequencies[c], many)
+                              observed_frequencies[c], many, rngs[c])
         except BaseException as e:  # re-raised in the caller's thread
             failures[c] = e
         finally:

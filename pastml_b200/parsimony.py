@@ -38,10 +38,19 @@ def is_parsimonious(method):
     return method in MP_METHODS | {MP}
 
 
+def _popcount(masks):
+    """Set bits per uint64 (np.bitwise_count needs numpy >= 2: older numpy takes the byte-table route)."""
+    masks = np.ascontiguousarray(masks, dtype=np.uint64)
+    if hasattr(np, 'bitwise_count'):
+        return np.bitwise_count(masks).astype(np.int64)
+    table = np.array([bin(b).count('1') for b in range(256)], dtype=np.int64)
+    return table[masks.view(np.uint8).reshape(masks.shape + (8,))].sum(axis=-1)
+
+
 def _set_stats(mask_column, num_nodes):
     """(num_scenarios, num_unresolved_nodes, states per node, % unresolved) of one column of state masks
     (``choose_parsimonious_states``, ``parsimony.py:334-357``)."""
-    sizes = np.bitwise_count(mask_column).astype(np.int64)
+    sizes = _popcount(mask_column)
     hist = np.bincount(sizes)
     scenarios = 1
     for k, cnt in enumerate(hist.tolist()):

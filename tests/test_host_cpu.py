@@ -555,3 +555,33 @@ def test_pipeline_input_validation_on_cpu(tmp_path):
     assert get_pastml_marginal_prob_file('JOINT', 'JC', 'Country') is None
     assert get_named_tree_file('/x/y/my.tree.nwk') == 'named.tree_my.tree.nwk'
     assert get_pastml_work_dir('/x/y/my.tree.nwk') == '/x/y/my.tree_pastml'
+
+
+# ------------------------------------------------------------------ array-native pipeline: input checks
+
+def test_flat_pipeline_checks_and_popcount():
+    """The array-native pipeline applies validate_input's sanity checks (>= 90% unknown tips, a state per tip), and
+    the state-set statistics do not depend on numpy >= 2."""
+    import pandas as pd
+    from pastml_b200.arrays import _check_table
+    from pastml_b200.parsimony import _popcount
+    from pastml_b200.tree import read_forest_flat
+    flat = read_forest_flat('((a:1,b:1):1,(c:1,d:1):1,(e:1,(f:1,(g:1,(h:1,(i:1,(j:1,k:1):1):1):1):1):1):1);')
+    names = read_forest_flat('((a:1,b:1):1,(c:1,d:1):1,(e:1,(f:1,(g:1,(h:1,(i:1,(j:1,k:1):1):1):1):1):1):1);', name_nodes=False).names
+    ok = pd.DataFrame({'x': ['s', 't', 's', 't', 's']}, index=list('abcde'))
+    _check_table(flat, names, ok, ['x'])
+    with pytest.raises(ValueError, match='are unknown'):
+        _check_table(flat, names, pd.DataFrame({'x': ['s']}, index=['a']), ['x'])
+    with pytest.raises(ValueError, match='unique states'):
+        _check_table(flat, names, pd.DataFrame({'x': list('pqrstuvwxyz')}, index=list('abcdefghijk')), ['x'])
+    masks = np.array([0, 1, 3, 0xffffffffffffffff, 1 << 61, 0x5555], dtype=np.uint64)
+    want = np.array([0, 1, 2, 64, 1, 8])
+    assert np.array_equal(_popcount(masks), want)
+    import pastml_b200.parsimony as P
+    saved = getattr(np, 'bitwise_count', None)
+    if saved is not None:
+        try:
+            del np.bitwise_count
+            assert np.array_equal(P._popcount(masks), want) and np.array_equal(P._popcount(masks.reshape(2, 3)), want.reshape(2, 3))
+        finally:
+            np.bitwise_count = saved
