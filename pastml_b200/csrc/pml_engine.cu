@@ -294,12 +294,20 @@ void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_
     static const bool no_mma = getenv("PASTML_B200_NO_MMA") != nullptr;
     const bool mma = !maxp && p->kind == PML_MODEL_EIG && p->eig_shared && !p->ext_index.ptr && !no_mma &&
                      mma_bu_applicable(p->K, ln.J);
+    const bool mma_maxp = maxp && p->kind == PML_MODEL_EIG && p->eig_shared && !p->ext_index.ptr && !no_mma &&
+                          n_lanes == 0 && mma_maxp_applicable(p->K);
     // the state pass of the marginal pipeline (one set, annotation masks, alter) also keeps P L_child for the top-down sweep
     if (mma && n_sets == 1 && n_lanes == 0 && alter && mask == p->mask[PML_MASK_ANNOTATION].ptr) a.v_all = p->v_all.ptr;
     // thread-per-item sweep with TMA-staged child vectors (F81 family, sum-product mode, no external tips)
     for (int lvl = p->n_levels - 1; lvl >= 0; --lvl) {
         const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
         if (ns <= 0) continue;
+        if (mma_maxp) {
+            mma_maxp_launch(p->stream, a, s0, ns);
+            p->launches++;
+            p->note("bu_maxp_mma_kernel", ns);
+            continue;
+        }
         if (mma) {
             mma_bu_launch(p->stream, a, s0, ns);
             p->launches++;

@@ -69,6 +69,9 @@ void tpi_bu_launch(int jt, cudaStream_t, const BuArgs &, int slot_begin, int n_s
 // Bottom-up sweep of the eigen-decomposition models on the FP64 tensor cores (pml_mma.cu): lanes share one decomposition
 bool mma_bu_applicable(int K, int J);
 void mma_bu_launch(cudaStream_t, const BuArgs &, int slot_begin, int n_slots);
+// max-product (JOINT) sweep with P formed on the tensor cores, one warp per (node, lane); lanes share one decomposition
+bool mma_maxp_applicable(int K);
+void mma_maxp_launch(cudaStream_t, const BuArgs &, int slot_begin, int n_slots);
 // top-down vectors of one level on the tensor cores (needs BuArgs::v_all of the preceding bottom-up sweep): writes
 // td_all [N][K][C] / td_ex_all [N][C]
 void mma_td_launch(cudaStream_t, const TdArgs &, const double *v_all, double *td_all, int *td_ex_all, int node_begin,

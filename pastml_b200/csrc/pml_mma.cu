@@ -412,6 +412,161 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) td_mma_kernel(TdArgs
     }
 }
 
+// Max-product bottom-up sweep (JOINT: calc_node_bu_likelihood with is_marginal = False, ml.py:124-148) for lanes that
+// share one decomposition.  The max-product needs the entries of P(t') themselves, K^3 multiply-adds per (branch,
+// lane) -- on the CUDA cores that is 125 ms for the 1M-tip JTT workload.  Here one warp takes one (node, lane) item and
+// forms P = A (exp(d t') o A^-1) on the tensor cores, an MT x NT grid of 8 x 8 D tiles from constant A fragments and
+// B fragments that are the constant A^-1 fragments scaled by this branch's exp(d_k t') (one exponential per state, computed
+// by lane k of the warp and fetched with shuffles).  A thread then holds P[8 mt + g][8 nt + 2 t4 (+1)]: it multiplies
+// by the child's vector, keeps its best (value, child state) per row, and the four threads of a row group finish the
+// arg-max with two shuffle steps (ties to the lower state index, as np.argmax).  Column tiles are processed one after
+// the other so that only MT D tiles are live.
+template <int MT, int KS>
+__global__ void __launch_bounds__(kMmaBlock, 3) bu_maxp_mma_kernel(BuArgs a, int slot_begin, int n_slots) {
+    const int K = a.ln.K, J = a.ln.J, C = a.ln.C;
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const double *dv = a.ln.params + 4 + K, *Am = dv + K, *Ai = Am + (size_t) K * K;
+    // A fragments of A: (row 8 mt + g, col 4 s + t4); B fragments of A^-1: (row 4 s + t4, col 8 nt + g)
+    double f_a[MT][KS], f_b[KS][MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const int r = 8 * mt + g, c4 = 4 * s + t4;
+            f_a[mt][s] = (r < K && c4 < K) ? Am[r * K + c4] : 0.;
+            f_b[s][mt] = (c4 < K && r < K) ? Ai[c4 * K + r] : 0.;
+        }
+    const double d_lane = (lane < K) ? dv[lane] : 0.;
+    pdl_launch_dependents();
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const long long n_items = (long long) n_slots * J;
+    pdl_wait();
+    for (long long w = warp_global; w < n_items; w += n_warps) {
+        const int sl = (int) (w / J), j = (int) (w - (long long) sl * J);
+        const int slot = slot_begin + sl;
+        const int c = j % C;
+        const double *pj = a.ln.params + (size_t) j * a.ln.stride;
+        const double sf = pj[0], tau = pj[1], tf = pj[2];
+        const bool use_alt = a.alter && tau == 0.;
+        const int4 top = a.t.bu_desc[2 * (size_t) slot], len = a.t.bu_desc[2 * (size_t) slot + 1];
+        const int node = a.t.int_nodes[slot];
+        const int fc = top.x, nc = top.y;
+        double acc[MT];
+        {
+            const uint64_t m = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) acc[mt] = (8 * mt + g < K) ? bit_as_double(m, 8 * mt + g) : 0.;
+        }
+        int ex = 0, bad = -1;
+        for (int q = 0; q < nc; ++q) {
+            const int ch = fc + q;
+            const int cs = (q == 0) ? top.z : (q == 1) ? top.w : a.t.slot[ch];
+            const double dist = (q == 0) ? __hiloint2double(len.y, len.x) : (q == 1) ? __hiloint2double(len.w, len.z) : a.t.dist[ch];
+            const double tt = (dist + tau) * tf * sf;
+            // exp(d_k t'): lane k computes state k's
+            double e_lane;
+            {
+                double xs[1] = {d_lane * tt}, es[1];
+                exp_nonpos_n<1>(xs, es);
+                e_lane = es[0];
+            }
+            double ek[KS];
+#pragma unroll
+            for (int s = 0; s < KS; ++s) ek[s] = __shfl_sync(kFullMask, e_lane, (4 * s + t4) & 31);
+            // the child's vector at this thread's columns
+            const uint64_t cm = (cs >= 0) ? 0 : eff_mask(a.mask, a.t, a.zc, C, ch, c, use_alt, a.ln.kmask);
+            const double *src = a.bu + (size_t) (cs >= 0 ? cs : 0) * K * J + j;
+            double best[MT];
+            int arg[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) { best[mt] = -CUDART_INF; arg[mt] = 0; }
+#pragma unroll
+            for (int nt = 0; nt < MT; ++nt) {
+                const int i0 = 8 * nt + 2 * t4, i1 = i0 + 1;
+                double l0 = 0., l1 = 0.;
+                if (cs >= 0) {
+                    if (i0 < K) l0 = src[(size_t) i0 * J];
+                    if (i1 < K) l1 = src[(size_t) i1 * J];
+                } else {
+                    l0 = bit_as_double(cm, i0);
+                    l1 = bit_as_double(cm, i1);
+                }
+                double bfr[KS];   // B fragments of exp(d t') o A^-1 for this column tile
+#pragma unroll
+                for (int s = 0; s < KS; ++s) bfr[s] = f_b[s][nt] * ek[s];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    double p0 = 0., p1 = 0.;
+#pragma unroll
+                    for (int s = 0; s < KS; ++s) dmma(p0, p1, f_a[mt][s], bfr[s]);
+                    const double x0 = __dmul_rn(p0, l0), x1 = __dmul_rn(p1, l1);
+                    if (i0 < K && x0 > best[mt]) { best[mt] = x0; arg[mt] = i0; }
+                    if (i1 < K && x1 > best[mt]) { best[mt] = x1; arg[mt] = i1; }
+                }
+            }
+            // finish the arg-max over the four threads of a row group (columns interleave: lower index wins ties)
+            double vmax = 0.;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                for (int sh = 1; sh <= 2; sh <<= 1) {
+                    const double ob = __shfl_xor_sync(kFullMask, best[mt], sh);
+                    const int oa = __shfl_xor_sync(kFullMask, arg[mt], sh);
+                    if (ob > best[mt] || (ob == best[mt] && oa < arg[mt])) { best[mt] = ob; arg[mt] = oa; }
+                }
+                const int row = 8 * mt + g;
+                if (a.ptr && t4 == 0 && row < K) a.ptr[((size_t) ch * C + c) * K + row] = (uint8_t) arg[mt];
+                acc[mt] *= (row < K) ? fmax(best[mt], 0.) : 0.;
+                vmax = fmax(vmax, acc[mt]);
+            }
+            vmax = colmax(vmax);
+            if (cs >= 0) ex += a.bu_ex[(size_t) cs * J + j];
+            if (vmax == 0. && bad < 0) bad = ch;
+            const bool last = q == nc - 1;
+            if (vmax > 0. && !isinf(vmax)) {
+                int e = exponent_of(vmax);
+                if (last || e < -kKeep || e > kKeep) {
+                    int extra = 0;
+                    double lift = 1.;
+                    if (e == -1023) { lift = 0x1p+200; e = exponent_of(vmax * 0x1p+200); extra = -200; }
+                    const double s1 = pow2(-(e / 2)), s2 = pow2(-(e - e / 2));
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) acc[mt] = ((acc[mt] * lift) * s1) * s2;
+                    ex += e + extra;
+                }
+            }
+        }
+        if (t4 == 0) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+                if (8 * mt + g < K) a.bu[((size_t) slot * K + 8 * mt + g) * J + j] = acc[mt];
+        }
+        if (lane == 0) {
+            a.bu_ex[(size_t) slot * J + j] = ex;
+            if (bad >= 0 && atomicCAS(a.err + 2 * j, -1, node) == -1) a.err[2 * j + 1] = bad;
+        }
+    }
+}
+
+}  // namespace
+
+bool mma_maxp_applicable(int K) { return K > 8 && K <= kMmaKP; }
+
+void mma_maxp_launch(cudaStream_t st, const BuArgs &a, int s0, int ns) {
+    const long long items = (long long) ns * a.ln.J;
+    long long g = (items + kMmaBlock / 32 - 1) / (kMmaBlock / 32);
+    const long long cap = 148LL * 3;   // persistent grid
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    const int K = a.ln.K;
+    if (K <= 16) launch_pdl(bu_maxp_mma_kernel<2, 4>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
+    else if (K <= 20) launch_pdl(bu_maxp_mma_kernel<3, 5>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
+    else launch_pdl(bu_maxp_mma_kernel<3, 6>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
+}
+
+namespace {
 }  // namespace
 
 bool mma_bu_applicable(int K, int J) { return K >= 2 && K <= kMmaKP && J >= 8 && J % 8 == 0; }

@@ -218,6 +218,8 @@ def test_jtt_columns_on_tensor_cores(n_tips, C, kind):
     sets = np.stack([params, params])
     sets[1, :, 0] *= 1.3
     lh2 = pb.loglik(sets, n_sets=2)
+    lh_joint, joint_state = pb.joint(params)   # max-product sweep: P formed on the tensor cores (bu_maxp_mma_kernel)
+    assert 'bu_maxp_mma_kernel' in pb.last_kernels()['bottom_up']
     pb.close()
     full = np.uint64((1 << K) - 1)
     tree = cpu_oracle.OracleTree(flat)
@@ -235,6 +237,9 @@ def test_jtt_columns_on_tensor_cores(n_tips, C, kind):
             ref = cpu_oracle.ml_acr_fixed(flat, om, masks[c], has[c], method='MAP', force_joint=False)
             np.testing.assert_allclose(res['probs'][:, c, :], ref['marginal_probabilities'], rtol=0, atol=PROB_ATOL)
             assert np.array_equal(res['map_mask'][:, c], ref['map_mask'])
+            refj = cpu_oracle.ml_acr_fixed(flat, om, masks[c], has[c], method='JOINT')
+            assert np.array_equal(joint_state[:, c], refj['joint_state'])
+            assert lh_joint[c] == pytest.approx(refj['log_likelihood_restricted_JOINT'], rel=LH_RTOL)
 
 
 def test_lane_list_objective_equals_grid():
