@@ -28,6 +28,9 @@ constexpr uint64_t kExtFlag = 1ULL << 62;     // tip whose bottom-up vector is s
 #ifndef PML_TD_MINB
 #define PML_TD_MINB 3
 #endif
+#ifndef PML_TDSEL_MINB
+#define PML_TDSEL_MINB 3   // td_select_kernel: issue-bound, more resident warps pay (measured, profiles/README.md r2_w)
+#endif
 constexpr int kBlock = PML_BLOCK;
 
 struct TreeDev {
@@ -919,7 +922,7 @@ __global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_TD_MINB : 1)) td_level
 // td_all [N][K][C] / td_ex_all [N][C] (indexed by node, tips included).  No dependency between nodes: one launch for
 // the whole forest.
 template <int KP, template <int> class Lane>
-__global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_TD_MINB : 1)) td_select_kernel(TdArgs a, const double *td_all,
+__global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_TDSEL_MINB : 1)) td_select_kernel(TdArgs a, const double *td_all,
                                                                                       const int *td_ex_all, int n_nodes) {
     extern __shared__ double s_par[];
     const int C = a.ln.C, K = a.ln.K;

@@ -11,6 +11,7 @@
 //
 // Used for K <= 24, lanes a multiple of 8, sum-product mode, no external (subtree-sharding) tips; everything else
 // takes the thread-per-item kernels of pml_kernels.cuh.
+#include <algorithm>
 #include "pml_coop.cuh"
 #include "pml_launch.h"
 
@@ -20,7 +21,7 @@ namespace {
 constexpr int kMmaKP = 24;            // largest padded state count: 3 row tiles of 8, 6 steps of 4
 constexpr int kMmaBlock = 128;
 #ifndef PML_MMA_MINB
-#define PML_MMA_MINB 4
+#define PML_MMA_MINB 6   // latency-bound: resident warps beat spill-free registers (2: 14.3, 3: 11.7, 4: 10.6, 5: 10.5, 6: 10.0 ms per JTT step)
 #endif
 constexpr int kMmaMinBlocks = PML_MMA_MINB;
 
@@ -93,37 +94,39 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) bu_mma_kernel(BuArgs
         }
     }
     pdl_launch_dependents();   // the fragments above are loaded while the previous level drains
+    // the lane tile comes from blockIdx.y, so that everything that depends on it only is loop-invariant
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    const long long n_items = (long long) n_slots * tiles;
+    const int n_items = n_slots;
+    const int tile = blockIdx.y;
+    const int j0 = tile * 8;
+    const int jb = j0 + g;              // the lane this thread feeds as B operand
+    const int jd = j0 + 2 * t4;         // the two lanes of this thread's D elements: jd, jd + 1
+    const int cb = jb % C, cd0 = jd % C, cd1 = (jd + 1) % C;
+    const double *p0 = a.ln.params + (size_t) jd * a.ln.stride, *p1 = p0 + a.ln.stride;
+    const double sf0 = p0[0], tau0 = p0[1], tf0 = p0[2], sf1 = p1[0], tau1 = p1[1], tf1 = p1[2];
+    const bool alt_b = a.alter && a.ln.params[(size_t) jb * a.ln.stride + 1] == 0.;
+    (void) tiles;
     // the packed descriptor (and node id) of the next item is requested before the current one is processed
     int4 nx_top = make_int4(0, 0, 0, 0), nx_len = nx_top;
     int nx_node = 0;
     if (warp_global < n_items) {
-        const size_t s0 = (size_t) slot_begin + (size_t) (warp_global / tiles);
+        const size_t s0 = (size_t) slot_begin + (size_t) warp_global;
         nx_top = a.t.bu_desc[2 * s0];
         nx_len = a.t.bu_desc[2 * s0 + 1];
         nx_node = a.t.int_nodes[s0];
     }
     pdl_wait();   // from here on the previous level's vectors are read
-    for (long long w = warp_global; w < n_items; w += n_warps) {
-        const int sl = (int) (w / tiles), tile = (int) (w - (long long) sl * tiles);
-        const int slot = slot_begin + sl;
+    for (int w = warp_global; w < n_items; w += n_warps) {
+        const int slot = slot_begin + w;
         const int4 top = nx_top, len = nx_len;
         const int node = nx_node;
         if (w + n_warps < n_items) {
-            const size_t s1 = (size_t) slot_begin + (size_t) ((w + n_warps) / tiles);
+            const size_t s1 = (size_t) slot_begin + (size_t) (w + n_warps);
             nx_top = a.t.bu_desc[2 * s1];
             nx_len = a.t.bu_desc[2 * s1 + 1];
             nx_node = a.t.int_nodes[s1];
         }
-        const int j0 = tile * 8;
-        const int jb = j0 + g;              // the lane this thread feeds as B operand
-        const int jd = j0 + 2 * t4;         // the two lanes of this thread's D elements: jd, jd + 1
-        const int cb = jb % C, cd0 = jd % C, cd1 = (jd + 1) % C;
-        const double *p0 = a.ln.params + (size_t) jd * a.ln.stride, *p1 = p0 + a.ln.stride;
-        const double sf0 = p0[0], tau0 = p0[1], tf0 = p0[2], sf1 = p1[0], tau1 = p1[1], tf1 = p1[2];
-        const bool alt_b = a.alter && a.ln.params[(size_t) jb * a.ln.stride + 1] == 0.;
         const int fc = top.x, nc = top.y;
         double acc[MT][2];
         {
@@ -275,32 +278,35 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) td_mma_kernel(TdArgs
     pdl_launch_dependents();
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    const long long n_items = (long long) n_nodes * tiles;
+    const int n_items = n_nodes;
     const int n_root_slots = a.t.n_root_slots;
+    // the lane tile comes from blockIdx.y: this thread's two lanes and their parameters are loop-invariant
+    const int tile = blockIdx.y;
+    const int jd = tile * 8 + 2 * t4;   // the two lanes of this thread's D elements
+    const double *p0 = a.ln.params + (size_t) jd * a.ln.stride, *p1 = p0 + a.ln.stride;
+    const double sf0 = p0[0], tau0 = p0[1], tf0 = p0[2], sf1 = p1[0], tau1 = p1[1], tf1 = p1[2];
+    (void) tiles;
     int4 nx_desc = make_int4(-1, -1, 0, 0);
     int nx_par = -1;
     if (warp_global < n_items) {
-        const int n0 = node_begin + (int) (warp_global / tiles);
+        const int n0 = node_begin + warp_global;
         nx_desc = a.t.td_desc[n0];
         nx_par = a.t.parent[n0];
     }
     pdl_wait();   // from here on the previous level's vectors are read
-    for (long long w = warp_global; w < n_items; w += n_warps) {
-        const int nd = (int) (w / tiles), tile = (int) (w - (long long) nd * tiles);
-        const int node = node_begin + nd;
+    for (int w = warp_global; w < n_items; w += n_warps) {
+        const int node = node_begin + w;
         const int4 desc = nx_desc;
         const int par = nx_par;
         if (w + n_warps < n_items) {
-            const int n1 = node_begin + (int) ((w + n_warps) / tiles);
+            const int n1 = node_begin + w + n_warps;
             nx_desc = a.t.td_desc[n1];
             nx_par = a.t.parent[n1];
         }
         const int ps = desc.x, cs = desc.y;
         if (ps < 0) continue;   // a root: all ones, never stored (ml.py:274-277)
-        const int jd = tile * 8 + 2 * t4;   // the two lanes of this thread's D elements
-        const double *p0 = a.ln.params + (size_t) jd * a.ln.stride, *p1 = p0 + a.ln.stride;
         const double dist = __hiloint2double(desc.w, desc.z);
-        const double t0 = (dist + p0[1]) * p0[2] * p0[0], t1 = (dist + p1[1]) * p1[2] * p1[0];
+        const double t0 = (dist + tau0) * tf0 * sf0, t1 = (dist + tau1) * tf1 * sf1;
         // q = TD_p L_p / contribution, contribution <= 0 -> 1 (ml.py:281-283), in the D layout
         double q[MT][2];
         int pex0 = a.bu_ex[(size_t) ps * C + jd], pex1 = a.bu_ex[(size_t) ps * C + jd + 1];
@@ -441,15 +447,15 @@ __global__ void __launch_bounds__(kMmaBlock, 3) bu_maxp_mma_kernel(BuArgs a, int
     pdl_launch_dependents();
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    const long long n_items = (long long) n_slots * J;
+    // the lane comes from blockIdx.y: its column and parameters are loop-invariant
+    const int j = blockIdx.y;
+    const int c = j % C;
+    const double *pj = a.ln.params + (size_t) j * a.ln.stride;
+    const double sf = pj[0], tau = pj[1], tf = pj[2];
+    const bool use_alt = a.alter && tau == 0.;
     pdl_wait();
-    for (long long w = warp_global; w < n_items; w += n_warps) {
-        const int sl = (int) (w / J), j = (int) (w - (long long) sl * J);
-        const int slot = slot_begin + sl;
-        const int c = j % C;
-        const double *pj = a.ln.params + (size_t) j * a.ln.stride;
-        const double sf = pj[0], tau = pj[1], tf = pj[2];
-        const bool use_alt = a.alter && tau == 0.;
+    for (int w = warp_global; w < n_slots; w += n_warps) {
+        const int slot = slot_begin + w;
         const int4 top = a.t.bu_desc[2 * (size_t) slot], len = a.t.bu_desc[2 * (size_t) slot + 1];
         const int node = a.t.int_nodes[slot];
         const int fc = top.x, nc = top.y;
@@ -555,15 +561,15 @@ __global__ void __launch_bounds__(kMmaBlock, 3) bu_maxp_mma_kernel(BuArgs a, int
 bool mma_maxp_applicable(int K) { return K > 8 && K <= kMmaKP; }
 
 void mma_maxp_launch(cudaStream_t st, const BuArgs &a, int s0, int ns) {
-    const long long items = (long long) ns * a.ln.J;
-    long long g = (items + kMmaBlock / 32 - 1) / (kMmaBlock / 32);
-    const long long cap = 148LL * 3;   // persistent grid
+    long long g = ((long long) ns + kMmaBlock / 32 - 1) / (kMmaBlock / 32);
+    const long long cap = std::max(1LL, 148LL * 3 / a.ln.J);   // persistent grid, blockIdx.y = lane   // persistent grid
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     const int K = a.ln.K;
-    if (K <= 16) launch_pdl(bu_maxp_mma_kernel<2, 4>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
-    else if (K <= 20) launch_pdl(bu_maxp_mma_kernel<3, 5>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
-    else launch_pdl(bu_maxp_mma_kernel<3, 6>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
+    const dim3 grid((unsigned) g, (unsigned) a.ln.J);
+    if (K <= 16) launch_pdl(bu_maxp_mma_kernel<2, 4>, grid, dim3(kMmaBlock), 0, st, a, s0, ns);
+    else if (K <= 20) launch_pdl(bu_maxp_mma_kernel<3, 5>, grid, dim3(kMmaBlock), 0, st, a, s0, ns);
+    else launch_pdl(bu_maxp_mma_kernel<3, 6>, grid, dim3(kMmaBlock), 0, st, a, s0, ns);
 }
 
 namespace {
@@ -572,31 +578,33 @@ namespace {
 bool mma_bu_applicable(int K, int J) { return K >= 2 && K <= kMmaKP && J >= 8 && J % 8 == 0; }
 
 void mma_bu_launch(cudaStream_t st, const BuArgs &a, int s0, int ns) {
-    const long long items = (long long) ns * (a.ln.J / 8);
-    long long g = (items + kMmaBlock / 32 - 1) / (kMmaBlock / 32);
-    const long long cap = 148LL * kMmaMinBlocks;   // persistent grid
+    const int tiles = a.ln.J / 8;
+    long long g = ((long long) ns + kMmaBlock / 32 - 1) / (kMmaBlock / 32);
+    const long long cap = std::max(1LL, 148LL * kMmaMinBlocks / tiles);   // persistent grid, blockIdx.y = lane tile
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     const int K = a.ln.K;
-    if (K <= 8) launch_pdl(bu_mma_kernel<1, 2>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
-    else if (K <= 16) launch_pdl(bu_mma_kernel<2, 4>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
-    else if (K <= 20) launch_pdl(bu_mma_kernel<3, 5>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
-    else launch_pdl(bu_mma_kernel<3, 6>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, s0, ns);
+    const dim3 grid((unsigned) g, (unsigned) tiles);
+    if (K <= 8) launch_pdl(bu_mma_kernel<1, 2>, grid, dim3(kMmaBlock), 0, st, a, s0, ns);
+    else if (K <= 16) launch_pdl(bu_mma_kernel<2, 4>, grid, dim3(kMmaBlock), 0, st, a, s0, ns);
+    else if (K <= 20) launch_pdl(bu_mma_kernel<3, 5>, grid, dim3(kMmaBlock), 0, st, a, s0, ns);
+    else launch_pdl(bu_mma_kernel<3, 6>, grid, dim3(kMmaBlock), 0, st, a, s0, ns);
 }
 
 }  // namespace pml
 
 namespace pml {
 void mma_td_launch(cudaStream_t st, const TdArgs &a, const double *v_all, double *td_all, int *td_ex_all, int n0, int nn) {
-    const long long items = (long long) nn * (a.ln.C / 8);
-    long long g = (items + kMmaBlock / 32 - 1) / (kMmaBlock / 32);
-    const long long cap = 148LL * kMmaMinBlocks;   // persistent grid
+    const int tiles = a.ln.C / 8;
+    long long g = ((long long) nn + kMmaBlock / 32 - 1) / (kMmaBlock / 32);
+    const long long cap = std::max(1LL, 148LL * kMmaMinBlocks / tiles);   // persistent grid, blockIdx.y = lane tile
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     const int K = a.ln.K;
-    if (K <= 8) launch_pdl(td_mma_kernel<1, 2>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, v_all, td_all, td_ex_all, n0, nn);
-    else if (K <= 16) launch_pdl(td_mma_kernel<2, 4>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, v_all, td_all, td_ex_all, n0, nn);
-    else if (K <= 20) launch_pdl(td_mma_kernel<3, 5>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, v_all, td_all, td_ex_all, n0, nn);
-    else launch_pdl(td_mma_kernel<3, 6>, dim3((unsigned) g), dim3(kMmaBlock), 0, st, a, v_all, td_all, td_ex_all, n0, nn);
+    const dim3 grid((unsigned) g, (unsigned) tiles);
+    if (K <= 8) launch_pdl(td_mma_kernel<1, 2>, grid, dim3(kMmaBlock), 0, st, a, v_all, td_all, td_ex_all, n0, nn);
+    else if (K <= 16) launch_pdl(td_mma_kernel<2, 4>, grid, dim3(kMmaBlock), 0, st, a, v_all, td_all, td_ex_all, n0, nn);
+    else if (K <= 20) launch_pdl(td_mma_kernel<3, 5>, grid, dim3(kMmaBlock), 0, st, a, v_all, td_all, td_ex_all, n0, nn);
+    else launch_pdl(td_mma_kernel<3, 6>, grid, dim3(kMmaBlock), 0, st, a, v_all, td_all, td_ex_all, n0, nn);
 }
 }  // namespace pml
