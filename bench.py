@@ -34,7 +34,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
-TRAFFIC_FILE = 'r2_t_dram_traffic.json'   # ncu capture of one step of the default workload with the current kernels
+TRAFFIC_FILE = 'r2_w_dram_traffic.json'   # ncu capture of one step of the default workload with the current kernels
 METRIC = 'mppa_node_states_per_s'
 UNIT = 'node-states/s'
 
