@@ -386,16 +386,19 @@ def config4_line(device, steps, check, tips=1_000_000):
     pb = Problem(flat, K, models[0].engine_kind, masks, has, device=device)
     step, bu, td, launches = _sweeps(pb, params, steps)
     lh = pb.loglik(params)[0]
+    pb.joint(params, want_states=False)
+    joint_ms, _, _ = pb.bench_pass(params, which=2, n_iter=max(2, steps // 3), flush_l2=True)
     pb.close()
     n_edges = flat.n_nodes - 1
     out = {'workload': 'synthetic coalescent tree, {} tips ({} nodes, {} levels), K=20 JTT, 8 columns, MPPA'.format(
                tips, flat.n_nodes, flat.n_levels),
            'step_ms': step, 'node_states_per_s': flat.n_nodes * K * C / (step * 1e-3), 'bu_ms': bu, 'td_ms': td,
            'launches_per_step': int(launches),
+           'joint_ms': joint_ms,   # max-product sweep (P formed on the tensor cores, bu_maxp_mma_kernel) + traceback
            'fp64_tensor_TFLOPs': {'bu': 2 * 4 * K * K * n_edges * C / (bu * 1e-3) / 1e12, 'td': 2 * 2 * K * K * n_edges * C / (td * 1e-3) / 1e12,
                                   'note': 'useful flops of the products A^-1 v and A w (2 K^2 multiply-adds each; two applications of P '
                                           'per edge and lane bottom-up incl. the kept P L_child, one top-down)'},
-           'kernels': 'bu_mma_kernel / td_mma_kernel (mma.sync.m8n8k4.f64) + td_select_kernel'}
+           'kernels': 'bu_mma_kernel / td_mma_kernel / bu_maxp_mma_kernel (mma.sync.m8n8k4.f64) + td_select_kernel'}
     if check:   # log-likelihood of one column against the oracle's bottom-up pass on the same tree
         from oracle import cpu_oracle
         m = models[0]
