@@ -64,7 +64,10 @@ def test_option_fixture(name, tmp_path):
         if hasattr(mdl, 'frequencies'):
             np.testing.assert_allclose(mdl.frequencies, z['pi'], rtol=1e-13 if fixed else 2e-4, atol=1e-9)
         if model == 'HKY':
-            assert float(mdl.kappa) == pytest.approx(float(z['kappa']), rel=1e-14 if fixed else 1e-4)
+            # kappa is the least identified parameter: the reference moves it by ~1.2e-4 under one ulp of noise
+            ens_k = np.concatenate((z['ens_kappa'], [float(z['kappa'])])) if 'ens_kappa' in z else np.array([float(z['kappa'])])
+            self_k = float(np.abs(ens_k - float(z['kappa'])).max() / float(z['kappa']))
+            assert float(mdl.kappa) == pytest.approx(float(z['kappa']), rel=1e-14 if fixed else max(1e-4, 2 * self_k))
         for m in ('JOINT', 'MAP', 'MPPA'):
             key = 'log_likelihood_restricted_' + m
             if key in z and key in r:
