@@ -71,7 +71,9 @@ def test_option_fixture(name, tmp_path):
         for m in ('JOINT', 'MAP', 'MPPA'):
             key = 'log_likelihood_restricted_' + m
             if key in z and key in r:
-                assert r[key] == pytest.approx(float(z[key]), rel=1e-12 if fixed else 1e-7), key
+                # (a restricted likelihood is not at an optimum: it moves in first order with the fitted parameters,
+                # which carry the optimiser's own 1e-6 .. 1e-4 spread)
+                assert r[key] == pytest.approx(float(z[key]), rel=1e-12 if fixed else 1e-5), key
         assert np.array_equal(masks_from_feature(flat.nodes, states, column), z['state_mask'].astype(np.uint64))
         for key in ('num_unresolved_nodes', 'num_states_per_node_avg'):
             if key in z:
