@@ -206,6 +206,7 @@ int pml_last_kernels(pml_problem *p, char *buf, int32_t buf_len);
  *                         tree (the same on every rank; ml.py:82-121); out_loglh null = nothing fetched, no host sync;
  *   pml_shard_top_down    fused top-down / marginal / MAP / MPPA sweep (ml.py:240-290, 431-465, 505-595): top tree on
  *                         every rank, the rank's clade roots receive their top-down vectors on the device, clades;
+ *                         force_joint as in pml_marginal (after pml_shard_joint_finish);
  *   pml_shard_results     outputs of either problem (which: 0 = top tree, 1 = clade forest), shapes as pml_marginal.
  * NCCL is resolved from the running process (libnccl.so.2): pml_shard_unique_id on rank 0, the 128 bytes broadcast by the
  * caller, pml_shard_connect on every rank.  pml_shard_exchange_local replaces the all-gather when the ranks are
@@ -219,7 +220,15 @@ int pml_shard_connect(pml_shard *sh, const uint8_t *id128);
 int pml_shard_bottom_up(pml_shard *sh, const double *params, int32_t n_sets, int32_t mask_kind);
 int pml_shard_exchange_local(pml_shard **shards, int32_t world);
 int pml_shard_finish(pml_shard *sh, const double *params, int32_t n_sets, double *out_loglh);
-int pml_shard_top_down(pml_shard *sh, int32_t want_probs, int32_t want_node_lh);
+int pml_shard_top_down(pml_shard *sh, int32_t want_probs, int32_t want_node_lh, int32_t force_joint);
+/* JOINT on the sharded tree (ml.py:598-622, 687-695): max-product sweep of the clades + all-gather, then the top tree's
+ * max-product sweep, the joint log-likelihood of the whole tree (out_loglh [C], the same on every rank), the top tree's
+ * traceback, and the clades' traceback started from the states the top tree chose for their roots.  Afterwards
+ * pml_shard_bottom_up(mask_kind = PML_MASK_JOINT) gives the JOINT-restricted likelihood and pml_shard_top_down may
+ * force the joint state into the MPPA sets (ml.py:545). */
+int pml_shard_joint_bottom_up(pml_shard *sh, const double *params);
+int pml_shard_joint_finish(pml_shard *sh, const double *params, double *out_loglh);
+int pml_shard_joint_states(pml_shard *sh, int32_t which, int32_t *out_state);
 int pml_shard_results(pml_shard *sh, int32_t which, double *out_probs, double *out_node_log10lh, uint64_t *out_map_mask,
                       uint64_t *out_mppa_mask, int64_t *out_k_hist);
 /* device-timed sharded MPPA step, n_iter times (CUDA events on the clade stream around each step); phase_ms: clades

@@ -18,6 +18,7 @@ EXPORTS = ['pml_last_error', 'pml_version', 'pml_device_count', 'pml_param_strid
            'pml_last_call_stats', 'pml_last_kernels', 'pml_marginal_counts', 'pml_bench_pass', 'pml_supports_lane_lists', 'pml_loglik_lanes', 'pml_get_bottom_up',
            'pml_shard_create', 'pml_shard_destroy', 'pml_shard_unique_id', 'pml_shard_connect', 'pml_shard_bottom_up',
            'pml_shard_exchange_local', 'pml_shard_finish', 'pml_shard_top_down', 'pml_shard_results',
+           'pml_shard_joint_bottom_up', 'pml_shard_joint_finish', 'pml_shard_joint_states',
            'pml_shard_bench_step',
            'pml_newick_last_error', 'pml_newick_parse', 'pml_newick_num_nodes', 'pml_newick_num_trees',
            'pml_newick_names_bytes', 'pml_newick_name_nodes', 'pml_newick_fill', 'pml_newick_free']
@@ -69,7 +70,13 @@ def load():
     lib.pml_shard_finish.restype = C.c_int
     lib.pml_shard_finish.argtypes = [vp, vp, i32, vp]
     lib.pml_shard_top_down.restype = C.c_int
-    lib.pml_shard_top_down.argtypes = [vp, i32, i32]
+    lib.pml_shard_top_down.argtypes = [vp, i32, i32, i32]
+    lib.pml_shard_joint_bottom_up.restype = C.c_int
+    lib.pml_shard_joint_bottom_up.argtypes = [vp, vp]
+    lib.pml_shard_joint_finish.restype = C.c_int
+    lib.pml_shard_joint_finish.argtypes = [vp, vp, vp]
+    lib.pml_shard_joint_states.restype = C.c_int
+    lib.pml_shard_joint_states.argtypes = [vp, i32, vp]
     lib.pml_shard_results.restype = C.c_int
     lib.pml_shard_results.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.pml_shard_bench_step.restype = C.c_int

@@ -532,6 +532,19 @@ int ensure_mma_td_buffers(pml_problem *p) {
     return PML_OK;
 }
 
+int ensure_joint_buffers(pml_problem *p);
+
+// choose_ancestral_states_joint level by level on the pointers the max-product sweep left; root_state: see JointArgs
+void enqueue_joint_trace(pml_problem *p, const int *root_state) {
+    JointArgs a{p->tree(), p->zc(), p->lanes(1), p->mask[PML_MASK_ANNOTATION].ptr, p->bu.ptr, p->ptr.ptr,
+                p->joint_state.ptr, p->mask[PML_MASK_JOINT].ptr, root_state};
+    for (int lvl = 0; lvl < p->n_levels; ++lvl) {
+        const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
+        launch_pdl(joint_trace_kernel, dim3(grid_for((long long) nn * p->C)), dim3(kBlock), 0, p->stream, a, n0, nn);
+        p->launches++;
+    }
+}
+
 int ensure_joint_buffers(pml_problem *p) {
     const size_t nc = (size_t) p->N * p->C;
     if (!p->ptr.ptr) CUDA_TRY(p->ptr.alloc(nc * p->K));
@@ -963,13 +976,7 @@ int pml_joint(pml_problem *p, const double *params, double *out_loglh, int32_t *
     CallTimer timer(p);
     const uint64_t *base = p->mask[PML_MASK_ANNOTATION].ptr;
     run_bottom_up(p, 1, base, 0, 1, true);
-    JointArgs a{p->tree(), p->zc(), p->lanes(1), base, p->bu.ptr, p->ptr.ptr, p->joint_state.ptr,
-                p->mask[PML_MASK_JOINT].ptr};
-    for (int lvl = 0; lvl < p->n_levels; ++lvl) {
-        const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
-        launch_pdl(joint_trace_kernel, dim3(grid_for((long long) nn * p->C)), dim3(kBlock), 0, p->stream, a, n0, nn);
-        p->launches++;
-    }
+    enqueue_joint_trace(p, nullptr);
     timer.stop();
     CUDA_TRY(cudaGetLastError());
     p->mask_valid[PML_MASK_JOINT] = true;
@@ -1499,12 +1506,20 @@ __global__ void shard_root_td_kernel(const double *ext_td, const int *ext_td_ex,
     else root_td_ex[(size_t) i * C + c] = ext_td_ex[(size_t) row * C + c];
 }
 
+// joint states the top tree chose for this rank's clade roots -> preset root states of the clade forest
+__global__ void shard_root_state_kernel(const int *top_state, const int *my_top_nodes, int n_mine, int C, int *root_state) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_mine * C) return;
+    const int i = g / C, c = g - i * C;
+    root_state[g] = top_state[(size_t) my_top_nodes[i] * C + c];
+}
+
 }  // namespace
 
 struct pml_shard {
     pml_problem *clades = nullptr, *top = nullptr;
     int rank = 0, world = 1, n_clades = 0, n_mine = 0, n_max = 0;
-    DevBuf<int> row_src, my_rows;
+    DevBuf<int> row_src, my_rows, my_top_nodes, root_state;   // my_top_nodes: this rank's clade roots as nodes of the top tree
     DevBuf<double> xsend, xbuf;
     size_t slot_doubles = 0;   // capacity of one rank's part of the exchange: n_max * (K + 1) * B * C
     cudaEvent_t ev_gather = nullptr, ev_top = nullptr;
@@ -1565,6 +1580,13 @@ int pml_shard_create(pml_problem *clades, pml_problem *top, int32_t rank, int32_
     PML_SH_TRY(cudaMemset(sh->xsend.ptr, 0, sh->slot_doubles * sizeof(double)));
     PML_SH_TRY(cudaMemcpy(sh->row_src.ptr, row_src.data(), sizeof(int) * n_clades, cudaMemcpyHostToDevice));
     PML_SH_TRY(cudaMemcpy(sh->my_rows.ptr, mine.data(), sizeof(int) * mine.size(), cudaMemcpyHostToDevice));
+    {
+        std::vector<int> top_nodes(mine.size());
+        for (size_t i = 0; i < mine.size(); ++i) top_nodes[i] = boundary_top[mine[i]];
+        PML_SH_TRY(sh->my_top_nodes.alloc(std::max<size_t>(mine.size(), 1)));
+        PML_SH_TRY(sh->root_state.alloc(std::max<size_t>(mine.size(), 1) * top->C));
+        PML_SH_TRY(cudaMemcpy(sh->my_top_nodes.ptr, top_nodes.data(), sizeof(int) * mine.size(), cudaMemcpyHostToDevice));
+    }
     PML_SH_TRY(cudaEventCreateWithFlags(&sh->ev_gather, cudaEventDisableTiming));
     PML_SH_TRY(cudaEventCreateWithFlags(&sh->ev_top, cudaEventDisableTiming));
     // the clade forest's roots take their top-down vectors from the top tree from now on
@@ -1689,23 +1711,26 @@ int pml_shard_finish(pml_shard *sh, const double *params, int32_t n_sets, double
 // the fused top-down sweep of the sharded tree after pml_shard_bottom_up + pml_shard_finish with one parameter set:
 // top tree on every rank, then this rank's clades from the top-down vectors of their roots.  Outputs stay in the two
 // problems' device buffers (fetch them with pml_shard_results); the host is synchronised once, at the end.
-int pml_shard_top_down(pml_shard *sh, int32_t want_probs, int32_t want_node_lh) {
+int pml_shard_top_down(pml_shard *sh, int32_t want_probs, int32_t want_node_lh, int32_t force_joint) {
     if (!sh) return fail(PML_ERR_INVALID, "null argument");
     if (sh->last_sets != 1) return fail(PML_ERR_INVALID, "the top-down sweep takes one parameter set");
     pml_problem *t = sh->top, *c = sh->clades;
+    force_joint = force_joint ? 1 : 0;
+    if (force_joint && !(t->joint_done && c->joint_done))
+        return fail(PML_ERR_INVALID, "force_joint needs the JOINT states: call pml_shard_joint_finish first");
     CUDA_TRY(cudaSetDevice(t->device));
     int rc = ensure_marginal_buffers(t, want_probs != 0, want_node_lh != 0);
     if (rc) return rc;
     rc = ensure_marginal_buffers(c, want_probs != 0, want_node_lh != 0);
     if (rc) return rc;
-    run_top_down(t, 0, want_probs != 0, want_node_lh != 0);
+    run_top_down(t, force_joint, want_probs != 0, want_node_lh != 0);
     const long long n = (long long) sh->n_mine * (t->K + 1) * t->C;
     shard_root_td_kernel<<<grid_for(n), kBlock, 0, t->stream>>>(t->ext_td.ptr, t->ext_td_ex.ptr, sh->my_rows.ptr, sh->n_mine, t->K,
                                                               t->C, c->root_td.ptr, c->root_td_ex.ptr);
     t->launches++;
     CUDA_TRY(cudaEventRecord(sh->ev_top, t->stream));
     CUDA_TRY(cudaStreamWaitEvent(c->stream, sh->ev_top, 0));
-    run_top_down(c, 0, want_probs != 0, want_node_lh != 0);
+    run_top_down(c, force_joint, want_probs != 0, want_node_lh != 0);
     CUDA_TRY(cudaGetLastError());
     for (pml_problem *p : {t, c}) {
         p->mask_valid[PML_MASK_MAP] = p->mask_valid[PML_MASK_MPPA] = true;
@@ -1719,6 +1744,81 @@ int pml_shard_top_down(pml_shard *sh, int32_t want_probs, int32_t want_node_lh) 
     }
     CUDA_TRY(cudaStreamSynchronize(t->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PML_OK;
+}
+
+// JOINT on the sharded tree (ml.py:598-622, 687-695), two phases around the exchange like the sum-product pass.
+// Phase A: max-product sweep of this rank's clades (pointers kept), clade-root vectors packed and all-gathered.
+int pml_shard_joint_bottom_up(pml_shard *sh, const double *params) {
+    if (!sh || !params) return fail(PML_ERR_INVALID, "null argument");
+    pml_problem *p = sh->clades;
+    CUDA_TRY(cudaSetDevice(p->device));
+    int rc = ensure_joint_buffers(p);
+    if (rc) return rc;
+    rc = upload_params(p, params, 1);
+    if (rc) return rc;
+    run_bottom_up(p, 1, p->mask[PML_MASK_ANNOTATION].ptr, 0, 1, true);
+    const LaneDev ln = p->lanes(1);   // (the max-product sweep writes the plain layout)
+    const long long n = (long long) p->n_roots * (p->K + 1) * ln.J;
+    shard_pack_kernel<<<grid_for(n), kBlock, 0, p->stream>>>(p->tree(), ln, p->bu.ptr, p->bu_ex.ptr, p->n_roots, sh->xsend.ptr);
+    p->launches++;
+    sh->last_sets = 1;
+    sh->last_mask_kind = PML_MASK_ANNOTATION;
+    const size_t count = (size_t) sh->n_max * (p->K + 1) * ln.J;
+    if (sh->comm) {
+        const int nrc = nccl().AllGather(sh->xsend.ptr, sh->xbuf.ptr, count, 8 /* ncclFloat64 */, sh->comm, p->stream);
+        if (nrc) return fail(PML_ERR_CUDA, std::string("ncclAllGather: ") + nccl().GetErrorString(nrc));
+    }
+    CUDA_TRY(cudaEventRecord(sh->ev_gather, p->stream));
+    CUDA_TRY(cudaGetLastError());
+    return PML_OK;
+}
+
+// Phase B: the top tree's max-product sweep on the gathered vectors, its joint log-likelihood (the whole tree's, the same
+// on every rank) and traceback; the states it chose for this rank's clade roots start the clades' traceback.
+int pml_shard_joint_finish(pml_shard *sh, const double *params, double *out_loglh) {
+    if (!sh || !params) return fail(PML_ERR_INVALID, "null argument");
+    pml_problem *t = sh->top, *c = sh->clades;
+    if (sh->last_sets != 1) return fail(PML_ERR_INVALID, "call pml_shard_joint_bottom_up first");
+    CUDA_TRY(cudaSetDevice(t->device));
+    int rc = ensure_joint_buffers(t);
+    if (rc) return rc;
+    rc = upload_params(t, params, 1);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamWaitEvent(t->stream, sh->ev_gather, 0));
+    const long long n = (long long) sh->n_clades * (t->K + 1) * t->C;
+    shard_unpack_kernel<<<grid_for(n), kBlock, 0, t->stream>>>(sh->xbuf.ptr, sh->row_src.ptr, sh->n_clades, t->K, t->C,
+                                                             t->ext_bu.ptr, t->ext_bu_ex.ptr);
+    t->launches++;
+    t->ext_sets = 1;
+    run_bottom_up(t, 1, t->mask[PML_MASK_ANNOTATION].ptr, 0, 1, true);
+    enqueue_joint_trace(t, nullptr);
+    if (sh->n_mine) {
+        shard_root_state_kernel<<<grid_for((long long) sh->n_mine * t->C), kBlock, 0, t->stream>>>(
+            t->joint_state.ptr, sh->my_top_nodes.ptr, sh->n_mine, t->C, sh->root_state.ptr);
+        t->launches++;
+    }
+    CUDA_TRY(cudaEventRecord(sh->ev_top, t->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, sh->ev_top, 0));
+    enqueue_joint_trace(c, sh->root_state.ptr);
+    CUDA_TRY(cudaGetLastError());
+    for (pml_problem *p : {t, c}) {
+        p->mask_valid[PML_MASK_JOINT] = true;
+        p->joint_done = true;
+    }
+    rc = fetch_loglik(t, 1, out_loglh);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return rc;
+}
+
+// joint states [N][C] of one of the two problems after pml_shard_joint_finish (which: 0 = top tree, 1 = clade forest)
+int pml_shard_joint_states(pml_shard *sh, int32_t which, int32_t *out_state) {
+    if (!sh || which < 0 || which > 1 || !out_state) return fail(PML_ERR_INVALID, "bad argument");
+    pml_problem *p = which ? sh->clades : sh->top;
+    if (!p->joint_done) return fail(PML_ERR_INVALID, "call pml_shard_joint_finish first");
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(cudaMemcpyAsync(out_state, p->joint_state.ptr, sizeof(int) * (size_t) p->N * p->C, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
     return PML_OK;
 }
 
@@ -1885,13 +1985,7 @@ int pml_bench_pass(pml_problem *p, const double *params, int32_t n_sets, int32_t
             run_top_down(p, 0, true, true);
         } else {
             run_bottom_up(p, 1, base, 0, 1, true);
-            JointArgs a{p->tree(), p->zc(), p->lanes(1), base, p->bu.ptr, p->ptr.ptr, p->joint_state.ptr,
-                        p->mask[PML_MASK_JOINT].ptr};
-            for (int lvl = 0; lvl < p->n_levels; ++lvl) {
-                const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
-                launch_pdl(joint_trace_kernel, dim3(grid_for((long long) nn * p->C)), dim3(kBlock), 0, p->stream, a, n0, nn);
-                p->launches++;
-            }
+            enqueue_joint_trace(p, nullptr);
         }
         cudaEventRecord(p->ev1, p->stream);
         CUDA_TRY(cudaEventSynchronize(p->ev1));

@@ -22,6 +22,7 @@ constexpr uint64_t kExtFlag = 1ULL << 62;     // tip whose bottom-up vector is s
 #ifndef PML_BLOCK
 #define PML_BLOCK 128
 #endif
+// (instantiations with at most 4 states ask for 6 blocks per SM: HKY on 1M tips 2.09 -> 1.93 ms per step)
 #ifndef PML_BU_MINB
 #define PML_BU_MINB 3
 #endif
@@ -535,7 +536,7 @@ __device__ __forceinline__ int load_child(const TreeDev &t, const ZcDev &zc, con
 
 // calc_node_bu_likelihood (ml.py:124-148) for the internal nodes [slot_begin, slot_begin + n_slots) of one level.
 template <int KP, template <int> class Lane, bool MAXP>
-__global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_BU_MINB : 1)) bu_level_kernel(BuArgs a, int slot_begin, int n_slots) {
+__global__ void __launch_bounds__(kBlock, (KP <= 4 ? 6 : KP <= 20 ? PML_BU_MINB : 1)) bu_level_kernel(BuArgs a, int slot_begin, int n_slots) {
     extern __shared__ double s_par[];
     const int J = a.ln.J, K = a.ln.K, C = a.ln.C;
     const int nf = staged_fields(Lane<KP>::family, K);
@@ -653,6 +654,8 @@ struct JointArgs {
     const uint8_t *ptr;         // [N][C][K]
     int *state;                 // [N][C]
     uint64_t *out_mask;         // [N][C]
+    const int *root_state;      // [n_roots][C] states the roots take instead of their own arg-max (clade forests of a
+                                // tree cut by subtree: the state comes from the part of the tree above the cut), or null
 };
 
 // choose_ancestral_states_joint (ml.py:598-622) + unalter_zero_node_joint_states (ml.py:408-428) for the nodes
@@ -669,7 +672,17 @@ static __global__ void joint_trace_kernel(JointArgs a, int node_begin, int n_nod
         const int par = a.t.parent[node];
         const uint64_t base = a.base_mask[(size_t) node * C + c];
         int s;
-        if (par < 0) {
+        if (par < 0 && a.root_state) {
+            // the pointer of this node was followed above the cut; what is left is the node's own un-altering
+            s = a.root_state[(size_t) node * C + c];
+            if (base & kMemberFlag) {
+                const size_t r = (size_t) a.t.zc_index[node] * C + c;
+                if (a.zc.altflag[r]) {
+                    const uint64_t init = a.zc.initial[r];
+                    if (!((init >> s) & 1ULL) && init) s = __ffsll((long long) init) - 1;
+                }
+            }
+        } else if (par < 0) {
             const double *p = a.ln.params + (size_t) c * a.ln.stride;
             const int sl = a.t.slot[node];
             const bool use_alt = p[1] == 0.;
@@ -692,7 +705,7 @@ static __global__ void joint_trace_kernel(JointArgs a, int node_begin, int n_nod
             }
         }
         a.state[(size_t) node * C + c] = s;
-        a.out_mask[(size_t) node * C + c] = (1ULL << s) | (base & kMemberFlag);
+        a.out_mask[(size_t) node * C + c] = (1ULL << s) | (base & (kMemberFlag | kExtFlag));   // markers stay
     }
 }
 
@@ -826,7 +839,7 @@ __device__ __forceinline__ void emit_node(const TdArgs &a, const LaneT &lane, in
 // marginal probabilities, MAP and MPPA states.  Roots take the all-ones top-down vector (ml.py:274-277).
 // Shared memory: staged parameters, then the block's k histogram.
 template <int KP, template <int> class Lane>
-__global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_TD_MINB : 1)) td_level_kernel(TdArgs a, int node_begin, int n_nodes) {
+__global__ void __launch_bounds__(kBlock, (KP <= 4 ? 6 : KP <= 20 ? PML_TD_MINB : 1)) td_level_kernel(TdArgs a, int node_begin, int n_nodes) {
     extern __shared__ double s_par[];
     const int C = a.ln.C, K = a.ln.K;
     const int nf = staged_fields(Lane<KP>::family, K);

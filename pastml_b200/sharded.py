@@ -254,8 +254,34 @@ class DeviceShard(object):
             exchange_local([self])
         return self.finish(params, n_sets)
 
-    def top_down(self, want_probs=True, want_node_lh=False):
-        self.top._check(self.lib.pml_shard_top_down(self._h, 1 if want_probs else 0, 1 if want_node_lh else 0))
+    def top_down(self, want_probs=True, want_node_lh=False, force_joint=False):
+        self.top._check(self.lib.pml_shard_top_down(self._h, 1 if want_probs else 0, 1 if want_node_lh else 0,
+                                                    1 if force_joint else 0))
+
+    def joint_bottom_up(self, params):
+        params = self.clades._params(params, 1)
+        self.clades._check(self.lib.pml_shard_joint_bottom_up(self._h, _ptr(params)))
+
+    def joint_finish(self, params):
+        params = self.top._params(params, 1)
+        out = np.empty((1, self.C), dtype=np.float64)
+        self.top._check(self.lib.pml_shard_joint_finish(self._h, _ptr(params), _ptr(out)))
+        return out[0]
+
+    def joint(self, params):
+        """JOINT reconstruction of the sharded tree: (joint log-likelihoods [C] of the whole tree, states of the top
+        tree's nodes [n_top][C], states of this rank's clade nodes [n][C]); needs ``connect()`` (or one rank)."""
+        self.joint_bottom_up(params)
+        if not self.connected:
+            exchange_local([self])
+        lh = self.joint_finish(params)
+        return lh, self.joint_states(0), self.joint_states(1)
+
+    def joint_states(self, which):
+        pb = self.clades if which else self.top
+        out = np.empty((pb.N, pb.C), dtype=np.int32)
+        pb._check(self.lib.pml_shard_joint_states(self._h, which, _ptr(out)))
+        return out
 
     def results(self, which, want_probs=True, want_node_lh=False, want_masks=True):
         pb = self.clades if which else self.top
@@ -268,11 +294,12 @@ class DeviceShard(object):
                                              _ptr(k_hist)))
         return dict(probs=probs, node_log10lh=node_lh, map_mask=map_mask, mppa_mask=mppa_mask, k_hist=k_hist)
 
-    def marginal(self, params, want_probs=True, want_masks=True):
+    def marginal(self, params, want_probs=True, want_masks=True, force_joint=False):
         """The whole fixed-parameter pipeline on the sharded tree; returns (log-likelihoods [C], top-tree outputs with
-        global node ids ``plan.top_ids``, this rank's clade outputs with global node ids ``plan.nodes[rank]``)."""
+        global node ids ``plan.top_ids``, this rank's clade outputs with global node ids ``plan.nodes[rank]``).
+        ``force_joint`` (MPPA keeps the joint state, ml.py:545) needs a preceding :meth:`joint`."""
         loglh = self.loglik(params)[0]
-        self.top_down(want_probs=want_probs)
+        self.top_down(want_probs=want_probs, force_joint=force_joint)
         return loglh, self.results(0, want_probs, False, want_masks), self.results(1, want_probs, False, want_masks)
 
     def bench_step(self, params, n_iter, flush_l2=True, phases=False):

@@ -30,6 +30,7 @@ def main():
     want_lh = whole.loglik(sets, n_sets=2)
     want = whole.marginal(params, force_joint=False)
     want_map = whole.loglik(params, mask_kind=MASK_MAP)
+    want_lh_joint, want_joint_state = whole.joint(params)
     whole.close()
     plan = SubtreePlan(flat, world, clades_per_rank=4)
     sh = DeviceShard(plan, rank, K, 0, masks, has, max_param_sets=2, device=local)
@@ -38,9 +39,13 @@ def main():
     loglh, top, mine = sh.marginal(params)
     np.testing.assert_allclose(loglh, want['loglh'], rtol=1e-12)
     np.testing.assert_allclose(sh.loglik(params, mask_kind=MASK_MAP), want_map, rtol=1e-12)
+    lh_joint, top_states, my_states = sh.joint(params)   # max-product sweeps around the same all-gather
+    np.testing.assert_allclose(lh_joint, want_lh_joint, rtol=1e-12)
     ms = sh.bench_step(params, 3)
     pieces = gather_objects((top, mine))
+    joint_pieces = gather_objects(({'joint': top_states}, {'joint': my_states}))
     if rank == 0:
+        assert np.array_equal(merge_outputs(plan, joint_pieces, 'joint', flat.n_nodes), want_joint_state)
         for key in ('probs', 'map_mask', 'mppa_mask'):
             got = merge_outputs(plan, pieces, key, flat.n_nodes)
             if key == 'probs':

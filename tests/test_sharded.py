@@ -101,6 +101,10 @@ def test_device_shards_equal_unsharded(n_tips, K, C, world, kind):
     want_lh = whole.loglik(sets, n_sets=2)
     want = whole.marginal(params, force_joint=False)
     want_map = whole.loglik(params, mask_kind=MASK_MAP)
+    from pastml_b200.engine import MASK_JOINT
+    want_lh_joint, want_joint_state = whole.joint(params)
+    want_joint_restricted = whole.loglik(params, mask_kind=MASK_JOINT)
+    want_forced = whole.marginal(params, force_joint=True)
     whole.close()
 
     plan = SubtreePlan(flat, world, clades_per_rank=4)
@@ -134,6 +138,30 @@ def test_device_shards_equal_unsharded(n_tips, K, C, world, kind):
     exchange_local(ranks)
     for sh in ranks:
         np.testing.assert_allclose(sh.finish(params), want_map, rtol=1e-12)
+    # JOINT: max-product sweeps on both sides of the cut, the clades' traceback starts from the top tree's choice
+    for sh in ranks:
+        sh.joint_bottom_up(params)
+    exchange_local(ranks)
+    joint_pieces = []
+    for sh in ranks:
+        np.testing.assert_allclose(sh.joint_finish(params), want_lh_joint, rtol=1e-12)
+        joint_pieces.append(({'joint': sh.joint_states(0)}, {'joint': sh.joint_states(1)}))
+    assert np.array_equal(merge_outputs(plan, joint_pieces, 'joint', flat.n_nodes), want_joint_state)
+    for sh in ranks:
+        sh.bottom_up(params, mask_kind=MASK_JOINT)
+    exchange_local(ranks)
+    for sh in ranks:
+        np.testing.assert_allclose(sh.finish(params), want_joint_restricted, rtol=1e-12)
+    # ... and MPPA with the joint state forced into every set (ml.py:545)
+    for sh in ranks:
+        sh.bottom_up(params)
+    exchange_local(ranks)
+    forced = []
+    for sh in ranks:
+        sh.finish(params)
+        sh.top_down(force_joint=True)
+        forced.append((sh.results(0), sh.results(1)))
+    assert np.array_equal(merge_outputs(plan, forced, 'mppa_mask', flat.n_nodes), want_forced['mppa_mask'])
     for sh in ranks:
         sh.close()
 
