@@ -534,11 +534,82 @@ __device__ __forceinline__ int load_child(const TreeDev &t, const ZcDev &zc, con
     return 0;
 }
 
-// calc_node_bu_likelihood (ml.py:124-148) for the internal nodes [slot_begin, slot_begin + n_slots) of one level.
+// calc_node_bu_likelihood (ml.py:124-148) for ONE (internal node, lane): the children's vectors in, the node's vector
+// and exponent out.  s_par: the block's staged parameters.
+template <int KP, template <int> class Lane, bool MAXP>
+__device__ __forceinline__ void bu_item(const BuArgs &a, const double *s_par, int nf, bool with_eig, int slot, int j) {
+    const int J = a.ln.J, K = a.ln.K, C = a.ln.C;
+    const int c = j - (int) a.ln.divC.div((unsigned) j) * C;
+    Lane<KP> lane;
+    lane.init(LaneSmem{s_par + j, J}, a.ln.params + (size_t) j * a.ln.stride, K,
+              with_eig ? s_par + (size_t) nf * J + (size_t) j * eig_lane_stride(K) : nullptr);
+    const bool use_alt = a.alter && lane.tau == 0.;
+    const int fc = a.t.fc_slot[slot], nc = a.t.nc_slot[slot];
+    const int node = a.t.int_nodes[slot];
+
+    double acc[KP];
+    {
+        const uint64_t m = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) acc[k] = bit_as_double(m, k);   // 10 ** log10(allowed), ml.py:127
+    }
+    int ex = 0;
+    if (!MAXP && nc == 2) {
+        // binary node: both children's vectors are requested before any arithmetic (twice the bytes in flight)
+        double in0[KP], in1[KP];
+        uint64_t tm;
+        const double d0 = a.t.dist[fc], d1 = a.t.dist[fc + 1];
+        ex += load_child<KP>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc, j, c, use_alt, in0, tm);
+        ex += load_child<KP>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, j, c, use_alt, in1, tm);
+        const typename Lane<KP>::Branch b0 = lane.branch(d0, K), b1 = lane.branch(d1, K);
+        lane.mul_matvec(b0, in0, acc, K);
+        const double vmax0 = vec_max<KP>(acc);
+        lane.mul_matvec(b1, in1, acc, K);
+        const double vmax = vec_max<KP>(acc);
+        if (vmax == 0.) {   // all entries zero: PastMLLikelihoodError of ml.py:139-145
+            if (atomicCAS(a.err + 2 * j, -1, node) == -1) a.err[2 * j + 1] = (vmax0 == 0.) ? fc : fc + 1;
+        }
+        ex += rescale<KP>(acc, vmax, true);
+    } else {
+        for (int ch = fc; ch < fc + nc; ++ch) {
+            const typename Lane<KP>::Branch br = lane.branch(a.t.dist[ch], K);
+            double in[KP];
+            uint64_t tm;
+            ex += load_child<KP>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, ch, j, c, use_alt, in, tm);
+            if (MAXP) {
+                double v[KP];
+                uint8_t arg[KP];
+                lane.maxvec(br, in, v, arg, K);
+                if (a.ptr) {
+                    uint8_t *dst = a.ptr + ((size_t) ch * C + c) * K;
+#pragma unroll
+                    for (int k = 0; k < KP; ++k)
+                        if (k < K) dst[k] = arg[k];
+                }
+#pragma unroll
+                for (int k = 0; k < KP; ++k) acc[k] *= v[k];
+            } else {
+                lane.mul_matvec(br, in, acc, K);
+            }
+            const double vmax = vec_max<KP>(acc);
+            if (vmax == 0.) {   // all entries zero: PastMLLikelihoodError of ml.py:139-145
+                if (atomicCAS(a.err + 2 * j, -1, node) == -1) a.err[2 * j + 1] = ch;
+            }
+            ex += rescale<KP>(acc, vmax, ch == fc + nc - 1);   // always normalised when the node is complete
+        }
+    }
+    double *dst = a.bu + ((size_t) slot * K) * J + j;
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+        if (k < K) dst[(size_t) k * J] = acc[k];
+    a.bu_ex[(size_t) slot * J + j] = ex;
+}
+
+// ... for the internal nodes [slot_begin, slot_begin + n_slots) of one level.
 template <int KP, template <int> class Lane, bool MAXP>
 __global__ void __launch_bounds__(kBlock, (KP <= 4 ? 6 : KP <= 20 ? PML_BU_MINB : 1)) bu_level_kernel(BuArgs a, int slot_begin, int n_slots) {
     extern __shared__ double s_par[];
-    const int J = a.ln.J, K = a.ln.K, C = a.ln.C;
+    const int J = a.ln.J, K = a.ln.K;
     const int nf = staged_fields(Lane<KP>::family, K);
     const bool with_eig = eig_staged(Lane<KP>::family, K, J);
     pdl_launch_dependents();
@@ -547,72 +618,32 @@ __global__ void __launch_bounds__(kBlock, (KP <= 4 ? 6 : KP <= 20 ? PML_BU_MINB 
     const unsigned n_items = (unsigned) n_slots * (unsigned) J;
     for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n_items; g += gridDim.x * blockDim.x) {
         const unsigned sl = a.ln.divJ.div(g);
-        const int slot = slot_begin + (int) sl;
-        const int j = (int) (g - sl * (unsigned) J);
-        const int c = j - (int) a.ln.divC.div((unsigned) j) * C;
-        Lane<KP> lane;
-        lane.init(LaneSmem{s_par + j, J}, a.ln.params + (size_t) j * a.ln.stride, K,
-                  with_eig ? s_par + (size_t) nf * J + (size_t) j * eig_lane_stride(K) : nullptr);
-        const bool use_alt = a.alter && lane.tau == 0.;
-        const int fc = a.t.fc_slot[slot], nc = a.t.nc_slot[slot];
-        const int node = a.t.int_nodes[slot];
+        bu_item<KP, Lane, MAXP>(a, s_par, nf, with_eig, slot_begin + (int) sl, (int) (g - sl * (unsigned) J));
+    }
+}
 
-        double acc[KP];
-        {
-            const uint64_t m = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
-#pragma unroll
-            for (int k = 0; k < KP; ++k) acc[k] = bit_as_double(m, k);   // 10 ** log10(allowed), ml.py:127
+// Several consecutive THIN levels in one launch: a single block walks the levels [lvl_lo, lvl_hi) from the deepest up,
+// with a block barrier between them -- a level hand-over costs a barrier and one dependent load instead of a kernel
+// boundary (~3 us).  Used for runs of levels with at most kFusedItems (node, lane) items each: the top of every tree,
+// its sparse deepest levels, and the whole replicated top tree of a run sharded by subtree.
+constexpr int kFusedItems = 1024;
+constexpr int kFusedBlock = 256;
+template <int KP, template <int> class Lane>
+__global__ void __launch_bounds__(kFusedBlock, 1) bu_multi_kernel(BuArgs a, const int *int_level_ptr, int lvl_lo, int lvl_hi) {
+    extern __shared__ double s_par[];
+    const int J = a.ln.J, K = a.ln.K;
+    const int nf = staged_fields(Lane<KP>::family, K);
+    const bool with_eig = eig_staged(Lane<KP>::family, K, J);
+    pdl_launch_dependents();
+    stage_params(s_par, a.ln, nf, with_eig);
+    pdl_wait();
+    for (int lvl = lvl_hi - 1; lvl >= lvl_lo; --lvl) {
+        const int s0 = int_level_ptr[lvl], n_items = (int_level_ptr[lvl + 1] - s0) * J;
+        for (int g = threadIdx.x; g < n_items; g += blockDim.x) {
+            const int sl = (int) a.ln.divJ.div((unsigned) g);
+            bu_item<KP, Lane, false>(a, s_par, nf, with_eig, s0 + sl, g - sl * J);
         }
-        int ex = 0;
-        if (!MAXP && nc == 2) {
-            // binary node: both children's vectors are requested before any arithmetic (twice the bytes in flight)
-            double in0[KP], in1[KP];
-            uint64_t tm;
-            const double d0 = a.t.dist[fc], d1 = a.t.dist[fc + 1];
-            ex += load_child<KP>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc, j, c, use_alt, in0, tm);
-            ex += load_child<KP>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, fc + 1, j, c, use_alt, in1, tm);
-            const typename Lane<KP>::Branch b0 = lane.branch(d0, K), b1 = lane.branch(d1, K);
-            lane.mul_matvec(b0, in0, acc, K);
-            const double vmax0 = vec_max<KP>(acc);
-            lane.mul_matvec(b1, in1, acc, K);
-            const double vmax = vec_max<KP>(acc);
-            if (vmax == 0.) {   // all entries zero: PastMLLikelihoodError of ml.py:139-145
-                if (atomicCAS(a.err + 2 * j, -1, node) == -1) a.err[2 * j + 1] = (vmax0 == 0.) ? fc : fc + 1;
-            }
-            ex += rescale<KP>(acc, vmax, true);
-        } else {
-            for (int ch = fc; ch < fc + nc; ++ch) {
-                const typename Lane<KP>::Branch br = lane.branch(a.t.dist[ch], K);
-                double in[KP];
-                uint64_t tm;
-                ex += load_child<KP>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, ch, j, c, use_alt, in, tm);
-                if (MAXP) {
-                    double v[KP];
-                    uint8_t arg[KP];
-                    lane.maxvec(br, in, v, arg, K);
-                    if (a.ptr) {
-                        uint8_t *dst = a.ptr + ((size_t) ch * C + c) * K;
-#pragma unroll
-                        for (int k = 0; k < KP; ++k)
-                            if (k < K) dst[k] = arg[k];
-                    }
-#pragma unroll
-                    for (int k = 0; k < KP; ++k) acc[k] *= v[k];
-                } else {
-                    lane.mul_matvec(br, in, acc, K);
-                }
-                const double vmax = vec_max<KP>(acc);
-                if (vmax == 0.) {   // all entries zero: PastMLLikelihoodError of ml.py:139-145
-                    if (atomicCAS(a.err + 2 * j, -1, node) == -1) a.err[2 * j + 1] = ch;
-                }
-                ex += rescale<KP>(acc, vmax, ch == fc + nc - 1);   // always normalised when the node is complete
-            }
-        }
-        double *dst = a.bu + ((size_t) slot * K) * J + j;
-#pragma unroll
-        for (int k = 0; k < KP; ++k)
-            if (k < K) dst[(size_t) k * J] = acc[k];
-        a.bu_ex[(size_t) slot * J + j] = ex;
+        __syncthreads();   // the level's vectors (global memory, written by this block) are visible to the next one
     }
 }
 
@@ -731,6 +762,8 @@ struct TdArgs {
     unsigned long long *k_hist; // [C][K+1]
     double *zc_lh;              // [rows][C][K]  marginal mantissas of cluster members (for pml_mppa_finalize)
     uint8_t *zc_k;              // [rows][C]     best_k chosen here
+    int raw_node_lh = 0;        // the thread-per-item kernels leave (sum, exponent) like the cooperative ones: the sweep
+                                // ends with log10_finish_kernel over all nodes (mixed sweeps: fused thin levels)
 };
 
 // MPPA state selection (choose_ancestral_states_mppa, ml.py:539-572) on a likelihood vector already multiplied by
@@ -796,7 +829,14 @@ __device__ __forceinline__ void emit_node(const TdArgs &a, const LaneT &lane, in
         for (int k = 0; k < KP; ++k)
             if (k < K) dst[k] = m[k] * inv;
     }
-    if (a.node_log10lh) a.node_log10lh[nc] = log10(sum) + (double) ex * 0.30102999566398119521;
+    if (a.node_log10lh) {
+        if (a.raw_node_lh) {
+            a.node_log10lh[nc] = sum;
+            a.node_ex[nc] = ex;
+        } else {
+            a.node_log10lh[nc] = log10(sum) + (double) ex * 0.30102999566398119521;
+        }
+    }
     const uint64_t base = a.mask[nc];
     const uint64_t flag = base & kMemberFlag;
     if (flag) {
@@ -838,6 +878,83 @@ __device__ __forceinline__ void emit_node(const TdArgs &a, const LaneT &lane, in
 // vector (or tip mask), forms the node's top-down vector, stores it if the node is internal, and emits the node's
 // marginal probabilities, MAP and MPPA states.  Roots take the all-ones top-down vector (ml.py:274-277).
 // Shared memory: staged parameters, then the block's k histogram.
+// One (node, column) of the fused top-down step; sh_hist: the block's k histogram [C][K + 1]
+template <int KP, template <int> class Lane>
+__device__ __forceinline__ void td_item(const TdArgs &a, const double *s_par, int nf, bool with_eig, unsigned int *sh_hist,
+                                        int node, int c) {
+    const int C = a.ln.C, K = a.ln.K;
+    Lane<KP> lane;
+    lane.init(LaneSmem{s_par + c, C}, a.ln.params + (size_t) c * a.ln.stride, K,
+              with_eig ? s_par + (size_t) nf * C + (size_t) c * eig_lane_stride(K) : nullptr);
+    const bool use_alt = lane.tau == 0.;   // ml.py:702-703
+    const int ps = a.t.pslot[node];
+    const int cs = a.t.slot[node];
+
+    double Lc[KP], X[KP];
+    uint64_t mc;
+    const int exc = load_child<KP>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, node, c, c, use_alt, Lc, mc);
+    if (cs >= 0) mc = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
+    int ex_total;
+    if (ps < 0) {
+        ex_total = exc;
+        if (a.ext.root_td) {   // a clade root: its top-down vector arrives from the part of the tree above the cut
+            const double *src = a.ext.root_td + ((size_t) node * K) * C + c;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) X[k] = (k < K) ? Lc[k] * src[(size_t) k * C] : 0.;
+            ex_total += a.ext.root_td_ex[(size_t) node * C + c];
+        } else {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) X[k] = Lc[k];   // TD(root) = 1
+        }
+    } else {
+        // parent part of the node's top-down vector: TD_p * L_p, divided below by the node's own contribution
+        {
+            const double *src = a.bu + ((size_t) ps * K) * C + c;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) X[k] = (k < K) ? src[(size_t) k * C] : 0.;
+        }
+        int pex = a.bu_ex[(size_t) ps * C + c];
+        if (ps >= a.t.n_root_slots) {
+            const double *src = a.td + ((size_t) ps * K) * C + c;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) X[k] *= (k < K) ? src[(size_t) k * C] : 0.;
+            pex += a.td_ex[(size_t) ps * C + c];
+        } else if (a.ext.root_td) {   // child of a clade root: the root's top-down vector came from above the cut
+            const int rn = a.t.int_nodes[ps];
+            const double *src = a.ext.root_td + ((size_t) rn * K) * C + c;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) X[k] *= (k < K) ? src[(size_t) k * C] : 0.;
+            pex += a.ext.root_td_ex[(size_t) rn * C + c];
+        }
+        const typename Lane<KP>::Branch br = lane.branch(a.t.dist[node], K);
+        double q[KP];
+        lane.matvec(br, Lc, q, K);                                   // node_contribution, ml.py:280
+#pragma unroll
+        for (int k = 0; k < KP; ++k) q[k] = (q[k] > 0.) ? X[k] * __drcp_rn(q[k]) : X[k];   // ml.py:281-283
+        int qex = pex - exc + rescale<KP>(q, vec_max<KP>(q), false);                    // ml.py:284-286
+        lane.matvec(br, q, X, K);                                    // ml.py:288-289
+        if (cs >= 0) {
+            qex += rescale<KP>(X, vec_max<KP>(X), true);
+            double *dst = a.td + ((size_t) cs * K) * C + c;
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (k < K) dst[(size_t) k * C] = X[k];
+            a.td_ex[(size_t) cs * C + c] = qex;
+        } else if (a.mask[(size_t) node * C + c] & kExtFlag) {   // hand the vector to the clade below the cut
+            const int e = a.ext.index[node];
+            double *dst = a.ext.td + ((size_t) e * K) * C + c;
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (k < K) dst[(size_t) k * C] = X[k];
+            a.ext.td_ex[(size_t) e * C + c] = qex;
+        }
+#pragma unroll
+        for (int k = 0; k < KP; ++k) X[k] *= Lc[k];
+        ex_total = qex + exc;
+    }
+    emit_node<KP>(a, lane, node, c, X, mc, ex_total, sh_hist);
+}
+
 template <int KP, template <int> class Lane>
 __global__ void __launch_bounds__(kBlock, (KP <= 4 ? 6 : KP <= 20 ? PML_TD_MINB : 1)) td_level_kernel(TdArgs a, int node_begin, int n_nodes) {
     extern __shared__ double s_par[];
@@ -852,80 +969,33 @@ __global__ void __launch_bounds__(kBlock, (KP <= 4 ? 6 : KP <= 20 ? PML_TD_MINB 
     const unsigned n_items = (unsigned) n_nodes * (unsigned) C;
     for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n_items; g += gridDim.x * blockDim.x) {
         const unsigned nd = a.ln.divC.div(g);
-        const int node = node_begin + (int) nd;
-        const int c = (int) (g - nd * (unsigned) C);
-        Lane<KP> lane;
-        lane.init(LaneSmem{s_par + c, C}, a.ln.params + (size_t) c * a.ln.stride, K,
-                  with_eig ? s_par + (size_t) nf * C + (size_t) c * eig_lane_stride(K) : nullptr);
-        const bool use_alt = lane.tau == 0.;   // ml.py:702-703
-        const int ps = a.t.pslot[node];
-        const int cs = a.t.slot[node];
-
-        double Lc[KP], X[KP];
-        uint64_t mc;
-        const int exc = load_child<KP>(a.t, a.zc, a.ext, a.ln, a.mask, a.bu, a.bu_ex, node, c, c, use_alt, Lc, mc);
-        if (cs >= 0) mc = eff_mask(a.mask, a.t, a.zc, C, node, c, use_alt, a.ln.kmask);
-        int ex_total;
-        if (ps < 0) {
-            ex_total = exc;
-            if (a.ext.root_td) {   // a clade root: its top-down vector arrives from the part of the tree above the cut
-                const double *src = a.ext.root_td + ((size_t) node * K) * C + c;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) X[k] = (k < K) ? Lc[k] * src[(size_t) k * C] : 0.;
-                ex_total += a.ext.root_td_ex[(size_t) node * C + c];
-            } else {
-#pragma unroll
-                for (int k = 0; k < KP; ++k) X[k] = Lc[k];   // TD(root) = 1
-            }
-        } else {
-            // parent part of the node's top-down vector: TD_p * L_p, divided below by the node's own contribution
-            {
-                const double *src = a.bu + ((size_t) ps * K) * C + c;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) X[k] = (k < K) ? src[(size_t) k * C] : 0.;
-            }
-            int pex = a.bu_ex[(size_t) ps * C + c];
-            if (ps >= a.t.n_root_slots) {
-                const double *src = a.td + ((size_t) ps * K) * C + c;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) X[k] *= (k < K) ? src[(size_t) k * C] : 0.;
-                pex += a.td_ex[(size_t) ps * C + c];
-            } else if (a.ext.root_td) {   // child of a clade root: the root's top-down vector came from above the cut
-                const int rn = a.t.int_nodes[ps];
-                const double *src = a.ext.root_td + ((size_t) rn * K) * C + c;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) X[k] *= (k < K) ? src[(size_t) k * C] : 0.;
-                pex += a.ext.root_td_ex[(size_t) rn * C + c];
-            }
-            const typename Lane<KP>::Branch br = lane.branch(a.t.dist[node], K);
-            double q[KP];
-            lane.matvec(br, Lc, q, K);                                   // node_contribution, ml.py:280
-#pragma unroll
-            for (int k = 0; k < KP; ++k) q[k] = (q[k] > 0.) ? X[k] * __drcp_rn(q[k]) : X[k];   // ml.py:281-283
-            int qex = pex - exc + rescale<KP>(q, vec_max<KP>(q), false);                    // ml.py:284-286
-            lane.matvec(br, q, X, K);                                    // ml.py:288-289
-            if (cs >= 0) {
-                qex += rescale<KP>(X, vec_max<KP>(X), true);
-                double *dst = a.td + ((size_t) cs * K) * C + c;
-#pragma unroll
-                for (int k = 0; k < KP; ++k)
-                    if (k < K) dst[(size_t) k * C] = X[k];
-                a.td_ex[(size_t) cs * C + c] = qex;
-            } else if (a.mask[(size_t) node * C + c] & kExtFlag) {   // hand the vector to the clade below the cut
-                const int e = a.ext.index[node];
-                double *dst = a.ext.td + ((size_t) e * K) * C + c;
-#pragma unroll
-                for (int k = 0; k < KP; ++k)
-                    if (k < K) dst[(size_t) k * C] = X[k];
-                a.ext.td_ex[(size_t) e * C + c] = qex;
-            }
-#pragma unroll
-            for (int k = 0; k < KP; ++k) X[k] *= Lc[k];
-            ex_total = qex + exc;
-        }
-        emit_node<KP>(a, lane, node, c, X, mc, ex_total, sh_hist);
+        td_item<KP, Lane>(a, s_par, nf, with_eig, sh_hist, node_begin + (int) nd, (int) (g - nd * (unsigned) C));
     }
     __syncthreads();
+    for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x)
+        if (sh_hist[i]) atomicAdd(a.k_hist + i, (unsigned long long) sh_hist[i]);
+}
+
+// several consecutive thin levels [lvl_lo, lvl_hi), root side first, in one single-block launch (see bu_multi_kernel)
+template <int KP, template <int> class Lane>
+__global__ void __launch_bounds__(kFusedBlock, 1) td_multi_kernel(TdArgs a, const int *level_ptr, int lvl_lo, int lvl_hi) {
+    extern __shared__ double s_par[];
+    const int C = a.ln.C, K = a.ln.K;
+    const int nf = staged_fields(Lane<KP>::family, K);
+    const bool with_eig = eig_staged(Lane<KP>::family, K, C);
+    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(s_par + staged_doubles(Lane<KP>::family, K, C));
+    for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x) sh_hist[i] = 0u;
+    pdl_launch_dependents();
+    stage_params(s_par, a.ln, nf, with_eig);
+    pdl_wait();
+    for (int lvl = lvl_lo; lvl < lvl_hi; ++lvl) {
+        const int n0 = level_ptr[lvl], n_items = (level_ptr[lvl + 1] - n0) * C;
+        for (int g = threadIdx.x; g < n_items; g += blockDim.x) {
+            const int nd = (int) a.ln.divC.div((unsigned) g);
+            td_item<KP, Lane>(a, s_par, nf, with_eig, sh_hist, n0 + nd, g - nd * C);
+        }
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x)
         if (sh_hist[i]) atomicAdd(a.k_hist + i, (unsigned long long) sh_hist[i]);
 }
