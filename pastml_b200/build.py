@@ -32,7 +32,7 @@ HEADERS = [os.path.join(CSRC, 'pml_kernels.cuh'), os.path.join(CSRC, 'pml_counts
 # (family, KP): 0 = F81/JC/EFT, 1 = HKY, 2 = eigen-decomposition models (CUSTOM_RATES, JTT); keep in sync with
 # PML_ALL in pml_engine.cu
 INSTANCES = [(0, k) for k in (2, 4, 8, 12, 16, 20, 24, 32, 48, 62)] + [(1, 4)] + \
-            [(2, k) for k in (2, 4, 8, 12, 16, 20, 24, 32)]
+            [(2, k) for k in (2, 4, 8, 12, 16, 20, 24, 32, 48, 62)]
 
 # (G, KT) of the warp-cooperative F81 sweeps; keep in sync with PML_COOP_ALL in pml_engine.cu
 COOP_INSTANCES = [(2, k, 0) for k in (2, 3, 4, 5, 6, 8, 10, 12, 16)] + [(4, k, 0) for k in (2, 3, 4, 5, 6, 8, 10, 12, 16)] + \

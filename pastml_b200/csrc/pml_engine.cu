@@ -130,7 +130,7 @@ struct pml_problem {
     // topology
     DevBuf<int> parent, first_child, n_children, slot, int_nodes, zc_index, roots, fc_slot, nc_slot, pslot;
     DevBuf<int4> bu_desc, td_desc;
-    DevBuf<int> d_level_ptr, d_int_level_ptr;   // level boundaries on the device (fused thin-level kernels)
+    DevBuf<int> d_level_ptr, d_int_level_ptr;   // level boundaries on the device
     int n_root_slots = 0;
     DevBuf<double> dist;
     // zero clusters
@@ -299,29 +299,10 @@ void enqueue_bottom_up(pml_problem *p, int n_sets, const uint64_t *mask, int is_
                           n_lanes == 0 && mma_maxp_applicable(p->K);
     // the state pass of the marginal pipeline (one set, annotation masks, alter) also keeps P L_child for the top-down sweep
     if (mma && n_sets == 1 && n_lanes == 0 && alter && mask == p->mask[PML_MASK_ANNOTATION].ptr) a.v_all = p->v_all.ptr;
-    // PASTML_B200_FUSE=1: runs of thin levels go through ONE single-block launch (bu_multi_kernel; sum-product passes on
-    // the plain layout).  Off by default: measured SLOWER than per-level launches chained by programmatic dependent
-    // launch (2.91 against 2.70 ms per step on 1M tips, 0.273 against 0.214 ms on 10k tips) -- a level handed over inside
-    // one block still pays two dependent global loads per item, which is what the kernel boundary costs
-    static const bool no_fuse = getenv("PASTML_B200_FUSE") == nullptr;
-    const bool fuse = !no_fuse && !maxp && !mma && !ln.lane_col && (tpi_jt == 0 || tpi_jt == ln.J);
-    auto thin = [&](int lvl) {
-        const int ns = p->int_level_ptr[lvl + 1] - p->int_level_ptr[lvl];
-        return ns > 0 && (long long) ns * ln.J <= kFusedItems;
-    };
     // thread-per-item sweep with TMA-staged child vectors (F81 family, sum-product mode, no external tips)
     for (int lvl = p->n_levels - 1; lvl >= 0; --lvl) {
         const int s0 = p->int_level_ptr[lvl], ns = p->int_level_ptr[lvl + 1] - s0;
         if (ns <= 0) continue;
-        if (fuse && thin(lvl) && lvl > 0 && thin(lvl - 1)) {
-            int lo = lvl - 1;
-            while (lo > 0 && thin(lo - 1)) --lo;
-            p->ks->bu_multi(p->stream, a, p->d_int_level_ptr.ptr, lo, lvl + 1);
-            p->launches++;
-            p->note("bu_multi_kernel", p->int_level_ptr[lvl + 1] - p->int_level_ptr[lo]);
-            lvl = lo;
-            continue;
-        }
         if (mma_maxp) {
             mma_maxp_launch(p->stream, a, s0, ns);
             p->launches++;
@@ -519,21 +500,8 @@ void enqueue_top_down(pml_problem *p, int force_joint, bool want_probs, bool wan
     const CoopSet *coop = pick_coop(p, ln.C, tma_ok && !getenv("PASTML_B200_COOP_G"), false);
     const bool td_tma = coop && coop->td_tma && !p->ext_index.ptr && tma_enabled();
     a.raw_node_lh = coop ? 1 : 0;   // one finishing pass takes the logarithms when the cooperative kernels run the sweep
-    static const bool no_fuse = getenv("PASTML_B200_FUSE") == nullptr;   // (see enqueue_bottom_up)
-    auto thin = [&](int lvl) { return (long long) (p->level_ptr[lvl + 1] - p->level_ptr[lvl]) * ln.C <= kFusedItems; };
     for (int lvl = 0; lvl < p->n_levels; ++lvl) {
         const int n0 = p->level_ptr[lvl], nn = p->level_ptr[lvl + 1] - n0;
-        if (!no_fuse && thin(lvl) && lvl + 1 < p->n_levels && thin(lvl + 1)) {
-            // a run of thin levels in one single-block launch (td_multi_kernel)
-            int hi = lvl + 2;
-            while (hi < p->n_levels && thin(hi)) ++hi;
-            p->ks->td_multi(p->stream, a, p->d_level_ptr.ptr, lvl, hi);
-            p->launches++;
-            p->note("td_multi_kernel", p->level_ptr[hi] - n0);
-            if (hook) (*hook)(p->level_ptr[hi]);
-            lvl = hi - 1;
-            continue;
-        }
         if (coop) {
             (td_tma ? coop->td_tma : coop->td)(p->stream, a, n0, nn);
             p->launches++;
@@ -613,7 +581,7 @@ namespace pml {
 #define PML_ALL(X) X(0, 20)
 #else
 #define PML_ALL(X) X(0, 2) X(0, 4) X(0, 8) X(0, 12) X(0, 16) X(0, 20) X(0, 24) X(0, 32) X(0, 48) X(0, 62) \
-                   X(1, 4) X(2, 2) X(2, 4) X(2, 8) X(2, 12) X(2, 16) X(2, 20) X(2, 24) X(2, 32)
+                   X(1, 4) X(2, 2) X(2, 4) X(2, 8) X(2, 12) X(2, 16) X(2, 20) X(2, 24) X(2, 32) X(2, 48) X(2, 62)
 #endif
 PML_ALL(PML_DECL)
 const KernelSet *kernel_set(int family, int kp) {
@@ -722,8 +690,6 @@ int pml_problem_create(int32_t n_nodes, const int32_t *parent, const double *dis
     if (n_states < 1 || n_states > 62) return fail(PML_ERR_INVALID, "the number of states must be in [1, 62]");
     if (model_kind == PML_MODEL_HKY && n_states != 4) return fail(PML_ERR_INVALID, "HKY needs exactly 4 states");
     if (model_kind < 0 || model_kind > PML_MODEL_EIG) return fail(PML_ERR_INVALID, "unknown model family");
-    if (model_kind == PML_MODEL_EIG && n_states > 32)
-        return fail(PML_ERR_INVALID, "eigen-decomposition models support at most 32 states");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
         return fail(PML_ERR_NO_DEVICE, "no CUDA device available: pastml_b200 has no CPU fallback");

@@ -79,18 +79,6 @@ void mppa_fix_launch(cudaStream_t st, int n_rows, const int *row_node, int C, in
         n_rows, row_node, C, K, kmask, zc, base_mask, prev_initial, prev_hasinit, zc_lh, zc_k, joint_state,
         force_joint, mppa_mask, k_hist);
 }
-void bu_multi_launch(cudaStream_t st, const BuArgs &a, const int *int_level_ptr, int lvl_lo, int lvl_hi) {
-    const size_t sh = sizeof(double) * staged_doubles(kFamily, a.ln.K, a.ln.J);
-    allow_big_smem(bu_multi_kernel<KP, TheLane>, sh);
-    launch_pdl(bu_multi_kernel<KP, TheLane>, dim3(1), dim3(kFusedBlock), sh, st, a, int_level_ptr, lvl_lo, lvl_hi);
-}
-
-void td_multi_launch(cudaStream_t st, const TdArgs &a, const int *level_ptr, int lvl_lo, int lvl_hi) {
-    const size_t sh = td_smem(a);
-    allow_big_smem(td_multi_kernel<KP, TheLane>, sh);
-    launch_pdl(td_multi_kernel<KP, TheLane>, dim3(1), dim3(kFusedBlock), sh, st, a, level_ptr, lvl_lo, lvl_hi);
-}
-
 void counts_launch(cudaStream_t st, const CountsArgs &a, bool roots) {
     const size_t sh = counts_smem_bytes(kFamily, a.ln.K, a.ln.C);
     const dim3 grid((unsigned) std::max(1, std::min(a.n_slots, 148 * 8)), (unsigned) a.ln.C);
@@ -109,8 +97,7 @@ void counts_launch(cudaStream_t st, const CountsArgs &a, bool roots) {
 #define PML_KS_NAME PML_KS_NAME2(PML_FAMILY, PML_KP)
 
 const KernelSet *PML_KS_NAME() {
-    static const KernelSet ks = {bu_launch, root_launch, td_launch, td_select_launch, mppa_fix_launch, counts_launch, bu_multi_launch,
-                                 td_multi_launch};
+    static const KernelSet ks = {bu_launch, root_launch, td_launch, td_select_launch, mppa_fix_launch, counts_launch};
     return &ks;
 }
 

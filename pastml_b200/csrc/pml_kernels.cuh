@@ -398,6 +398,27 @@ struct EigLane {  // CUSTOM_RATES / JTT: P = A diag(exp(d t')) A^-1  (generator.
     // out = A (ed o (A^-1 in)): 2 K^2 fused multiply-adds instead of forming P (2 K^3)
     __device__ __forceinline__ void matvec(const Branch &b, const double (&in)[KP], double (&out)[KP], int K) const {
         double w[KP];
+        if constexpr (KP > 32) {
+            // large state spaces (codon-sized rate matrices): rolled loops -- the unrolled 2 KP^2 multiply-adds of the
+            // 48- and 62-state instantiations take minutes to compile; the vectors live in local memory here
+#pragma unroll 1
+            for (int m = 0; m < K; ++m) {
+                double s = 0.;
+#pragma unroll 1
+                for (int j = 0; j < K; ++j) s = fma(Ainv[m * K + j], in[j], s);
+                w[m] = s * b.ed[m];
+            }
+#pragma unroll 1
+            for (int i = 0; i < KP; ++i) {
+                double s = 0.;
+                if (i < K) {
+#pragma unroll 1
+                    for (int m = 0; m < K; ++m) s = fma(A[i * K + m], w[m], s);
+                }
+                out[i] = fmax(s, 0.);
+            }
+            return;
+        }
 #pragma unroll
         for (int m = 0; m < KP; ++m) {
             double s = 0.;
@@ -619,31 +640,6 @@ __global__ void __launch_bounds__(kBlock, (KP <= 4 ? 6 : KP <= 20 ? PML_BU_MINB 
     for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n_items; g += gridDim.x * blockDim.x) {
         const unsigned sl = a.ln.divJ.div(g);
         bu_item<KP, Lane, MAXP>(a, s_par, nf, with_eig, slot_begin + (int) sl, (int) (g - sl * (unsigned) J));
-    }
-}
-
-// Several consecutive THIN levels in one launch: a single block walks the levels [lvl_lo, lvl_hi) from the deepest up,
-// with a block barrier between them -- a level hand-over costs a barrier and one dependent load instead of a kernel
-// boundary (~3 us).  Used for runs of levels with at most kFusedItems (node, lane) items each: the top of every tree,
-// its sparse deepest levels, and the whole replicated top tree of a run sharded by subtree.
-constexpr int kFusedItems = 1024;
-constexpr int kFusedBlock = 256;
-template <int KP, template <int> class Lane>
-__global__ void __launch_bounds__(kFusedBlock, 1) bu_multi_kernel(BuArgs a, const int *int_level_ptr, int lvl_lo, int lvl_hi) {
-    extern __shared__ double s_par[];
-    const int J = a.ln.J, K = a.ln.K;
-    const int nf = staged_fields(Lane<KP>::family, K);
-    const bool with_eig = eig_staged(Lane<KP>::family, K, J);
-    pdl_launch_dependents();
-    stage_params(s_par, a.ln, nf, with_eig);
-    pdl_wait();
-    for (int lvl = lvl_hi - 1; lvl >= lvl_lo; --lvl) {
-        const int s0 = int_level_ptr[lvl], n_items = (int_level_ptr[lvl + 1] - s0) * J;
-        for (int g = threadIdx.x; g < n_items; g += blockDim.x) {
-            const int sl = (int) a.ln.divJ.div((unsigned) g);
-            bu_item<KP, Lane, false>(a, s_par, nf, with_eig, s0 + sl, g - sl * J);
-        }
-        __syncthreads();   // the level's vectors (global memory, written by this block) are visible to the next one
     }
 }
 
@@ -972,30 +968,6 @@ __global__ void __launch_bounds__(kBlock, (KP <= 4 ? 6 : KP <= 20 ? PML_TD_MINB 
         td_item<KP, Lane>(a, s_par, nf, with_eig, sh_hist, node_begin + (int) nd, (int) (g - nd * (unsigned) C));
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x)
-        if (sh_hist[i]) atomicAdd(a.k_hist + i, (unsigned long long) sh_hist[i]);
-}
-
-// several consecutive thin levels [lvl_lo, lvl_hi), root side first, in one single-block launch (see bu_multi_kernel)
-template <int KP, template <int> class Lane>
-__global__ void __launch_bounds__(kFusedBlock, 1) td_multi_kernel(TdArgs a, const int *level_ptr, int lvl_lo, int lvl_hi) {
-    extern __shared__ double s_par[];
-    const int C = a.ln.C, K = a.ln.K;
-    const int nf = staged_fields(Lane<KP>::family, K);
-    const bool with_eig = eig_staged(Lane<KP>::family, K, C);
-    unsigned int *sh_hist = reinterpret_cast<unsigned int *>(s_par + staged_doubles(Lane<KP>::family, K, C));
-    for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x) sh_hist[i] = 0u;
-    pdl_launch_dependents();
-    stage_params(s_par, a.ln, nf, with_eig);
-    pdl_wait();
-    for (int lvl = lvl_lo; lvl < lvl_hi; ++lvl) {
-        const int n0 = level_ptr[lvl], n_items = (level_ptr[lvl + 1] - n0) * C;
-        for (int g = threadIdx.x; g < n_items; g += blockDim.x) {
-            const int nd = (int) a.ln.divC.div((unsigned) g);
-            td_item<KP, Lane>(a, s_par, nf, with_eig, sh_hist, n0 + nd, g - nd * C);
-        }
-        __syncthreads();
-    }
     for (int i = threadIdx.x; i < C * (K + 1); i += blockDim.x)
         if (sh_hist[i]) atomicAdd(a.k_hist + i, (unsigned long long) sh_hist[i]);
 }

@@ -22,9 +22,6 @@ struct KernelSet {
                      uint64_t *mppa_mask, unsigned long long *k_hist);
     // scenario sampling for marginal_counts (pml_counts.cuh): the roots' states, then one level of branches
     void (*counts)(cudaStream_t, const CountsArgs &, bool roots);
-    // runs of thin levels [lvl_lo, lvl_hi) in one single-block launch (sum-product bottom-up; fused top-down)
-    void (*bu_multi)(cudaStream_t, const BuArgs &, const int *int_level_ptr, int lvl_lo, int lvl_hi);
-    void (*td_multi)(cudaStream_t, const TdArgs &, const int *level_ptr, int lvl_lo, int lvl_hi);
 };
 
 // Launch of a level kernel with programmatic stream serialization (see pdl_wait in pml_coop.cuh); PASTML_B200_NO_PDL=1

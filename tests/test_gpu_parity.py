@@ -267,3 +267,38 @@ def test_lane_list_objective_equals_grid():
     with pytest.raises(Exception):
         pb.loglik_lanes(np.stack([sets[0, 3]] * 3), [3] * 3)   # not a multiple of 4
     pb.close()
+
+
+@pytest.mark.parametrize('n_tips,K,C', [(300, 40, 2), (200, 61, 1), (250, 28, 3)])
+def test_custom_rates_with_many_states(n_tips, K, C):
+    """Rate-matrix models beyond 32 states (a 61-state codon-sized matrix): per-column decompositions, every pass of the
+    ML pipeline against the oracle.  (The 48- and 62-state instantiations of the eigen kernels run rolled loops.)"""
+    from pastml_b200.engine import Problem, pack_params
+    from pastml_b200.models.generator import get_diagonalisation
+    from pastml_b200 import synth
+    from oracle import cpu_oracle
+    rng = np.random.default_rng(31 * K + n_tips)
+    flat = synth.yule_tree(n_tips, rng)
+    masks, has, pis, sfs = synth.simulate_tip_masks(flat, K, C, rng, missing=0.05)
+    blocks, models = [], []
+    for c in range(C):
+        rates = rng.random((K, K)) + 0.05
+        rates = rates + rates.T
+        np.fill_diagonal(rates, 0.)
+        d, A, Ainv = get_diagonalisation(pis[c], rates)
+        d, A, Ainv = np.real(d), np.real(A), np.real(Ainv)
+        blocks.append(pack_params(2, K, sfs[c], 0., 1., pis[c], d=d, A=A, Ainv=Ainv))
+        models.append(cpu_oracle.OracleModel(2, pis[c], sfs[c], d=d, A=A, Ainv=Ainv))
+    params = np.stack(blocks)
+    pb = Problem(flat, K, 2, masks, has)
+    r = _run_ml(pb, params, True)
+    pb.close()
+    for c in range(C):
+        want = cpu_oracle.ml_acr_fixed(flat, models[c], masks[c], has[c], method='MPPA', force_joint=True)
+        assert r['lh'][c] == pytest.approx(want['log_likelihood'], rel=LH_RTOL)
+        assert r['lh_joint'][c] == pytest.approx(want['log_likelihood_restricted_JOINT'], rel=LH_RTOL)
+        assert r['lh_mppa'][c] == pytest.approx(want['log_likelihood_restricted_MPPA'], rel=LH_RTOL)
+        np.testing.assert_allclose(r['probs'][:, c, :], want['marginal_probabilities'], rtol=0, atol=PROB_ATOL)
+        assert np.array_equal(r['joint_state'][:, c], want['joint_state'])
+        assert np.array_equal(r['map_mask'][:, c], want['map_mask'])
+        assert np.array_equal(r['mppa_mask'][:, c], want['mppa_mask'])
