@@ -21,9 +21,14 @@ namespace {
 constexpr int kMmaKP = 24;            // largest padded state count: 3 row tiles of 8, 6 steps of 4
 constexpr int kMmaBlock = 128;
 #ifndef PML_MMA_MINB
-#define PML_MMA_MINB 6   // latency-bound: resident warps beat spill-free registers (2: 14.3, 3: 11.7, 4: 10.6, 5: 10.5, 6: 10.0 ms per JTT step)
+#define PML_MMA_MINB 8   // latency-bound: resident warps beat registers; with the A fragments in shared memory 64 registers
+                         // hold the rest (JTT step, 1M tips x 8 columns: 4 blocks 10.6 ms, 6 blocks 10.0 ms; fragments in
+                         // shared memory: 6 blocks 8.9 ms, 8 blocks 8.74 ms, 10 blocks 9.3 ms)
 #endif
 constexpr int kMmaMinBlocks = PML_MMA_MINB;
+#ifndef PML_MMA_SMEM_FRAG
+#define PML_MMA_SMEM_FRAG 1
+#endif
 
 __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -80,19 +85,36 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) bu_mma_kernel(BuArgs
 
     // the shared decomposition, from lane 0's parameter block: A fragments of A^-1 and of A, this thread's eigenvalues
     const double *dv = a.ln.params + 4 + K, *Am = dv + K, *Ai = Am + (size_t) K * K;
-    double f_inv[MT][KS], f_a[MT][KS], dm[MT];
+    double dm[MT];
+#if PML_MMA_SMEM_FRAG
+    // the A fragments of both matrices are the same for every warp of the block: kept in shared memory ([fragment][lane],
+    // conflict-free), which frees 4 MT KS registers per thread -- at 6 blocks per SM they would be spilled
+    __shared__ double s_fi[MT * KS][32], s_fa[MT * KS][32];
+#define F_INV(mt, s) s_fi[(mt) * KS + (s)][lane]
+#define F_A(mt, s) s_fa[(mt) * KS + (s)][lane]
+#else
+    double f_inv[MT][KS], f_a[MT][KS];
+#define F_INV(mt, s) f_inv[mt][s]
+#define F_A(mt, s) f_a[mt][s]
+#endif
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         const int row = 8 * mt + g;
         dm[mt] = (row < K) ? dv[row] : 0.;
+#if PML_MMA_SMEM_FRAG
+        if (warp == 0)
+#endif
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
             const int col = 4 * s + t4;
             const bool in = row < K && col < K;
-            f_inv[mt][s] = in ? Ai[row * K + col] : 0.;
-            f_a[mt][s] = in ? Am[row * K + col] : 0.;
+            F_INV(mt, s) = in ? Ai[row * K + col] : 0.;
+            F_A(mt, s) = in ? Am[row * K + col] : 0.;
         }
     }
+#if PML_MMA_SMEM_FRAG
+    __syncthreads();
+#endif
     pdl_launch_dependents();   // the fragments above are loaded while the previous level drains
     // the lane tile comes from blockIdx.y, so that everything that depends on it only is loop-invariant
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -160,7 +182,7 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) bu_mma_kernel(BuArgs
             for (int mt = 0; mt < MT; ++mt) {
                 wv[mt][0] = wv[mt][1] = 0.;
 #pragma unroll
-                for (int s = 0; s < KS; ++s) dmma(wv[mt][0], wv[mt][1], f_inv[mt][s], lf[s]);
+                for (int s = 0; s < KS; ++s) dmma(wv[mt][0], wv[mt][1], F_INV(mt, s), lf[s]);
             }
             // W o exp(d t'), handed over as B fragments through the warp's shared-memory slot
             const double t0 = (dist + tau0) * tf0 * sf0, t1 = (dist + tau1) * tf1 * sf1;
@@ -187,7 +209,7 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) bu_mma_kernel(BuArgs
             for (int mt = 0; mt < MT; ++mt) {
                 double v0 = 0., v1 = 0.;
 #pragma unroll
-                for (int s = 0; s < KS; ++s) dmma(v0, v1, f_a[mt][s], bf[s]);
+                for (int s = 0; s < KS; ++s) dmma(v0, v1, F_A(mt, s), bf[s]);
                 if (a.v_all && 8 * mt + g < K)   // kept for the top-down sweep: its node_contribution (ml.py:280)
                     *reinterpret_cast<double2 *>(a.v_all + ((size_t) ch * K + 8 * mt + g) * J + jd) = make_double2(v0, v1);
                 acc[mt][0] *= fmax(v0, 0.);
@@ -262,19 +284,36 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) td_mma_kernel(TdArgs
     const int tiles = C >> 3;
     double *sw = s_w[warp];
     const double *dv = a.ln.params + 4 + K, *Am = dv + K, *Ai = Am + (size_t) K * K;
-    double f_inv[MT][KS], f_a[MT][KS], dm[MT];
+    double dm[MT];
+#if PML_MMA_SMEM_FRAG
+    // the A fragments of both matrices are the same for every warp of the block: kept in shared memory ([fragment][lane],
+    // conflict-free), which frees 4 MT KS registers per thread -- at 6 blocks per SM they would be spilled
+    __shared__ double s_fi[MT * KS][32], s_fa[MT * KS][32];
+#define F_INV(mt, s) s_fi[(mt) * KS + (s)][lane]
+#define F_A(mt, s) s_fa[(mt) * KS + (s)][lane]
+#else
+    double f_inv[MT][KS], f_a[MT][KS];
+#define F_INV(mt, s) f_inv[mt][s]
+#define F_A(mt, s) f_a[mt][s]
+#endif
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         const int row = 8 * mt + g;
         dm[mt] = (row < K) ? dv[row] : 0.;
+#if PML_MMA_SMEM_FRAG
+        if (warp == 0)
+#endif
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
             const int col = 4 * s + t4;
             const bool in = row < K && col < K;
-            f_inv[mt][s] = in ? Ai[row * K + col] : 0.;
-            f_a[mt][s] = in ? Am[row * K + col] : 0.;
+            F_INV(mt, s) = in ? Ai[row * K + col] : 0.;
+            F_A(mt, s) = in ? Am[row * K + col] : 0.;
         }
     }
+#if PML_MMA_SMEM_FRAG
+    __syncthreads();
+#endif
     pdl_launch_dependents();
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -371,7 +410,7 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) td_mma_kernel(TdArgs
         for (int mt = 0; mt < MT; ++mt) {
             wv[mt][0] = wv[mt][1] = 0.;
 #pragma unroll
-            for (int s = 0; s < KS; ++s) dmma(wv[mt][0], wv[mt][1], f_inv[mt][s], bf[s]);
+            for (int s = 0; s < KS; ++s) dmma(wv[mt][0], wv[mt][1], F_INV(mt, s), bf[s]);
         }
         {
             double xs[2 * MT], es[2 * MT];
@@ -396,7 +435,7 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) td_mma_kernel(TdArgs
         for (int mt = 0; mt < MT; ++mt) {
             double v0 = 0., v1 = 0.;
 #pragma unroll
-            for (int s = 0; s < KS; ++s) dmma(v0, v1, f_a[mt][s], bf[s]);
+            for (int s = 0; s < KS; ++s) dmma(v0, v1, F_A(mt, s), bf[s]);
             td[mt][0] = fmax(v0, 0.);
             td[mt][1] = fmax(v1, 0.);
             m0 = fmax(m0, td[mt][0]);
@@ -427,22 +466,29 @@ __global__ void __launch_bounds__(kMmaBlock, kMmaMinBlocks) td_mma_kernel(TdArgs
 // by the child's vector, keeps its best (value, child state) per row, and the four threads of a row group finish the
 // arg-max with two shuffle steps (ties to the lower state index, as np.argmax).  Column tiles are processed one after
 // the other so that only MT D tiles are live.
+#ifndef PML_MAXP_MINB
+#define PML_MAXP_MINB 5   // (JOINT on the same workload: 3 blocks 26.1 ms, 5 blocks 22.8 ms, 6 blocks 24.2 ms)
+#endif
 template <int MT, int KS>
-__global__ void __launch_bounds__(kMmaBlock, 3) bu_maxp_mma_kernel(BuArgs a, int slot_begin, int n_slots) {
+__global__ void __launch_bounds__(kMmaBlock, PML_MAXP_MINB) bu_maxp_mma_kernel(BuArgs a, int slot_begin, int n_slots) {
     const int K = a.ln.K, J = a.ln.J, C = a.ln.C;
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t4 = lane & 3;
     const double *dv = a.ln.params + 4 + K, *Am = dv + K, *Ai = Am + (size_t) K * K;
     // A fragments of A: (row 8 mt + g, col 4 s + t4); B fragments of A^-1: (row 4 s + t4, col 8 nt + g)
-    double f_a[MT][KS], f_b[KS][MT];
+    // both fragment sets are the same for every warp of the block: shared memory, [fragment][lane]
+    __shared__ double s_fa[MT * KS][32], s_fb[KS * MT][32];
+    if (threadIdx.x < 32) {
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int s = 0; s < KS; ++s) {
-            const int r = 8 * mt + g, c4 = 4 * s + t4;
-            f_a[mt][s] = (r < K && c4 < K) ? Am[r * K + c4] : 0.;
-            f_b[s][mt] = (c4 < K && r < K) ? Ai[c4 * K + r] : 0.;
-        }
+            for (int s = 0; s < KS; ++s) {
+                const int r = 8 * mt + g, c4 = 4 * s + t4;
+                s_fa[mt * KS + s][lane] = (r < K && c4 < K) ? Am[r * K + c4] : 0.;
+                s_fb[s * MT + mt][lane] = (c4 < K && r < K) ? Ai[c4 * K + r] : 0.;
+            }
+    }
+    __syncthreads();
     const double d_lane = (lane < K) ? dv[lane] : 0.;
     pdl_launch_dependents();
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -501,12 +547,12 @@ __global__ void __launch_bounds__(kMmaBlock, 3) bu_maxp_mma_kernel(BuArgs a, int
                 }
                 double bfr[KS];   // B fragments of exp(d t') o A^-1 for this column tile
 #pragma unroll
-                for (int s = 0; s < KS; ++s) bfr[s] = f_b[s][nt] * ek[s];
+                for (int s = 0; s < KS; ++s) bfr[s] = s_fb[s * MT + nt][lane] * ek[s];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
                     double p0 = 0., p1 = 0.;
 #pragma unroll
-                    for (int s = 0; s < KS; ++s) dmma(p0, p1, f_a[mt][s], bfr[s]);
+                    for (int s = 0; s < KS; ++s) dmma(p0, p1, s_fa[mt * KS + s][lane], bfr[s]);
                     const double x0 = __dmul_rn(p0, l0), x1 = __dmul_rn(p1, l1);
                     if (i0 < K && x0 > best[mt]) { best[mt] = x0; arg[mt] = i0; }
                     if (i1 < K && x1 > best[mt]) { best[mt] = x1; arg[mt] = i1; }
@@ -562,7 +608,7 @@ bool mma_maxp_applicable(int K) { return K > 8 && K <= kMmaKP; }
 
 void mma_maxp_launch(cudaStream_t st, const BuArgs &a, int s0, int ns) {
     long long g = ((long long) ns + kMmaBlock / 32 - 1) / (kMmaBlock / 32);
-    const long long cap = std::max(1LL, 148LL * 3 / a.ln.J);   // persistent grid, blockIdx.y = lane   // persistent grid
+    const long long cap = std::max(1LL, 148LL * PML_MAXP_MINB / a.ln.J);   // persistent grid, blockIdx.y = lane
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     const int K = a.ln.K;
