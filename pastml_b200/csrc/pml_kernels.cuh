@@ -987,9 +987,20 @@ __global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_TDSEL_MINB : 1)) td_se
     pdl_launch_dependents();
     stage_params(s_par, a.ln, nf, false);
     pdl_wait();
-    const long long n_items = (long long) n_nodes * C;
-    for (long long g = (long long) blockIdx.x * blockDim.x + threadIdx.x; g < n_items; g += (long long) gridDim.x * blockDim.x) {
-        const int node = (int) (g / C), c = (int) (g - (long long) node * C);
+    const unsigned n_items = (unsigned) n_nodes * (unsigned) C;   // (< 2^31: the vectors alone would not fit otherwise)
+    for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < n_items; g += gridDim.x * blockDim.x) {
+        const unsigned nd = a.ln.divC.div(g);
+        const int node = (int) nd, c = (int) (g - nd * (unsigned) C);
+        // the node's top-down vector does not depend on anything looked up: requested first, so that it travels while
+        // the slot -> bottom-up vector chain resolves (a root's entry is never written: read, and ignored below)
+        double T[KP];
+        {
+            const double *src = td_all + ((size_t) node * K) * C + c;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) T[k] = (k < K) ? src[(size_t) k * C] : 0.;
+        }
+        const int t_ex = td_ex_all[(size_t) node * C + c];
+        const int par = a.t.parent[node];
         Lane<KP> lane;
         lane.init(LaneSmem{s_par + c, C}, a.ln.params + (size_t) c * a.ln.stride, K, nullptr);
         const bool use_alt = lane.tau == 0.;   // ml.py:702-703
@@ -1006,11 +1017,10 @@ __global__ void __launch_bounds__(kBlock, (KP <= 20 ? PML_TDSEL_MINB : 1)) td_se
 #pragma unroll
             for (int k = 0; k < KP; ++k) X[k] = bit_as_double(mc, k);
         }
-        if (a.t.parent[node] >= 0) {   // (a root's top-down vector is all ones, ml.py:274-277)
-            const double *src = td_all + ((size_t) node * K) * C + c;
+        if (par >= 0) {   // (a root's top-down vector is all ones, ml.py:274-277)
 #pragma unroll
-            for (int k = 0; k < KP; ++k) X[k] *= (k < K) ? src[(size_t) k * C] : 0.;
-            ex_total += td_ex_all[(size_t) node * C + c];
+            for (int k = 0; k < KP; ++k) X[k] *= T[k];
+            ex_total += t_ex;
         }
         emit_node<KP>(a, lane, node, c, X, mc, ex_total, sh_hist);
     }
