@@ -49,8 +49,15 @@ def pack_params(kind, K, sf, tau, tau_factor, pi, mu=None, kappa=None, d=None, A
     return out
 
 
+_STRIDES = {}
+
+
 def param_stride(kind, K):
-    return int(_lib.load().pml_param_stride(kind, K))
+    """Doubles per lane of a parameter block (pml_param_stride; cached: it is asked for with every packed block)."""
+    key = (int(kind), int(K))
+    if key not in _STRIDES:
+        _STRIDES[key] = int(_lib.load().pml_param_stride(*key))
+    return _STRIDES[key]
 
 
 class Problem(object):

@@ -164,6 +164,7 @@ class LockstepEvaluator(object):
         self.last_block = [m.engine_block() for m in batch.models]
         self.n_passes = 0
         self.n_lane_evaluations = 0
+        self.device_ms = 0.   # device time of the objective passes (the rest of the fit's wall time is the host's)
 
     def _flush(self):
         cols = sorted(self.pending)
@@ -180,6 +181,12 @@ class LockstepEvaluator(object):
                 self.errors[c] = e
                 self.results[c] = None
         finally:
+            stats = getattr(getattr(self.batch, 'problem', None), 'last_call_stats', None)
+            if stats is not None:
+                try:
+                    self.device_ms += stats()[0]
+                except Exception:   # measurement only
+                    pass
             self.pending.clear()
             self.cond.notify_all()
 
@@ -342,14 +349,8 @@ def optimize_likelihood_params(evaluate, observed_frequencies, model, evaluate_m
         # scipy's finite-difference driver maps the objective over the perturbed points of one gradient: same points,
         # same order as its sequential loop (the model ends up at the last one, as it would there)
         points = list(points)
-        blocks, ok = [], []
-        for ps in points:
-            if np.any(pd.isnull(ps)):
-                ok.append(False)
-                continue
-            model.set_params_from_optimised(ps)
-            blocks.append(model.engine_block())
-            ok.append(True)
+        ok = (~np.isnan(np.asarray(points, dtype=np.float64)).any(axis=1)).tolist() if points else []
+        blocks = model.engine_blocks([ps for ps, good in zip(points, ok) if good])
         values = iter(evaluate_many(blocks) if blocks else [])
         out = []
         for good in ok:
@@ -455,6 +456,7 @@ def fit_batch(batch, observed_frequencies):
             t.start()
         for t in threads:
             t.join()
+    batch.last_fit_device_ms = ev.device_ms
     for e in failures:
         if e is not None:
             raise e

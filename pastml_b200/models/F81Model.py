@@ -30,3 +30,33 @@ class F81Model(ModelWithFrequencies):
     def _engine_fields(self):
         with np.errstate(divide='ignore'):
             return dict(pi=self.frequencies, mu=self.get_mu())
+
+    def engine_blocks(self, points):
+        """All the blocks of a finite-difference batch in a handful of array operations -- the same floating-point
+        operations, row by row, as the point-by-point route (row sums of a C-contiguous array use numpy's pairwise
+        summation per row like the 1-D sum; the dot product of ``get_mu`` stays a per-row BLAS call); checked bit for
+        bit in tests/test_host_cpu.py.  Smoothing (tau or the frequency-smoothing scalar in the vector) takes the
+        point-by-point route."""
+        points = list(points)
+        if not points or self._optimise_tau or self._frequency_smoothing or type(self)._engine_fields is not F81Model._engine_fields:
+            return ModelWithFrequencies.engine_blocks(self, points)
+        from pastml_b200.engine import param_stride
+        pts = np.asarray(points, dtype=np.float64)
+        n, K = len(pts), len(self.states)
+        out = np.zeros((n, param_stride(self.engine_kind, K)), dtype=np.float64)
+        out[:, 0] = pts[:, 0] if self._optimise_sf else float(self.sf)
+        out[:, 1] = float(self.tau)
+        out[:, 2] = float(self._tau_factor)
+        if not self.extra_params_fixed() and self._optimise_frequencies:
+            first = self._basic_count()
+            freqs = np.empty((n, K), dtype=np.float64)
+            freqs[:, :K - 1] = pts[:, first: first + K - 1]
+            freqs[:, K - 1] = 1.
+            freqs /= freqs.sum(axis=1)[:, np.newaxis]
+        else:
+            freqs = np.broadcast_to(np.asarray(self.frequencies, dtype=np.float64), (n, K))
+        with np.errstate(divide='ignore'):
+            out[:, 3] = [np.float64(1.) / (1. - f.dot(f)) for f in freqs]
+        out[:, 4:4 + K] = freqs
+        self.set_params_from_optimised(points[-1])   # the state the point-by-point loop leaves behind
+        return list(out)

@@ -585,3 +585,56 @@ def test_flat_pipeline_checks_and_popcount():
             assert np.array_equal(P._popcount(masks), want) and np.array_equal(P._popcount(masks.reshape(2, 3)), want.reshape(2, 3))
         finally:
             np.bitwise_count = saved
+
+
+# ------------------------------------------------------------------ parameter blocks of a finite-difference batch
+
+def test_engine_blocks_equal_the_point_by_point_route():
+    """``Model.engine_blocks(points)`` (all the blocks of one gradient in a few array operations, F81 family) gives bit
+    for bit what ``set_params_from_optimised(ps); engine_block()`` gives point by point, for both stages of the fit, and
+    leaves the model at the last point; the other models and the smoothing options take the point-by-point route."""
+    from pastml_b200.annotation import ForestStats
+    from pastml_b200.models.F81Model import F81Model
+    from pastml_b200.models.JCModel import JCModel
+    from pastml_b200.models.EFTModel import EFTModel
+    from pastml_b200.models.HKYModel import HKYModel
+    from pastml_b200.tree import FlatForest
+    flat = FlatForest(np.array([-1, 0, 0, 1, 1], dtype=np.int32), np.array([0., 1., 2., 1., 1.]))
+    fs = ForestStats(flat=flat)
+    rng = np.random.default_rng(11)
+
+    def make(kind, K, **kw):
+        states = np.array(['s%02d' % i for i in range(K)])
+        if kind == 'F81':
+            return F81Model(states=states, forest_stats=fs, **kw)
+        if kind == 'JC':
+            return JCModel(states=states, forest_stats=fs, **kw)
+        if kind == 'EFT':
+            return EFTModel(states=states, forest_stats=fs, observed_frequencies=rng.dirichlet(np.ones(K)), **kw)
+        return HKYModel(states=np.array(list('ACGT')), forest_stats=fs, **kw)
+
+    cases = [('F81', K, {}) for K in (2, 3, 5, 7, 8, 9, 10, 16, 17, 20, 33, 62)] + \
+            [('JC', 5, {}), ('EFT', 6, {}), ('HKY', 4, {}), ('F81', 6, dict(frequency_smoothing=True)),
+             ('F81', 6, dict(tau=0., optimise_tau=True))]
+    for kind, K, kw in cases:
+        for fix_extra in (True, False):
+            a, b = make(kind, K, **kw), make(kind, K, **kw)
+            b._frequencies = a._frequencies if hasattr(a, '_frequencies') else None
+            if fix_extra:
+                a.fix_extra_params()
+                b.fix_extra_params()
+            n_par = a.get_num_params() if not fix_extra else len(a.get_optimised_parameters())
+            if n_par == 0:
+                continue
+            lo, hi = a.get_bounds()[:, 0], a.get_bounds()[:, 1]
+            points = [np.clip(rng.random(n_par) * 3. + 0.05, lo, hi) for _ in range(n_par + 3)]
+            want = []
+            for ps in points:
+                a.set_params_from_optimised(ps)
+                want.append(a.engine_block())
+            got = b.engine_blocks(points)
+            assert len(got) == len(want)
+            for g, w in zip(got, want):
+                assert np.array_equal(np.asarray(g), np.asarray(w)), (kind, K, fix_extra)
+            assert np.array_equal(a.engine_block(), b.engine_block())   # same state afterwards
+            assert np.array_equal(a.get_optimised_parameters(), b.get_optimised_parameters())

@@ -42,7 +42,7 @@ pb.loglik(params, mask_kind=MASK_MAP)
 pb.mppa_finalize(force_joint=True, want_masks=False)
 pb.loglik(params, mask_kind=MASK_MPPA)
 t2 = time.perf_counter()
-print('tips={} K={} C={}: fit {:.3f} s ({} lock-step passes, {:.3f} ms per pass), reconstruction passes {:.3f} s; '
-      'log-lh[0]={:.6f} sf[0]={:.6g} (simulated with {:.6g})'.format(tips, K, C, t1 - t0, passes, (t1 - t0) / passes * 1e3,
+print('tips={} K={} C={}: fit {:.3f} s ({} lock-step passes, {:.3f} ms per pass, device {:.3f} s), reconstruction passes {:.3f} s; '
+      'log-lh[0]={:.6f} sf[0]={:.6g} (simulated with {:.6g})'.format(tips, K, C, t1 - t0, passes, (t1 - t0) / passes * 1e3, getattr(batch, 'last_fit_device_ms', 0.) / 1e3,
                                                                     t2 - t1, lhs[0], models[0].sf, sfs[0]))
 batch.close()
