@@ -427,8 +427,158 @@ def _fit_one(evaluate, character, model, observed_frequencies, evaluate_many=Non
     return likelihood
 
 
+# ---- the same fit as coroutines: every column's optimiser in ONE thread, one device pass per round of requests
+
+def _values_gen(model, points):
+    """Objective values (-log-likelihood; inf where the likelihood is undefined, nan for a nan point) at the given
+    optimiser vectors: yields the parameter blocks, is sent their log-likelihoods (what ``get_v`` does point by point)."""
+    points = list(points)
+    ok = (~np.isnan(np.asarray(points, dtype=np.float64)).any(axis=1)).tolist() if points else []
+    blocks = model.engine_blocks([ps for ps, good in zip(points, ok) if good])
+    results = iter((yield blocks) if blocks else [])
+    out = []
+    for good in ok:
+        if not good:
+            out.append(np.nan)
+        else:
+            res = next(results)
+            out.append(np.inf if pd.isnull(res) else -res)
+    return out
+
+
+def _minimize_gen(model, x0, bounds):
+    """One bounded L-BFGS-B run from x0 (:mod:`pastml_b200.lbfgsb`: scipy's iterates bit for bit)."""
+    from pastml_b200.lbfgsb import minimize_lbfgsb
+    run = minimize_lbfgsb(x0, bounds)
+    try:
+        request = next(run)
+        while True:
+            values = yield from _values_gen(model, request)
+            request = run.send(values)
+    except StopIteration as stop:
+        return stop.value
+
+
+def _optimize_stage_gen(model, observed_frequencies, rng):
+    """:func:`optimize_likelihood_params` as a coroutine (same starting points, same acceptance rule)."""
+    bounds = model.get_bounds()
+    if np.any(observed_frequencies <= 0):
+        observed_frequencies = np.maximum(observed_frequencies, 1e-10)
+    x0_JC = model.get_optimised_parameters()
+    optimise_frequencies = isinstance(model, ModelWithFrequencies) and model._optimise_frequencies
+    x0_EFT = x0_JC
+    if optimise_frequencies:
+        model.frequencies = observed_frequencies
+        x0_EFT = model.get_optimised_parameters()
+    starts = yield from _values_gen(model, [x0_JC, x0_EFT] if optimise_frequencies else [x0_JC])
+    log_lh_JC = -starts[0]
+    log_lh_EFT = -starts[1] if optimise_frequencies else log_lh_JC
+    best_log_lh = max(log_lh_JC, log_lh_EFT)
+    for i in range(100):
+        if i == 0:
+            vs = x0_JC
+        elif optimise_frequencies and i == 1:
+            vs = x0_EFT
+        else:
+            vs = (rng or np.random).uniform(bounds[:, 0], bounds[:, 1])
+        fres = yield from _minimize_gen(model, vs, bounds)
+        if fres.success and not np.any(np.isnan(fres.x)):
+            if -fres.fun >= best_log_lh:
+                model.set_params_from_optimised(fres.x)
+                return -fres.fun
+    model.set_params_from_optimised(x0_JC if log_lh_JC >= log_lh_EFT else x0_EFT)
+    return best_log_lh
+
+
+def _fit_one_gen(character, model, observed_frequencies, rng):
+    """:func:`_fit_one` as a coroutine: yields lists of parameter blocks, is sent their log-likelihoods, returns the
+    fitted log-likelihood."""
+    logger = logging.getLogger('pastml')
+    likelihood = (yield [model.engine_block()])[0]
+    if np.isnan(likelihood):
+        raise PastMLLikelihoodError('Failed to calculate the likelihood for your tree, please check that you do not '
+                                    'have contradicting {} states specified for internal tree nodes, and if not - '
+                                    'submit a bug at https://github.com/evolbioinfo/pastml/issues'.format(character))
+    if not model.get_num_params():
+        logger.debug('All the parameters are fixed for {}:\n{}\tlog likelihood:\t{:.6f}.'
+                     .format(character, model._print_parameters(), likelihood))
+        return likelihood
+    logger.debug('Initial values for {} parameter optimisation:\n{}\tlog likelihood:\t{:.6f}.'
+                 .format(character, model._print_parameters(), likelihood))
+    failure = 'Failed to optimise the likelihood for your tree, please check that you do not have contradicting {} ' \
+              'states specified for internal tree nodes, and if not - submit a bug at ' \
+              'https://github.com/evolbioinfo/pastml/issues'.format(character)
+    if not model.basic_params_fixed():
+        model.fix_extra_params()
+        likelihood = yield from _optimize_stage_gen(model, observed_frequencies, rng)
+        if np.isnan(likelihood) or likelihood == -np.inf:
+            raise PastMLLikelihoodError(failure)
+        model.unfix_extra_params()
+        if not model.extra_params_fixed():
+            logger.debug('Pre-optimised basic parameters for {}:\n{}\tlog likelihood:\t{:.6f}.'
+                         .format(character, model._print_basic_parameters(), likelihood))
+    if not model.extra_params_fixed():
+        likelihood = yield from _optimize_stage_gen(model, observed_frequencies, rng)
+        if np.isnan(likelihood) or likelihood == -np.inf:
+            raise PastMLLikelihoodError(failure)
+    logger.debug('Optimised parameters for {}:\n{}\tlog likelihood:\t{:.6f}'
+                 .format(character, model._print_parameters(), likelihood))
+    return likelihood
+
+
+def _fit_batch_coroutines(batch, observed_frequencies):
+    """All the columns' fits advanced in lock step by ONE thread: a round collects every running column's request,
+    evaluates them in one device pass (:class:`LockstepEvaluator` does the packing) and sends the values back."""
+    ev = LockstepEvaluator(batch)
+    out = [None] * batch.C
+    failures = [None] * batch.C
+    rngs = [None] if batch.C == 1 else [np.random.default_rng(int(seed)) for seed in np.random.randint(0, 2 ** 31 - 1, size=batch.C)]
+    running, requests = {}, {}
+    for c in range(batch.C):
+        gen = _fit_one_gen(batch.characters[c], batch.models[c], observed_frequencies[c], rngs[c])
+        try:
+            requests[c] = next(gen)
+            running[c] = gen
+        except StopIteration as stop:
+            out[c] = stop.value
+        except BaseException as e:
+            failures[c] = e
+    while running:
+        with ev.cond:
+            ev.pending = {c: list(requests[c]) for c in running}
+            ev.results.clear()
+            ev._flush()
+        for c in list(running):
+            gen = running[c]
+            try:
+                if c in ev.errors:
+                    requests[c] = gen.throw(ev.errors.pop(c))
+                else:
+                    requests[c] = gen.send(ev.results[c])
+            except StopIteration as stop:
+                out[c] = stop.value
+                del running[c]
+            except BaseException as e:
+                failures[c] = e
+                del running[c]
+    batch.last_fit_device_ms = ev.device_ms
+    for e in failures:
+        if e is not None:
+            raise e
+    return out, ev.n_passes
+
+
 def fit_batch(batch, observed_frequencies):
-    """Fits all the columns of a batch concurrently; returns ([log-likelihood per column], n device passes)."""
+    """Fits all the columns of a batch concurrently; returns ([log-likelihood per column], n device passes).
+
+    Default driver: the coroutine one above.  PASTML_B200_FIT_DRIVER=threads takes the original one (one scipy
+    ``minimize`` call per column in its own thread, meeting in :class:`LockstepEvaluator`), which is also what columns
+    with frequency smoothing use: their model is stateful across evaluations (``models/__init__.py:331-335``), so the
+    order of the evaluations is part of the result."""
+    import os
+    stateful = any(getattr(m, '_frequency_smoothing', False) for m in batch.models)
+    if os.environ.get('PASTML_B200_FIT_DRIVER', 'coroutines') != 'threads' and batch.batched_fd and not stateful:
+        return _fit_batch_coroutines(batch, observed_frequencies)
     ev = LockstepEvaluator(batch)
     out = [None] * batch.C
     failures = [None] * batch.C

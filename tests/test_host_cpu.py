@@ -638,3 +638,68 @@ def test_engine_blocks_equal_the_point_by_point_route():
                 assert np.array_equal(np.asarray(g), np.asarray(w)), (kind, K, fix_extra)
             assert np.array_equal(a.engine_block(), b.engine_block())   # same state afterwards
             assert np.array_equal(a.get_optimised_parameters(), b.get_optimised_parameters())
+
+
+# ------------------------------------------------------------------ the coroutine L-BFGS-B driver
+
+def _drive(gen, fun):
+    """Runs a minimize_lbfgsb generator against a plain function."""
+    try:
+        request = next(gen)
+        while True:
+            request = gen.send([fun(p) for p in request])
+    except StopIteration as stop:
+        return stop.value
+
+
+def test_coroutine_lbfgsb_is_scipy_minimize_bit_for_bit():
+    """``lbfgsb.minimize_lbfgsb`` (requests batched as one point + its forward differences) walks through the same
+    iterates as ``scipy.optimize.minimize(method='L-BFGS-B')`` with bounds: same x, same value, same iteration count and
+    status, on objectives shaped like the fit's (log-scale parameter, ratios bounded by [1e-6, 1e7], optimum on a
+    bound, a start on a bound, a flat direction, inf on part of the domain)."""
+    from scipy.optimize import minimize
+    from pastml_b200.lbfgsb import minimize_lbfgsb
+    rng = np.random.default_rng(5)
+
+    def rosen(x):
+        return float(sum(100. * (x[1:] - x[:-1] ** 2) ** 2 + (1 - x[:-1]) ** 2))
+
+    def likelihood_like(x):
+        sf, ratios = x[0], x[1:]
+        pi = np.hstack((ratios, [1.]))
+        pi = pi / pi.sum()
+        target = np.linspace(1, 2, len(pi))
+        target = target / target.sum()
+        return float(40. * (np.log(sf) - np.log(3.)) ** 2 - 300. * (target * np.log(pi)).sum())
+
+    def with_inf(x):
+        return np.inf if x[0] > 7.5 else float((x[0] - 2.) ** 2 + (x[1] + 1.) ** 4 + 0. * x[2])
+
+    cases = [
+        (rosen, np.array([-1.2, 1., 0.5]), np.array([[-2., 2.]] * 3)),
+        (rosen, np.array([0.5, 0.5, 0.5, 0.5]), np.array([[0., 0.8]] * 4)),                      # optimum on a bound
+        (likelihood_like, np.r_[1., np.ones(4)], np.array([[0.001, 10.]] + [[1e-6, 10e6]] * 4)),
+        (likelihood_like, np.r_[10., rng.random(9) + .5], np.array([[0.001, 10.]] + [[1e-6, 10e6]] * 9)),   # start on a bound
+        (with_inf, np.array([5., 3., 1.]), np.array([[0., 10.], [-5., 5.], [0., 2.]])),
+    ]
+    for fun, x0, bounds in cases:
+        want = minimize(fun, x0=x0, method='L-BFGS-B', bounds=bounds)
+        got = _drive(minimize_lbfgsb(x0, bounds), fun)
+        assert np.array_equal(got.x, want.x), (fun.__name__, got.x, want.x)
+        assert got.fun == want.fun and got.nit == want.nit and got.success == want.success and got.status == want.status
+
+
+def test_coroutine_fit_equals_the_threaded_fit(monkeypatch):
+    """The two drivers of the lock-step fit -- one scipy ``minimize`` per column in its own thread, and all the columns
+    as coroutines in one thread (``lbfgsb.minimize_lbfgsb``) -- return the same log-likelihoods and leave the same
+    parameters on the models, bit for bit; the coroutine driver needs about half the device passes (a point travels with
+    its forward differences)."""
+    monkeypatch.setenv('PASTML_B200_FIT_DRIVER', 'threads')
+    t_out, t_passes, _, t_models = _fake_fit(True)
+    monkeypatch.setenv('PASTML_B200_FIT_DRIVER', 'coroutines')
+    c_out, c_passes, c_batch, c_models = _fake_fit(True)
+    assert t_out == c_out
+    for a, b in zip(t_models, c_models):
+        assert a.sf == b.sf and np.array_equal(a.frequencies, b.frequencies)
+    assert c_passes < 0.7 * t_passes
+    assert all(kind == 'lanes' for kind, _ in c_batch.calls)
