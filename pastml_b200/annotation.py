@@ -41,14 +41,27 @@ class ForestStats(object):
 
 
 def df2gdf(df):
-    """Groups a (node id x columns) table by node id into sets of non-empty values."""
-    df = df.copy()
-    df = df.astype(object).where(pd.notnull(df), '')
-    grouped = df.groupby(df.index)
-    gdf = pd.DataFrame(index=list(grouped.groups.keys()), columns=df.columns, dtype=object)
+    """Groups a (node id x columns) table by node id into sets of non-empty values (``annotation.py:104-110``: ids in
+    sorted order, one set per id and column, a repeated id collecting the values of all its rows).  One pass over each
+    column instead of a pandas ``groupby().apply`` per group -- 300k groups x 82 columns took 6 of the 8.6 s of an
+    82-column ``acr()`` call."""
+    keys = df.index.unique()
+    try:
+        keys = keys.sort_values()
+    except TypeError:   # ids of mixed types: keep the order of appearance
+        pass
+    codes = keys.get_indexer(df.index).tolist()
+    data = {}
     for c in df.columns:
-        gdf[c] = grouped[c].apply(lambda vs: {v for v in vs if not pd.isnull(v) and v != ''})
-    return gdf
+        column = df[c]
+        missing = column.isna().to_numpy()
+        values = column.astype(object).to_numpy().tolist()
+        sets = [set() for _ in range(len(keys))]
+        for k, v, gone in zip(codes, values, missing.tolist()):
+            if not gone and v != '':
+                sets[k].add(v)
+        data[c] = pd.Series(sets, index=keys, dtype=object)
+    return pd.DataFrame(data, index=keys, columns=df.columns, dtype=object)
 
 
 def preannotate_forest(forest, df=None, gdf=None):
