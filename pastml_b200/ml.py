@@ -149,10 +149,11 @@ def lane_list_size(n):
 
 
 class LockstepEvaluator(object):
-    """Rendezvous of the per-column optimiser threads: when every column that is still being fitted has asked
-    for objective values, a single batched pass evaluates all of them.  A request is a list of parameter blocks
-    (one for a plain evaluation, n_params + 1 for the finite-difference batch of one L-BFGS-B gradient): the pass
-    runs max(len) parameter sets x all columns."""
+    """One batched device pass for the requests of all the columns that are still being fitted.  A request is a list
+    of parameter blocks (one for a plain evaluation, the point and its n_params forward differences for one L-BFGS-B
+    step); a pass runs over exactly the requested lanes (lane lists) or over max(len) parameter sets x all columns.
+    The coroutine driver (``_fit_batch_coroutines``) fills ``pending`` and calls ``_flush`` itself; for the threads
+    driver this is also the rendezvous (``evaluate`` blocks until every active column has asked)."""
 
     def __init__(self, batch):
         self.batch = batch
