@@ -651,6 +651,125 @@ def get_bottom_up_loglikelihood(tree, character, model, is_marginal=True, alter=
         batch.close()
 
 
+# ---------------------------------------------------------------------------------------- allowed-state bookkeeping
+#
+# Host-side helpers with the reference's names and side effects on the nodes, for code that prepares or inspects the
+# ``<character>_ALLOWED_STATES`` features itself and then calls :func:`get_bottom_up_loglikelihood` (which reads them).
+# No likelihood arithmetic happens here; inside :func:`ml_acr` the same steps run on the device (``alter_kernel``).
+
+def _allowed_feature(feature):
+    return get_personalized_feature_name(feature, ALLOWED_STATES)
+
+
+def get_state2allowed_states(states, by_name=True):
+    """(all-ones array, {state (or its index): one-hot array}); missing values map to all ones (``ml.py:625-637``)."""
+    n = len(states)
+    everything = np.ones(n, int)
+    table = {}
+    for index, state in enumerate(states):
+        table[state if by_name else index] = (np.arange(n) == index).astype(int)
+    if by_name:
+        table[None] = table[''] = everything
+    return everything, table
+
+
+def initialize_allowed_states(tree, feature, states):
+    """0/1 array per node from its annotation set: every state where the set is empty or missing (``ml.py:293-318``)."""
+    index = {state: i for i, state in enumerate(states)}
+    n = len(states)
+    for node in tree.traverse():
+        annotated = getattr(node, feature, set())
+        allowed = np.zeros(n, dtype=int)
+        if annotated:
+            allowed[[index[state] for state in annotated]] = 1
+        else:
+            allowed[:] = 1
+        node.add_feature(_allowed_feature(feature), allowed)
+
+
+def get_zero_clusters_with_states(tree, feature):
+    """Groups of at least two annotated nodes connected by zero-length branches (``ml.py:321-349``)."""
+    def annotated(node):
+        value = getattr(node, feature, None)
+        return value is not None and value != ''
+
+    tops = [tree]
+    while tops:
+        members, frontier = [], [tops.pop()]
+        while frontier:
+            node = frontier.pop()
+            if annotated(node):
+                members.append(node)
+            for child in node.children:
+                (frontier if child.dist == 0 else tops).append(child)
+        if len(members) > 1:
+            yield members
+
+
+def alter_zero_node_allowed_states(tree, feature):
+    """Where the members of a zero-branch cluster share no allowed state, every member gets the running union of the
+    members' arrays (one shared array object, as in the reference) and keeps its own in ``.initial``; returns the
+    altered nodes (``ml.py:352-387``)."""
+    allowed_feature = _allowed_feature(feature)
+    altered = []
+    for members in get_zero_clusters_with_states(tree, feature):
+        votes = np.sum([getattr(node, allowed_feature) for node in members], axis=0)
+        if votes.max() == len(members):
+            continue
+        union = None
+        for node in members:
+            own = getattr(node, allowed_feature).copy()
+            if union is None:
+                union = own.copy()
+            else:
+                union[np.nonzero(own)] = 1
+            node.add_feature(allowed_feature, union)
+            node.add_feature(allowed_feature + '.initial', own)
+            altered.append(node)
+    return altered
+
+
+def unalter_zero_node_allowed_states(altered_nodes, feature):
+    """Back to the node's own states: what is left of them in the current array, or all of them (``ml.py:390-405``)."""
+    allowed_feature = _allowed_feature(feature)
+    for node in altered_nodes:
+        own = getattr(node, allowed_feature + '.initial')
+        kept = getattr(node, allowed_feature) & own
+        node.add_feature(allowed_feature, kept if np.any(kept > 0) else own)
+
+
+def unalter_zero_node_joint_states(altered_nodes, feature):
+    """Joint pointers of altered nodes that point outside the node's own states are redirected to its first own
+    state (``ml.py:408-428``)."""
+    pointer_feature = get_personalized_feature_name(feature, BU_LH_JOINT_STATES)
+    for node in altered_nodes:
+        own = getattr(node, _allowed_feature(feature) + '.initial')
+        first = np.argmax(own)
+        if np.count_nonzero(own > 0) == 1:
+            node.add_feature(pointer_feature, np.ones(len(own), int) * first)
+            continue
+        pointers = getattr(node, pointer_feature)
+        for i in range(len(own)):
+            if not own[pointers[i]]:
+                pointers[i] = first
+
+
+def convert_allowed_states2feature(tree, feature, states, out_feature=None):
+    """``node.<out_feature>`` = the set of state names the node's array allows (``ml.py:923-928``)."""
+    states = np.asarray(states)
+    for node in tree.traverse():
+        node.add_feature(out_feature or feature, set(states[getattr(node, _allowed_feature(feature)).astype(bool)]))
+
+
+def _parsimonious_states2allowed_states(tree, ps_feature, feature, states):
+    """Allowed-state arrays from the state sets a parsimonious reconstruction left in ``ps_feature`` (``ml.py:931-940``)."""
+    index = {state: i for i, state in enumerate(states)}
+    for node in tree.traverse():
+        allowed = np.zeros(len(states), dtype=int)
+        allowed[[index[state] for state in getattr(node, ps_feature)]] = 1
+        node.add_feature(_allowed_feature(feature), allowed)
+
+
 # ---------------------------------------------------------------------------------------- reconstruction
 
 STATE_MASKS = 'state_masks'   # array-native result: uint64 [N], bit k = state k, in the forest's level order

@@ -172,3 +172,28 @@ def test_columns_batched_like_separate_runs(tmp_path):
     flat = flatten_forest(forest)
     assert np.array_equal(masks_from_feature(flat.nodes, ga.states, 'Location'), ga['mppa_mask'])
     assert np.array_equal(masks_from_feature(flat.nodes, gb.states, 'genotype'), gb['mppa_mask'])
+
+
+def test_allowed_state_helpers_feed_the_likelihood():
+    """The reference's own calling pattern around ``get_bottom_up_loglikelihood`` (``ml.py:786-790``): allowed-state
+    arrays initialised and altered by the caller, then the likelihood with ``alter=False`` -- equal to letting the engine
+    alter, and to the reference's value at the same parameters."""
+    from pastml_b200.annotation import ForestStats
+    from pastml_b200.ml import (get_bottom_up_loglikelihood, initialize_allowed_states, alter_zero_node_allowed_states,
+                                unalter_zero_node_allowed_states)
+    from pastml_b200.models.F81Model import F81Model
+    g = Golden('albania_f81')
+    col = g.meta['column']
+    roots = annotated_forest(g)
+    tree = roots[0]
+    model = F81Model(states=np.array(g.states), forest_stats=ForestStats(roots), sf=float(g['sf']),
+                     frequencies=np.array(g['pi'], dtype=float), tau=float(g['tau']))
+    model.freeze()
+    by_engine = get_bottom_up_loglikelihood(tree, col, model, is_marginal=True, alter=True)
+    initialize_allowed_states(tree, col, np.array(g.states))
+    altered = alter_zero_node_allowed_states(tree, col)
+    assert altered   # this tree has contradicting annotations across zero-length branches
+    by_caller = get_bottom_up_loglikelihood(tree, col, model, is_marginal=True, alter=False)
+    unalter_zero_node_allowed_states(altered, col)
+    assert by_caller == pytest.approx(by_engine, rel=1e-13)
+    assert by_engine == pytest.approx(float(g['log_likelihood']), rel=1e-10)

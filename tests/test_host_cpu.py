@@ -703,3 +703,60 @@ def test_coroutine_fit_equals_the_threaded_fit(monkeypatch):
         assert a.sf == b.sf and np.array_equal(a.frequencies, b.frequencies)
     assert c_passes < 0.7 * t_passes
     assert all(kind == 'lanes' for kind, _ in c_batch.calls)
+
+
+# ------------------------------------------------------------------ allowed-state bookkeeping helpers
+
+def test_allowed_state_helpers_match_the_reference():
+    """initialize / alter / unalter of the ``_ALLOWED_STATES`` features and their conversions: same features on the
+    same nodes as the reference's functions, on random trees with zero-length branches and annotated internal nodes."""
+    from oracle import ref_env
+    if not ref_env.reference_available():
+        pytest.skip('the reference sources are not present')
+    ref_env.install()
+    import pastml.ml as R
+    import pastml_b200.ml as O
+    from pastml_b200 import tree as T
+    rng = np.random.default_rng(12)
+    states = np.array(['a', 'b', 'c', 'd'])
+    for trial in range(12):
+        text = _random_newick(rng, 25, named_internal=1.)
+        trees = [T.read_tree(text), T.read_tree(text)]
+        for tree in trees:
+            r2 = np.random.default_rng(100 + trial)
+            for node in tree.traverse('preorder'):
+                if not node.is_root() and r2.random() < .35:
+                    node.dist = 0.
+                u = r2.random()
+                if node.is_leaf() or u < .4:
+                    node.add_feature('x', set(r2.choice(states, size=r2.integers(0, 3), replace=False).tolist()))
+        ref_tree, our_tree = trees
+        R.initialize_allowed_states(ref_tree, 'x', states)
+        O.initialize_allowed_states(our_tree, 'x', states)
+        ref_alt = R.alter_zero_node_allowed_states(ref_tree, 'x')
+        our_alt = O.alter_zero_node_allowed_states(our_tree, 'x')
+        assert [n.name for n in ref_alt] == [n.name for n in our_alt]
+
+        def same(feature):
+            for a, b in zip(ref_tree.traverse(), our_tree.traverse()):
+                va, vb = getattr(a, feature, None), getattr(b, feature, None)
+                assert (va is None) == (vb is None), feature
+                if va is not None:
+                    assert np.array_equal(va, vb) if isinstance(va, np.ndarray) else va == vb, feature
+        same('x_ALLOWED_STATES')
+        same('x_ALLOWED_STATES.initial')
+        for tree, mod, alt in ((ref_tree, R, ref_alt), (our_tree, O, our_alt)):
+            for node in tree.traverse():
+                node.add_feature('x_BOTTOM_UP_LIKELIHOOD_JOINT_STATES', (np.arange(4) + len(node.name)) % 4)
+            mod.unalter_zero_node_joint_states(alt, 'x')
+            mod.unalter_zero_node_allowed_states(alt, 'x')
+            mod.convert_allowed_states2feature(tree, 'x', states, out_feature='y')
+            mod._parsimonious_states2allowed_states(tree, 'y', 'z', states)
+        same('x_ALLOWED_STATES')
+        same('x_BOTTOM_UP_LIKELIHOOD_JOINT_STATES')
+        same('y')
+        same('z_ALLOWED_STATES')
+    ones, table = O.get_state2allowed_states(states)
+    r_ones, r_table = R.get_state2allowed_states(states)
+    assert np.array_equal(ones, r_ones) and table.keys() == r_table.keys()
+    assert all(np.array_equal(table[k], r_table[k]) for k in table)
