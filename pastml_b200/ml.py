@@ -579,7 +579,12 @@ def fit_batch(batch, observed_frequencies):
     import os
     stateful = any(getattr(m, '_frequency_smoothing', False) for m in batch.models)
     if os.environ.get('PASTML_B200_FIT_DRIVER', 'coroutines') != 'threads' and batch.batched_fd and not stateful:
-        return _fit_batch_coroutines(batch, observed_frequencies)
+        try:
+            import pastml_b200.lbfgsb  # noqa: F401  (binds scipy's reverse-communication routine: private names)
+        except ImportError:   # another scipy layout: the threads driver goes through scipy's public minimize()
+            logging.getLogger('pastml').debug('coroutine L-BFGS-B driver unavailable with this scipy, using threads')
+        else:
+            return _fit_batch_coroutines(batch, observed_frequencies)
     ev = LockstepEvaluator(batch)
     out = [None] * batch.C
     failures = [None] * batch.C
