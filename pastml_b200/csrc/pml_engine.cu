@@ -1069,16 +1069,17 @@ int pml_marginal(pml_problem *p, const double *params, int32_t force_joint, doub
         CUDA_TRY(cudaMemcpyAsync(out_probs, p->probs.ptr, nc * p->K * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     if (out_node_log10lh)
         CUDA_TRY(cudaMemcpyAsync(out_node_log10lh, p->node_lh.ptr, nc * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (stream_out) {   // (before anything below may return: the copy stream writes into the caller's buffers)
+        const cudaError_t e = cudaStreamSynchronize(p->copy_stream);
+        if (copy_rc == cudaSuccess) copy_rc = e;
+    }
     CUDA_TRY(cudaStreamSynchronize(p->stream));
+    CUDA_TRY(copy_rc);
     if (!stream_out) {
         if (out_map_mask) { int r2 = copy_masks_out(p, p->mask[PML_MASK_MAP].ptr, out_map_mask); if (r2) return r2; }
         if (out_mppa_mask) { int r2 = copy_masks_out(p, p->mask[PML_MASK_MPPA].ptr, out_mppa_mask); if (r2) return r2; }
     }
     if (out_k_hist) { int r2 = copy_khist_out(p, out_k_hist); if (r2) return r2; }
-    if (stream_out) {
-        CUDA_TRY(cudaStreamSynchronize(p->copy_stream));
-        CUDA_TRY(copy_rc);
-    }
     return rc;
 }
 
