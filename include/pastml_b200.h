@@ -261,6 +261,13 @@ int64_t pml_newick_num_nodes(const pml_newick *nw);
 int64_t pml_newick_num_trees(const pml_newick *nw);
 int64_t pml_newick_names_bytes(const pml_newick *nw);
 int pml_newick_name_nodes(pml_newick *nw, int use_tree_suffix);
+
+/* A table of floats as text, the way the reference writes marginal probabilities (acr.py:45-73,
+ * DataFrame.to_csv(sep='\t', index_label='node')): `header` + '\n', then per row its label (labels: one UTF-8 blob,
+ * label r = [label_offsets[r], label_offsets[r + 1])), a tab and the Python repr() of every value ([n_rows][n_cols];
+ * empty cell for NaN).  Host only.  Returns 0, or 1 with pml_newick_last_error(). */
+int pml_write_float_table(const char *path, const char *header, const char *labels, const int64_t *label_offsets,
+                          const double *values, int64_t n_rows, int32_t n_cols);
 int pml_newick_fill(const pml_newick *nw, int32_t *parent, double *dist, int64_t *name_offsets, char *names);
 void pml_newick_free(pml_newick *nw);
 

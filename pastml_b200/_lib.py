@@ -21,7 +21,8 @@ EXPORTS = ['pml_last_error', 'pml_version', 'pml_device_count', 'pml_param_strid
            'pml_shard_joint_bottom_up', 'pml_shard_joint_finish', 'pml_shard_joint_states',
            'pml_shard_bench_step',
            'pml_newick_last_error', 'pml_newick_parse', 'pml_newick_num_nodes', 'pml_newick_num_trees',
-           'pml_newick_names_bytes', 'pml_newick_name_nodes', 'pml_newick_fill', 'pml_newick_free']
+           'pml_newick_names_bytes', 'pml_newick_name_nodes', 'pml_newick_fill', 'pml_newick_free',
+           'pml_write_float_table']
 
 PML_OK, PML_ERR_INVALID, PML_ERR_CUDA, PML_ERR_ZERO_LIKELIHOOD, PML_ERR_NO_DEVICE = 0, 1, 2, 3, 4
 MODEL_F81, MODEL_HKY, MODEL_EIG = 0, 1, 2
@@ -122,6 +123,8 @@ def load():
     lib.pml_newick_num_trees.argtypes = [vp]
     lib.pml_newick_names_bytes.restype = i64
     lib.pml_newick_names_bytes.argtypes = [vp]
+    lib.pml_write_float_table.restype = C.c_int
+    lib.pml_write_float_table.argtypes = [C.c_char_p, C.c_char_p, vp, vp, vp, C.c_int64, C.c_int32]
     lib.pml_newick_name_nodes.restype = C.c_int
     lib.pml_newick_name_nodes.argtypes = [vp, C.c_int]
     lib.pml_newick_fill.restype = C.c_int

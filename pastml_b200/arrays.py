@@ -28,25 +28,36 @@ def table_masks(flat, df, column, states=None, names=None):
     names (a node listed several times gets the union of its states, as ``annotation.df2gdf`` does;
     ``annotation.py:104-123``; ``has_state`` marks every node the table lists).  ``states`` defaults to the sorted values of the column (``acr.py:211-213``)."""
     values = df[column]
-    # node index of every table row (-1: the id is not a node name); get_indexer is one vectorised hash join
-    # (``names``: join on these instead of flat.names -- the names as written in the tree file, before name_tree)
-    node_names = pd.Index(np.asarray(flat.names if names is None else names, dtype=object))
-    if node_names.has_duplicates:
-        node_names = pd.Index(np.where(node_names.duplicated(), None, node_names))   # first occurrence wins
-    row_node = node_names.get_indexer(pd.Index(values.index.astype(str)))
     text = values.astype(object).where(values.notna(), None)
     filled = np.array([v is not None and str(v) != '' for v in text], dtype=bool)
     if states is None:
         states = np.array(sorted({str(v) for v in text[filled]}))
-    codes = pd.Index(np.asarray(states, dtype=object)).get_indexer(pd.Index([str(v) for v in text[filled]]))
-    rows = row_node[filled]
-    ok = (rows >= 0) & (codes >= 0)
+    codes = np.full(len(values), -1, dtype=np.int64)
+    codes[filled] = pd.Index(np.asarray(states, dtype=object)).get_indexer(pd.Index([str(v) for v in text[filled]]))
+    # (table row, node) pairs by name: one vectorised hash join.  ``names``: join on these instead of flat.names -- the
+    # names as written in the tree file, before name_tree; there a name may repeat, and like preannotate_forest
+    # (annotation.py:113-123, which runs before the nodes are renamed) EVERY node of that name takes the row; unnamed
+    # nodes ('') match nothing
+    node_names = np.asarray(flat.names if names is None else names, dtype=object)
+    index = pd.Index(node_names)
+    ids = pd.Index(values.index.astype(str))
+    if index.is_unique:
+        node = index.get_indexer(ids)
+        row = np.arange(len(ids))
+        keep = node >= 0
+        row, node = row[keep], node[keep]
+    else:
+        named = np.flatnonzero(node_names != '')
+        pairs = pd.DataFrame({'name': ids, 'row': np.arange(len(ids))}).merge(
+            pd.DataFrame({'name': node_names[named], 'node': named}), on='name', how='inner')
+        row, node = pairs['row'].to_numpy(), pairs['node'].to_numpy()
     mask = np.zeros(flat.n_nodes, dtype=np.uint64)
-    np.bitwise_or.at(mask, rows[ok], np.uint64(1) << codes[ok].astype(np.uint64))
+    ok = codes[row] >= 0
+    np.bitwise_or.at(mask, node[ok], np.uint64(1) << codes[row][ok].astype(np.uint64))
     # "has a state" in the reference's zero-branch clusters = the node carries the feature at all, and
     # preannotate_forest gives it (as an empty set) to every node the table lists, missing values included (ml.py:329-331)
     has = np.zeros(flat.n_nodes, dtype=np.uint8)
-    has[row_node[row_node >= 0]] = 1
+    has[node] = 1
     return np.asarray(states), mask, has
 
 

@@ -760,3 +760,52 @@ def test_allowed_state_helpers_match_the_reference():
     r_ones, r_table = R.get_state2allowed_states(states)
     assert np.array_equal(ones, r_ones) and table.keys() == r_table.keys()
     assert all(np.array_equal(table[k], r_table[k]) for k in table)
+
+
+def test_table_masks_with_unnamed_and_repeated_node_names():
+    """Joining the annotation table on the names as written in the tree file: unnamed internal nodes (all '') match
+    nothing, and every node of a repeated name takes the row (preannotate_forest runs before the nodes are renamed)."""
+    import pandas as pd
+    from pastml_b200.arrays import table_masks
+    from pastml_b200.tree import read_forest_flat
+    text = '((a:1,b:1):1,(c:1,a:1):1,d:2);'
+    flat = read_forest_flat(text)
+    raw = read_forest_flat(text, name_nodes=False).names
+    assert list(raw).count('') == 3 and list(raw).count('a') == 2
+    df = pd.DataFrame({'x': ['s', 't', 's', None]}, index=['a', 'b', 'd', 'zzz'])
+    states, mask, has = table_masks(flat, df, 'x', names=raw)
+    assert list(states) == ['s', 't']
+    raw = np.asarray(raw, dtype=object)
+    want_mask = np.zeros(flat.n_nodes, dtype=np.uint64)
+    want_mask[raw == 'a'] = 1
+    want_mask[raw == 'b'] = 2
+    want_mask[raw == 'd'] = 1
+    assert np.array_equal(mask, want_mask)
+    assert has.sum() == 4 and np.all(has[raw == 'a'] == 1) and not has[raw == ''].any()
+
+
+def test_probability_table_writer_equals_pandas(tmp_path):
+    """The fast writer of the marginal-probability tables produces pandas' ``to_csv(sep='\t', index_label='node')``
+    text byte for byte (shortest round-trip floats, exponents, zeros and ones, NaN as an empty cell), and defers to
+    pandas for anything that is not a plain float table."""
+    import pandas as pd
+    from pastml_b200.pipeline import write_probability_table
+    rng = np.random.default_rng(2)
+    values = rng.random((500, 6))
+    values /= values.sum(axis=1)[:, None]
+    values[0] = [1., 0., 0., 0., 0., 0.]
+    values[1] = [1e-300, 1e-5, 0.1, 1 / 3, 2 / 3, 123456789.125]
+    values[2, 3] = np.nan
+    values[3] = [5e-324, 1e22, 1e16, 1e15, 0.5, 1e-4]
+    values[4] = [-0.0, np.inf, -np.inf, -2.5e-7, 9999999999999998., 1.7976931348623157e308]
+    values[100:400] = 10. ** rng.uniform(-320, 308, (300, 6)) * rng.choice([-1., 1.], (300, 6))   # every magnitude
+    values[400:450] = rng.integers(0, 10 ** 17, (50, 6)).astype(float)
+    df = pd.DataFrame(values, index=['n%d' % i for i in range(500)], columns=list('ABCDEF'))
+    fast, slow = str(tmp_path / 'fast.tab'), str(tmp_path / 'slow.tab')
+    write_probability_table(df, fast)
+    df.to_csv(slow, sep='\t', index_label='node')
+    assert open(fast, 'rb').read() == open(slow, 'rb').read()
+    odd = pd.DataFrame({'A': [1, 2]}, index=['x\ty', 'z'])   # integers, a tab in a label: pandas' quoting rules
+    write_probability_table(odd, fast)
+    odd.to_csv(slow, sep='\t', index_label='node')
+    assert open(fast, 'rb').read() == open(slow, 'rb').read()
