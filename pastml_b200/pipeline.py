@@ -178,7 +178,11 @@ def write_probability_table(df, path):
         not any(ch in str(c) for c in df.columns for ch in '\t\n\r"') and df.index.nlevels == 1
     if plain:
         labels = df.index.tolist()
-        plain = all(isinstance(v, str) and not any(ch in v for ch in '\t\n\r"') for v in labels)
+        try:   # labels that would need pandas' quoting rules (or are not text) go through pandas
+            text = '\x00'.join(labels)
+            plain = not any(ch in text for ch in '\t\n\r"')
+        except TypeError:
+            plain = False
     if not plain:
         df.to_csv(path, sep='\t', index_label='node')
         return
