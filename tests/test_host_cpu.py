@@ -809,3 +809,17 @@ def test_probability_table_writer_equals_pandas(tmp_path):
     write_probability_table(odd, fast)
     odd.to_csv(slow, sep='\t', index_label='node')
     assert open(fast, 'rb').read() == open(slow, 'rb').read()
+
+
+def test_probability_table_writer_edge_cases(tmp_path):
+    """Empty tables, one column, non-ASCII labels: still pandas' text."""
+    import pandas as pd
+    from pastml_b200.pipeline import write_probability_table
+    cases = [pd.DataFrame(np.zeros((0, 3)), index=[], columns=['a', 'b', 'c']),
+             pd.DataFrame([[0.25], [0.75]], index=['nœud_é', 'узел'], columns=['état']),
+             pd.DataFrame(np.full((2, 2), np.nan), index=['x', 'y'], columns=['p', 'q'])]
+    for i, df in enumerate(cases):
+        fast, slow = str(tmp_path / 'fast{}.tab'.format(i)), str(tmp_path / 'slow{}.tab'.format(i))
+        write_probability_table(df, fast)
+        df.to_csv(slow, sep='\t', index_label='node')
+        assert open(fast, 'rb').read() == open(slow, 'rb').read(), i
