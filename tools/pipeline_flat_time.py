@@ -14,9 +14,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pastml_b200 import synth  # noqa: E402
 from pastml_b200.arrays import pastml_pipeline_flat  # noqa: E402
 
-tips = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
-K = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-C = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+args = [a for a in sys.argv[1:] if not a.startswith('--')]
+tips = int(args[0]) if len(args) > 0 else 100000
+K = int(args[1]) if len(args) > 1 else 10
+C = int(args[2]) if len(args) > 2 else 4
 rng = np.random.default_rng(9)
 flat = synth.yule_tree(tips, rng)
 masks, has, pis, sfs = synth.simulate_tip_masks(flat, K, C, rng)
@@ -39,10 +40,12 @@ pd.DataFrame(data, index=[names[i] for i in tip_ids]).to_csv(table_file, sep='\t
 out = os.path.join(work, 'out')
 pastml_pipeline_flat(tree_file, table_file, work_dir=os.path.join(work, 'warm'))   # CUDA context, kernels loaded
 t0 = time.perf_counter()
-pr = cProfile.Profile()
-pr.enable()
 flat2, results = pastml_pipeline_flat(tree_file, table_file, work_dir=out)
-pr.disable()
-print('tips={} K={} columns={}: pastml_pipeline_flat {:.2f} s (fit + reconstruction + result files)'.format(
+print('tips={} K={} columns={}: pastml_pipeline_flat {:.2f} s (parsing + fit + reconstruction + result files)'.format(
     tips, K, C, time.perf_counter() - t0))
-pstats.Stats(pr).sort_stats('cumtime').print_stats(16)
+if '--profile' in sys.argv:
+    pr = cProfile.Profile()
+    pr.enable()
+    pastml_pipeline_flat(tree_file, table_file, work_dir=out)
+    pr.disable()
+    pstats.Stats(pr).sort_stats('cumtime').print_stats(16)
